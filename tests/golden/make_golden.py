@@ -1,0 +1,274 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py        (build container only)
+
+/root/reference is put on sys.path read-only (after tests/golden/ref_shims.install()).  Nothing
+here is imported by the product or by the GPU-side tests; the fixtures it writes are.
+Fixtures (all small):
+  schema.json            state-dict keys/shapes of vnet(1,2), vbnet(1,5)       (network/vnet.py, vbnet.py)
+  weights_sha256.json    sha256 of seeded kaiming/gaussian-initialised weights  (module/weight_init.py)
+  forward.npz            reference net outputs on seeded inputs                 (SegmentationNet.forward)
+  grids.json             image_partition_by_fixed_size outputs                  (utils/image_tools.py:163-218)
+  loss.npz               Dice / focal values and gradients                      (loss/*.py)
+  sliding_window.npz     core.seg_infer.segmentation_volume end to end          (core/seg_infer.py:249-350)
+  train_step.npz         one Adam step of the reference training loop body      (core/seg_train.py:119-127)
+"""
+import copy
+import hashlib
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shims  # noqa: E402
+
+sitk = ref_shims.install()
+sys.path.insert(0, '/root/reference')
+sys.dont_write_bytecode = True
+
+from segmentation3d.utils import image_tools as ref_it            # noqa: E402
+from segmentation3d.core import seg_infer as ref_infer            # noqa: E402
+from segmentation3d.loss.multi_dice_loss import MultiDiceLoss    # noqa: E402
+from segmentation3d.loss.focal_loss import FocalLoss              # noqa: E402
+from segmentation3d.loss.binary_dice_loss import BinaryDiceLoss  # noqa: E402
+from segmentation3d.utils.normalizer import FixedNormalizer, AdaptiveNormalizer  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def make_net(arch, cin, cout, seed, mode='kaiming'):
+    mod = importlib.import_module('segmentation3d.network.' + arch)
+    torch.manual_seed(seed)
+    net = mod.SegmentationNet(cin, cout)
+    (mod.parameters_kaiming_init if mode == 'kaiming' else mod.parameters_gaussian_init)(net)
+    return net.eval()
+
+
+def sd_hash(sd):
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(v.detach().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def seeded_input(seed, shape, kind='noise'):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(shape, generator=g)
+    if kind == 'smooth':   # CT-like: low-frequency field + noise
+        lo = torch.randn((shape[0], shape[1]) + tuple(max(2, s // 8) for s in shape[2:]), generator=g)
+        x = torch.nn.functional.interpolate(lo, size=shape[2:], mode='trilinear', align_corners=False) * 2 + 0.3 * x
+    return x
+
+
+def randomize_affine(sd, seed):
+    """must mirror oracle/init.py:randomize_affine"""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, v in sd.items():
+        if v.dim() == 1:
+            if '.gn' in k or '_gn' in k:
+                out[k] = (1.0 + 0.2 * torch.randn(v.shape, generator=g)) if k.endswith('.weight') \
+                    else 0.1 * torch.randn(v.shape, generator=g)
+            else:
+                out[k] = 0.05 * torch.randn(v.shape, generator=g)
+        else:
+            out[k] = v.clone()
+    return out
+
+
+def gen_schema_and_hashes():
+    schema, hashes = {}, {}
+    for arch, cin, cout in (('vnet', 1, 2), ('vbnet', 1, 5)):
+        net = make_net(arch, cin, cout, 0)
+        sd = net.state_dict()
+        schema['%s_%d_%d' % (arch, cin, cout)] = [[k, list(v.shape)] for k, v in sd.items()]
+        for seed in (0, 1):
+            hashes['%s_%d_%d_seed%d_kaiming' % (arch, cin, cout, seed)] = sd_hash(make_net(arch, cin, cout, seed).state_dict())
+        hashes['%s_%d_%d_seed0_gaussian' % (arch, cin, cout)] = sd_hash(make_net(arch, cin, cout, 0, 'gaussian').state_dict())
+    json.dump(schema, open(os.path.join(HERE, 'schema.json'), 'w'), indent=0)
+    json.dump(hashes, open(os.path.join(HERE, 'weights_sha256.json'), 'w'), indent=1)
+
+
+FORWARD_CASES = [
+    # name, arch, cin, cout, weight seed, affine seed (None = as initialised), input seed, shape [B,C,D,H,W], kind
+    ('vnet_c2_32', 'vnet', 1, 2, 0, None, 100, (1, 1, 32, 32, 32), 'noise'),
+    ('vnet_c2_aff_16x32x48', 'vnet', 1, 2, 1, 7, 101, (2, 1, 16, 32, 48), 'smooth'),
+    ('vbnet_c5_32', 'vbnet', 1, 5, 0, None, 102, (1, 1, 32, 32, 32), 'noise'),
+    ('vbnet_c5_aff_32x16x48', 'vbnet', 1, 5, 1, 8, 103, (1, 1, 32, 16, 48), 'smooth'),
+]
+
+
+def gen_forward():
+    out = {}
+    meta = []
+    for name, arch, cin, cout, wseed, aseed, iseed, shape, kind in FORWARD_CASES:
+        net = make_net(arch, cin, cout, wseed)
+        if aseed is not None:
+            net.load_state_dict(randomize_affine(net.state_dict(), aseed))
+        x = seeded_input(iseed, shape, kind)
+        with torch.no_grad():
+            y = net(x)
+        out[name] = y.numpy().astype(np.float32)
+        meta.append([name, arch, cin, cout, wseed, aseed, iseed, list(shape), kind])
+        print(name, tuple(y.shape), float(y.min()), float(y.max()))
+    out['meta'] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, 'forward.npz'), **out)
+
+
+GRID_CASES = [
+    # size xyz, spacing, bbox_start, bbox_end (None = whole), partition_size mm, stride mm
+    ([512, 512, 400], [1, 1, 1], None, None, [96, 96, 96], [96, 96, 96]),
+    ([512, 512, 400], [1, 1, 1], None, None, [96, 96, 96], [48, 48, 48]),
+    ([256, 256, 256], [1, 1, 1], None, None, [96, 96, 96], [96, 96, 96]),
+    ([256, 256, 256], [1, 1, 1], None, None, [96, 96, 96], [48, 48, 48]),
+    ([96, 96, 96], [1, 1, 1], None, None, [96, 96, 96], [96, 96, 96]),
+    ([192, 192, 192], [1, 1, 1], None, None, [96, 96, 96], [96, 96, 96]),
+    ([512, 512, 400], [0.4, 0.4, 0.4], None, None, [89.6, 89.6, 89.6], [89.6, 89.6, 89.6]),
+    ([400, 400, 320], [1, 1, 1], None, None, [96, 96, 96], [96, 96, 96]),
+    ([64, 48, 80], [1, 1, 1], None, None, [32, 32, 32], [16, 16, 16]),
+    ([160, 128, 96], [0.8, 0.8, 1.25], None, None, [51.2, 51.2, 51.2], [25.6, 25.6, 25.6]),
+    ([160, 128, 96], [1, 1, 1], [13, 20, 5], [120, 99, 70], [48, 48, 48], [24, 24, 24]),
+    ([160, 128, 96], [1, 1, 1], [100, 60, 40], [160, 128, 96], [64, 64, 64], [64, 64, 64]),
+    ([64, 64, 64], [1, 1, 1], [10, 10, 10], [20, 20, 20], [96, 96, 96], [96, 96, 96]),
+    ([128, 128, 128], [1.5, 1.5, 1.5], None, None, [100, 100, 100], [33, 33, 33]),
+]
+
+
+def gen_grids():
+    res = []
+    for size, spacing, bs, be, psize, pstride in GRID_CASES:
+        im = sitk.Image(size, sitk.sitkFloat32)
+        im.SetSpacing(spacing)
+        bs_ = copy.deepcopy(bs) if bs is not None else [0, 0, 0]
+        be_ = copy.deepcopy(be) if be is not None else list(size)
+        s, e = ref_it.image_partition_by_fixed_size(im, bs_, be_, copy.deepcopy(psize), copy.deepcopy(pstride), 16)
+        res.append({'size': size, 'spacing': spacing, 'bbox_start': bs, 'bbox_end': be, 'partition_size': psize,
+                    'partition_stride': pstride, 'n': len(s),
+                    'starts': [[int(v) for v in p] for p in s], 'ends': [[int(v) for v in p] for p in e],
+                    'bbox_start_after': [int(v) for v in bs_], 'bbox_end_after': [int(v) for v in be_]})
+        print('grid', size, psize, pstride, len(s))
+    json.dump(res, open(os.path.join(HERE, 'grids.json'), 'w'))
+
+
+def gen_loss():
+    out = {}
+    g = torch.Generator().manual_seed(5)
+    for c, shape in ((2, (2, 2, 8, 8, 8)), (5, (3, 5, 4, 8, 6))):
+        logits = torch.randn(shape, generator=g) * 2
+        probs = torch.softmax(logits, 1)
+        # exact ties at 1/C on some voxels
+        probs[:, :, 0, 0, :] = 1.0 / c
+        target = torch.randint(0, c, (shape[0], 1) + shape[2:], generator=g).float()
+        w = [1.0 + i for i in range(c)]
+        p1 = probs.clone().requires_grad_(True)
+        l1 = MultiDiceLoss(w, c, False)(p1, target)
+        l1.backward()
+        p2 = probs.clone().requires_grad_(True)
+        l2 = FocalLoss(c, alpha=w, gamma=2, size_average=True, use_gpu=False)(p2, target)
+        l2.backward()
+        p3 = probs.clone().requires_grad_(True)
+        l3 = FocalLoss(c, alpha=None, gamma=0, size_average=False, use_gpu=False)(p3, target)
+        l3.backward()
+        k = 'c%d_' % c
+        out[k + 'probs'], out[k + 'target'], out[k + 'weights'] = probs.numpy(), target.numpy(), np.array(w, np.float32)
+        out[k + 'dice'], out[k + 'dice_grad'] = l1.detach().numpy(), p1.grad.numpy()
+        out[k + 'focal'], out[k + 'focal_grad'] = l2.detach().numpy(), p2.grad.numpy()
+        out[k + 'focal_g0_sum'], out[k + 'focal_g0_sum_grad'] = l3.detach().numpy(), p3.grad.numpy()
+        print('loss c=%d dice=%.6f focal=%.6f' % (c, float(l1), float(l2)))
+    pb = torch.softmax(torch.randn((2, 2, 6, 6, 6), generator=g), 1)
+    tb = torch.randint(0, 2, (2, 1, 6, 6, 6), generator=g).float()
+    out['bin_probs'], out['bin_target'] = pb.numpy(), tb.numpy()
+    out['bin_dice'] = BinaryDiceLoss()(pb.clone(), tb).numpy()
+    np.savez_compressed(os.path.join(HERE, 'loss.npz'), **out)
+
+
+SW_CASES = [
+    # name, arch, cout, wseed, aseed, size xyz, psize, pstride, normalizer, vol seed
+    ('sw_vnet_fixed', 'vnet', 2, 0, 3, [64, 48, 80], [32, 32, 32], [16, 16, 16], ('fixed', 50.0, 200.0, True), 11),
+    ('sw_vnet_adaptive', 'vnet', 2, 1, None, [48, 48, 64], [32, 32, 32], [32, 32, 32], ('adaptive', 2.5), 12),
+    ('sw_vbnet_fixed', 'vbnet', 5, 0, 4, [48, 64, 48], [32, 32, 32], [16, 32, 16], ('fixed', 0.0, 1.0, False), 13),
+]
+
+
+def synth_volume(seed, size_xyz, scale):
+    x = seeded_input(seed, (1, 1, size_xyz[2], size_xyz[1], size_xyz[0]), 'smooth')[0, 0].numpy()
+    return (x * scale).astype(np.float32)
+
+
+def gen_sliding_window():
+    from easydict import EasyDict as edict
+    out, meta = {}, []
+    for name, arch, cout, wseed, aseed, size, psize, pstride, norm, vseed in SW_CASES:
+        net = make_net(arch, 1, cout, wseed)
+        if aseed is not None:
+            net.load_state_dict(randomize_affine(net.state_dict(), aseed))
+        model = edict()
+        model.net = net
+        model.spacing, model.max_stride, model.interpolation = [1.0, 1.0, 1.0], 16, 'LINEAR'
+        model.in_channels, model.out_channels = 1, cout
+        if norm[0] == 'fixed':
+            model.crop_normalizers = [FixedNormalizer(norm[1], norm[2], norm[3])]
+            scale = 300.0 if norm[2] > 1 else 1.0
+        else:
+            model.crop_normalizers = [AdaptiveNormalizer(norm[1])]
+            scale = 300.0
+        cfg = edict()
+        cfg.partition_type, cfg.partition_size, cfg.partition_stride = 'SIZE', psize, pstride
+        cfg.cpu_model_spacing_increase_ratio, cfg.cpu_partition_decrease_ratio = 1.0, 1.0
+        cfg.pick_largest_cc, cfg.remove_small_cc = False, 0
+        vol = synth_volume(vseed, size, scale)
+        image = sitk.GetImageFromArray(vol)
+        mean_probs, mask = ref_infer.segmentation_volume(model, cfg, image, None, None, False)
+        probs = np.stack([sitk.GetArrayFromImage(p) for p in mean_probs], 0).astype(np.float32)
+        out[name + '_probs'] = probs
+        out[name + '_mask'] = sitk.GetArrayFromImage(mask).astype(np.int8)
+        meta.append([name, arch, cout, wseed, aseed, size, psize, pstride, list(norm), vseed, scale])
+        print(name, probs.shape, 'fg frac', float((out[name + '_mask'] > 0).mean()))
+    out['meta'] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, 'sliding_window.npz'), **out)
+
+
+def gen_train_step():
+    """core/seg_train.py:83,119-127 on one synthetic batch: Adam(lr=1e-4, betas=(0.9,0.999))."""
+    out = {}
+    for name, arch, cout, lossname in (('vnet_dice', 'vnet', 2, 'Dice'), ('vbnet_focal', 'vbnet', 5, 'Focal')):
+        net = make_net(arch, 1, cout, 0).train()
+        g = torch.Generator().manual_seed(21)
+        crops = torch.randn((2, 1, 16, 16, 32), generator=g)
+        masks = torch.randint(0, cout, (2, 1, 16, 16, 32), generator=g).float()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.999))
+        if lossname == 'Dice':
+            loss_func = MultiDiceLoss([1.0] * cout, cout, False)
+        else:
+            loss_func = FocalLoss(cout, alpha=[1.0] * cout, gamma=2, use_gpu=False)
+        losses = []
+        for _ in range(2):
+            opt.zero_grad()
+            loss = loss_func(net(crops), masks)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        sd = net.state_dict()
+        out[name + '_losses'] = np.array(losses, np.float64)
+        for k in ('in_block.conv.weight', 'down_64.down_conv.weight', 'up_32.up_conv.weight', 'out_block.conv2.weight',
+                  'out_block.gn1.weight', 'up_128.up_gn.bias'):
+            out[name + '/' + k] = sd[k].detach().numpy()
+        out[name + '_grad_in_block'] = net.in_block.conv.weight.grad.numpy()
+        print(name, losses)
+    np.savez_compressed(os.path.join(HERE, 'train_step.npz'), **out)
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['schema', 'forward', 'grids', 'loss', 'sw', 'train']
+    if 'schema' in which: gen_schema_and_hashes()
+    if 'forward' in which: gen_forward()
+    if 'grids' in which: gen_grids()
+    if 'loss' in which: gen_loss()
+    if 'sw' in which: gen_sliding_window()
+    if 'train' in which: gen_train_step()

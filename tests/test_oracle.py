@@ -1,0 +1,165 @@
+"""The oracle against the golden fixtures produced by the live reference (tests/golden/make_golden.py)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import init as oinit
+from oracle import loss as oloss
+from oracle import net as onet
+from oracle import sliding_window as osw
+from oracle.metrics import cal_dsc
+
+G = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def seeded_input(seed, shape, kind='noise'):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(shape, generator=g)
+    if kind == 'smooth':
+        lo = torch.randn((shape[0], shape[1]) + tuple(max(2, s // 8) for s in shape[2:]), generator=g)
+        x = torch.nn.functional.interpolate(lo, size=shape[2:], mode='trilinear', align_corners=False) * 2 + 0.3 * x
+    return x
+
+
+def sd_hash(sd):
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(v.detach().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def test_schema_matches_reference():
+    schema = json.load(open(os.path.join(G, 'schema.json')))
+    for key, ref in schema.items():
+        arch, cin, cout = key.split('_')
+        mine = oinit.state_dict_schema(arch, int(cin), int(cout))
+        assert [[k, list(s)] for k, s in mine] == ref
+    assert sum(int(np.prod(s)) for _, s in oinit.state_dict_schema('vnet', 1, 2)) == 14563296
+    assert sum(int(np.prod(s)) for _, s in oinit.state_dict_schema('vbnet', 1, 5)) == 8666727
+
+
+def test_seeded_init_is_bit_identical_to_reference():
+    hashes = json.load(open(os.path.join(G, 'weights_sha256.json')))
+    for key, ref in hashes.items():
+        arch, cin, cout, seed, mode = key.split('_')
+        sd = oinit.init_state_dict(arch, int(cin), int(cout), int(seed[4:]), mode)
+        assert sd_hash(sd) == ref, key
+
+
+def test_forward_matches_reference():
+    z = np.load(os.path.join(G, 'forward.npz'))
+    meta = json.loads(str(z['meta']))
+    for name, arch, cin, cout, wseed, aseed, iseed, shape, kind in meta:
+        sd = oinit.init_state_dict(arch, cin, cout, wseed)
+        if aseed is not None:
+            sd = oinit.randomize_affine(sd, aseed)
+        y = onet.forward(sd, seeded_input(iseed, tuple(shape), kind)).numpy()
+        assert y.shape == z[name].shape
+        # same ATen ops in the same order: bit-equal in practice, allow 1 ulp-ish slack
+        assert np.abs(y - z[name]).max() <= 1e-6, name
+
+
+def test_module_prefix_is_stripped():
+    sd = oinit.init_state_dict('vnet', 1, 2, 0)
+    x = seeded_input(3, (1, 1, 16, 16, 16))
+    a = onet.forward(sd, x)
+    b = onet.forward({'module.' + k: v for k, v in sd.items()}, x)
+    assert torch.equal(a, b)
+
+
+def test_partition_grid_bit_exact():
+    cases = json.load(open(os.path.join(G, 'grids.json')))
+    assert len(cases) >= 10
+    for c in cases:
+        bs = list(c['bbox_start']) if c['bbox_start'] is not None else [0, 0, 0]
+        be = list(c['bbox_end']) if c['bbox_end'] is not None else list(c['size'])
+        s, e = osw.partition_grid(c['size'], c['spacing'], bs, be, list(c['partition_size']),
+                                  list(c['partition_stride']), 16)
+        assert s == c['starts'] and e == c['ends']
+        assert bs == c['bbox_start_after'] and be == c['bbox_end_after']   # in-place mutation, image_tools.py:184-187
+    # SURVEY A.3 table
+    n = {(tuple(c['size']), c['partition_stride'][0]): c['n'] for c in cases if c['bbox_start'] is None}
+    assert n[((512, 512, 400), 96)] == 180 and n[((512, 512, 400), 48)] == 800
+    assert n[((256, 256, 256), 96)] == 27 and n[((256, 256, 256), 48)] == 125
+
+
+def test_losses_match_reference():
+    z = np.load(os.path.join(G, 'loss.npz'))
+    for c in (2, 5):
+        k = 'c%d_' % c
+        probs, target, w = torch.from_numpy(z[k + 'probs']), torch.from_numpy(z[k + 'target']), z[k + 'weights'].tolist()
+        p = probs.clone().requires_grad_(True)
+        l = oloss.multi_dice_loss(p, target, w)
+        l.backward()
+        assert abs(float(l) - float(z[k + 'dice'])) <= 1e-7
+        assert np.abs(p.grad.numpy() - z[k + 'dice_grad']).max() <= 1e-9
+        p = probs.clone().requires_grad_(True)
+        l = oloss.focal_loss(p, target, c, alpha=w, gamma=2, size_average=True)
+        l.backward()
+        assert abs(float(l) - float(z[k + 'focal'])) <= 1e-7
+        assert np.abs(p.grad.numpy() - z[k + 'focal_grad']).max() <= 1e-9
+        p = probs.clone().requires_grad_(True)
+        l = oloss.focal_loss(p, target, c, alpha=None, gamma=0, size_average=False)
+        l.backward()
+        assert abs(float(l) - float(z[k + 'focal_g0_sum'])) <= 1e-3 * abs(float(z[k + 'focal_g0_sum'])) * 1e-3 + 1e-4
+        assert np.abs(p.grad.numpy() - z[k + 'focal_g0_sum_grad']).max() <= 1e-6
+        # closed form used by the fused CUDA reduction
+        terms = oloss.multi_dice_terms(probs, target)
+        wn = np.array(w) / np.sum(w)
+        per = 1.0 - (2 * terms[:, :, 0] + 1e-6) / (terms[:, :, 1] + terms[:, :, 2] + 1e-6)
+        closed = float((per.mean(0).numpy() * wn).sum())
+        assert abs(closed - float(z[k + 'dice'])) <= 1e-6
+    l = oloss.binary_dice_loss(torch.from_numpy(z['bin_probs']), torch.from_numpy(z['bin_target']))
+    assert abs(float(l) - float(z['bin_dice'])) <= 1e-7
+
+
+def test_sliding_window_matches_reference():
+    z = np.load(os.path.join(G, 'sliding_window.npz'))
+    meta = json.loads(str(z['meta']))
+    for name, arch, cout, wseed, aseed, size, psize, pstride, norm, vseed, scale in meta:
+        sd = oinit.init_state_dict(arch, 1, cout, wseed)
+        if aseed is not None:
+            sd = oinit.randomize_affine(sd, aseed)
+        vol = (seeded_input(vseed, (1, 1, size[2], size[1], size[0]), 'smooth')[0, 0].numpy() * scale).astype(np.float32)
+        if norm[0] == 'fixed':
+            nd = {'type': 0, 'mean': norm[1], 'stddev': norm[2], 'clip': norm[3]}
+        else:
+            nd = {'type': 1, 'clip_sigma': norm[1]}
+        probs, mask, starts, ends = osw.segmentation_volume(sd, vol, [1.0, 1.0, 1.0], nd, 'SIZE', psize, pstride, 16)
+        assert np.abs(probs - z[name + '_probs']).max() <= 1e-6, name
+        assert (mask == z[name + '_mask']).mean() >= 0.99999, name
+        # single forward == double forward, and no-copy accumulate == faithful accumulate
+        if name == 'sw_vnet_adaptive':
+            p1, m1, _, _ = osw.segmentation_volume(sd, vol, [1.0, 1.0, 1.0], nd, 'SIZE', psize, pstride, 16,
+                                                   double_forward=False, faithful_copies=False)
+            assert np.array_equal(p1, probs) and np.array_equal(m1, mask)
+        cnt = osw.overlap_count_axes(size, starts, ends)
+        assert cnt.min() >= 1
+
+
+def test_argmax_ties_pick_lowest_class():
+    p = np.zeros((3, 2, 2, 2), np.float32)
+    p[:] = 1.0 / 3
+    p[2, 0, 0, 0] = 0.5
+    m = osw.argmax_first(p)
+    assert m.dtype == np.int8 and m[0, 0, 0] == 2 and m[1, 1, 1] == 0
+
+
+def test_cal_dsc():
+    a = np.zeros((4, 4, 4), np.int8)
+    b = np.zeros((4, 4, 4), np.int8)
+    a[:2] = 1
+    b[1:3] = 1
+    assert cal_dsc(a, b, 1, 1) == (0.5, 'TP')
+    assert cal_dsc(a, b, 2, 1) == (1.0, 'TN')
+    assert cal_dsc(a, np.zeros_like(a), 1, 1) == (0.0, 'FN')
+
+
+def test_resample_out_size_rounding():
+    assert osw.resample_out_size([512, 512, 400], [1, 1, 1], [1, 1, 1], 16) == [512, 512, 400]
+    assert osw.resample_out_size([300, 300, 200], [0.5, 0.5, 1.0], [0.4, 0.4, 0.4], 16) == [384, 384, 512]
