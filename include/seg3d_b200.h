@@ -1,0 +1,132 @@
+/* seg3d_b200.h - C ABI of the B200-native volumetric-segmentation hot path.
+ *
+ * Drop-in boundary for qinliuliuqin/Medical-Segmentation3d-Toolkit (reference paths below are
+ * relative to that repository).  The reference has no FFI of its own: its hot path is a chain
+ * of torch.nn layer calls made from Python.  Each entry point here replaces one such call
+ * site; the Python host package `segmentation3d` (same import paths, same signatures as the
+ * reference) binds this library with ctypes and is the only caller.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in
+ *    `_host`.  Nothing is allocated, retained or freed by the library: the caller owns all
+ *    buffers and workspaces.  Calls are asynchronous on `stream` (a cudaStream_t passed as
+ *    void*), thread-compatible, and hold no global mutable state.
+ *  - Return value: 0 on success, negative seg3d_status otherwise; seg3d_last_error() gives the
+ *    message for the calling thread.  The Python binding raises RuntimeError on non-zero.
+ *  - Activations are channels-last "NDHWC": element (n,z,y,x,c) of a tensor with channel pitch
+ *    `ld` (elements, ld >= C) lives at base[(((n*D+z)*H+y)*W+x)*ld + c].  A pitch larger than C
+ *    lets two producers write the two halves of a concat buffer (vnet_upblock.py:21) in place.
+ *  - `dtype` selects the STORAGE type of activations (and, for the tensor-core path, the MMA
+ *    operand type).  Accumulation, GroupNorm statistics, softmax and all reductions are fp32
+ *    (fp64 for the per-sample sums).
+ *  - GroupNorm(1,C) is split in two: the producing convolution adds per-sample sum(y), sum(y*y)
+ *    of its fp32 results to `stats[n][2]` (doubles, zeroed by the caller), and the consumer
+ *    (seg3d_gn_apply / the out-block tail) turns them into mean / rstd.
+ */
+#ifndef SEG3D_B200_H
+#define SEG3D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { SEG3D_OK = 0, SEG3D_EINVAL = -1, SEG3D_ECUDA = -2, SEG3D_EUNSUPPORTED = -3 } seg3d_status;
+typedef enum { SEG3D_F32 = 0, SEG3D_F16 = 1, SEG3D_BF16 = 2 } seg3d_dtype;
+typedef enum {
+  SEG3D_CONV_K3 = 0,   /* k=3 s=1 p=1   nn.Conv3d          conv_gn_relu3.py:10, vnet_inblock.py:9, vnet_outblock.py:13 */
+  SEG3D_CONV_K2S2 = 1, /* k=2 s=2 p=0   nn.Conv3d          vnet_downblock.py:11 */
+  SEG3D_CONV_T2S2 = 2, /* k=2 s=2       nn.ConvTranspose3d vnet_upblock.py:11   */
+  SEG3D_CONV_K1 = 3    /* k=1           nn.Conv3d          vnet_outblock.py:16  */
+} seg3d_conv_mode;
+typedef enum { SEG3D_IMPL_AUTO = 0, SEG3D_IMPL_SIMT = 1, SEG3D_IMPL_TCGEN05 = 2 } seg3d_impl;
+typedef enum { SEG3D_NORM_NONE = 0, SEG3D_NORM_FIXED = 1, SEG3D_NORM_ADAPTIVE = 2 } seg3d_norm;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int seg3d_version(void);
+const char* seg3d_last_error(void);
+/* 0 if `device` is an sm_100 part this library can run on. */
+int seg3d_device_check(int device);
+
+/* ---- convolutions (replace nn.Conv3d / nn.ConvTranspose3d forward) ------------------------
+ * x: [N,D,H,W,Cin] pitch x_ld.  y: raw conv result + bias, pitch y_ld:
+ *   K3, K1 : [N,D,H,W,Cout]      K2S2 : [N,D/2,H/2,W/2,Cout]      T2S2 : [N,2D,2H,2W,Cout]
+ * w (packed by the host from the reference's OIDHW / IODHW fp32 weights):
+ *   SIMT path    (fp32)    : [taps][Cin][Cout]  (T2S2: [Cin][8*Cout], column = tap*Cout+co)
+ *   TCGEN05 path (dtype)   : [taps][Cout][Cin]  (T2S2: [8*Cout][Cin])
+ *   tap = (kd*k + kh)*k + kw.
+ * bias: fp32 [Cout] (may be NULL).  stats: double [N][2] accumulated (may be NULL).
+ * Supported shapes: SIMT any Cin with Cin==1 or Cin%8==0; TCGEN05 needs Cin%16==0, Cout%16==0,
+ * Cout<=256, dtype f16/bf16.  AUTO picks TCGEN05 when it applies and dtype != f32. */
+int seg3d_conv3d_fwd(int mode, int dtype, int impl,
+                     const void* x, int x_ld, int Cin,
+                     const void* w, const float* bias,
+                     void* y, int y_ld, int Cout,
+                     int N, int D, int H, int W,
+                     double* stats, void* stream);
+
+/* ---- GroupNorm(1,C) apply + ReLU + residual (replaces nn.GroupNorm, nn.ReLU, `input + output`,
+ * torch.cat: conv_gn_relu3.py:17-19, residual_block3.py:24,46, vnet_upblock.py:20-21) ----------
+ * out = [relu]( (y-mean)*rstd*gamma + beta [+ res] ), mean/rstd from stats over C*nvox elements
+ * (biased variance, eps inside the sqrt).  C % 8 == 0.  out may alias y. */
+int seg3d_gn_apply(int dtype, const void* y, int y_ld, int C,
+                   const double* stats, const float* gamma, const float* beta, float eps,
+                   const void* res, int res_ld,
+                   void* out, int out_ld, int relu,
+                   int N, int64_t nvox, void* stream);
+
+/* ---- output-block tail (vnet_outblock.py:20-24 after conv1) --------------------------------
+ * y1: raw conv1 output [N,nvox,C] pitch ld (C <= 8).  Pass 1 accumulates the statistics of
+ * z = conv2(relu(gn1(y1))) into stats2; pass 2 recomputes z, applies gn2 and the channel softmax
+ * and writes fp32 probabilities in the reference's NCDHW order: probs[n][c][vox]. */
+int seg3d_outblock_tail_stats(int dtype, const void* y1, int ld, int C,
+                              const double* stats1, const float* gamma1, const float* beta1,
+                              const float* w2 /*[C][C] out,in*/, const float* bias2, float eps,
+                              double* stats2, int N, int64_t nvox, void* stream);
+int seg3d_outblock_tail_probs(int dtype, const void* y1, int ld, int C,
+                              const double* stats1, const float* gamma1, const float* beta1,
+                              const float* w2, const float* bias2,
+                              const double* stats2, const float* gamma2, const float* beta2, float eps,
+                              float* probs, int N, int64_t nvox, void* stream);
+
+/* ---- sliding window (core/seg_infer.py:208-246,313-339; utils/image_tools.py:221-238,435-469) -
+ * Volumes are fp32 [Z][Y][X] (the reference's numpy order); voxel coordinates are (x,y,z) int32
+ * triples like the reference's start_voxel lists. */
+/* per-patch sum / sum-of-squares (double [N][2]) for the adaptive normaliser (normalizer.py:59) */
+int seg3d_patch_stats(const float* vol, int Z, int Y, int X, const int32_t* starts, int N,
+                      int pz, int py, int px, double* stats, void* stream);
+/* crop N patches and normalise: out[n][z][y][x] (Cin == 1) stored as dtype.
+ * FIXED: (v-mean)/stddev, optional clip to [clip_lo,clip_hi]; ADAPTIVE: mean/std from `stats`. */
+int seg3d_patch_gather(const float* vol, int Z, int Y, int X, const int32_t* starts, int N,
+                       int pz, int py, int px, int norm, float mean, float stddev, int clip,
+                       float clip_lo, float clip_hi, const double* stats,
+                       int dtype, void* out, void* stream);
+/* acc[c][z0+z][y0+y][x0+x] += probs[n][c][z][y][x]  (add_image_region) */
+int seg3d_blend_accumulate(const float* probs, int N, int C, int pz, int py, int px,
+                           const int32_t* starts, float* acc, int Z, int Y, int X, void* stream);
+/* acc[c] *= float(1.0/count) with count = cx[x]*cy[y]*cz[z] (add_image_value, seg_infer.py:325-327),
+ * then mask = first argmax over c (seg_infer.py:337), int8.  mask may be NULL. */
+int seg3d_blend_finalize_argmax(float* acc, int C, int Z, int Y, int X,
+                                const int32_t* cx, const int32_t* cy, const int32_t* cz,
+                                int8_t* mask, void* stream);
+
+/* ---- losses on probabilities (loss/multi_dice_loss.py, loss/binary_dice_loss.py, loss/focal_loss.py) -
+ * probs fp32 [B][C][n], target fp32 [B][n] (class index stored as float, dataloader/dataset.py:208). */
+/* terms[b][c] = { sum q*t, sum q*q, sum t*t } with q = p*[p > 1/C], t = [target == c] (double) */
+int seg3d_dice_terms(const float* probs, const float* target, int B, int C, int64_t n,
+                     double* terms, void* stream);
+/* grad[b][c][i] = coef[b][c][0]*t*m + coef[b][c][1]*q   (m = [p > 1/C]); coef computed by the host
+ * from the terms (closed form of d loss / d p). */
+int seg3d_dice_bwd(const float* probs, const float* target, int B, int C, int64_t n,
+                   const float* coef, float* grad, void* stream);
+/* focal: partial[0] += sum_i -alpha[t_i] * (1-p_t)^gamma * log(p_t + 1e-10) (double) */
+int seg3d_focal_fwd(const float* probs, const float* target, int B, int C, int64_t n,
+                    const float* alpha, float gamma, double* partial, void* stream);
+int seg3d_focal_bwd(const float* probs, const float* target, int B, int C, int64_t n,
+                    const float* alpha, float gamma, float scale, float* grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEG3D_B200_H */

@@ -1,0 +1,30 @@
+// conv.cu - C-ABI dispatch of the convolution entry point to the SIMT or tcgen05 implementation.
+#include "common.cuh"
+
+int seg3d_conv_simt(int mode, int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
+                    void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st);
+int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
+                  void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st);
+int seg3d_conv_tc_supported(int mode, int dtype, int Cin, int Cout, int x_ld, int y_ld, int D, int H, int W);
+
+extern "C" int seg3d_conv3d_fwd(int mode, int dtype, int impl, const void* x, int x_ld, int Cin, const void* w,
+                                const float* bias, void* y, int y_ld, int Cout, int N, int D, int H, int W,
+                                double* stats, void* stream) {
+  SEG3D_REQUIRE(x && w && y, "conv3d_fwd: null pointer");
+  SEG3D_REQUIRE(Cin > 0 && Cout > 0 && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_fwd: bad dims");
+  SEG3D_REQUIRE(x_ld >= Cin && y_ld >= Cout, "conv3d_fwd: pitch smaller than channel count");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == SEG3D_IMPL_AUTO)
+    impl = seg3d_conv_tc_supported(mode, dtype, Cin, Cout, x_ld, y_ld, D, H, W) ? SEG3D_IMPL_TCGEN05 : SEG3D_IMPL_SIMT;
+  if (impl == SEG3D_IMPL_TCGEN05) {
+    if (!seg3d_conv_tc_supported(mode, dtype, Cin, Cout, x_ld, y_ld, D, H, W)) {
+      seg3d_set_error("conv3d_fwd: tcgen05 path does not take mode=%d dtype=%d Cin=%d Cout=%d", mode, dtype, Cin, Cout);
+      return SEG3D_EUNSUPPORTED;
+    }
+    return seg3d_conv_tc(mode, dtype, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, stats, st);
+  }
+  if (impl == SEG3D_IMPL_SIMT)
+    return seg3d_conv_simt(mode, dtype, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, stats, st);
+  seg3d_set_error("conv3d_fwd: unknown impl %d", impl);
+  return SEG3D_EINVAL;
+}

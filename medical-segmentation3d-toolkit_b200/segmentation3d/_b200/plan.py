@@ -1,0 +1,305 @@
+"""Forward plan of VNet / VBNet on the C-ABI kernels.
+
+Host-side plumbing only: packs the reference-layout fp32 weights (OIDHW / IODHW) into the kernel
+layouts, owns the NDHWC workspaces (torch tensors = device memory), and issues the kernel
+sequence that restates SegmentationNet.forward (reference network/vnet.py:36-48, vbnet.py:38-50).
+All arithmetic happens in libseg3d_b200.so.
+
+Data layout in HBM (per forward of B patches of D x H x W):
+  * activations NDHWC, storage dtype = the plan's mode (fp32 strict / fp16 / bf16);
+  * skip tensors live inside their concat buffers from the moment they are produced
+    (channel offset + pitch), so torch.cat (vnet_upblock.py:21) never runs;
+  * one `raw` scratch holds each convolution's pre-GroupNorm result until the next
+    seg3d_gn_apply consumes it;
+  * one double[n_gn][B][2] tensor carries the GroupNorm partial sums.
+"""
+import os
+
+import torch
+
+from . import lib
+
+MODES = {'fp32': lib.F32, 'fp16': lib.F16, 'bf16': lib.BF16}
+GN_EPS = 1e-5
+
+
+def detect_arch(sd):
+    return 'vbnet' if any('.conv1.conv.weight' in k for k in sd) else 'vnet'
+
+
+def strip_prefix(sd):
+    if any(k.startswith('module.') for k in sd):
+        return {k[7:]: v for k, v in sd.items()}
+    return dict(sd)
+
+
+class _Conv(object):
+    """One packed convolution.  `load` (re)packs in place so kernel-argument pointers stay valid."""
+
+    def __init__(self, sd, name, mode, dt, device, allow_tc):
+        w = sd[name + '.weight']
+        self.name, self.mode, self.dt, self.device = name, mode, dt, device
+        if mode == lib.CONV_T2S2:
+            self.cin, self.cout = w.shape[0], w.shape[1]
+        else:
+            self.cout, self.cin = w.shape[0], w.shape[1]
+        tc_ok = (allow_tc and dt != lib.F32 and self.cin % 16 == 0 and self.cout % 16 == 0 and self.cout <= 256
+                 and mode in allow_tc)
+        self.impl = lib.IMPL_TCGEN05 if tc_ok else lib.IMPL_SIMT
+        self.w, self.bias = None, None
+        self.load(sd)
+
+    def load(self, sd):
+        w = sd[self.name + '.weight'].detach().to(device=self.device, dtype=torch.float32)
+        b = sd.get(self.name + '.bias')
+        if self.impl == lib.IMPL_SIMT:
+            if self.mode == lib.CONV_T2S2:      # [Cin][8*Cout], column = tap*Cout + co
+                p = w.permute(0, 2, 3, 4, 1).reshape(self.cin, 8 * self.cout)
+            else:                               # [taps][Cin][Cout]
+                p = w.permute(2, 3, 4, 1, 0).reshape(-1, self.cin, self.cout)
+            p = p.contiguous()
+        else:
+            if self.mode == lib.CONV_T2S2:      # [8*Cout][Cin]
+                p = w.permute(2, 3, 4, 1, 0).reshape(8 * self.cout, self.cin)
+            else:                               # [taps][Cout][Cin]
+                p = w.permute(2, 3, 4, 0, 1).reshape(-1, self.cout, self.cin)
+            p = p.contiguous().to(lib.TORCH_DTYPE[self.dt])
+        if self.w is None:
+            self.w = p
+            self.bias = None if b is None else b.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        else:
+            self.w.copy_(p)
+            if b is not None:
+                self.bias.copy_(b.detach())
+
+
+class _GN(object):
+    def __init__(self, sd, name, device):
+        self.name = name
+        self.gamma = sd[name + '.weight'].detach().to(device=device, dtype=torch.float32).contiguous().clone()
+        self.beta = sd[name + '.bias'].detach().to(device=device, dtype=torch.float32).contiguous().clone()
+
+    def load(self, sd):
+        self.gamma.copy_(sd[self.name + '.weight'].detach())
+        self.beta.copy_(sd[self.name + '.bias'].detach())
+
+
+class _View(object):
+    """Channel window [off, off+C) of an NDHWC buffer with pitch ld."""
+    __slots__ = ('buf', 'off', 'ld', 'C')
+
+    def __init__(self, buf, off, ld, C):
+        self.buf, self.off, self.ld, self.C = buf, off, ld, C
+
+    @property
+    def p(self):
+        return lib.ptr(self.buf, self.off)
+
+
+class NetPlan(object):
+    def __init__(self, state_dict, mode='fp16', device=None, arch=None, tc_modes=None):
+        lib.load()
+        if mode not in MODES:
+            raise ValueError('mode must be one of %s' % sorted(MODES))
+        self.mode, self.dt = mode, MODES[mode]
+        self.tdtype = lib.TORCH_DTYPE[self.dt]
+        self.device = torch.device(device if device is not None else 'cuda')
+        if self.device.type != 'cuda':
+            raise RuntimeError('seg3d_b200 runs on CUDA devices only (no CPU fallback)')
+        sd = strip_prefix(state_dict)
+        self.arch = arch or detect_arch(sd)
+        if tc_modes is None:
+            tc_modes = () if os.environ.get('SEG3D_FORCE_SIMT') == '1' else DEFAULT_TC_MODES
+        self.tc_modes = tuple(tc_modes)
+        self.in_channels = sd['in_block.conv.weight'].shape[1]
+        self.out_channels = sd['out_block.conv2.weight'].shape[0]
+        if self.out_channels > 8:
+            raise RuntimeError('seg3d_b200: at most 8 output classes are supported by the out-block tail')
+        self.convs, self.gns = {}, {}
+        for k in sd:
+            if not k.endswith('.weight'):
+                continue
+            name = k[:-7]
+            if sd[k].dim() == 5:
+                if name.endswith('up_conv'):
+                    m = lib.CONV_T2S2
+                elif name.endswith('down_conv'):
+                    m = lib.CONV_K2S2
+                elif name == 'out_block.conv2':
+                    continue
+                else:
+                    m = lib.CONV_K3
+                self.convs[name] = _Conv(sd, name, m, self.dt, self.device, self.tc_modes)
+            else:
+                self.gns[name] = _GN(sd, name, self.device)
+        self.w2 = sd['out_block.conv2.weight'].detach().to(self.device, torch.float32).reshape(
+            self.out_channels, self.out_channels).contiguous()
+        self.b2 = sd['out_block.conv2.bias'].detach().to(self.device, torch.float32).contiguous()
+        self.w2 = self.w2.clone()
+        self.b2 = self.b2.clone()
+        self.gn_names = sorted(self.gns)
+        self.gn_index = {n: i for i, n in enumerate(self.gn_names)}
+        self._plans = {}
+        self.launches_per_forward = 0
+
+    def refresh(self, state_dict):
+        """Re-pack changed weights in place (pointers captured by cached plans stay valid)."""
+        sd = strip_prefix(state_dict)
+        for c in self.convs.values():
+            c.load(sd)
+        for g in self.gns.values():
+            g.load(sd)
+        self.w2.copy_(sd['out_block.conv2.weight'].detach().reshape(self.out_channels, self.out_channels))
+        self.b2.copy_(sd['out_block.conv2.bias'].detach())
+
+    # ------------------------------------------------------------------------------------
+    def _rblock_len(self, prefix):
+        n = 0
+        while ('%s.ops.%d.conv' % (prefix, n)) in self.convs or ('%s.ops.%d.conv1.conv' % (prefix, n)) in self.convs:
+            n += 1
+        return n
+
+    def _build(self, B, D, H, W):
+        dev, td, dt = self.device, self.tdtype, self.dt
+        assert D % 16 == 0 and H % 16 == 0 and W % 16 == 0, 'spatial dims must be multiples of max_stride=16'
+        dims = [(D >> l, H >> l, W >> l) for l in range(5)]
+        vox = [d[0] * d[1] * d[2] for d in dims]
+
+        def buf(l, C):
+            return torch.empty((B, vox[l], C), dtype=td, device=dev)
+
+        ws = {}
+        ws['x_in'] = torch.empty((B, vox[0], self.in_channels), dtype=td, device=dev)
+        ws['raw'] = torch.empty((B * vox[0] * 32,), dtype=td, device=dev)
+        ws['stats'] = torch.zeros((len(self.gn_names), B, 2), dtype=torch.float64, device=dev)
+        ws['stats2'] = torch.zeros((B, 2), dtype=torch.float64, device=dev)
+        ws['probs'] = torch.empty((B, self.out_channels, D, H, W), dtype=torch.float32, device=dev)
+        widths = [32, 64, 128, 256, 256]
+        for l in range(5):
+            C = widths[l]
+            ws['cat%d' % l] = buf(l, C) if l < 4 else None
+            ws['A%d' % l] = buf(l, C) if l >= 1 else None       # down-path rblock input
+            ws['T%da' % l], ws['T%db' % l] = buf(l, C), buf(l, C)
+            ws['U%d' % l] = buf(l, C)                            # rblock result (up path; level 4: down_256 output)
+            ws['M%da' % l], ws['M%db' % l] = buf(l, C // 4), buf(l, C // 4)   # bottleneck mids (VBNet)
+        ops = []
+        st = lib.stream_ptr
+        raw = ws['raw']
+
+        def conv(name, x, xdims, y, stats_name):
+            c = self.convs[name]
+            assert c.cin == x.C and c.cout == y.C, (name, c.cin, x.C, c.cout, y.C)
+            sp = lib.ptr(ws['stats'][self.gn_index[stats_name]]) if stats_name else None
+            args = (c.mode, dt, c.impl, x.p, x.ld, c.cin, lib.ptr(c.w), lib.ptr(c.bias), y.p, y.ld, c.cout,
+                    B, xdims[0], xdims[1], xdims[2], sp)
+            ops.append(lambda a=args: lib.call('seg3d_conv3d_fwd', *a, st()))
+
+        def gn(name, y, out, nvox, relu, res=None):
+            g = self.gns[name]
+            sp = lib.ptr(ws['stats'][self.gn_index[name]])
+            args = (dt, y.p, y.ld, y.C, sp, lib.ptr(g.gamma), lib.ptr(g.beta), GN_EPS,
+                    res.p if res is not None else None, res.ld if res is not None else 0,
+                    out.p, out.ld, 1 if relu else 0, B, nvox)
+            ops.append(lambda a=args: lib.call('seg3d_gn_apply', *a, st()))
+
+        def rawview(C):
+            return _View(raw, 0, C, C)
+
+        def conv_gn(cname, gname, x, l, out, relu, res=None):
+            C = self.convs[cname].cout
+            conv(cname, x, dims[l], rawview(C), gname)
+            gn(gname, rawview(C), out, vox[l], relu, res)
+
+        def rblock(prefix, X, l, dest):
+            n = self._rblock_len(prefix)
+            C = X.C
+            cur = X
+            tmps = [_View(ws['T%da' % l], 0, C, C), _View(ws['T%db' % l], 0, C, C)]
+            for i in range(n):
+                last = i == n - 1
+                out = dest if last else tmps[i % 2]
+                op = '%s.ops.%d' % (prefix, i)
+                if (op + '.conv') in self.convs:
+                    conv_gn(op + '.conv', op + '.gn', cur, l, out, relu=True, res=X if last else None)
+                else:
+                    m1 = _View(ws['M%da' % l], 0, C // 4, C // 4)
+                    m2 = _View(ws['M%db' % l], 0, C // 4, C // 4)
+                    conv_gn(op + '.conv1.conv', op + '.conv1.gn', cur, l, m1, relu=True)
+                    conv_gn(op + '.conv2.conv', op + '.conv2.gn', m1, l, m2, relu=True)
+                    conv_gn(op + '.conv3.conv', op + '.conv3.gn', m2, l, out, relu=True, res=X if last else None)
+                cur = out
+            # relu(X + ops(X)): the last apply carries relu=True with the residual (residual_block3.py:24,46);
+            # for i < n-1 relu=True is ConvGnRelu3's own activation.
+
+        # in_block -> second half of cat0
+        x_in = _View(ws['x_in'], 0, self.in_channels, self.in_channels)
+        skip = [_View(ws['cat%d' % l], widths[l] // 2, widths[l], widths[l] // 2) for l in range(4)]
+        conv_gn('in_block.conv', 'in_block.gn', x_in, 0, skip[0], relu=True)
+        # down path
+        src = skip[0]
+        for l, name in ((1, 'down_32'), (2, 'down_64'), (3, 'down_128'), (4, 'down_256')):
+            C = widths[l] // 2 if l < 4 else 256
+            A = _View(ws['A%d' % l], 0, C, C)
+            conv(name + '.down_conv', src, dims[l - 1], rawview(C), name + '.down_gn')
+            gn(name + '.down_gn', rawview(C), A, vox[l], relu=True)
+            dest = skip[l] if l < 4 else _View(ws['U4'], 0, 256, 256)
+            rblock(name + '.rblock', A, l, dest)
+            src = dest
+        # up path
+        for l, name in ((3, 'up_256'), (2, 'up_128'), (1, 'up_64'), (0, 'up_32')):
+            C = widths[l]
+            up = _View(ws['cat%d' % l], 0, C, C // 2)
+            conv(name + '.up_conv', src, dims[l + 1], rawview(C // 2), name + '.up_gn')
+            gn(name + '.up_gn', rawview(C // 2), up, vox[l], relu=True)
+            cat = _View(ws['cat%d' % l], 0, C, C)
+            dest = _View(ws['U%d' % l], 0, C, C)
+            rblock(name + '.rblock', cat, l, dest)
+            src = dest
+        # out block: conv1 -> raw, then the fused tail
+        nc = self.out_channels
+        conv('out_block.conv1', src, dims[0], rawview(nc), 'out_block.gn1')
+        g1, g2 = self.gns['out_block.gn1'], self.gns['out_block.gn2']
+        s1 = lib.ptr(ws['stats'][self.gn_index['out_block.gn1']])
+        s2 = lib.ptr(ws['stats2'])
+        a1 = (dt, lib.ptr(raw), nc, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),
+              GN_EPS, s2, B, vox[0])
+        ops.append(lambda a=a1: lib.call('seg3d_outblock_tail_stats', *a, st()))
+        a2 = (dt, lib.ptr(raw), nc, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),
+              s2, lib.ptr(g2.gamma), lib.ptr(g2.beta), GN_EPS, lib.ptr(ws['probs']), B, vox[0])
+        ops.append(lambda a=a2: lib.call('seg3d_outblock_tail_probs', *a, st()))
+        return ws, ops
+
+    def plan(self, B, D, H, W):
+        key = (B, D, H, W)
+        if key not in self._plans:
+            self._plans[key] = self._build(B, D, H, W)
+        return self._plans[key]
+
+    def load_input(self, ws, x):
+        """x: [B,Cin,D,H,W] float32 CUDA tensor -> NDHWC storage dtype."""
+        B = x.shape[0]
+        if self.in_channels == 1:
+            ws['x_in'].view(-1).copy_(x.reshape(-1))
+        else:
+            ws['x_in'].copy_(x.reshape(B, self.in_channels, -1).permute(0, 2, 1))
+
+    def run(self, ws, ops):
+        ws['stats'].zero_()
+        ws['stats2'].zero_()
+        for op in ops:
+            op()
+        self.launches_per_forward = len(ops)
+        return ws['probs']
+
+    def forward(self, x):
+        """probabilities [B,C,D,H,W] float32 (a view of the plan's output buffer; clone to keep)."""
+        if not x.is_cuda:
+            raise RuntimeError('seg3d_b200: input must be a CUDA tensor (no CPU fallback)')
+        B, Cin, D, H, W = x.shape
+        assert Cin == self.in_channels
+        ws, ops = self.plan(B, D, H, W)
+        self.load_input(ws, x.float())
+        return self.run(ws, ops)
+
+
+DEFAULT_TC_MODES = ()

@@ -1,0 +1,214 @@
+"""GPU parity tests of the C-ABI kernels against the oracle (run on the B200 box: pytest -m gpu)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import init as oinit
+from oracle import net as onet
+from oracle.metrics import parity_report
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from segmentation3d._b200 import lib as L
+    L.load()
+    assert L.load().seg3d_device_check(0) == 0, L.load().seg3d_last_error()
+    return L
+
+
+def seeded_input(seed, shape, kind='noise'):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(shape, generator=g)
+    if kind == 'smooth':
+        lo = torch.randn((shape[0], shape[1]) + tuple(max(2, s // 8) for s in shape[2:]), generator=g)
+        x = torch.nn.functional.interpolate(lo, size=shape[2:], mode='trilinear', align_corners=False) * 2 + 0.3 * x
+    return x
+
+
+def to_ndhwc(x, dtype):   # [N,C,D,H,W] -> [N,D,H,W,C]
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(dtype).cuda()
+
+
+def from_ndhwc(y):
+    return y.float().cpu().permute(0, 4, 1, 2, 3).contiguous()
+
+
+def pack_simt(w, mode, L):
+    if mode == L.CONV_T2S2:
+        return w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], -1).contiguous().cuda()
+    return w.permute(2, 3, 4, 1, 0).reshape(-1, w.shape[1], w.shape[0]).contiguous().cuda()
+
+
+def pack_tc(w, mode, L, dtype):
+    if mode == L.CONV_T2S2:
+        return w.permute(2, 3, 4, 1, 0).reshape(-1, w.shape[0]).contiguous().to(dtype).cuda()
+    return w.permute(2, 3, 4, 0, 1).reshape(-1, w.shape[0], w.shape[1]).contiguous().to(dtype).cuda()
+
+
+def run_conv(L, mode, dt, impl, x, w, b, with_stats=True):
+    N, Cin, D, H, W = x.shape
+    tdt = L.TORCH_DTYPE[dt]
+    xd = to_ndhwc(x, tdt)
+    if mode == L.CONV_T2S2:
+        Cout, od = w.shape[1], (2 * D, 2 * H, 2 * W)
+    elif mode == L.CONV_K2S2:
+        Cout, od = w.shape[0], (D // 2, H // 2, W // 2)
+    else:
+        Cout, od = w.shape[0], (D, H, W)
+    wp = pack_simt(w, mode, L) if impl == L.IMPL_SIMT else pack_tc(w, mode, L, tdt)
+    y = torch.full((N,) + od + (Cout,), float('nan'), dtype=tdt, device='cuda')
+    stats = torch.zeros((N, 2), dtype=torch.float64, device='cuda')
+    bd = b.cuda() if b is not None else None
+    L.call('seg3d_conv3d_fwd', mode, dt, impl, L.ptr(xd), Cin, Cin, L.ptr(wp), L.ptr(bd), L.ptr(y), Cout, Cout,
+           N, D, H, W, L.ptr(stats) if with_stats else None, L.stream_ptr())
+    torch.cuda.synchronize()
+    return from_ndhwc(y), stats.cpu()
+
+
+def ref_conv(mode, L, x, w, b):
+    if mode == L.CONV_K3:
+        return F.conv3d(x, w, b, padding=1)
+    if mode == L.CONV_K2S2:
+        return F.conv3d(x, w, b, stride=2)
+    if mode == L.CONV_T2S2:
+        return F.conv_transpose3d(x, w, b, stride=2)
+    return F.conv3d(x, w, b)
+
+
+CONV_CASES = [
+    # mode name, Cin, Cout, N, D, H, W
+    ('K3', 1, 16, 2, 8, 12, 16), ('K3', 16, 32, 1, 6, 10, 8), ('K3', 32, 2, 2, 8, 8, 8), ('K3', 32, 5, 1, 8, 8, 16),
+    ('K3', 64, 64, 1, 6, 6, 6), ('K3', 2, 16, 1, 8, 8, 8),
+    ('K2S2', 16, 32, 2, 8, 12, 16), ('K2S2', 128, 256, 1, 4, 4, 4),
+    ('T2S2', 64, 16, 2, 4, 6, 8), ('T2S2', 256, 128, 1, 2, 2, 2),
+    ('K1', 32, 16, 1, 4, 4, 8),
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES, ids=lambda c: '-'.join(map(str, c)))
+def test_conv_simt_fp32_matches_torch(lib, case):
+    L = lib
+    mname, Cin, Cout, N, D, H, W = case
+    mode = getattr(L, 'CONV_' + mname)
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn((N, Cin, D, H, W), generator=g)
+    wshape = (Cin, Cout, 2, 2, 2) if mode == L.CONV_T2S2 else (Cout, Cin) + {L.CONV_K3: (3, 3, 3), L.CONV_K2S2: (2, 2, 2), L.CONV_K1: (1, 1, 1)}[mode]
+    w = torch.randn(wshape, generator=g) * 0.1
+    b = torch.randn((Cout,), generator=g) * 0.1
+    ref = ref_conv(mode, L, x, w, b)
+    y, stats = run_conv(L, mode, L.F32, L.IMPL_SIMT, x, w, b)
+    assert y.shape == ref.shape
+    assert not torch.isnan(y).any()
+    assert (y - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max())        # fp32 FFMA, different summation order
+    s_ref = torch.stack([ref.double().flatten(1).sum(1), (ref.double() ** 2).flatten(1).sum(1)], 1)
+    assert torch.allclose(stats, s_ref, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize('dt_name', ['F16', 'BF16'])
+def test_conv_simt_half_storage(lib, dt_name):
+    L = lib
+    dt = getattr(L, dt_name)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((1, 32, 6, 8, 8), generator=g)
+    w = torch.randn((32, 32, 3, 3, 3), generator=g) * 0.05
+    xr = x.to(L.TORCH_DTYPE[dt]).float()
+    ref = F.conv3d(xr, w, None, padding=1)
+    y, _ = run_conv(L, L.CONV_K3, dt, L.IMPL_SIMT, x, w, None)
+    tol = 4e-3 if dt == L.F16 else 3e-2
+    assert (y - ref).abs().max() <= tol * max(1.0, ref.abs().max())
+
+
+@pytest.mark.parametrize('dt_name,relu,use_res', [('F32', True, True), ('F32', False, False), ('F16', True, False), ('F16', True, True)])
+def test_gn_apply_matches_group_norm(lib, dt_name, relu, use_res):
+    L = lib
+    dt = getattr(L, dt_name)
+    tdt = L.TORCH_DTYPE[dt]
+    g = torch.Generator().manual_seed(5)
+    N, C, D, H, W = 2, 32, 6, 4, 8
+    y = torch.randn((N, C, D, H, W), generator=g) * 2 + 0.5
+    res = torch.randn((N, C, D, H, W), generator=g)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    yq, rq = y.to(tdt).float(), res.to(tdt).float()
+    ref = F.group_norm(y, 1, gamma, beta, 1e-5)          # statistics come from the un-rounded fp32 conv results
+    mean = y.flatten(1).mean(1).view(N, 1, 1, 1, 1)
+    rstd = 1.0 / torch.sqrt(y.flatten(1).var(1, unbiased=False).view(N, 1, 1, 1, 1) + 1e-5)
+    ref = (yq - mean) * rstd * gamma.view(1, C, 1, 1, 1) + beta.view(1, C, 1, 1, 1)
+    if use_res:
+        ref = ref + rq
+    if relu:
+        ref = F.relu(ref)
+    stats = torch.stack([y.double().flatten(1).sum(1), (y.double() ** 2).flatten(1).sum(1)], 1).cuda()
+    yd, rd = to_ndhwc(y, tdt), to_ndhwc(res, tdt)
+    # write into the second half of a wider (concat) buffer
+    out = torch.zeros((N, D, H, W, 2 * C), dtype=tdt, device='cuda')
+    L.call('seg3d_gn_apply', dt, L.ptr(yd), C, C, L.ptr(stats), L.ptr(gamma.cuda()), L.ptr(beta.cuda()), 1e-5,
+           L.ptr(rd) if use_res else None, C, L.ptr(out, C), 2 * C, 1 if relu else 0, N, D * H * W, L.stream_ptr())
+    torch.cuda.synchronize()
+    got = from_ndhwc(out[..., C:])
+    assert (out[..., :C] == 0).all()
+    tol = 1e-5 if dt == L.F32 else 4e-3
+    assert (got - ref).abs().max() <= tol * max(1.0, ref.abs().max())
+
+
+def _plan_forward(L, sd, x, mode, **kw):
+    from segmentation3d._b200.plan import NetPlan
+    plan = NetPlan(sd, mode=mode, device='cuda', **kw)
+    y = plan.forward(x.cuda()).clone()
+    torch.cuda.synchronize()
+    return y.cpu()
+
+
+def test_forward_fp32_matches_golden_and_oracle(lib):
+    z = np.load(os.path.join(G, 'forward.npz'))
+    meta = json.loads(str(z['meta']))
+    for name, arch, cin, cout, wseed, aseed, iseed, shape, kind in meta:
+        sd = oinit.init_state_dict(arch, cin, cout, wseed)
+        if aseed is not None:
+            sd = oinit.randomize_affine(sd, aseed)
+        x = seeded_input(iseed, tuple(shape), kind)
+        y = _plan_forward(lib, sd, x, 'fp32').numpy()
+        gold = z[name]
+        d = np.abs(y - gold).max()
+        print(name, 'fp32 max|dp| vs reference golden = %.3g' % d)
+        assert d <= 1e-3, name                       # BASELINE.json fp32 bar; expected ~1e-5
+        assert np.abs(y.sum(1) - 1).max() <= 1e-5
+
+
+def test_forward_fp32_ties_are_bit_equal(lib):
+    """~27% of voxels are exact 0.5/0.5 ties on kaiming-init VNet; they must stay exact."""
+    sd = oinit.init_state_dict('vnet', 1, 2, 0)
+    x = seeded_input(100, (1, 1, 32, 32, 32))
+    ref = onet.forward(sd, x)
+    y = _plan_forward(lib, sd, x, 'fp32')
+    tie_ref = (ref[0, 0] == ref[0, 1])
+    tie_new = (y[0, 0] == y[0, 1])
+    assert tie_ref.float().mean() > 0.05
+    assert (tie_ref == tie_new).float().mean() >= 0.999
+    rep = parity_report(ref[0].numpy(), y[0].numpy())
+    assert rep['agree'] >= 0.999 and min(rep['dice']) >= 0.999, rep
+
+
+@pytest.mark.parametrize('arch,cout', [('vnet', 2), ('vbnet', 5)])
+def test_forward_fp16_meets_reduced_precision_bars(lib, arch, cout):
+    sd = oinit.init_state_dict(arch, 1, cout, 0)
+    x = seeded_input(7, (1, 1, 64, 64, 64), 'smooth')
+    ref = onet.forward(sd, x)
+    y = _plan_forward(lib, sd, x, 'fp16')
+    rep = parity_report(ref[0].numpy(), y[0].numpy())
+    print(arch, 'fp16', rep)
+    assert rep['max_abs'] <= 1e-2 and rep['agree'] >= 0.999 and min(rep['dice']) >= 0.999, rep
+
+
+def test_forward_batch_equals_single(lib):
+    sd = oinit.init_state_dict('vnet', 1, 2, 1)
+    x = seeded_input(9, (3, 1, 16, 32, 16))
+    yb = _plan_forward(lib, sd, x, 'fp32')
+    y0 = _plan_forward(lib, sd, x[1:2], 'fp32')
+    assert (yb[1:2] - y0).abs().max() <= 1e-6     # GroupNorm is per sample: batching must not change results
