@@ -1,6 +1,342 @@
-// conv_tc.cu - placeholder until the tcgen05 kernel lands (next commit).
+// conv_tc.cu - k=3 s=1 p=1 Conv3d as an implicit GEMM on the 5th-gen tensor cores (sm_100a).
+//
+//   D[128 voxels x Cout] (fp32, TMEM)  +=  A[128 voxels x KC] (smem, K-major)  *  B[Cout x KC]^T (smem, K-major)
+//
+// summed over the 27 filter taps and the Cin/KC channel chunks.  One CTA owns one output tile: a
+// tw x th x td box of voxels (tw*th*td = 128) of one sample.  For every (tap, chunk) the TMA
+// producer warp loads the box shifted by the tap offset from the NDHWC activation tensor through
+// a 5-D tensor map - out-of-bounds coordinates are zero-filled by the TMA unit, which IS the
+// "same" padding - and the matching [Cout x KC] weight slab through a 2-D map.  Both land in
+// 128B/64B/32B-swizzled K-major layouts that tcgen05.mma consumes through shared-memory
+// descriptors.  One elected thread issues the MMAs; the accumulator lives in TMEM; four epilogue
+// warps read it back with tcgen05.ld, add the bias, take the GroupNorm partial sums from the
+// fp32 values, and store fp16/bf16 NDHWC rows with 16-byte stores.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+// Several CTAs are co-resident per SM (smem and TMEM columns permitting) so one tile's prologue
+// and epilogue overlap its neighbours' main loops.
 #include "common.cuh"
-int seg3d_conv_tc_supported(int, int, int, int, int, int, int, int, int) { return 0; }
-int seg3d_conv_tc(int, int, const void*, int, int, const void*, const float*, void*, int, int, int, int, int, int, double*, cudaStream_t) {
-  seg3d_set_error("tcgen05 conv not built"); return SEG3D_EUNSUPPORTED;
+#include <cuda.h>
+
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int TILE_M = 128;
+
+struct TcParams {
+  int Cin, Cout, KC, nchunk;        // KC = channels per K block, nchunk = Cin / KC
+  int D, H, W, N;
+  int tw, th, td;                   // tile box
+  int ntx, nty, ntz;                // tiles per axis
+  int y_ld;
+  int stages, a_bytes, b_bytes;     // per-stage operand slab pitches (1024-aligned)
+  int tx_bytes;                     // bytes the two TMA loads of one stage actually write
+  int tmem_cols;
+  uint32_t idesc;
+  uint32_t sbo;                     // stride between 8-row groups, bytes
+  uint32_t layout_type;             // UMMA smem descriptor swizzle code
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base offset | [61,64) layout type
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TC_THREADS)
+conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                    const TcParams p, const float* __restrict__ bias, T* __restrict__ y, double* __restrict__ stats) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x A][stages x B] operand ring (1024-aligned), then barriers
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + p.stages * p.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + p.stages * (p.a_bytes + p.b_bytes));
+  const uint32_t full_bar = smem_u32(bars);                  // [stages]
+  const uint32_t empty_bar = full_bar + 8 * p.stages;        // [stages]
+  const uint32_t tmem_full_bar = empty_bar + 8 * p.stages;   // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+  float* red = reinterpret_cast<float*>(tmem_slot + 2);      // [8] epilogue partial sums
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile -> (n, z0, y0, x0)
+  int t = blockIdx.x;
+  const int tx = t % p.ntx; t /= p.ntx;
+  const int ty = t % p.nty; t /= p.nty;
+  const int tz = t % p.ntz; const int n = t / p.ntz;
+  const int x0 = tx * p.tw, y0 = ty * p.th, z0 = tz * p.td;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kiters = 27 * p.nchunk;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < kiters; ++it) {
+        const int tap = it / p.nchunk, ck = it - tap * p.nchunk;
+        const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+        mbar_expect_tx(full_bar + 8 * stage, (uint32_t)p.tx_bytes);
+        tma_load_5d(a_base + stage * p.a_bytes, &map_x, full_bar + 8 * stage, ck * p.KC, x0 + kw - 1, y0 + kh - 1, z0 + kd - 1, n);
+        tma_load_2d(b_base + stage * p.b_bytes, &map_w, full_bar + 8 * stage, ck * p.KC, tap * p.Cout);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const int ksteps = p.KC / 16;
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(full_bar + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t a_addr = a_base + stage * p.a_bytes, b_addr = b_base + stage * p.b_bytes;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ad = make_desc(a_addr + k * 32, p.sbo, p.layout_type);
+          const uint64_t bd = make_desc(b_addr + k * 32, p.sbo, p.layout_type);
+          tc_mma_f16(tmem_base, ad, bd, p.idesc, (it | k) != 0);
+        }
+        tc_commit(empty_bar + 8 * stage);          // frees the smem slot when these MMAs retire
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(tmem_full_bar);                    // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> (+bias, stats) -> global =====
+    const int q = warp & 3;                        // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;                   // GEMM row = voxel of the tile
+    const int lx = r % p.tw, ly = (r / p.tw) % p.th, lz = r / (p.tw * p.th);
+    const int gx = x0 + lx, gy = y0 + ly, gz = z0 + lz;
+    const bool valid = (gx < p.W) && (gy < p.H) && (gz < p.D);
+    const size_t vox = (((size_t)n * p.D + gz) * p.H + gy) * p.W + gx;
+    T* yrow = y + vox * p.y_ld;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    float s = 0.f, ss = 0.f;
+    for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+      uint32_t v[16];
+      tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tc_wait_ld();
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        f[j] = __uint_as_float(v[j]) + (bias ? bias[c0 + j] : 0.f);
+        if (valid) { s += f[j]; ss += f[j] * f[j]; }
+      }
+      if (valid) {
+        Vec8<T> o; o.set(f); o.store(yrow + c0);
+        o.set(f + 8); o.store(yrow + c0 + 8);
+      }
+    }
+    if (stats) {
+      s = warp_sum(s); ss = warp_sum(ss);
+      if (lane == 0) { red[2 * q] = s; red[2 * q + 1] = ss; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
+      if (warp == 2 && lane == 0) {
+        const double a = (double)red[0] + (double)red[2] + (double)red[4] + (double)red[6];
+        const double b = (double)red[1] + (double)red[3] + (double)red[5] + (double)red[7];
+        atomicAdd(stats + 2 * n, a); atomicAdd(stats + 2 * n + 1, b);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+}  // namespace
+
+int seg3d_conv_tc_supported(int mode, int dtype, int Cin, int Cout, int x_ld, int y_ld, int D, int H, int W) {
+  if (mode != SEG3D_CONV_K3) return 0;
+  if (dtype != SEG3D_F16 && dtype != SEG3D_BF16) return 0;
+  if (Cin % 16 || Cout % 16 || Cout > 256 || Cin > 1024) return 0;
+  if (x_ld % 8 || y_ld % 8) return 0;
+  (void)D; (void)H; (void)W;
+  return 1;
+}
+
+int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
+                  void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st) {
+  (void)mode;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { seg3d_set_error("conv_tc: cuTensorMapEncodeTiled entry point not available"); return SEG3D_ECUDA; }
+  SEG3D_REQUIRE(((uintptr_t)x) % 16 == 0 && ((uintptr_t)w) % 16 == 0 && ((uintptr_t)y) % 16 == 0, "conv_tc: pointers must be 16-byte aligned");
+
+  TcParams p;
+  p.Cin = Cin; p.Cout = Cout; p.D = D; p.H = H; p.W = W; p.N = N; p.y_ld = y_ld;
+  p.KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
+  p.nchunk = Cin / p.KC;
+  // tile box: power-of-two dims with product 128 minimising the tile count (then preferring a wide x extent)
+  long long best = -1; p.tw = 8; p.th = 4; p.td = 4;
+  for (int tw = 1; tw <= 32; tw *= 2)
+    for (int th = 1; th <= 128 / tw; th *= 2) {
+      const int td = 128 / (tw * th);
+      const long long tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th) * ((D + td - 1) / td);
+      const long long score = tiles * 1024 - tw * 8 - th;       // fewer tiles first, then wider x, then wider y
+      const long long spread = (tw > 16 || th > 16 || td > 16) ? 1 : 0;  // keep the box compact
+      const long long sc = score + spread * 512;
+      if (best < 0 || sc < best) { best = sc; p.tw = tw; p.th = th; p.td = td; }
+    }
+  p.ntx = (W + p.tw - 1) / p.tw; p.nty = (H + p.th - 1) / p.th; p.ntz = (D + p.td - 1) / p.td;
+  const long long ntiles = (long long)p.ntx * p.nty * p.ntz * N;
+  SEG3D_REQUIRE(ntiles > 0 && ntiles < (1ll << 31), "conv_tc: tile count out of range");
+
+  const int row_bytes = p.KC * 2;
+  p.a_bytes = TILE_M * row_bytes;
+  p.b_bytes = Cout * row_bytes;
+  p.b_bytes = (p.b_bytes + 1023) & ~1023;           // keep every operand slab 1024-byte aligned
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  int stages = (96 * 1024) / stage_bytes;            // <= ~96 KB of ring so two CTAs can share an SM
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  { const int deep = (200 * 1024) / stage_bytes; const int want = deep < 4 ? deep : 4; if (stages < want) stages = want; }
+  if (stages * stage_bytes > 200 * 1024) stages = (200 * 1024) / stage_bytes;
+  SEG3D_REQUIRE(stages >= 2, "conv_tc: operand ring does not fit in shared memory");
+  p.stages = stages;
+  p.sbo = 8 * row_bytes;
+  p.layout_type = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  p.tmem_cols = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256));
+  const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+
+  const CUtensorMapDataType tdt = dtype == SEG3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap map_x, map_w;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2, (cuuint64_t)D * H * W * x_ld * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.KC, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.td, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&map_x, tdt, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { seg3d_set_error("conv_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SEG3D_ECUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.KC, (cuuint32_t)Cout};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&map_w, tdt, 2, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { seg3d_set_error("conv_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SEG3D_ECUDA; }
+  }
+  // the weight slab the TMA writes is Cout*row_bytes; b_bytes is its 1024-aligned pitch
+  p.tx_bytes = p.a_bytes + Cout * row_bytes;
+  TcParams pk = p;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 8 + 8 * sizeof(float) + 64;
+
+  struct Launch {
+    static cudaError_t go(bool bf16, dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mx, const CUtensorMap& mw,
+                          const TcParams& pk, const float* bias, void* y, double* stats) {
+      cudaError_t e;
+      if (bf16) {
+        e = cudaFuncSetAttribute(conv3d_k3_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        conv3d_k3_tc_kernel<__nv_bfloat16><<<grid, TC_THREADS, smem, st>>>(mx, mw, pk, bias, (__nv_bfloat16*)y, stats);
+      } else {
+        e = cudaFuncSetAttribute(conv3d_k3_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        conv3d_k3_tc_kernel<__half><<<grid, TC_THREADS, smem, st>>>(mx, mw, pk, bias, (__half*)y, stats);
+      }
+      return cudaGetLastError();
+    }
+  };
+  cudaError_t e = Launch::go(dtype == SEG3D_BF16, dim3((unsigned)ntiles), smem, st, map_x, map_w, pk, bias, y, stats);
+  if (e != cudaSuccess) { seg3d_set_error("conv3d_k3_tc_kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
+  return SEG3D_OK;
 }

@@ -182,7 +182,8 @@ class NetPlan(object):
             ws['T%da' % l], ws['T%db' % l] = buf(l, C), buf(l, C)
             ws['U%d' % l] = buf(l, C)                            # rblock result (up path; level 4: down_256 output)
             ws['M%da' % l], ws['M%db' % l] = buf(l, C // 4), buf(l, C // 4)   # bottleneck mids (VBNet)
-        ops = []
+        ops, meta = [], []
+        ws['meta'] = meta
         st = lib.stream_ptr
         raw = ws['raw']
 
@@ -193,6 +194,14 @@ class NetPlan(object):
             args = (c.mode, dt, c.impl, x.p, x.ld, c.cin, lib.ptr(c.w), lib.ptr(c.bias), y.p, y.ld, c.cout,
                     B, xdims[0], xdims[1], xdims[2], sp)
             ops.append(lambda a=args: lib.call('seg3d_conv3d_fwd', *a, st()))
+            nv_in = B * xdims[0] * xdims[1] * xdims[2]
+            taps = {lib.CONV_K3: 27, lib.CONV_K2S2: 1, lib.CONV_T2S2: 8, lib.CONV_K1: 1}[c.mode]   # MACs per INPUT voxel / (cin*cout)
+            nv_out = nv_in // 8 if c.mode == lib.CONV_K2S2 else (nv_in * 8 if c.mode == lib.CONV_T2S2 else nv_in)
+            esz = 4 if dt == lib.F32 else 2
+            meta.append({'name': name, 'kind': ('conv_tc' if c.impl == lib.IMPL_TCGEN05 else 'conv_simt') + '_' +
+                         {lib.CONV_K3: 'k3', lib.CONV_K2S2: 'k2s2', lib.CONV_T2S2: 't2s2', lib.CONV_K1: 'k1'}[c.mode],
+                         'flops': 2.0 * nv_in * taps * c.cin * c.cout,
+                         'bytes': esz * (nv_in * c.cin + nv_out * c.cout) + c.w.numel() * c.w.element_size()})
 
         def gn(name, y, out, nvox, relu, res=None):
             g = self.gns[name]
@@ -201,6 +210,9 @@ class NetPlan(object):
                     res.p if res is not None else None, res.ld if res is not None else 0,
                     out.p, out.ld, 1 if relu else 0, B, nvox)
             ops.append(lambda a=args: lib.call('seg3d_gn_apply', *a, st()))
+            esz = 4 if dt == lib.F32 else 2
+            meta.append({'name': name, 'kind': 'gn_apply', 'flops': 0.0,
+                         'bytes': esz * B * nvox * y.C * (3 if res is not None else 2)})
 
         def rawview(C):
             return _View(raw, 0, C, C)
@@ -264,6 +276,9 @@ class NetPlan(object):
         a1 = (dt, lib.ptr(raw), nc, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),
               GN_EPS, s2, B, vox[0])
         ops.append(lambda a=a1: lib.call('seg3d_outblock_tail_stats', *a, st()))
+        esz = 4 if dt == lib.F32 else 2
+        meta.append({'name': 'out_block.tail_stats', 'kind': 'tail', 'flops': 0.0, 'bytes': esz * B * vox[0] * nc})
+        meta.append({'name': 'out_block.tail_probs', 'kind': 'tail', 'flops': 0.0, 'bytes': (esz + 4) * B * vox[0] * nc})
         a2 = (dt, lib.ptr(raw), nc, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),
               s2, lib.ptr(g2.gamma), lib.ptr(g2.beta), GN_EPS, lib.ptr(ws['probs']), B, vox[0])
         ops.append(lambda a=a2: lib.call('seg3d_outblock_tail_probs', *a, st()))
@@ -291,6 +306,21 @@ class NetPlan(object):
         self.launches_per_forward = len(ops)
         return ws['probs']
 
+    def run_profiled(self, ws, ops):
+        """Same as run() with a CUDA-event pair around every launch (current stream).  Returns
+        [(meta dict, milliseconds)] - used by bench.py for the per-kernel roofline table."""
+        ws['stats'].zero_()
+        ws['stats2'].zero_()
+        evs = []
+        for op in ops:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            op()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return [(m, a.elapsed_time(b)) for m, (a, b) in zip(ws['meta'], evs)]
+
     def forward(self, x):
         """probabilities [B,C,D,H,W] float32 (a view of the plan's output buffer; clone to keep)."""
         if not x.is_cuda:
@@ -302,4 +332,4 @@ class NetPlan(object):
         return self.run(ws, ops)
 
 
-DEFAULT_TC_MODES = ()
+DEFAULT_TC_MODES = (lib.CONV_K3,)

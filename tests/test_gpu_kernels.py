@@ -148,7 +148,8 @@ def test_gn_apply_matches_group_norm(lib, dt_name, relu, use_res):
     yd, rd = to_ndhwc(y, tdt), to_ndhwc(res, tdt)
     # write into the second half of a wider (concat) buffer
     out = torch.zeros((N, D, H, W, 2 * C), dtype=tdt, device='cuda')
-    L.call('seg3d_gn_apply', dt, L.ptr(yd), C, C, L.ptr(stats), L.ptr(gamma.cuda()), L.ptr(beta.cuda()), 1e-5,
+    gd, bd = gamma.cuda(), beta.cuda()
+    L.call('seg3d_gn_apply', dt, L.ptr(yd), C, C, L.ptr(stats), L.ptr(gd), L.ptr(bd), 1e-5,
            L.ptr(rd) if use_res else None, C, L.ptr(out, C), 2 * C, 1 if relu else 0, N, D * H * W, L.stream_ptr())
     torch.cuda.synchronize()
     got = from_ndhwc(out[..., C:])
@@ -204,6 +205,46 @@ def test_forward_fp16_meets_reduced_precision_bars(lib, arch, cout):
     rep = parity_report(ref[0].numpy(), y[0].numpy())
     print(arch, 'fp16', rep)
     assert rep['max_abs'] <= 1e-2 and rep['agree'] >= 0.999 and min(rep['dice']) >= 0.999, rep
+
+
+TC_CASES = [
+    # Cin, Cout, N, D, H, W
+    (32, 32, 1, 8, 8, 8), (64, 64, 2, 8, 4, 8), (16, 16, 1, 4, 8, 16), (128, 128, 1, 4, 4, 8), (256, 256, 1, 6, 6, 6),
+    (32, 64, 1, 12, 12, 12), (64, 16, 1, 16, 16, 16), (256, 64, 2, 2, 6, 10),
+]
+
+
+@pytest.mark.parametrize('dt_name', ['F16', 'BF16'])
+@pytest.mark.parametrize('case', TC_CASES, ids=lambda c: '-'.join(map(str, c)))
+def test_conv_k3_tcgen05_matches_torch(lib, case, dt_name):
+    L = lib
+    dt = getattr(L, dt_name)
+    tdt = L.TORCH_DTYPE[dt]
+    Cin, Cout, N, D, H, W = case
+    g = torch.Generator().manual_seed(Cin * 7 + Cout)
+    x = torch.randn((N, Cin, D, H, W), generator=g)
+    w = torch.randn((Cout, Cin, 3, 3, 3), generator=g) * (1.0 / (27 * Cin) ** 0.5)
+    b = torch.randn((Cout,), generator=g) * 0.1
+    xr, wr = x.to(tdt).float(), w.to(tdt).float()          # operands as the tensor core sees them
+    ref = F.conv3d(xr.double(), wr.double(), b.double(), padding=1).float()
+    y, stats = run_conv(L, L.CONV_K3, dt, L.IMPL_TCGEN05, x, w, b)
+    assert not torch.isnan(y).any()
+    tol = 2e-3 if dt == L.F16 else 1.6e-2                  # output rounding to the storage type
+    err = (y - ref).abs().max()
+    assert err <= tol * max(1.0, ref.abs().max()), err
+    s_ref = torch.stack([ref.double().flatten(1).sum(1), (ref.double() ** 2).flatten(1).sum(1)], 1)
+    assert torch.allclose(stats, s_ref, rtol=1e-4, atol=1e-2)   # stats are taken before the output rounding
+
+
+def test_forward_fp16_tcgen05_equals_simt_path(lib):
+    sd = oinit.init_state_dict('vnet', 1, 2, 0)
+    x = seeded_input(11, (2, 1, 32, 32, 32), 'smooth')
+    a = _plan_forward(lib, sd, x, 'fp16', tc_modes=())
+    b = _plan_forward(lib, sd, x, 'fp16', tc_modes=(lib.CONV_K3,))
+    ref = onet.forward(sd, x)
+    print('simt-vs-tc max', float((a - b).abs().max()), 'tc-vs-oracle', float((b - ref).abs().max()))
+    assert (b - ref).abs().max() <= 1e-2
+    assert (a - b).abs().max() <= 5e-3
 
 
 def test_forward_batch_equals_single(lib):
