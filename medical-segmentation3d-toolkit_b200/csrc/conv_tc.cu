@@ -18,6 +18,7 @@
 // and epilogue overlap its neighbours' main loops.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -34,8 +35,13 @@ struct TcParams {
   int tx_bytes;                     // bytes the two TMA loads of one stage actually write
   int tmem_cols;
   uint32_t idesc;
-  uint32_t sbo;                     // stride between 8-row groups, bytes
+  uint32_t sbo;                     // B operand: stride between 8-row groups, bytes
+  uint32_t a_sbo;                   // A operand: stride between 8-row groups (one x-line of the box), bytes
   uint32_t layout_type;             // UMMA smem descriptor swizzle code
+  int kwfuse;                       // 1: one A box (tw+2 wide) per (kd,kh) serves the three kw taps via x-shifted descriptors
+  int b_slab;                       // pitch of one kw weight slab inside a stage (kwfuse)
+  int row_bytes;
+  int use_base_offset;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -89,11 +95,15 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 // K-major UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
 // [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base offset | [61,64) layout type
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint32_t layout_type) {
+// base offset: phase of the start address inside the 8 x 128 B swizzle repeat; non-zero only for the
+// x-shifted A views of the kw-fused path (PTX ISA: (start_address >> 7) & 7 when the matrix start is not
+// aligned to the repeating pattern).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint32_t layout_type, uint32_t base_offset = 0) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_offset & 7) << 49;
   d |= (uint64_t)(layout_type & 7) << 61;
   return d;
 }
@@ -140,7 +150,7 @@ conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int kiters = 27 * p.nchunk;
+  const int kiters = (p.kwfuse ? 9 : 27) * p.nchunk;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -148,11 +158,18 @@ conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < kiters; ++it) {
         const int tap = it / p.nchunk, ck = it - tap * p.nchunk;
-        const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
         mbar_wait(empty_bar + 8 * stage, phase ^ 1);
         mbar_expect_tx(full_bar + 8 * stage, (uint32_t)p.tx_bytes);
-        tma_load_5d(a_base + stage * p.a_bytes, &map_x, full_bar + 8 * stage, ck * p.KC, x0 + kw - 1, y0 + kh - 1, z0 + kd - 1, n);
-        tma_load_2d(b_base + stage * p.b_bytes, &map_w, full_bar + 8 * stage, ck * p.KC, tap * p.Cout);
+        if (p.kwfuse) {          // tap = kd*3 + kh; the box starts one voxel to the left and is tw+2 wide
+          const int kd = tap / 3, kh = tap % 3;
+          tma_load_5d(a_base + stage * p.a_bytes, &map_x, full_bar + 8 * stage, ck * p.KC, x0 - 1, y0 + kh - 1, z0 + kd - 1, n);
+          for (int kw = 0; kw < 3; ++kw)
+            tma_load_2d(b_base + stage * p.b_bytes + kw * p.b_slab, &map_w, full_bar + 8 * stage, ck * p.KC, (tap * 3 + kw) * p.Cout);
+        } else {
+          const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+          tma_load_5d(a_base + stage * p.a_bytes, &map_x, full_bar + 8 * stage, ck * p.KC, x0 + kw - 1, y0 + kh - 1, z0 + kd - 1, n);
+          tma_load_2d(b_base + stage * p.b_bytes, &map_w, full_bar + 8 * stage, ck * p.KC, tap * p.Cout);
+        }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -165,10 +182,20 @@ conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         mbar_wait(full_bar + 8 * stage, phase);
         tc_fence_after();
         const uint32_t a_addr = a_base + stage * p.a_bytes, b_addr = b_base + stage * p.b_bytes;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t ad = make_desc(a_addr + k * 32, p.sbo, p.layout_type);
-          const uint64_t bd = make_desc(b_addr + k * 32, p.sbo, p.layout_type);
-          tc_mma_f16(tmem_base, ad, bd, p.idesc, (it | k) != 0);
+        if (p.kwfuse) {
+          for (int kw = 0; kw < 3; ++kw)
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t sa = a_addr + kw * p.row_bytes + k * 32;
+              const uint64_t ad = make_desc(sa, p.a_sbo, p.layout_type, p.use_base_offset ? ((sa >> 7) & 7) : 0);
+              const uint64_t bd = make_desc(b_addr + kw * p.b_slab + k * 32, p.sbo, p.layout_type);
+              tc_mma_f16(tmem_base, ad, bd, p.idesc, (it | kw | k) != 0);
+            }
+        } else {
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = make_desc(a_addr + k * 32, p.a_sbo, p.layout_type);
+            const uint64_t bd = make_desc(b_addr + k * 32, p.sbo, p.layout_type);
+            tc_mma_f16(tmem_base, ad, bd, p.idesc, (it | k) != 0);
+          }
         }
         tc_commit(empty_bar + 8 * stage);          // frees the smem slot when these MMAs retire
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -239,6 +266,8 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+int g_kwfuse_default = 1;
+
 }  // namespace
 
 int seg3d_conv_tc_supported(int mode, int dtype, int Cin, int Cout, int x_ld, int y_ld, int D, int H, int W) {
@@ -272,14 +301,34 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
       const long long sc = score + spread * 512;
       if (best < 0 || sc < best) { best = sc; p.tw = tw; p.th = th; p.td = td; }
     }
+  // kw-fused variant: x extent of the tile must be exactly 8 so that every 8-row MMA group is one x-line
+  // of the (tw+2)-wide box.  SEG3D_TC_KWFUSE=0/1 overrides (default: on when W is a multiple of 8).
+  {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("SEG3D_TC_KWFUSE"); env = e ? atoi(e) : 2; }
+    p.kwfuse = (env == 2) ? (g_kwfuse_default && W % 8 == 0) : (env == 1 && W % 8 == 0);
+  }
+  { const char* e = getenv("SEG3D_TC_BASEOFF"); p.use_base_offset = e ? atoi(e) : 0; }
+  if (p.kwfuse) {
+    p.tw = 8;
+    long long bt = -1;
+    for (int th = 1; th <= 16; th *= 2) {
+      const int td = 16 / th;
+      const long long tiles = (long long)((H + th - 1) / th) * ((D + td - 1) / td);
+      const long long sc = tiles * 64 + (th > td ? th - td : td - th);
+      if (bt < 0 || sc < bt) { bt = sc; p.th = th; p.td = td; }
+    }
+  }
   p.ntx = (W + p.tw - 1) / p.tw; p.nty = (H + p.th - 1) / p.th; p.ntz = (D + p.td - 1) / p.td;
   const long long ntiles = (long long)p.ntx * p.nty * p.ntz * N;
   SEG3D_REQUIRE(ntiles > 0 && ntiles < (1ll << 31), "conv_tc: tile count out of range");
 
   const int row_bytes = p.KC * 2;
-  p.a_bytes = TILE_M * row_bytes;
-  p.b_bytes = Cout * row_bytes;
-  p.b_bytes = (p.b_bytes + 1023) & ~1023;           // keep every operand slab 1024-byte aligned
+  p.row_bytes = row_bytes;
+  const int a_rows = p.kwfuse ? (p.tw + 2) * p.th * p.td : TILE_M;
+  p.a_bytes = (a_rows * row_bytes + 1023) & ~1023;
+  p.b_slab = (Cout * row_bytes + 1023) & ~1023;     // keep every operand slab 1024-byte aligned
+  p.b_bytes = p.kwfuse ? 3 * p.b_slab : p.b_slab;
   const int stage_bytes = p.a_bytes + p.b_bytes;
   int stages = (96 * 1024) / stage_bytes;            // <= ~96 KB of ring so two CTAs can share an SM
   if (stages > 8) stages = 8;
@@ -289,6 +338,7 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   SEG3D_REQUIRE(stages >= 2, "conv_tc: operand ring does not fit in shared memory");
   p.stages = stages;
   p.sbo = 8 * row_bytes;
+  p.a_sbo = p.kwfuse ? (p.tw + 2) * row_bytes : 8 * row_bytes;
   p.layout_type = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
   p.tmem_cols = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256));
   const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
@@ -300,7 +350,7 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   {
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2, (cuuint64_t)D * H * W * x_ld * 2};
-    cuuint32_t box[5] = {(cuuint32_t)p.KC, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.td, 1};
+    cuuint32_t box[5] = {(cuuint32_t)p.KC, (cuuint32_t)(p.kwfuse ? p.tw + 2 : p.tw), (cuuint32_t)p.th, (cuuint32_t)p.td, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&map_x, tdt, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -316,7 +366,7 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
     if (r != CUDA_SUCCESS) { seg3d_set_error("conv_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SEG3D_ECUDA; }
   }
   // the weight slab the TMA writes is Cout*row_bytes; b_bytes is its 1024-aligned pitch
-  p.tx_bytes = p.a_bytes + Cout * row_bytes;
+  p.tx_bytes = a_rows * row_bytes + (p.kwfuse ? 3 : 1) * Cout * row_bytes;
   TcParams pk = p;
   const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 8 + 8 * sizeof(float) + 64;
 

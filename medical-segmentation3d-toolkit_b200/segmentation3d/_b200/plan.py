@@ -36,13 +36,19 @@ def strip_prefix(sd):
 class _Conv(object):
     """One packed convolution.  `load` (re)packs in place so kernel-argument pointers stay valid."""
 
-    def __init__(self, sd, name, mode, dt, device, allow_tc):
+    def __init__(self, sd, name, mode, dt, device, allow_tc, pad_cout=0):
         w = sd[name + '.weight']
         self.name, self.mode, self.dt, self.device = name, mode, dt, device
         if mode == lib.CONV_T2S2:
             self.cin, self.cout = w.shape[0], w.shape[1]
         else:
             self.cout, self.cin = w.shape[0], w.shape[1]
+        # pad_cout: zero-pad the output channels (weights and bias) so a narrow conv (out_block.conv1,
+        # Cout = classes) can run on the tensor cores, whose minimum N is 16 at M=128.  The padded
+        # channels are exactly 0, so they add nothing to the GroupNorm sums.
+        self.real_cout = self.cout
+        if pad_cout and allow_tc and dt != lib.F32 and mode in allow_tc and self.cout < pad_cout:
+            self.cout = pad_cout
         tc_ok = (allow_tc and dt != lib.F32 and self.cin % 16 == 0 and self.cout % 16 == 0 and self.cout <= 256
                  and mode in allow_tc)
         self.impl = lib.IMPL_TCGEN05 if tc_ok else lib.IMPL_SIMT
@@ -52,6 +58,14 @@ class _Conv(object):
     def load(self, sd):
         w = sd[self.name + '.weight'].detach().to(device=self.device, dtype=torch.float32)
         b = sd.get(self.name + '.bias')
+        if self.cout != self.real_cout:
+            wp = torch.zeros((self.cout,) + tuple(w.shape[1:]), dtype=torch.float32, device=self.device)
+            wp[:self.real_cout] = w
+            w = wp
+            if b is not None:
+                bp = torch.zeros((self.cout,), dtype=torch.float32, device=self.device)
+                bp[:self.real_cout] = b.detach().to(self.device)
+                b = bp
         if self.impl == lib.IMPL_SIMT:
             if self.mode == lib.CONV_T2S2:      # [Cin][8*Cout], column = tap*Cout + co
                 p = w.permute(0, 2, 3, 4, 1).reshape(self.cin, 8 * self.cout)
@@ -129,7 +143,8 @@ class NetPlan(object):
                     continue
                 else:
                     m = lib.CONV_K3
-                self.convs[name] = _Conv(sd, name, m, self.dt, self.device, self.tc_modes)
+                self.convs[name] = _Conv(sd, name, m, self.dt, self.device, self.tc_modes,
+                                         pad_cout=16 if name == 'out_block.conv1' else 0)
             else:
                 self.gns[name] = _GN(sd, name, self.device)
         self.w2 = sd['out_block.conv2.weight'].detach().to(self.device, torch.float32).reshape(
@@ -269,17 +284,18 @@ class NetPlan(object):
             src = dest
         # out block: conv1 -> raw, then the fused tail
         nc = self.out_channels
-        conv('out_block.conv1', src, dims[0], rawview(nc), 'out_block.gn1')
+        ncp = self.convs['out_block.conv1'].cout          # = nc, or 16 when padded for the tensor-core path
+        conv('out_block.conv1', src, dims[0], rawview(ncp), 'out_block.gn1')
         g1, g2 = self.gns['out_block.gn1'], self.gns['out_block.gn2']
         s1 = lib.ptr(ws['stats'][self.gn_index['out_block.gn1']])
         s2 = lib.ptr(ws['stats2'])
-        a1 = (dt, lib.ptr(raw), nc, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),
+        a1 = (dt, lib.ptr(raw), ncp, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),
               GN_EPS, s2, B, vox[0])
         ops.append(lambda a=a1: lib.call('seg3d_outblock_tail_stats', *a, st()))
         esz = 4 if dt == lib.F32 else 2
         meta.append({'name': 'out_block.tail_stats', 'kind': 'tail', 'flops': 0.0, 'bytes': esz * B * vox[0] * nc})
         meta.append({'name': 'out_block.tail_probs', 'kind': 'tail', 'flops': 0.0, 'bytes': (esz + 4) * B * vox[0] * nc})
-        a2 = (dt, lib.ptr(raw), nc, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),
+        a2 = (dt, lib.ptr(raw), ncp, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),
               s2, lib.ptr(g2.gamma), lib.ptr(g2.beta), GN_EPS, lib.ptr(ws['probs']), B, vox[0])
         ops.append(lambda a=a2: lib.call('seg3d_outblock_tail_probs', *a, st()))
         return ws, ops

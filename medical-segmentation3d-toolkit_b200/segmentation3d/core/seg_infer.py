@@ -1,0 +1,346 @@
+"""Inference engine (drop-in for reference segmentation3d/core/seg_infer.py).
+
+Same entry points, argument meaning and error behaviour as the reference:
+  load_single_model / load_models      (:99-205)   model-folder + checkpoint layout unchanged
+  segmentation_volume                  (:249-350)  resample -> grid -> patch loop -> blend -> argmax -> CC
+  segmentation                         (:353-493)  txt / single file / folder input, same outputs on disk
+  read_test_txt / read_test_csv / read_test_folder (:23-96)
+
+What differs is where the work runs: the resampled volume, the per-class accumulators and the
+mask stay on the GPU; patches are cropped/normalised, pushed through the network (several per
+forward), blended and arg-maxed by the CUDA kernels of libseg3d_b200.so
+(segmentation3d/_b200/sliding.py).  The reference's second forward per patch (:230-234) returns the
+same bits as the first and is not repeated.  There is no CPU path: gpu_id < 0 raises.
+"""
+import copy
+import glob
+import importlib
+import os
+import time
+
+import numpy as np
+import torch
+
+from segmentation3d._b200.sliding import SlidingWindow, axis_counts
+from segmentation3d.utils.attrdict import AttrDict as edict
+from segmentation3d.utils.file_io import load_config, readlines
+from segmentation3d.utils.image3d import Image3d, as_image3d, read_image, write_image
+from segmentation3d.utils.image_tools import image_partition_by_fixed_size, is_identity_resample
+from segmentation3d.utils.model_io import get_checkpoint_folder
+from segmentation3d.utils.normalizer import normalizer_from_dict
+
+DEFAULT_PATCH_BATCH = int(os.environ.get('SEG3D_PATCH_BATCH', '6'))
+
+
+# ---- test-list readers -----------------------------------------------------------------------------
+def read_test_txt(txt_file):
+    """First line = number of cases, then one '<case_name> <path>' line per case."""
+    lines = readlines(txt_file)
+    case_num = int(lines[0])
+    if len(lines) - 1 < case_num:
+        raise ValueError('case num cannot be greater than path num!')
+    names, paths = [], []
+    for i in range(case_num):
+        tokens = lines[1 + i].split()
+        if len(tokens) != 2:
+            raise ValueError('invalid line: %s' % lines[1 + i])
+        names.append(tokens[0])
+        paths.append(tokens[1])
+    return names, paths
+
+
+def read_test_csv(csv_file):
+    """csv with columns image_name,image_path."""
+    import pandas as pd
+    df = pd.read_csv(csv_file)
+    return df['image_name'].tolist(), df['image_path'].tolist()
+
+
+def read_test_folder(folder_path, is_dicom_folder=False):
+    """Every .mha/.mhd/.nii/.nii.gz/.hdr/.image3d file (or the folder itself for a DICOM series)."""
+    if is_dicom_folder:
+        return [os.path.basename(os.path.normpath(folder_path))], [folder_path]
+    names, paths = [], []
+    for ext in ('*.mha', '*.mhd', '*.nii.gz', '*.nii', '*.hdr', '*.image3d'):
+        for p in sorted(glob.glob(os.path.join(folder_path, ext))):
+            names.append(os.path.basename(p))
+            paths.append(p)
+    return names, paths
+
+
+# ---- model loading -----------------------------------------------------------------------------------
+def _device_for(gpu_id):
+    if gpu_id is None or int(gpu_id) < 0:
+        raise RuntimeError('segmentation3d (B200 build) has no CPU inference path: pass gpu_id >= 0')
+    if not torch.cuda.is_available():
+        raise RuntimeError('segmentation3d (B200 build): no CUDA device visible')
+    return torch.device('cuda:%d' % int(gpu_id)) if int(gpu_id) < torch.cuda.device_count() else torch.device('cuda:0')
+
+
+def make_model(net, spacing, normalizer=None, max_stride=16, interpolation='LINEAR', batch=None):
+    """Wrap an on-device network into the model record `segmentation_volume` consumes."""
+    model = edict()
+    model.net = net
+    model.spacing, model.max_stride, model.interpolation = list(spacing), max_stride, interpolation
+    model.in_channels, model.out_channels = net.in_channels, net.out_channels
+    if normalizer is None:
+        model.crop_normalizers = None
+    else:
+        model.crop_normalizers = [normalizer_from_dict(normalizer) if isinstance(normalizer, dict) else normalizer]
+    dict.__setitem__(model, 'engine', SlidingWindow(net._current_plan(), batch or DEFAULT_PATCH_BATCH))
+    return model
+
+
+def load_single_model(model_folder, gpu_id=0):
+    """<model_folder>/checkpoints/chk_<latest>/params.pth -> model record on cuda:<gpu_id>."""
+    assert os.path.isdir(model_folder), 'Model folder does not exist: {}'.format(model_folder)
+    device = _device_for(gpu_id)
+    chk_dir = get_checkpoint_folder(os.path.join(model_folder, 'checkpoints'), -1)
+    state = torch.load(os.path.join(chk_dir, 'params.pth'), map_location='cpu', weights_only=False)
+    net_module = importlib.import_module('segmentation3d.network.' + state['net'])
+    net = net_module.SegmentationNet(state['in_channels'], state['out_channels'])
+    sd = state['state_dict']
+    if any(k.startswith('module.') for k in sd):          # written under nn.DataParallel (core/seg_train.py:77,148)
+        sd = {k[7:]: v for k, v in sd.items()}
+    net.load_state_dict(sd)
+    net = net.to(device).eval()
+    norms = state['crop_normalizers']
+    for d in norms:
+        if d['type'] not in (0, 1):
+            raise ValueError('Unsupported normalization type.')
+    model = make_model(net, state['spacing'], norms[0] if norms else None, state['max_stride'], state['interpolation'])
+    model.crop_normalizers = [normalizer_from_dict(d) for d in norms]
+    return model
+
+
+def load_models(model_folder, gpu_id=0):
+    assert os.path.isdir(model_folder), 'Model folder does not exist: {}'.format(model_folder)
+    models = edict()
+    dict.__setitem__(models, 'infer_cfg', load_config(os.path.join(model_folder, 'infer_config.py')))
+    cfg = models.infer_cfg
+    scale = cfg.general.single_scale
+    if scale not in ('coarse', 'fine', 'DISABLE'):
+        raise ValueError('Unsupported single scale type!')
+    coarse = fine = None
+    if scale in ('coarse', 'DISABLE'):
+        coarse = load_single_model(os.path.join(model_folder, cfg.coarse.model_name), gpu_id)
+    if scale in ('fine', 'DISABLE'):
+        fine = load_single_model(os.path.join(model_folder, cfg.fine.model_name), gpu_id)
+    dict.__setitem__(models, 'coarse_model', coarse)
+    dict.__setitem__(models, 'fine_model', fine)
+    return models
+
+
+# ---- the hot path --------------------------------------------------------------------------------------
+def _cfg_get(cfg, key, default=None):
+    return cfg[key] if key in cfg else default
+
+
+def _grid(model, cfg, size_xyz, spacing, bbox_start_voxel, bbox_end_voxel, use_gpu=True):
+    ptype = cfg['partition_type']
+    if ptype == 'DISABLE':
+        return [[0, 0, 0]], [[int(v) for v in size_xyz]]
+    if ptype != 'SIZE':
+        raise ValueError('Unsupported partition type!')
+    psize, pstride = copy.deepcopy(list(cfg['partition_size'])), copy.deepcopy(list(cfg['partition_stride']))
+    if not use_gpu:
+        r = _cfg_get(cfg, 'cpu_partition_decrease_ratio', 1.0)
+        psize, pstride = [v * r for v in psize], [v * r for v in pstride]
+    if bbox_start_voxel is not None and bbox_end_voxel is not None:
+        bs = [max(0, int(v)) for v in bbox_start_voxel]
+        be = [min(int(bbox_end_voxel[a]), int(size_xyz[a])) for a in range(3)]
+    else:
+        bs, be = [0, 0, 0], [int(v) for v in size_xyz]
+    frame = Image3d(np.empty((0, 0, 0), np.float32), spacing)
+    frame.GetSize = lambda: tuple(int(v) for v in size_xyz)
+    return image_partition_by_fixed_size(frame, bs, be, psize, pstride, model['max_stride'])
+
+
+def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_start_voxel=None, bbox_end_voxel=None,
+                               use_gpu=True, spacing=None):
+    """Device-resident core of segmentation_volume: `vol` is a CUDA float32 [z,y,x] tensor already at
+    the model spacing.  Returns (mean_probs [C,z,y,x] fp32, mask [z,y,x] int8) on the device.
+    shard=(rank, world): this process runs patches rank::world and the accumulators are summed with
+    an all-reduce over the default process group (NCCL) before the count normalisation."""
+    eng = model['engine']
+    if batch:
+        eng.batch = int(batch)
+    eng.plan = model['net']._current_plan()
+    Z, Y, X = vol.shape
+    starts, ends = _grid(model, cfg, [X, Y, Z], spacing or model['spacing'], bbox_start_voxel, bbox_end_voxel, use_gpu)
+    norm = model['crop_normalizers'][0].to_dict() if model['crop_normalizers'] else None
+    patch = [ends[0][a] - starts[0][a] for a in range(3)]
+    acc = torch.zeros((model['out_channels'], Z, Y, X), dtype=torch.float32, device=vol.device)
+    mine = starts if shard is None else starts[shard[0]::shard[1]]
+    eng.accumulate(vol, mine, patch, norm, acc)
+    if shard is not None and shard[1] > 1:
+        import torch.distributed as dist
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    counts = axis_counts([X, Y, Z], starts, ends)
+    if bbox_start_voxel is not None:
+        # voxels outside the partitioned box have count 0: the reference divides by zero there (inf*0 = nan
+        # -> argmax 0); keep them at probability 0 / label 0 by treating the count as 1.
+        counts = [np.maximum(c, 1) for c in counts]
+    mask = eng.finalize(acc, counts)
+    return acc, mask
+
+
+def segmentation_volume_host(model, cfg, host_vol, host_mask=None, batch=None, shard=None):
+    """End-to-end call with HOST buffers: (pinned) float32 [z,y,x] in, int8 mask out; probabilities stay
+    on the device and are returned as a tensor.  Copies are issued on the current stream."""
+    dev = next(model['net'].parameters()).device
+    vol = torch.empty(host_vol.shape, dtype=torch.float32, device=dev)
+    vol.copy_(host_vol, non_blocking=True)
+    acc, mask = segmentation_volume_device(model, cfg, vol, batch=batch, shard=shard)
+    if host_mask is None:
+        host_mask = torch.empty(mask.shape, dtype=torch.int8, pin_memory=True)
+    host_mask.copy_(mask, non_blocking=True)
+    return acc, host_mask
+
+
+def _largest_cc(mask_np, labels, keep_threshold=None):
+    """pick_largest_connected_component / remove_small_connected_component (utils/image_tools.py:380-432)
+    with 26-connectivity, on the host (post-processing, outside the hot path)."""
+    from scipy import ndimage
+    out = np.zeros_like(mask_np)
+    st = np.ones((3, 3, 3), dtype=bool)
+    for lab in labels:
+        cc, n = ndimage.label(mask_np == lab, structure=st)
+        if n == 0:
+            continue
+        sizes = np.bincount(cc.ravel())[1:]
+        if keep_threshold is None:
+            keep = [int(np.argmax(sizes)) + 1]
+        else:
+            keep = [i + 1 for i, s in enumerate(sizes) if s >= keep_threshold]
+        out[np.isin(cc, keep)] = lab
+    return out
+
+
+def segmentation_volume(model, cfg, image, bbox_start_voxel, bbox_end_voxel, use_gpu):
+    """Segment one volume.  Returns (mean_probs: list of per-class images, mask image) like the
+    reference; the images are backed by CUDA tensors (`.to_numpy()` copies to the host on demand)."""
+    image = as_image3d(image)
+    model_spacing = list(copy.deepcopy(model['spacing']))
+    if not use_gpu:
+        r = _cfg_get(cfg, 'cpu_model_spacing_increase_ratio', 1.0)
+        model_spacing = [v * r for v in model_spacing]
+    if not is_identity_resample(image, model_spacing, model['max_stride']):
+        raise NotImplementedError('resampling to the model spacing is not built yet (SURVEY.md 8f-2): image spacing %s / '
+                                  'size %s must equal model spacing %s with size %% %d == 0'
+                                  % (image.GetSpacing(), image.GetSize(), model_spacing, model['max_stride']))
+    dev = next(model['net'].parameters()).device
+    data = image.data
+    vol = (data if torch.is_tensor(data) else torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)))
+    vol = vol.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+    if bbox_start_voxel is not None and bbox_end_voxel is not None:
+        # identity resample: the iso frame equals the image frame (:292-302)
+        bbox_start_voxel = [max(0, int(v)) for v in bbox_start_voxel]
+        bbox_end_voxel = [min(int(bbox_end_voxel[a]), image.GetSize()[a]) for a in range(3)]
+    acc, mask = segmentation_volume_device(model, cfg, vol, bbox_start_voxel=bbox_start_voxel,
+                                           bbox_end_voxel=bbox_end_voxel, use_gpu=use_gpu, spacing=model_spacing)
+    num_classes = model['out_channels']
+    mean_probs = []
+    for c in range(num_classes):
+        im = Image3d(acc[c])
+        im.CopyInformation(image)
+        mean_probs.append(im)
+    if _cfg_get(cfg, 'pick_largest_cc', False) or _cfg_get(cfg, 'remove_small_cc', 0) > 0:
+        m = mask.cpu().numpy()
+        labels = list(range(1, num_classes))
+        if _cfg_get(cfg, 'pick_largest_cc', False):
+            m = _largest_cc(m, labels)
+        if _cfg_get(cfg, 'remove_small_cc', 0) > 0:
+            m = _largest_cc(m, labels, keep_threshold=cfg['remove_small_cc'])
+        mask = torch.from_numpy(m.astype(np.int8))
+    mask_im = Image3d(mask)
+    mask_im.CopyInformation(image)
+    return mean_probs, mask_im
+
+
+def get_bounding_box(mask, selected_labels):
+    """[x,y,z] start (inclusive) / end (exclusive) of the selected labels (utils/image_tools.py:481-510)."""
+    m = as_image3d(mask).data
+    m = m if torch.is_tensor(m) else torch.from_numpy(np.ascontiguousarray(m))
+    sel = (m > 0) if selected_labels is None else torch.isin(m, torch.tensor(list(selected_labels), device=m.device, dtype=m.dtype))
+    if not bool(sel.any()):
+        print('Fail to get the bounding box.')
+        return None, None
+    nz = sel.nonzero()
+    lo, hi = nz.min(0)[0].tolist(), nz.max(0)[0].tolist()
+    return [lo[2], lo[1], lo[0]], [hi[2] + 1, hi[1] + 1, hi[0] + 1]
+
+
+def segmentation(input_path, model_folder, output_folder, seg_name, gpu_id, return_mask, save_mask, save_image, save_prob):
+    """Volumetric segmentation engine: same inputs/outputs as the reference (:353-493)."""
+    begin = time.time()
+    models = load_models(model_folder, gpu_id)
+    load_model_time = time.time() - begin
+
+    is_dicom_folder = False
+    if os.path.isfile(input_path):
+        if input_path.endswith('.txt'):
+            file_name_list, file_path_list = read_test_txt(input_path)
+        elif input_path.endswith(('.mhd', '.mha', '.nii.gz', '.nii', '.hdr', '.image3d')):
+            file_name_list, file_path_list = [os.path.basename(input_path)], [input_path]
+        else:
+            raise ValueError('Unsupported input path.')
+    elif os.path.isdir(input_path):
+        if glob.glob(os.path.join(input_path, '*.dcm')):
+            raise NotImplementedError('DICOM series input needs SimpleITK/GDCM, which this build does not bundle')
+        file_name_list, file_path_list = read_test_folder(input_path, is_dicom_folder)
+        if len(file_name_list) == 0:
+            raise ValueError('Empty test folder!')
+    else:
+        raise ValueError('The file {} does not exist.'.format(input_path))
+
+    infer_cfg = models['infer_cfg']
+    scale = infer_cfg.general.single_scale
+    use_gpu = gpu_id > 0          # reference quirk kept (core/seg_infer.py:420): only selects the cpu_*_ratio knobs
+    masks, total_inference_time, num_success_case = [], 0, 0
+    for i, file_path in enumerate(file_path_list):
+        print('{}: {}'.format(i, file_path))
+        begin = time.time()
+        image = read_image(file_path, np.float32)
+        read_image_time = time.time() - begin
+
+        begin = time.time()
+        if scale == 'coarse':
+            mean_probs, mask = segmentation_volume(models['coarse_model'], infer_cfg.coarse, image, None, None, use_gpu)
+        elif scale == 'fine':
+            mean_probs, mask = segmentation_volume(models['fine_model'], infer_cfg.fine, image, None, None, use_gpu)
+        elif scale == 'DISABLE':
+            print('Coarse segmentation: ')
+            _, mask = segmentation_volume(models['coarse_model'], infer_cfg.coarse, image, None, None, use_gpu)
+            start_voxel, end_voxel = get_bounding_box(mask, None)
+            bbox_ratio = 100
+            for a in range(3):
+                bbox_ratio *= (end_voxel[a] - start_voxel[a]) / mask.GetSize()[a]
+            print('Fine segmentation (bbox ratio: {:.2f}%): '.format(bbox_ratio))
+            mean_probs, mask = segmentation_volume(models['fine_model'], infer_cfg.fine, image, start_voxel, end_voxel, use_gpu)
+        else:
+            raise ValueError('Unsupported scale type!')
+        torch.cuda.synchronize()
+        inference_time = time.time() - begin
+        if return_mask:
+            masks.append(mask)
+
+        begin = time.time()
+        case_name = file_name_list[i]
+        if save_mask or save_image or save_prob:
+            os.makedirs(os.path.join(output_folder, case_name), exist_ok=True)
+        if save_mask:
+            write_image(mask, os.path.join(output_folder, case_name, seg_name), True)
+        if save_image:
+            write_image(image, os.path.join(output_folder, case_name, 'org.mha'), True)
+        if save_prob:
+            for c, prob in enumerate(mean_probs):
+                write_image(prob, os.path.join(output_folder, case_name, 'mean_prob_{}.mha'.format(c)), True)
+        save_time = time.time() - begin
+
+        total_test_time = load_model_time + read_image_time + inference_time + save_time
+        total_inference_time += inference_time
+        num_success_case += 1
+        print('total test time: {:.2f}, average inference time: {:.2f}'.format(
+            total_test_time, total_inference_time / num_success_case))
+    return masks

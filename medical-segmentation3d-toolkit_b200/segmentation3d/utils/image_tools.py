@@ -1,0 +1,133 @@
+"""Host-side image helpers on the inference path (drop-in subset of reference utils/image_tools.py).
+
+Bit-exact integer pieces: `image_partition_by_fixed_size` (image_tools.py:163-218) and the output
+size rounding of `resample_spacing` (:363-366).  The array work the reference does here on host
+numpy (normalise :221-238, add_image_region/add_image_value :435-469, argmax) runs in CUDA kernels
+in this build (segmentation3d/_b200/sliding.py); the host versions below exist for API parity on
+small images and are not on the engine's path.
+"""
+import math
+
+import numpy as np
+import torch
+
+from segmentation3d.utils.image3d import Image3d, as_image3d
+
+
+def image_partition_by_fixed_size(image, bbox_start_voxel, bbox_end_voxel, partition_size, partition_stride, max_stride):
+    """Sliding-window lattice.  Returns (start_voxels, end_voxels): lists of [x,y,z], x outermost,
+    z innermost; the last box per axis is clamped back inside the (max_stride-rounded) bounding box.
+    Like the reference, the two bbox list arguments are updated in place."""
+    size, spacing = image.GetSize(), image.GetSpacing()
+    for a in range(3):
+        assert size[a] >= max_stride and size[a] % max_stride == 0
+    extent = [0, 0, 0]
+    for a in range(3):
+        e = min(size[a], bbox_end_voxel[a] - bbox_start_voxel[a])
+        if e % max_stride:
+            e = (e // max_stride + 1) * max_stride
+        extent[a] = min(e, size[a])
+        bbox_end_voxel[a] = bbox_start_voxel[a] + extent[a]
+        if bbox_end_voxel[a] > size[a]:
+            bbox_end_voxel[a] = size[a]
+            bbox_start_voxel[a] = size[a] - extent[a]
+        assert bbox_start_voxel[a] >= 0
+    box, step, count = [0, 0, 0], [0, 0, 0], [0, 0, 0]
+    for a in range(3):
+        b = int(partition_size[a] / spacing[a] + 0.5)
+        if b % max_stride:
+            b = (b // max_stride + 1) * max_stride
+        box[a] = min(extent[a], b)
+        step[a] = min(extent[a], int(partition_stride[a] / spacing[a] + 0.5))
+        count[a] = int(np.ceil((extent[a] - box[a]) / step[a]) + 1)
+    axis_starts = []
+    for a in range(3):
+        lst = []
+        for i in range(count[a]):
+            s = bbox_start_voxel[a] + i * step[a]
+            if s + box[a] > bbox_end_voxel[a]:
+                s = bbox_end_voxel[a] - box[a]
+                assert s >= 0
+            lst.append(s)
+        axis_starts.append(lst)
+    starts = [[sx, sy, sz] for sx in axis_starts[0] for sy in axis_starts[1] for sz in axis_starts[2]]
+    ends = [[s[0] + box[0], s[1] + box[1], s[2] + box[2]] for s in starts]
+    return starts, ends
+
+
+def resample_size(in_size, in_spacing, out_spacing, max_stride):
+    """Output size of resample_spacing: round(size*spacing_in/spacing_out), then up to a multiple of max_stride."""
+    out = []
+    for a in range(3):
+        n = int(in_size[a] * in_spacing[a] / out_spacing[a] + 0.5)
+        if n % max_stride:
+            n = (n // max_stride + 1) * max_stride
+        out.append(n)
+    return out
+
+
+def is_identity_resample(image, spacing, max_stride):
+    size = image.GetSize()
+    same = all(abs(float(image.GetSpacing()[a]) - float(spacing[a])) <= 1e-9 * max(1.0, abs(float(spacing[a]))) for a in range(3))
+    return same and resample_size(size, image.GetSpacing(), spacing, max_stride) == list(size)
+
+
+def convert_image_to_tensor(image):
+    """Image (or list of images) -> float tensor [1,z,y,x] ([n,z,y,x] for a list)."""
+    if isinstance(image, (list, tuple)):
+        return torch.cat([convert_image_to_tensor(im) for im in image], 0)
+    img = as_image3d(image)
+    data = img.data if torch.is_tensor(img.data) else torch.from_numpy(np.ascontiguousarray(img.data))
+    return data.unsqueeze(0).float()
+
+
+def convert_tensor_to_image(tensor, dtype=None):
+    """3-D tensor -> Image3d; 4-D tensor -> list of Image3d."""
+    assert isinstance(tensor, torch.Tensor), 'input must be a tensor'
+    if tensor.dim() == 4:
+        return [convert_tensor_to_image(t, dtype) for t in tensor]
+    if tensor.dim() != 3:
+        raise ValueError('Only supports 3-dimsional or 4-dimensional image volume')
+    arr = tensor.detach().cpu().numpy()
+    if dtype is not None:
+        arr = arr.astype({float: np.float32, int: np.int32}.get(dtype, dtype))
+    return Image3d(arr)
+
+
+def add_image_region(image, start_voxel, end_voxel, patch):
+    """image[start:end] += patch on the host (API parity; the engine blends on the device)."""
+    img, pat = as_image3d(image), as_image3d(patch)
+    s, e = [int(v) for v in start_voxel], [int(v) for v in end_voxel]
+    for a in range(3):
+        assert pat.GetSize()[a] == e[a] - s[a]
+    out = np.array(img.to_numpy(), copy=True)
+    out[s[2]:e[2], s[1]:e[1], s[0]:e[0]] += pat.to_numpy()
+    res = Image3d(out)
+    res.CopyInformation(img)
+    return res
+
+
+def add_image_value(image, start_voxel, end_voxel, value):
+    img = as_image3d(image)
+    s, e = [int(v) for v in start_voxel], [int(v) for v in end_voxel]
+    out = np.array(img.to_numpy(), copy=True)
+    out[s[2]:e[2], s[1]:e[1], s[0]:e[0]] += value
+    res = Image3d(out)
+    res.CopyInformation(img)
+    return res
+
+
+def normalize_image(image, mean, std, clip, clip_min=-1.0, clip_max=1.0):
+    """(v-mean)/std with optional clipping, float32 numpy (host; API parity)."""
+    img = as_image3d(image)
+    a = (np.asarray(img.to_numpy(), dtype=np.float32) - mean) / std
+    if clip:
+        np.clip(a, clip_min, clip_max, out=a)
+    res = Image3d(a.astype(np.float32))
+    res.CopyInformation(img)
+    return res
+
+
+def get_mean_std_from_image(image):
+    a = as_image3d(image).to_numpy()
+    return np.mean(a), np.std(a)

@@ -1,0 +1,122 @@
+"""GPU parity of the device sliding-window engine against the reference goldens and the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import init as oinit
+from oracle import sliding_window as osw
+from oracle.metrics import parity_report
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def seeded_input(seed, shape, kind='noise'):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(shape, generator=g)
+    if kind == 'smooth':
+        lo = torch.randn((shape[0], shape[1]) + tuple(max(2, s // 8) for s in shape[2:]), generator=g)
+        x = torch.nn.functional.interpolate(lo, size=shape[2:], mode='trilinear', align_corners=False) * 2 + 0.3 * x
+    return x
+
+
+def build_model(arch, cout, sd, mode, norm):
+    import importlib
+    from segmentation3d.core.seg_infer import make_model
+    mod = importlib.import_module('segmentation3d.network.' + arch)
+    net = mod.SegmentationNet(1, cout)
+    net.load_state_dict(sd)
+    net.b200_mode = mode
+    net = net.cuda().eval()
+    return make_model(net, [1.0, 1.0, 1.0], norm, batch=3)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'fp16'])
+def test_segmentation_volume_matches_reference_golden(mode):
+    from segmentation3d.core.seg_infer import segmentation_volume
+    from segmentation3d.utils.image3d import Image3d
+    z = np.load(os.path.join(G, 'sliding_window.npz'))
+    meta = json.loads(str(z['meta']))
+    for name, arch, cout, wseed, aseed, size, psize, pstride, norm, vseed, scale in meta:
+        sd = oinit.init_state_dict(arch, 1, cout, wseed)
+        if aseed is not None:
+            sd = oinit.randomize_affine(sd, aseed)
+        vol = (seeded_input(vseed, (1, 1, size[2], size[1], size[0]), 'smooth')[0, 0].numpy() * scale).astype(np.float32)
+        nd = {'type': 0, 'mean': norm[1], 'stddev': norm[2], 'clip': norm[3]} if norm[0] == 'fixed' else {'type': 1, 'clip_sigma': norm[1]}
+        model = build_model(arch, cout, sd, mode, nd)
+        cfg = {'partition_type': 'SIZE', 'partition_size': psize, 'partition_stride': pstride,
+               'pick_largest_cc': False, 'remove_small_cc': 0}
+        probs_im, mask_im = segmentation_volume(model, cfg, Image3d(vol), None, None, True)
+        probs = np.stack([p.to_numpy() for p in probs_im], 0)
+        mask = mask_im.to_numpy()
+        rep = parity_report(z[name + '_probs'], probs)
+        agree_mask = float((mask == z[name + '_mask']).mean())
+        print(name, mode, rep, 'mask agreement vs reference mask %.5f' % agree_mask)
+        assert mask.dtype == np.int8
+        if mode == 'fp32':
+            assert rep['max_abs'] <= 1e-3, (name, rep)
+            assert agree_mask >= 0.999, name
+        else:
+            assert rep['max_abs'] <= 2e-2, (name, rep)     # small 32^3 random-init patches; full-size bars are checked in test_gpu_kernels
+            assert agree_mask >= 0.99, name
+        # mask must be the first-argmax of the returned probabilities
+        assert np.array_equal(mask, osw.argmax_first(probs))
+
+
+def test_patch_grid_count_and_blend_kernels():
+    """blend + finalize kernels against the oracle's numpy accumulate on random probabilities."""
+    from segmentation3d._b200 import lib as L
+    from segmentation3d._b200.sliding import axis_counts
+    L.load()
+    size = [64, 48, 80]
+    starts, ends = osw.partition_grid(size, [1, 1, 1], [0, 0, 0], list(size), [32, 32, 32], [16, 16, 16], 16)
+    C, n = 3, len(starts)
+    g = torch.Generator().manual_seed(1)
+    probs = torch.rand((n, C, 32, 32, 32), generator=g)
+    acc_ref = np.zeros((C, size[2], size[1], size[0]), np.float32)
+    for i, (s, e) in enumerate(zip(starts, ends)):
+        acc_ref[:, s[2]:e[2], s[1]:e[1], s[0]:e[0]] += probs[i].numpy()
+    cnt = osw.overlap_count_axes(size, starts, ends)
+    cx, cy, cz = axis_counts(size, starts, ends)
+    assert np.array_equal(cnt, (cz[:, None, None] * cy[None, :, None] * cx[None, None, :]).astype(np.float32))
+    ref = acc_ref * (np.float32(1.0) / cnt)
+    acc = torch.zeros((C, size[2], size[1], size[0]), device='cuda')
+    sd = torch.tensor(np.asarray(starts, np.int32), device='cuda')
+    pd = probs.cuda()
+    L.call('seg3d_blend_accumulate', L.ptr(pd), n, C, 32, 32, 32, L.ptr(sd), L.ptr(acc), size[2], size[1], size[0], L.stream_ptr())
+    mask = torch.empty((size[2], size[1], size[0]), dtype=torch.int8, device='cuda')
+    cxd, cyd, czd = [torch.tensor(c, device='cuda') for c in (cx, cy, cz)]
+    L.call('seg3d_blend_finalize_argmax', L.ptr(acc), C, size[2], size[1], size[0], L.ptr(cxd), L.ptr(cyd), L.ptr(czd), L.ptr(mask), L.stream_ptr())
+    torch.cuda.synchronize()
+    got = acc.cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-5          # float add order differs across overlapping patches
+    assert np.array_equal(mask.cpu().numpy(), osw.argmax_first(got))
+
+
+def test_patch_gather_normalisers_bit_exact_fixed():
+    from segmentation3d._b200 import lib as L
+    L.load()
+    g = torch.Generator().manual_seed(2)
+    vol = (torch.randn((40, 48, 56), generator=g) * 300).float()
+    starts = [[3, 5, 7], [24, 16, 8]]
+    sd = torch.tensor(np.asarray(starts, np.int32), device='cuda')
+    vd = vol.cuda()
+    out = torch.empty((2, 32, 32, 32), device='cuda')
+    L.call('seg3d_patch_gather', L.ptr(vd), 40, 48, 56, L.ptr(sd), 2, 32, 32, 32, L.NORM_FIXED, 50.0, 200.0, 1, -1.0, 1.0,
+           None, L.F32, L.ptr(out), L.stream_ptr())
+    torch.cuda.synchronize()
+    for i, s in enumerate(starts):
+        ref = osw.normalize_fixed(vol.numpy()[s[2]:s[2] + 32, s[1]:s[1] + 32, s[0]:s[0] + 32], 50.0, 200.0, True)
+        assert np.array_equal(out[i].cpu().numpy(), ref)         # float32 sub + div: bit-exact
+    # adaptive: statistics are reduced in a different order -> tolerance
+    stats = torch.zeros((2, 2), dtype=torch.float64, device='cuda')
+    L.call('seg3d_patch_stats', L.ptr(vd), 40, 48, 56, L.ptr(sd), 2, 32, 32, 32, L.ptr(stats), L.stream_ptr())
+    L.call('seg3d_patch_gather', L.ptr(vd), 40, 48, 56, L.ptr(sd), 2, 32, 32, 32, L.NORM_ADAPTIVE, 0.0, 1.0, 1, -2.5, 2.5,
+           L.ptr(stats), L.F32, L.ptr(out), L.stream_ptr())
+    torch.cuda.synchronize()
+    for i, s in enumerate(starts):
+        ref = osw.normalize_adaptive(np.ascontiguousarray(vol.numpy()[s[2]:s[2] + 32, s[1]:s[1] + 32, s[0]:s[0] + 32]), 2.5)
+        assert np.abs(out[i].cpu().numpy() - ref).max() <= 1e-5
