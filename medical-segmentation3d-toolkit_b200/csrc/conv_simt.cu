@@ -136,6 +136,73 @@ conv_simt_kernel(const ConvGeom g, const T* __restrict__ x, const float* __restr
   if (stats) block_stats_atomic(s, ss, stats + 2 * n, red);
 }
 
+
+// ---- input block: k3 conv with a single input channel (vnet_inblock.py:9), Cout == 16 ---------------
+// Direct convolution: one thread per output voxel keeps the 16 outputs in registers; the 8x8x4 tile
+// reads its 10x10x6 input halo and the 27x16 filter bank from shared memory.  HBM traffic is the
+// output write (16 channels per voxel); zero padding comes from the halo fill.
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv3d_k3_cin1_kernel(const T* __restrict__ x, const float* __restrict__ w /*[27][16]*/, const float* __restrict__ bias,
+                      T* __restrict__ y, int y_ld, int D, int H, int W, int ntx, int nty, int ntz, double* __restrict__ stats) {
+  __shared__ float halo[6][10][10];
+  __shared__ __align__(16) float sw[27][16];
+  __shared__ float red[64];
+  int t = blockIdx.x;
+  const int x0 = (t % ntx) * 8; t /= ntx;
+  const int y0 = (t % nty) * 8; t /= nty;
+  const int z0 = (t % ntz) * 4; const int n = t / ntz;
+  const T* xn = x + (size_t)n * D * H * W;
+  for (int i = threadIdx.x; i < 600; i += 256) {
+    const int hx = i % 10, hy = (i / 10) % 10, hz = i / 100;
+    const int gx = x0 + hx - 1, gy = y0 + hy - 1, gz = z0 + hz - 1;
+    float v = 0.f;
+    if (gx >= 0 && gx < W && gy >= 0 && gy < H && gz >= 0 && gz < D) v = to_f32<T>(xn[((size_t)gz * H + gy) * W + gx]);
+    halo[hz][hy][hx] = v;
+  }
+  for (int i = threadIdx.x; i < 27 * 16; i += 256) sw[i / 16][i % 16] = w[i];
+  __syncthreads();
+  const int lx = threadIdx.x & 7, ly = (threadIdx.x >> 3) & 7, lz = threadIdx.x >> 6;
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = bias ? bias[c] : 0.f;
+#pragma unroll
+  for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float v = halo[lz + kd][ly + kh][lx + kw];
+        const float4* wr = reinterpret_cast<const float4*>(&sw[(kd * 3 + kh) * 3 + kw][0]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 wv = wr[q];
+          acc[4 * q] = fmaf(v, wv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
+        }
+      }
+  const int gx = x0 + lx, gy = y0 + ly, gz = z0 + lz;
+  float s = 0.f, ss = 0.f;
+  if (gx < W && gy < H && gz < D) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { s += acc[c]; ss += acc[c] * acc[c]; }
+    T* dst = y + ((((size_t)n * D + gz) * H + gy) * W + gx) * y_ld;
+    Vec8<T> o; o.set(acc); o.store(dst); o.set(acc + 8); o.store(dst + 8);
+  }
+  if (stats) block_stats_atomic(s, ss, stats + 2 * n, red);
+}
+
+template <typename T>
+static int launch_cin1(const void* x, const void* w, const float* bias, void* y, int y_ld, int N, int D, int H, int W,
+                       double* stats, cudaStream_t st) {
+  const int ntx = (W + 7) / 8, nty = (H + 7) / 8, ntz = (D + 3) / 4;
+  const long long blocks = (long long)ntx * nty * ntz * N;
+  SEG3D_REQUIRE(blocks > 0 && blocks < (1ll << 31), "conv cin1: bad dims");
+  conv3d_k3_cin1_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, (const float*)w, bias, (T*)y, y_ld, D, H, W, ntx, nty, ntz, stats);
+  SEG3D_CHECK_LAUNCH("conv3d_k3_cin1_kernel");
+  return SEG3D_OK;
+}
+
 template <typename T>
 static int launch_simt(const ConvGeom& g, const void* x, const void* w, const float* bias, void* y,
                        double* stats, cudaStream_t st) {
@@ -150,6 +217,9 @@ static int launch_simt(const ConvGeom& g, const void* x, const void* w, const fl
 
 int seg3d_conv_simt(int mode, int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
                     void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st) {
+  if (mode == SEG3D_CONV_K3 && Cin == 1 && Cout == 16 && x_ld == 1 && y_ld % 8 == 0 && ((uintptr_t)y) % 16 == 0) {
+    SEG3D_DISPATCH_DTYPE(dtype, T, return launch_cin1<T>(x, w, bias, y, y_ld, N, D, H, W, stats, st));
+  }
   ConvGeom g;
   g.mode = mode; g.N = N; g.D = D; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.x_ld = x_ld; g.y_ld = y_ld;
   g.Do = D; g.Ho = H; g.Wo = W; g.Ng = Cout;

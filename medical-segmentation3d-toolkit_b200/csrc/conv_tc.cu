@@ -19,9 +19,11 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
+constexpr int g_kwfuse_default = 1;
 constexpr int TC_THREADS = 192;
 constexpr int TILE_M = 128;
 
@@ -42,6 +44,11 @@ struct TcParams {
   int b_slab;                       // pitch of one kw weight slab inside a stage (kwfuse)
   int row_bytes;
   int use_base_offset;
+  int conv;                         // 0: k3 s1 p1, 1: k2 s2 (folded-stride tensor map), 2: transposed k2 s2
+  int cout_real, npass;             // transposed conv: real Cout; GEMM N = 8*Cout split into npass passes of p.Cout columns
+  int ntaps;                        // outer tap count of the K loop (27, 9 when kw-fused, 8 for k2s2)
+  int x_ld, halfW, halfH;           // k2s2 coordinate folding
+  int ntiles, acc_cols;             // persistent kernel: total tiles, TMEM columns per accumulator buffer
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -250,6 +257,179 @@ conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   }
 }
 
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent variant: each CTA walks tiles blockIdx.x, +gridDim.x, ...; the operand ring keeps
+// streaming across tile boundaries and two TMEM accumulator buffers let the epilogue of tile i
+// overlap the MMAs of tile i+1.  GroupNorm partial sums stay in registers until the sample changes.
+template <typename T>
+__global__ void __launch_bounds__(TC_THREADS)
+conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                            const TcParams p, const float* __restrict__ bias, T* __restrict__ y, double* __restrict__ stats) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + p.stages * p.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + p.stages * (p.a_bytes + p.b_bytes));
+  const uint32_t full_bar = smem_u32(bars);                   // [stages]
+  const uint32_t empty_bar = full_bar + 8 * p.stages;         // [stages]
+  const uint32_t tfull_bar = empty_bar + 8 * p.stages;        // [2]
+  const uint32_t tempty_bar = tfull_bar + 16;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + 8 * b, 1); mbar_init(tempty_bar + 8 * b, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int kiters = p.ntaps * p.nchunk;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int pass = t % p.npass; t /= p.npass;
+        const int x0 = (t % p.ntx) * p.tw; t /= p.ntx;
+        const int y0 = (t % p.nty) * p.th; t /= p.nty;
+        const int z0 = (t % p.ntz) * p.td; const int n = t / p.ntz;
+        for (int it = 0; it < kiters; ++it) {
+          const int tap = it / p.nchunk, ck = it - tap * p.nchunk;
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          mbar_expect_tx(full_bar + 8 * stage, (uint32_t)p.tx_bytes);
+          const uint32_t fb = full_bar + 8 * stage, sa = a_base + stage * p.a_bytes, sb = b_base + stage * p.b_bytes;
+          if (p.conv == 2) {         // transposed conv: plain GEMM rows, weight rows of this N-pass
+            tma_load_5d(sa, &map_x, fb, ck * p.KC, x0, y0, z0, n);
+            tma_load_2d(sb, &map_w, fb, ck * p.KC, pass * p.Cout);
+          } else if (p.conv == 1) {  // k2 s2: tap = (kd*2+kh)*2+kw folded into the (channel, x, y) coordinates
+            const int kd = tap >> 2, kh = (tap >> 1) & 1, kw = tap & 1;
+            tma_load_5d(sa, &map_x, fb, kw * p.x_ld + ck * p.KC, x0 + kh * p.halfW, y0 + kd * p.halfH, z0, n);
+            tma_load_2d(sb, &map_w, fb, ck * p.KC, tap * p.Cout);
+          } else if (p.kwfuse) {
+            const int kd = tap / 3, kh = tap % 3;
+            tma_load_5d(sa, &map_x, fb, ck * p.KC, x0 - 1, y0 + kh - 1, z0 + kd - 1, n);
+            for (int kw = 0; kw < 3; ++kw)
+              tma_load_2d(sb + kw * p.b_slab, &map_w, fb, ck * p.KC, (tap * 3 + kw) * p.Cout);
+          } else {
+            const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+            tma_load_5d(sa, &map_x, fb, ck * p.KC, x0 + kw - 1, y0 + kh - 1, z0 + kd - 1, n);
+            tma_load_2d(sb, &map_w, fb, ck * p.KC, tap * p.Cout);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0; int j = 0;
+      const int ksteps = p.KC / 16;
+      const int nkw = (p.conv == 0 && p.kwfuse) ? 3 : 1;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++j) {
+        const int buf = j & 1;
+        mbar_wait(tempty_bar + 8 * buf, ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t dcol = tmem_base + (uint32_t)(buf * p.acc_cols);
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = a_base + stage * p.a_bytes, b_addr = b_base + stage * p.b_bytes;
+          for (int kw = 0; kw < nkw; ++kw)
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = make_desc(a_addr + kw * p.row_bytes + k * 32, p.a_sbo, p.layout_type);
+              const uint64_t bd = make_desc(b_addr + kw * p.b_slab + k * 32, p.sbo, p.layout_type);
+              tc_mma_f16(dcol, ad, bd, p.idesc, (it | kw | k) != 0);
+            }
+          tc_commit(empty_bar + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar + 8 * buf);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int lx = r % p.tw, ly = (r / p.tw) % p.th, lz = r / (p.tw * p.th);
+    float s = 0.f, ss = 0.f;
+    int cur_n = -1, j = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++j) {
+      int t = tile;
+      const int pass = t % p.npass; t /= p.npass;
+      const int x0 = (t % p.ntx) * p.tw; t /= p.ntx;
+      const int y0 = (t % p.nty) * p.th; t /= p.nty;
+      const int z0 = (t % p.ntz) * p.td; const int n = t / p.ntz;
+      if (stats && n != cur_n) {
+        if (cur_n >= 0) {
+          s = warp_sum(s); ss = warp_sum(ss);
+          if (lane == 0) { atomicAdd(stats + 2 * cur_n, (double)s); atomicAdd(stats + 2 * cur_n + 1, (double)ss); }
+        }
+        s = 0.f; ss = 0.f; cur_n = n;
+      }
+      const int gx = x0 + lx, gy = y0 + ly, gz = z0 + lz;
+      const bool valid = (gx < p.W) && (gy < p.H) && (gz < p.D);      // W/H/D = OUTPUT dims here
+      const size_t vox = (((size_t)n * p.D + gz) * p.H + gy) * p.W + gx;
+      T* yrow = y + vox * p.y_ld;
+      const int buf = j & 1;
+      mbar_wait(tfull_bar + 8 * buf, (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.acc_cols);
+      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+        uint32_t v[16];
+        tc_ld16(tcol + (uint32_t)c0, v);
+        tc_wait_ld();
+        float f[16];
+        int co = c0;
+        T* dst = yrow + c0;
+        if (p.conv == 2) {           // column -> (tap, co); scatter to output voxel (2z+kd, 2y+kh, 2x+kw)
+          const int col = pass * p.Cout + c0;
+          const int tap = col / p.cout_real; co = col - tap * p.cout_real;
+          const size_t ov = (((size_t)n * 2 * p.D + 2 * gz + (tap >> 2)) * 2 * p.H + 2 * gy + ((tap >> 1) & 1)) * 2 * p.W + 2 * gx + (tap & 1);
+          dst = y + ov * p.y_ld + co;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          f[jj] = __uint_as_float(v[jj]) + (bias ? bias[co + jj] : 0.f);
+          if (valid) { s += f[jj]; ss += f[jj] * f[jj]; }
+        }
+        if (valid) {
+          Vec8<T> o; o.set(f); o.store(dst);
+          o.set(f + 8); o.store(dst + 8);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
+    }
+    if (stats && cur_n >= 0) {
+      s = warp_sum(s); ss = warp_sum(ss);
+      if (lane == 0) { atomicAdd(stats + 2 * cur_n, (double)s); atomicAdd(stats + 2 * cur_n + 1, (double)ss); }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -266,90 +446,132 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int g_kwfuse_default = 1;
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
+template <typename T>
+cudaError_t launch_tc(bool persistent, dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mx, const CUtensorMap& mw,
+                      const TcParams& p, const float* bias, void* y, double* stats) {
+  cudaError_t e;
+  if (persistent) {
+    e = cudaFuncSetAttribute(conv3d_tc_persistent_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    conv3d_tc_persistent_kernel<T><<<grid, TC_THREADS, smem, st>>>(mx, mw, p, bias, (T*)y, stats);
+  } else {
+    e = cudaFuncSetAttribute(conv3d_k3_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    conv3d_k3_tc_kernel<T><<<grid, TC_THREADS, smem, st>>>(mx, mw, p, bias, (T*)y, stats);
+  }
+  return cudaGetLastError();
+}
 
 }  // namespace
 
 int seg3d_conv_tc_supported(int mode, int dtype, int Cin, int Cout, int x_ld, int y_ld, int D, int H, int W) {
-  if (mode != SEG3D_CONV_K3) return 0;
+  if (mode != SEG3D_CONV_K3 && mode != SEG3D_CONV_K2S2 && mode != SEG3D_CONV_T2S2) return 0;
   if (dtype != SEG3D_F16 && dtype != SEG3D_BF16) return 0;
   if (Cin % 16 || Cout % 16 || Cout > 256 || Cin > 1024) return 0;
   if (x_ld % 8 || y_ld % 8) return 0;
-  (void)D; (void)H; (void)W;
+  if (mode == SEG3D_CONV_K2S2 && (D % 2 || H % 2 || W % 2)) return 0;
   return 1;
 }
 
 int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
                   void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st) {
-  (void)mode;
   EncodeTiledFn encode = get_encode();
   if (!encode) { seg3d_set_error("conv_tc: cuTensorMapEncodeTiled entry point not available"); return SEG3D_ECUDA; }
   SEG3D_REQUIRE(((uintptr_t)x) % 16 == 0 && ((uintptr_t)w) % 16 == 0 && ((uintptr_t)y) % 16 == 0, "conv_tc: pointers must be 16-byte aligned");
 
   TcParams p;
-  p.Cin = Cin; p.Cout = Cout; p.D = D; p.H = H; p.W = W; p.N = N; p.y_ld = y_ld;
+  memset(&p, 0, sizeof(p));
+  p.conv = mode == SEG3D_CONV_K2S2 ? 1 : (mode == SEG3D_CONV_T2S2 ? 2 : 0);
+  const int Do = p.conv == 1 ? D / 2 : D, Ho = p.conv == 1 ? H / 2 : H, Wo = p.conv == 1 ? W / 2 : W;   // GEMM row space
+  p.cout_real = Cout; p.npass = 1;
+  if (p.conv == 2) {                 // GEMM N = 8*Cout in passes of <= 256 columns
+    const int ntot = 8 * Cout;
+    const int npc = ntot < 256 ? ntot : 256;
+    p.npass = ntot / npc;
+    Cout = npc;
+  }
+  p.Cin = Cin; p.Cout = Cout; p.D = Do; p.H = Ho; p.W = Wo; p.N = N; p.y_ld = y_ld;
+  p.x_ld = x_ld; p.halfW = W / 2; p.halfH = H / 2;
   p.KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
   p.nchunk = Cin / p.KC;
-  // tile box: power-of-two dims with product 128 minimising the tile count (then preferring a wide x extent)
-  long long best = -1; p.tw = 8; p.th = 4; p.td = 4;
-  for (int tw = 1; tw <= 32; tw *= 2)
-    for (int th = 1; th <= 128 / tw; th *= 2) {
-      const int td = 128 / (tw * th);
-      const long long tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th) * ((D + td - 1) / td);
-      const long long score = tiles * 1024 - tw * 8 - th;       // fewer tiles first, then wider x, then wider y
-      const long long spread = (tw > 16 || th > 16 || td > 16) ? 1 : 0;  // keep the box compact
-      const long long sc = score + spread * 512;
-      if (best < 0 || sc < best) { best = sc; p.tw = tw; p.th = th; p.td = td; }
-    }
-  // kw-fused variant: x extent of the tile must be exactly 8 so that every 8-row MMA group is one x-line
-  // of the (tw+2)-wide box.  SEG3D_TC_KWFUSE=0/1 overrides (default: on when W is a multiple of 8).
-  {
-    static int env = -1;
-    if (env < 0) { const char* e = getenv("SEG3D_TC_KWFUSE"); env = e ? atoi(e) : 2; }
-    p.kwfuse = (env == 2) ? (g_kwfuse_default && W % 8 == 0) : (env == 1 && W % 8 == 0);
-  }
-  { const char* e = getenv("SEG3D_TC_BASEOFF"); p.use_base_offset = e ? atoi(e) : 0; }
-  if (p.kwfuse) {
-    p.tw = 8;
-    long long bt = -1;
-    for (int th = 1; th <= 16; th *= 2) {
-      const int td = 16 / th;
-      const long long tiles = (long long)((H + th - 1) / th) * ((D + td - 1) / td);
-      const long long sc = tiles * 64 + (th > td ? th - td : td - th);
-      if (bt < 0 || sc < bt) { bt = sc; p.th = th; p.td = td; }
-    }
-  }
-  p.ntx = (W + p.tw - 1) / p.tw; p.nty = (H + p.th - 1) / p.th; p.ntz = (D + p.td - 1) / p.td;
-  const long long ntiles = (long long)p.ntx * p.nty * p.ntz * N;
-  SEG3D_REQUIRE(ntiles > 0 && ntiles < (1ll << 31), "conv_tc: tile count out of range");
-
   const int row_bytes = p.KC * 2;
   p.row_bytes = row_bytes;
+  const bool persistent = env_int("SEG3D_TC_PERSIST", 1) != 0;
+
+  // kw-fused variant (k3 only): one (tw+2)-wide box per (kd,kh) serves the three kw taps through x-shifted
+  // descriptors (the swizzle is a function of the absolute smem address, so any row-aligned start works).
+  // Needs tw == 8 (every 8-row MMA group is one x-line of the box) and pays 3 weight slabs per stage.
+  {
+    const int env = env_int("SEG3D_TC_KWFUSE", 2);
+    const int slab = (Cout * row_bytes + 1023) & ~1023;
+    const bool fits = (10 * 16 * row_bytes + 3 * slab) <= 48 * 1024;
+    p.kwfuse = (p.conv == 0 && Wo % 8 == 0 && fits && (env == 1 || (env == 2 && g_kwfuse_default))) ? 1 : 0;
+  }
+  // tile box: power-of-two dims with product 128 minimising the tile count
+  long long best = -1; p.tw = 8; p.th = 4; p.td = 4;
+  for (int tw = (p.kwfuse ? 8 : 1); tw <= (p.kwfuse ? 8 : 32); tw *= 2)
+    for (int th = 1; th <= 128 / tw; th *= 2) {
+      const int td = 128 / (tw * th);
+      const long long tiles = (long long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((Do + td - 1) / td);
+      const long long spread = (tw > 16 || th > 16 || td > 16) ? 512 : 0;      // keep the box compact
+      const long long sc = tiles * 1024 - tw * 8 - th + spread;                 // fewer tiles, then wider x, then wider y
+      if (best < 0 || sc < best) { best = sc; p.tw = tw; p.th = th; p.td = td; }
+    }
+  p.ntx = (Wo + p.tw - 1) / p.tw; p.nty = (Ho + p.th - 1) / p.th; p.ntz = (Do + p.td - 1) / p.td;
+  const long long ntiles = (long long)p.ntx * p.nty * p.ntz * N * p.npass;
+  SEG3D_REQUIRE(ntiles > 0 && ntiles < (1ll << 31), "conv_tc: tile count out of range");
+  p.ntiles = (int)ntiles;
+  p.ntaps = p.conv == 1 ? 8 : (p.conv == 2 ? 1 : (p.kwfuse ? 9 : 27));
+
   const int a_rows = p.kwfuse ? (p.tw + 2) * p.th * p.td : TILE_M;
   p.a_bytes = (a_rows * row_bytes + 1023) & ~1023;
-  p.b_slab = (Cout * row_bytes + 1023) & ~1023;     // keep every operand slab 1024-byte aligned
+  p.b_slab = (Cout * row_bytes + 1023) & ~1023;     // every operand slab stays 1024-byte aligned
   p.b_bytes = p.kwfuse ? 3 * p.b_slab : p.b_slab;
+  p.tx_bytes = a_rows * row_bytes + (p.kwfuse ? 3 : 1) * Cout * row_bytes;
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  int stages = (96 * 1024) / stage_bytes;            // <= ~96 KB of ring so two CTAs can share an SM
-  if (stages > 8) stages = 8;
-  if (stages < 2) stages = 2;
-  { const int deep = (200 * 1024) / stage_bytes; const int want = deep < 4 ? deep : 4; if (stages < want) stages = want; }
-  if (stages * stage_bytes > 200 * 1024) stages = (200 * 1024) / stage_bytes;
-  SEG3D_REQUIRE(stages >= 2, "conv_tc: operand ring does not fit in shared memory");
-  p.stages = stages;
   p.sbo = 8 * row_bytes;
   p.a_sbo = p.kwfuse ? (p.tw + 2) * row_bytes : 8 * row_bytes;
   p.layout_type = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
-  p.tmem_cols = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256));
+  p.use_base_offset = env_int("SEG3D_TC_BASEOFF", 0);
   const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+
+  int stages, ctas_per_sm = 1;
+  if (persistent) {
+    p.acc_cols = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256)));
+    p.tmem_cols = 2 * p.acc_cols;
+    ctas_per_sm = 512 / p.tmem_cols; if (ctas_per_sm > 2) ctas_per_sm = 2;
+    ctas_per_sm = env_int("SEG3D_TC_CTAS_PER_SM", ctas_per_sm);
+    if (ctas_per_sm * p.tmem_cols > 512) ctas_per_sm = 512 / p.tmem_cols;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    stages = (200 * 1024 / ctas_per_sm) / stage_bytes;
+    if (stages > 8) stages = 8;
+  } else {
+    p.tmem_cols = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256));
+    p.acc_cols = p.tmem_cols;
+    stages = 3;
+    if (3 * stage_bytes > 200 * 1024) stages = 2;
+  }
+  { const int e = env_int("SEG3D_TC_STAGES", 0); if (e >= 2 && e * stage_bytes <= 200 * 1024) stages = e; }
+  SEG3D_REQUIRE(stages >= 2, "conv_tc: operand ring does not fit in shared memory (stage %d bytes)", stage_bytes);
+  p.stages = stages;
 
   const CUtensorMapDataType tdt = dtype == SEG3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap map_x, map_w;
   {
-    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
-    cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2, (cuuint64_t)D * H * W * x_ld * 2};
+    cuuint64_t dims[5], strides[4];
+    if (p.conv == 1) {   // stride-2 taps folded into the coordinates: c' = kw*ld + c, x' = x + kh*W/2, y' = y + kd*H/2
+      dims[0] = (cuuint64_t)x_ld + Cin; dims[1] = (cuuint64_t)W; dims[2] = (cuuint64_t)H; dims[3] = (cuuint64_t)D / 2; dims[4] = (cuuint64_t)N;
+      strides[0] = (cuuint64_t)2 * x_ld * 2; strides[1] = (cuuint64_t)2 * W * x_ld * 2; strides[2] = (cuuint64_t)2 * H * W * x_ld * 2;
+      strides[3] = (cuuint64_t)D * H * W * x_ld * 2;
+    } else {
+      dims[0] = (cuuint64_t)Cin; dims[1] = (cuuint64_t)W; dims[2] = (cuuint64_t)H; dims[3] = (cuuint64_t)D; dims[4] = (cuuint64_t)N;
+      strides[0] = (cuuint64_t)x_ld * 2; strides[1] = (cuuint64_t)W * x_ld * 2; strides[2] = (cuuint64_t)H * W * x_ld * 2;
+      strides[3] = (cuuint64_t)D * H * W * x_ld * 2;
+    }
     cuuint32_t box[5] = {(cuuint32_t)p.KC, (cuuint32_t)(p.kwfuse ? p.tw + 2 : p.tw), (cuuint32_t)p.th, (cuuint32_t)p.td, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&map_x, tdt, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
@@ -357,7 +579,7 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
     if (r != CUDA_SUCCESS) { seg3d_set_error("conv_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SEG3D_ECUDA; }
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * Cout};
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)(p.conv == 1 ? 8 * Cout : (p.conv == 2 ? 8 * p.cout_real : 27 * Cout))};
     cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
     cuuint32_t box[2] = {(cuuint32_t)p.KC, (cuuint32_t)Cout};
     cuuint32_t estr[2] = {1, 1};
@@ -365,28 +587,12 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { seg3d_set_error("conv_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SEG3D_ECUDA; }
   }
-  // the weight slab the TMA writes is Cout*row_bytes; b_bytes is its 1024-aligned pitch
-  p.tx_bytes = a_rows * row_bytes + (p.kwfuse ? 3 : 1) * Cout * row_bytes;
-  TcParams pk = p;
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 8 + 8 * sizeof(float) + 64;
-
-  struct Launch {
-    static cudaError_t go(bool bf16, dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mx, const CUtensorMap& mw,
-                          const TcParams& pk, const float* bias, void* y, double* stats) {
-      cudaError_t e;
-      if (bf16) {
-        e = cudaFuncSetAttribute(conv3d_k3_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        conv3d_k3_tc_kernel<__nv_bfloat16><<<grid, TC_THREADS, smem, st>>>(mx, mw, pk, bias, (__nv_bfloat16*)y, stats);
-      } else {
-        e = cudaFuncSetAttribute(conv3d_k3_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        conv3d_k3_tc_kernel<__half><<<grid, TC_THREADS, smem, st>>>(mx, mw, pk, bias, (__half*)y, stats);
-      }
-      return cudaGetLastError();
-    }
-  };
-  cudaError_t e = Launch::go(dtype == SEG3D_BF16, dim3((unsigned)ntiles), smem, st, map_x, map_w, pk, bias, y, stats);
-  if (e != cudaSuccess) { seg3d_set_error("conv3d_k3_tc_kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 64;
+  SEG3D_REQUIRE(!p.conv || persistent, "conv_tc: k2s2 / transposed conv need the persistent kernel");
+  const long long max_grid = (long long)ctas_per_sm * seg3d_num_sms();
+  dim3 grid((unsigned)(persistent ? (ntiles < max_grid ? ntiles : max_grid) : ntiles));
+  cudaError_t e = dtype == SEG3D_BF16 ? launch_tc<__nv_bfloat16>(persistent, grid, smem, st, map_x, map_w, p, bias, y, stats)
+                                      : launch_tc<__half>(persistent, grid, smem, st, map_x, map_w, p, bias, y, stats);
+  if (e != cudaSuccess) { seg3d_set_error("conv_tc kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
   return SEG3D_OK;
 }

@@ -348,4 +348,4 @@ class NetPlan(object):
         return self.run(ws, ops)
 
 
-DEFAULT_TC_MODES = (lib.CONV_K3,)
+DEFAULT_TC_MODES = (lib.CONV_K3, lib.CONV_K2S2, lib.CONV_T2S2)
