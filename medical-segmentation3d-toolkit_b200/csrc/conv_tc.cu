@@ -430,6 +430,180 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// z-marching variant for the narrow layers (Cin <= 64 in one K block, all 27 weight slabs resident in
+// shared memory).  A CTA owns an 8(x) x 16(y) column and walks along z: every input plane (a
+// 10 x 18 voxel halo box, one TMA load) is read from L2 exactly once and feeds the three output planes
+// z-1, z, z+1 through 27 row-shifted descriptors (the 128B/64B/32B swizzle is a function of the absolute
+// shared-memory address, so any row-aligned start address addresses the halo correctly).  Four TMEM
+// accumulators rotate: three receive MMAs while the fourth is drained by the epilogue warps.
+// L2->SM traffic per output voxel drops from 27 (per-tap boxes) to ~1.5 voxel reads.
+struct ZmParams {
+  int Cout, KC, row_bytes;
+  int D, H, W, N, y_ld;
+  int ntx, nty, nseg, lseg, nitems;
+  int ring, plane_bytes, w_slab, plane_tx, w_tx;
+  int acc_cols, tmem_cols;
+  uint32_t idesc, sbo, a_sbo, layout_type;
+};
+constexpr int ZM_NB = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(TC_THREADS)
+conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                        const ZmParams p, const float* __restrict__ bias, T* __restrict__ y, double* __restrict__ stats) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t w_base = smem_base;
+  const uint32_t a_base = smem_base + 27 * p.w_slab;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + 27 * p.w_slab + p.ring * p.plane_bytes);
+  const uint32_t full_bar = smem_u32(bars);                   // [ring]
+  const uint32_t empty_bar = full_bar + 8 * p.ring;           // [ring]
+  const uint32_t tfull_bar = empty_bar + 8 * p.ring;          // [ZM_NB]
+  const uint32_t tempty_bar = tfull_bar + 8 * ZM_NB;          // [ZM_NB]
+  const uint32_t wfull_bar = tempty_bar + 8 * ZM_NB;          // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.ring + 2 * ZM_NB + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < p.ring; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int b = 0; b < ZM_NB; ++b) { mbar_init(tfull_bar + 8 * b, 1); mbar_init(tempty_bar + 8 * b, 4); }
+    mbar_init(wfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull_bar, (uint32_t)p.w_tx);
+      for (int tap = 0; tap < 27; ++tap) tma_load_2d(w_base + tap * p.w_slab, &map_w, wfull_bar, 0, tap * p.Cout);
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        int t = item;
+        const int seg = t % p.nseg; t /= p.nseg;
+        const int x0 = (t % p.ntx) * 8; t /= p.ntx;
+        const int y0 = (t % p.nty) * 16; const int n = t / p.nty;
+        const int zs = seg * p.lseg;
+        const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
+        for (int ip = 0; ip < L + 2; ++ip) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          mbar_expect_tx(full_bar + 8 * stage, (uint32_t)p.plane_tx);
+          tma_load_5d(a_base + stage * p.plane_bytes, &map_x, full_bar + 8 * stage, 0, x0 - 1, y0 - 1, zs - 1 + ip, n);
+          if (++stage == p.ring) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(wfull_bar, 0);
+      int stage = 0; uint32_t phase = 0; int oc = 0;
+      const int ksteps = p.KC / 16;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        const int seg = item % p.nseg;
+        const int zs = seg * p.lseg;
+        const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
+        for (int ip = 0; ip < L + 2; ++ip) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = a_base + stage * p.plane_bytes;
+          for (int kd = 2; kd >= 0; --kd) {
+            const int zl = ip - kd;
+            if (zl < 0 || zl >= L) continue;
+            const int ocz = oc + zl, buf = ocz % ZM_NB;
+            if (kd == 0) { mbar_wait(tempty_bar + 8 * buf, ((ocz / ZM_NB) & 1) ^ 1); tc_fence_after(); }
+            const uint32_t dcol = tmem_base + (uint32_t)(buf * p.acc_cols);
+            for (int kh = 0; kh < 3; ++kh)
+              for (int kw = 0; kw < 3; ++kw) {
+                const uint32_t sa = a_addr + (kh * 10 + kw) * p.row_bytes;
+                const uint32_t sb = w_base + ((kd * 3 + kh) * 3 + kw) * p.w_slab;
+                for (int k = 0; k < ksteps; ++k)
+                  tc_mma_f16(dcol, make_desc(sa + k * 32, p.a_sbo, p.layout_type), make_desc(sb + k * 32, p.sbo, p.layout_type),
+                             p.idesc, (kd | kh | kw | k) != 0);
+              }
+          }
+          tc_commit(empty_bar + 8 * stage);
+          if (ip >= 2) tc_commit(tfull_bar + 8 * ((oc + ip - 2) % ZM_NB));
+          if (++stage == p.ring) { stage = 0; phase ^= 1; }
+        }
+        oc += L;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int lx = r & 7, ly = r >> 3;
+    float s = 0.f, ss = 0.f;
+    int cur_n = -1, oc = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      int t = item;
+      const int seg = t % p.nseg; t /= p.nseg;
+      const int x0 = (t % p.ntx) * 8; t /= p.ntx;
+      const int y0 = (t % p.nty) * 16; const int n = t / p.nty;
+      const int zs = seg * p.lseg;
+      const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
+      if (stats && n != cur_n) {
+        if (cur_n >= 0) {
+          s = warp_sum(s); ss = warp_sum(ss);
+          if (lane == 0) { atomicAdd(stats + 2 * cur_n, (double)s); atomicAdd(stats + 2 * cur_n + 1, (double)ss); }
+        }
+        s = 0.f; ss = 0.f; cur_n = n;
+      }
+      const int gx = x0 + lx, gy = y0 + ly;
+      const bool valid = (gx < p.W) && (gy < p.H);
+      for (int zl = 0; zl < L; ++zl) {
+        const int ocz = oc + zl, buf = ocz % ZM_NB;
+        const size_t vox = (((size_t)n * p.D + (zs + zl)) * p.H + gy) * p.W + gx;
+        T* yrow = y + vox * p.y_ld;
+        mbar_wait(tfull_bar + 8 * buf, (ocz / ZM_NB) & 1);
+        tc_fence_after();
+        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.acc_cols);
+        for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+          uint32_t v[16];
+          tc_ld16(tcol + (uint32_t)c0, v);
+          tc_wait_ld();
+          float f[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            f[jj] = __uint_as_float(v[jj]) + (bias ? bias[c0 + jj] : 0.f);
+            if (valid) { s += f[jj]; ss += f[jj] * f[jj]; }
+          }
+          if (valid) {
+            Vec8<T> o; o.set(f); o.store(yrow + c0);
+            o.set(f + 8); o.store(yrow + c0 + 8);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
+      }
+      oc += L;
+    }
+    if (stats && cur_n >= 0) {
+      s = warp_sum(s); ss = warp_sum(ss);
+      if (lane == 0) { atomicAdd(stats + 2 * cur_n, (double)s); atomicAdd(stats + 2 * cur_n + 1, (double)ss); }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -480,6 +654,77 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   EncodeTiledFn encode = get_encode();
   if (!encode) { seg3d_set_error("conv_tc: cuTensorMapEncodeTiled entry point not available"); return SEG3D_ECUDA; }
   SEG3D_REQUIRE(((uintptr_t)x) % 16 == 0 && ((uintptr_t)w) % 16 == 0 && ((uintptr_t)y) % 16 == 0, "conv_tc: pointers must be 16-byte aligned");
+
+  // ---- z-marching kernel for narrow k3 layers --------------------------------------------------------
+  if (mode == SEG3D_CONV_K3 && Cin <= 64 && W % 8 == 0 && D >= 4 && env_int("SEG3D_TC_ZMARCH", 1) != 0) {
+    ZmParams z;
+    memset(&z, 0, sizeof(z));
+    z.Cout = Cout; z.KC = Cin; z.row_bytes = Cin * 2;
+    z.D = D; z.H = H; z.W = W; z.N = N; z.y_ld = y_ld;
+    z.w_slab = (Cout * z.row_bytes + 1023) & ~1023;
+    z.plane_tx = 180 * z.row_bytes;
+    z.plane_bytes = (z.plane_tx + 1023) & ~1023;
+    z.w_tx = 27 * Cout * z.row_bytes;
+    if (27 * z.w_slab <= 112 * 1024) {
+      z.ntx = W / 8; z.nty = (H + 15) / 16;
+      z.acc_cols = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : 64);
+      z.tmem_cols = ZM_NB * z.acc_cols;
+      int ctas_per_sm = env_int("SEG3D_ZM_CTAS_PER_SM", 2);
+      if (ctas_per_sm * z.tmem_cols > 512) ctas_per_sm = 512 / z.tmem_cols;
+      int ring = ((200 * 1024 / ctas_per_sm) - 27 * z.w_slab) / z.plane_bytes;
+      if (ring < 3) { ctas_per_sm = 1; ring = (200 * 1024 - 27 * z.w_slab) / z.plane_bytes; }
+      if (ring > 8) ring = 8;
+      { const int e = env_int("SEG3D_ZM_RING", 0); if (e >= 2) ring = e; }
+      z.ring = ring;
+      // z segments: enough work items to balance ~4 per resident CTA, halo overhead 2/lseg
+      const long long cols = (long long)N * z.ntx * z.nty;
+      const long long want = 4ll * ctas_per_sm * seg3d_num_sms();
+      int nseg = (int)((want + cols - 1) / cols);
+      if (nseg < 1) nseg = 1;
+      int lseg = (D + nseg - 1) / nseg;
+      if (lseg < 8) lseg = D < 8 ? D : 8;
+      { const int e = env_int("SEG3D_ZM_LSEG", 0); if (e >= 1) lseg = e; }
+      z.lseg = lseg; z.nseg = (D + lseg - 1) / lseg;
+      const long long nitems = cols * z.nseg;
+      if (ring >= 3 && nitems < (1ll << 31)) {
+        z.nitems = (int)nitems;
+        z.sbo = 8 * z.row_bytes; z.a_sbo = 10 * z.row_bytes;
+        z.layout_type = z.row_bytes == 128 ? 2u : (z.row_bytes == 64 ? 4u : 6u);
+        const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
+        z.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+        const CUtensorMapDataType tdt = dtype == SEG3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+        const CUtensorMapSwizzle sw = z.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (z.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        CUtensorMap map_x, map_w;
+        cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+        cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2, (cuuint64_t)D * H * W * x_ld * 2};
+        cuuint32_t box[5] = {(cuuint32_t)Cin, 10, 18, 1, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = encode(&map_x, tdt, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { seg3d_set_error("conv_tc(zmarch): cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SEG3D_ECUDA; }
+        cuuint64_t wdims[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * Cout};
+        cuuint64_t wstr[1] = {(cuuint64_t)Cin * 2};
+        cuuint32_t wbox[2] = {(cuuint32_t)Cin, (cuuint32_t)Cout};
+        cuuint32_t westr[2] = {1, 1};
+        r = encode(&map_w, tdt, 2, const_cast<void*>(w), wdims, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { seg3d_set_error("conv_tc(zmarch): cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SEG3D_ECUDA; }
+        const size_t smem = 1024 + (size_t)27 * z.w_slab + (size_t)ring * z.plane_bytes + (2 * ring + 2 * ZM_NB + 1) * 8 + 64;
+        const long long max_grid = (long long)ctas_per_sm * seg3d_num_sms();
+        dim3 grid((unsigned)(nitems < max_grid ? nitems : max_grid));
+        cudaError_t e;
+        if (dtype == SEG3D_BF16) {
+          e = cudaFuncSetAttribute(conv3d_k3_zmarch_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e == cudaSuccess) { conv3d_k3_zmarch_kernel<__nv_bfloat16><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, z, bias, (__nv_bfloat16*)y, stats); e = cudaGetLastError(); }
+        } else {
+          e = cudaFuncSetAttribute(conv3d_k3_zmarch_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e == cudaSuccess) { conv3d_k3_zmarch_kernel<__half><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, z, bias, (__half*)y, stats); e = cudaGetLastError(); }
+        }
+        if (e != cudaSuccess) { seg3d_set_error("conv3d_k3_zmarch_kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
+        return SEG3D_OK;
+      }
+    }
+  }
 
   TcParams p;
   memset(&p, 0, sizeof(p));

@@ -1,0 +1,173 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/seg3d_b200.h declares, and the
+host-side logic of the drop-in package matches the reference goldens."""
+import ctypes
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, 'tests', 'golden')
+
+
+@pytest.fixture(scope='module')
+def built_lib():
+    import __graft_entry__ as ge
+    return ge.build()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, 'include', 'seg3d_b200.h')).read()
+    declared = sorted(set(re.findall(r'\b(seg3d_[a-z0-9_]+)\s*\(', hdr)))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(lib, name), 'missing export: ' + name
+    from segmentation3d._b200 import lib as L
+    assert sorted(L.EXPORTED_SYMBOLS) == declared          # the ctypes binding covers the whole header
+    L.load()
+    assert L.load().seg3d_version() == 100                 # no GPU needed
+
+
+def test_no_cpu_fallback():
+    from segmentation3d.network import vnet
+    net = vnet.SegmentationNet(1, 2)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        net(torch.zeros(1, 1, 16, 16, 16))
+    from segmentation3d.core import seg_infer
+    with pytest.raises(RuntimeError, match='no CPU inference path'):
+        seg_infer._device_for(-1)
+
+
+def sd_hash(sd):
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(v.detach().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def test_plugin_state_dict_schema_and_seeded_init_match_reference():
+    import importlib
+    schema = json.load(open(os.path.join(G, 'schema.json')))
+    hashes = json.load(open(os.path.join(G, 'weights_sha256.json')))
+    for key, ref in schema.items():
+        arch, cin, cout = key.split('_')
+        mod = importlib.import_module('segmentation3d.network.' + arch)
+        torch.manual_seed(0)
+        net = mod.SegmentationNet(int(cin), int(cout))
+        assert [[k, list(v.shape)] for k, v in net.state_dict().items()] == ref
+        assert net.max_stride() == 16
+        mod.parameters_kaiming_init(net)
+        assert sd_hash(net.state_dict()) == hashes['%s_seed0_kaiming' % key]
+        torch.manual_seed(0)
+        net = mod.SegmentationNet(int(cin), int(cout))
+        mod.parameters_gaussian_init(net)
+        assert sd_hash(net.state_dict()) == hashes['%s_seed0_gaussian' % key]
+        # DataParallel-style 'module.' prefix (core/seg_train.py:77,148 / core/seg_infer.py:119-142)
+        dp = torch.nn.DataParallel(net)
+        assert all(k.startswith('module.') for k in dp.state_dict())
+        net.load_state_dict({k[7:]: v for k, v in dp.state_dict().items()})
+
+
+def test_partition_grid_bit_exact_vs_reference():
+    from segmentation3d.utils.image3d import Image3d
+    from segmentation3d.utils.image_tools import image_partition_by_fixed_size, resample_size
+    cases = json.load(open(os.path.join(G, 'grids.json')))
+    for c in cases:
+        im = Image3d(np.zeros((1, 1, 1), np.float32), c['spacing'])
+        im.GetSize = lambda c=c: tuple(c['size'])
+        bs = list(c['bbox_start']) if c['bbox_start'] is not None else [0, 0, 0]
+        be = list(c['bbox_end']) if c['bbox_end'] is not None else list(c['size'])
+        s, e = image_partition_by_fixed_size(im, bs, be, list(c['partition_size']), list(c['partition_stride']), 16)
+        assert s == c['starts'] and e == c['ends']
+        assert bs == c['bbox_start_after'] and be == c['bbox_end_after']
+    assert resample_size([300, 300, 200], [0.5, 0.5, 1.0], [0.4, 0.4, 0.4], 16) == [384, 384, 512]
+
+
+def test_axis_counts_equal_rasterised_count():
+    from segmentation3d._b200.sliding import axis_counts
+    for c in json.load(open(os.path.join(G, 'grids.json'))):
+        if c['bbox_start'] is not None or c['n'] > 1000:
+            continue
+        cx, cy, cz = axis_counts(c['size'], c['starts'], c['ends'])
+        cnt = np.zeros((c['size'][2], c['size'][1], c['size'][0]), np.int32)
+        for s, e in zip(c['starts'], c['ends']):
+            cnt[s[2]:e[2], s[1]:e[1], s[0]:e[0]] += 1
+        assert np.array_equal(cnt, cz[:, None, None] * cy[None, :, None] * cx[None, None, :])
+
+
+def test_checkpoint_layout_roundtrip(tmp_path):
+    from segmentation3d.network import vnet
+    from segmentation3d.utils.attrdict import AttrDict
+    from segmentation3d.utils.model_io import get_checkpoint_folder, load_checkpoint, save_checkpoint
+    from segmentation3d.utils.normalizer import AdaptiveNormalizer, FixedNormalizer
+    net = vnet.SegmentationNet(1, 2)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.999))
+    cfg = AttrDict({'general': {'save_dir': str(tmp_path), 'model_scale': 'fine'}, 'net': {'name': 'vnet'},
+                    'dataset': {'spacing': [1, 1, 1], 'interpolation': 'LINEAR', 'num_classes': 2}})
+    cfg.dataset.crop_normalizers = [FixedNormalizer(0, 1000, True), AdaptiveNormalizer(3)]
+    os.makedirs(os.path.join(str(tmp_path), 'fine'))
+    open(os.path.join(str(tmp_path), 'fine', 'train_config.py'), 'w').write('cfg = {}\n')
+    for epoch in (3, 12):
+        save_checkpoint(net, opt, epoch, epoch * 10, cfg, 16, 1)
+    chk = get_checkpoint_folder(os.path.join(str(tmp_path), 'fine', 'checkpoints'), -1)
+    assert chk.endswith('chk_12')
+    assert sorted(os.listdir(chk)) == ['optimizer.pth', 'params.pth', 'train_config.py']
+    state = torch.load(os.path.join(chk, 'params.pth'), weights_only=False)
+    assert sorted(state) == sorted(['epoch', 'batch', 'net', 'max_stride', 'state_dict', 'spacing', 'interpolation',
+                                    'in_channels', 'out_channels', 'crop_normalizers'])
+    assert state['crop_normalizers'] == [{'type': 0, 'mean': 0, 'stddev': 1000, 'clip': True}, {'type': 1, 'clip_sigma': 3}]
+    net2 = vnet.SegmentationNet(1, 2)
+    opt2 = torch.optim.Adam(net2.parameters(), lr=1e-4)
+    assert load_checkpoint(12, net2, opt2, os.path.join(str(tmp_path), 'fine')) == (12, 120)
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), net2.state_dict().values()))
+
+
+def test_config_loading_without_easydict(tmp_path):
+    from segmentation3d.utils.file_io import load_config
+    p = tmp_path / 'infer_config.py'
+    p.write_text("from easydict import EasyDict as edict\n__C = edict()\ncfg = __C\n__C.general = {}\n"
+                 "__C.general.single_scale = 'fine'\n__C.fine = {}\n__C.fine.partition_size = [96, 96, 96]\n")
+    cfg = load_config(str(p))
+    assert cfg.general.single_scale == 'fine' and cfg.fine.partition_size == [96, 96, 96]
+    p.write_text(p.read_text().replace("= 'fine'", "= 'coarse'"))
+    assert load_config(str(p)).general.single_scale == 'coarse'      # re-read, not cached
+
+
+def test_metaimage_roundtrip_and_list_readers(tmp_path):
+    from segmentation3d.core.seg_infer import read_test_folder, read_test_txt
+    from segmentation3d.utils.image3d import Image3d, read_image, write_image
+    rng = np.random.default_rng(0)
+    for dtype, comp in ((np.float32, True), (np.int8, True), (np.float32, False)):
+        a = (rng.standard_normal((5, 6, 7)) * 50).astype(dtype)
+        im = Image3d(a, (0.5, 0.75, 1.25), (1.0, -2.0, 3.5))
+        path = str(tmp_path / ('im_%s_%d.mha' % (np.dtype(dtype).name, comp)))
+        write_image(im, path, comp)
+        back = read_image(path)
+        assert np.array_equal(back.to_numpy(), a) and back.GetSpacing() == im.GetSpacing() and back.GetOrigin() == im.GetOrigin()
+        assert back.GetSize() == (7, 6, 5)
+    txt = tmp_path / 'test.txt'
+    txt.write_text('2\ncase_a %s\ncase_b %s\n' % (tmp_path / 'a.mha', tmp_path / 'b.mha'))
+    names, paths = read_test_txt(str(txt))
+    assert names == ['case_a', 'case_b'] and paths[1].endswith('b.mha')
+    names, paths = read_test_folder(str(tmp_path))
+    assert len(names) == 3 and all(n.endswith('.mha') for n in names)
+    bad = tmp_path / 'bad.txt'
+    bad.write_text('3\ncase_a x\n')
+    with pytest.raises(ValueError):
+        read_test_txt(str(bad))
+
+
+def test_cal_dsc_matches_oracle_definition():
+    from oracle.metrics import cal_dsc as ref
+    from segmentation3d.utils.metrics import cal_dsc
+    rng = np.random.default_rng(1)
+    a, b = rng.integers(0, 3, (8, 8, 8)), rng.integers(0, 3, (8, 8, 8))
+    for lab in (0, 1, 2, 5):
+        for thr in (1, 400):
+            assert cal_dsc(a, b, lab, thr) == ref(a, b, lab, thr)
