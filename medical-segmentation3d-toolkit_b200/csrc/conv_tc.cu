@@ -115,6 +115,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint
   return d;
 }
 
+// The MMA-issuing thread is a single lane: every instruction between two tcgen05.mma costs issue slots
+// of that one thread, so the hot loops keep the descriptor's high word in a register and only add a
+// compile-time byte offset (>>4) to the low word.
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo, uint32_t layout_type) {
+  return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
+}
+__device__ __forceinline__ uint64_t desc_pack(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+
 template <typename T>
 __global__ void __launch_bounds__(TC_THREADS)
 conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -265,7 +273,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Persistent variant: each CTA walks tiles blockIdx.x, +gridDim.x, ...; the operand ring keeps
 // streaming across tile boundaries and two TMEM accumulator buffers let the epilogue of tile i
 // overlap the MMAs of tile i+1.  GroupNorm partial sums stay in registers until the sample changes.
-template <typename T>
+template <typename T, int KC>
 __global__ void __launch_bounds__(TC_THREADS)
 conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                             const TcParams p, const float* __restrict__ bias, T* __restrict__ y, double* __restrict__ stats) {
@@ -338,8 +346,11 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   } else if (warp == 1) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0; int j = 0;
-      const int ksteps = p.KC / 16;
-      const int nkw = (p.conv == 0 && p.kwfuse) ? 3 : 1;
+      constexpr int KSTEPS = KC / 16;
+      constexpr uint32_t ROWB = KC * 2;
+      const bool fused = (p.conv == 0 && p.kwfuse);
+      const uint32_t hi_a = desc_hi(p.a_sbo, p.layout_type), hi_b = desc_hi(p.sbo, p.layout_type);
+      const uint32_t slab16 = (uint32_t)p.b_slab >> 4;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++j) {
         const int buf = j & 1;
         mbar_wait(tempty_bar + 8 * buf, ((j >> 1) & 1) ^ 1);
@@ -348,13 +359,19 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t a_addr = a_base + stage * p.a_bytes, b_addr = b_base + stage * p.b_bytes;
-          for (int kw = 0; kw < nkw; ++kw)
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t ad = make_desc(a_addr + kw * p.row_bytes + k * 32, p.a_sbo, p.layout_type);
-              const uint64_t bd = make_desc(b_addr + kw * p.b_slab + k * 32, p.sbo, p.layout_type);
-              tc_mma_f16(dcol, ad, bd, p.idesc, (it | kw | k) != 0);
-            }
+          const uint32_t lo_a = (a_base + stage * p.a_bytes) >> 4, lo_b = (b_base + stage * p.b_bytes) >> 4;
+          if (fused) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k)
+                tc_mma_f16(dcol, desc_pack(hi_a, lo_a + ((kw * ROWB + k * 32) >> 4)), desc_pack(hi_b, lo_b + kw * slab16 + ((k * 32) >> 4)),
+                           p.idesc, (it | kw | k) != 0);
+          } else {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+              tc_mma_f16(dcol, desc_pack(hi_a, lo_a + ((k * 32) >> 4)), desc_pack(hi_b, lo_b + ((k * 32) >> 4)), p.idesc, (it | k) != 0);
+          }
           tc_commit(empty_bar + 8 * stage);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -449,7 +466,7 @@ struct ZmParams {
 };
 constexpr int ZM_NB = 4;
 
-template <typename T>
+template <typename T, int KC>
 __global__ void __launch_bounds__(TC_THREADS)
 conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                         const ZmParams p, const float* __restrict__ bias, T* __restrict__ y, double* __restrict__ stats) {
@@ -508,7 +525,10 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     if (lane == 0) {
       mbar_wait(wfull_bar, 0);
       int stage = 0; uint32_t phase = 0; int oc = 0;
-      const int ksteps = p.KC / 16;
+      constexpr int KSTEPS = KC / 16;
+      constexpr uint32_t ROWB = KC * 2;
+      const uint32_t hi_a = desc_hi(p.a_sbo, p.layout_type), hi_b = desc_hi(p.sbo, p.layout_type);
+      const uint32_t slab16 = (uint32_t)p.w_slab >> 4, w16 = w_base >> 4;
       for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
         const int seg = item % p.nseg;
         const int zs = seg * p.lseg;
@@ -516,21 +536,24 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         for (int ip = 0; ip < L + 2; ++ip) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t a_addr = a_base + stage * p.plane_bytes;
+          const uint32_t lo_a = (a_base + stage * p.plane_bytes) >> 4;
+#pragma unroll
           for (int kd = 2; kd >= 0; --kd) {
             const int zl = ip - kd;
             if (zl < 0 || zl >= L) continue;
             const int ocz = oc + zl, buf = ocz % ZM_NB;
             if (kd == 0) { mbar_wait(tempty_bar + 8 * buf, ((ocz / ZM_NB) & 1) ^ 1); tc_fence_after(); }
             const uint32_t dcol = tmem_base + (uint32_t)(buf * p.acc_cols);
+            const uint32_t lo_w = w16 + (uint32_t)(kd * 9) * slab16;
+#pragma unroll
             for (int kh = 0; kh < 3; ++kh)
-              for (int kw = 0; kw < 3; ++kw) {
-                const uint32_t sa = a_addr + (kh * 10 + kw) * p.row_bytes;
-                const uint32_t sb = w_base + ((kd * 3 + kh) * 3 + kw) * p.w_slab;
-                for (int k = 0; k < ksteps; ++k)
-                  tc_mma_f16(dcol, make_desc(sa + k * 32, p.a_sbo, p.layout_type), make_desc(sb + k * 32, p.sbo, p.layout_type),
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k)
+                  tc_mma_f16(dcol, desc_pack(hi_a, lo_a + (((kh * 10 + kw) * ROWB + k * 32) >> 4)),
+                             desc_pack(hi_b, lo_w + (uint32_t)(kh * 3 + kw) * slab16 + ((k * 32) >> 4)),
                              p.idesc, (kd | kh | kw | k) != 0);
-              }
           }
           tc_commit(empty_bar + 8 * stage);
           if (ip >= 2) tc_commit(tfull_bar + 8 * ((oc + ip - 2) % ZM_NB));
@@ -627,9 +650,12 @@ cudaError_t launch_tc(bool persistent, dim3 grid, size_t smem, cudaStream_t st, 
                       const TcParams& p, const float* bias, void* y, double* stats) {
   cudaError_t e;
   if (persistent) {
-    e = cudaFuncSetAttribute(conv3d_tc_persistent_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    conv3d_tc_persistent_kernel<T><<<grid, TC_THREADS, smem, st>>>(mx, mw, p, bias, (T*)y, stats);
+#define SEG3D_LAUNCH_P(KCV)                                                                                              \
+    e = cudaFuncSetAttribute(conv3d_tc_persistent_kernel<T, KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                                      \
+    conv3d_tc_persistent_kernel<T, KCV><<<grid, TC_THREADS, smem, st>>>(mx, mw, p, bias, (T*)y, stats);
+    if (p.KC == 64) { SEG3D_LAUNCH_P(64) } else if (p.KC == 32) { SEG3D_LAUNCH_P(32) } else { SEG3D_LAUNCH_P(16) }
+#undef SEG3D_LAUNCH_P
   } else {
     e = cudaFuncSetAttribute(conv3d_k3_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -656,7 +682,7 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   SEG3D_REQUIRE(((uintptr_t)x) % 16 == 0 && ((uintptr_t)w) % 16 == 0 && ((uintptr_t)y) % 16 == 0, "conv_tc: pointers must be 16-byte aligned");
 
   // ---- z-marching kernel for narrow k3 layers --------------------------------------------------------
-  if (mode == SEG3D_CONV_K3 && Cin <= 64 && W % 8 == 0 && D >= 4 && env_int("SEG3D_TC_ZMARCH", 1) != 0) {
+  if (mode == SEG3D_CONV_K3 && (Cin == 16 || Cin == 32 || Cin == 64) && W % 8 == 0 && D >= 4 && env_int("SEG3D_TC_ZMARCH", 1) != 0) {
     ZmParams z;
     memset(&z, 0, sizeof(z));
     z.Cout = Cout; z.KC = Cin; z.row_bytes = Cin * 2;
@@ -712,14 +738,16 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
         const size_t smem = 1024 + (size_t)27 * z.w_slab + (size_t)ring * z.plane_bytes + (2 * ring + 2 * ZM_NB + 1) * 8 + 64;
         const long long max_grid = (long long)ctas_per_sm * seg3d_num_sms();
         dim3 grid((unsigned)(nitems < max_grid ? nitems : max_grid));
-        cudaError_t e;
+        cudaError_t e = cudaSuccess;
+#define SEG3D_LAUNCH_Z(TT, KCV)                                                                                             \
+        { e = cudaFuncSetAttribute(conv3d_k3_zmarch_kernel<TT, KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+          if (e == cudaSuccess) { conv3d_k3_zmarch_kernel<TT, KCV><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, z, bias, (TT*)y, stats); e = cudaGetLastError(); } }
         if (dtype == SEG3D_BF16) {
-          e = cudaFuncSetAttribute(conv3d_k3_zmarch_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          if (e == cudaSuccess) { conv3d_k3_zmarch_kernel<__nv_bfloat16><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, z, bias, (__nv_bfloat16*)y, stats); e = cudaGetLastError(); }
+          if (Cin == 64) SEG3D_LAUNCH_Z(__nv_bfloat16, 64) else if (Cin == 32) SEG3D_LAUNCH_Z(__nv_bfloat16, 32) else SEG3D_LAUNCH_Z(__nv_bfloat16, 16)
         } else {
-          e = cudaFuncSetAttribute(conv3d_k3_zmarch_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          if (e == cudaSuccess) { conv3d_k3_zmarch_kernel<__half><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, z, bias, (__half*)y, stats); e = cudaGetLastError(); }
+          if (Cin == 64) SEG3D_LAUNCH_Z(__half, 64) else if (Cin == 32) SEG3D_LAUNCH_Z(__half, 32) else SEG3D_LAUNCH_Z(__half, 16)
         }
+#undef SEG3D_LAUNCH_Z
         if (e != cudaSuccess) { seg3d_set_error("conv3d_k3_zmarch_kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
         return SEG3D_OK;
       }
