@@ -126,6 +126,37 @@ int seg3d_focal_fwd(const float* probs, const float* target, int B, int C, int64
 int seg3d_focal_bwd(const float* probs, const float* target, int B, int C, int64_t n,
                     const float* alpha, float gamma, float scale, float* grad, void* stream);
 
+/* ---- training: backward of the conv + GroupNorm + ReLU (+ residual) unit (core/seg_train.py:124, i.e. the
+ * autograd of conv_gn_relu3.py:16-20 / residual_block3.py:24) -------------------------------------------------
+ * Data gradients of the convolutions reuse seg3d_conv3d_fwd with transformed weights (k3: flipped taps and
+ * swapped channels; k2s2 <-> transposed conv).
+ * seg3d_gn_bwd, two passes over the same arguments:
+ *   g0..g2 : up to three gradient contributions wrt `out` (g1/g2 may be NULL), each with its own pitch;
+ *   out    : the unit's saved post-ReLU output (mask = out > 0);  y : saved raw conv output;  stats : forward sums.
+ *   pass 0 : sums[n] += {sum gamma*dz, sum gamma*dz*xhat} (double), dgamma[c] += sum dz*xhat, dbeta[c] += sum dz.
+ *   pass 1 : dy = rstd*(gamma*dz - mean(gamma dz) - xhat*mean(gamma dz xhat)) stored with pitch dy_ld;
+ *            dres (optional) = dz (the residual branch's gradient); dbias[c] (optional) += sum dy.
+ * C % 8 == 0, 256 % (C/8) == 0. */
+int seg3d_gn_bwd(int dtype, int pass, const void* g0, int ld0, const void* g1, int ld1, const void* g2, int ld2,
+                 const void* out, int out_ld, const void* y, int y_ld, int C, const double* stats,
+                 const float* gamma, float eps, double* sums, float* dgamma, float* dbeta,
+                 void* dy, int dy_ld, void* dres, int dres_ld, float* dbias, int N, int64_t nvox, void* stream);
+/* dw (fp32, SIMT weight layout of seg3d_conv3d_fwd: [taps][Cin][Cout], T2S2 [Cin][8*Cout]) += x (*) dy; the caller
+ * zeroes dw.  D,H,W are the spatial dims of x (the convolution's input). */
+int seg3d_conv3d_wgrad(int mode, int dtype, const void* x, int x_ld, int Cin, const void* dy, int dy_ld, int Cout,
+                       float* dw, int N, int D, int H, int W, void* stream);
+/* backward of seg3d_outblock_tail_*: pass 0 (softmax bwd, GN2 sums, dgamma2/dbeta2), pass 1 (dw2/db2, GN1 sums,
+ * dgamma1/dbeta1), pass 2 (dy1 = gradient wrt the raw conv1 output, stored with pitch dy_ld; db1 += sum dy1).
+ * dprobs is fp32 [N][C][nvox]; all gradient outputs are accumulated (caller zeroes). */
+int seg3d_outblock_tail_bwd(int dtype, int pass, const void* y1, int ld, int C,
+                            const double* stats1, const float* gamma1, const float* beta1,
+                            const float* w2, const float* bias2,
+                            const double* stats2, const float* gamma2, const float* beta2, float eps,
+                            const float* dprobs, double* sums2, double* sums1,
+                            float* dgamma2, float* dbeta2, float* dw2, float* db2,
+                            float* dgamma1, float* dbeta1, float* db1,
+                            void* dy1, int dy_ld, int N, int64_t nvox, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,216 @@
+"""Training forward/backward of the V-shaped networks on the C-ABI kernels (reference core/seg_train.py:122-124:
+`outputs = net(crops); loss.backward()`).
+
+Forward = the same kernel plan as inference, built in `train` mode so every pre-GroupNorm tensor and every
+activation is kept.  Backward walks the recorded conv->GN->ReLU units in reverse:
+
+    gn_bwd pass 0/1  (dz = g*[out>0], GroupNorm backward, dgamma/dbeta/dbias, residual gradient)
+    conv wgrad       (seg3d_conv3d_wgrad, fp32 accumulation)
+    conv dgrad       (seg3d_conv3d_fwd on transformed weights: flipped k3, k2s2 <-> transposed conv)
+
+An activation can have up to three consumers (next conv, residual add, skip connection); each consumer writes
+its contribution into its own buffer and the producer's gn_bwd sums them on the fly, so nothing is accumulated
+read-modify-write.  All arithmetic is in libseg3d_b200.so; torch only owns the buffers and the autograd node.
+"""
+import torch
+
+from . import lib
+from .plan import GN_EPS, _Conv, _View
+
+
+def _k3_dgrad_weight(w):        # [Co,Ci,3,3,3] -> conv weight of the data-gradient convolution [Ci,Co,3,3,3]
+    return w.flip(2, 3, 4).permute(1, 0, 2, 3, 4).contiguous()
+
+
+class _Backward(object):
+    """Per (plan, shape) backward state: gradient buffers, dgrad convolutions, parameter-gradient slots."""
+
+    def __init__(self, plan, ws):
+        self.plan, self.ws = plan, ws
+        dev, td = plan.device, plan.tdtype
+        B, vox = ws['B'], ws['vox']
+        self.units = ws['units']
+        self.gy, self.gd, self.dres = {}, {}, {}
+        self.dconv = {}
+        self.produced = {}                    # (id(buf), off) -> producing unit's out view
+        for u in self.units:
+            self.produced[(id(u['out'].buf), u['out'].off)] = u['out']
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.pgrad = {}                        # parameter gradients in kernel layouts (fp32, zeroed every step)
+        for u in self.units:
+            c = plan.convs[u['conv']]
+            C = c.cout
+            self.gy[u['conv']] = _View(torch.empty((B, vox[u['lout']], C), dtype=td, device=dev), 0, C, C)
+            if u['res'] is not None:
+                r = u['res']
+                self.dres[u['conv']] = _View(torch.empty((B, vox[u['lout']], r.C), dtype=td, device=dev), 0, r.C, r.C)
+            if self._has_producer(u['x']):
+                self.gd[u['conv']] = _View(torch.empty((B, vox[u['lin']], u['x'].C), dtype=td, device=dev), 0, u['x'].C, u['x'].C)
+            taps = {lib.CONV_K3: 27, lib.CONV_K2S2: 8, lib.CONV_T2S2: 8}[c.mode]
+            self.pgrad[u['conv'] + '.weight'] = torch.zeros((taps * c.cin * c.cout,), **f32)
+            self.pgrad[u['conv'] + '.bias'] = torch.zeros((c.cout,), **f32)
+            self.pgrad[u['gn'] + '.weight'] = torch.zeros((c.cout,), **f32)
+            self.pgrad[u['gn'] + '.bias'] = torch.zeros((c.cout,), **f32)
+        nc = plan.out_channels
+        c1 = plan.convs['out_block.conv1']
+        self.pgrad['out_block.conv1.weight'] = torch.zeros((27 * c1.cin * nc,), **f32)
+        for k, n in (('out_block.conv1.bias', nc), ('out_block.gn1.weight', nc), ('out_block.gn1.bias', nc),
+                     ('out_block.conv2.weight', nc * nc), ('out_block.conv2.bias', nc),
+                     ('out_block.gn2.weight', nc), ('out_block.gn2.bias', nc)):
+            self.pgrad[k] = torch.zeros((n,), **f32)
+        ncp = ws['tail']['ncp']
+        self.gy_tail = _View(torch.zeros((B, vox[0], ncp), dtype=td, device=dev), 0, ncp, ncp)   # pad channels stay 0
+        tx = ws['tail']['x']
+        self.gd_tail = _View(torch.empty((B, vox[0], tx.C), dtype=td, device=dev), 0, tx.C, tx.C)
+        self.sums = torch.zeros((len(self.units) + 2, B, 2), dtype=torch.float64, device=dev)
+        self._make_dgrad_convs()
+
+    def _has_producer(self, x):
+        return any(id(x.buf) == k[0] and x.off <= k[1] < x.off + x.C for k in self.produced)
+
+    def _make_dgrad_convs(self):
+        plan = self.plan
+        sd = self._weights()
+        for name, c in list(plan.convs.items()):
+            if name == 'in_block.conv':
+                continue
+            if c.mode == lib.CONV_K3:
+                pad = c.cout if c.cout != c.real_cout else 0
+                self.dconv[name] = _Conv(sd, name, lib.CONV_K3, plan.dt, plan.device, plan.tc_modes,
+                                         transform=_k3_dgrad_weight, pad_dim0=pad)
+            elif c.mode == lib.CONV_K2S2:    # dgrad of the stride-2 conv = transposed conv with the same tensor
+                self.dconv[name] = _Conv(sd, name, lib.CONV_T2S2, plan.dt, plan.device, plan.tc_modes, transform=lambda w: w)
+            else:                            # dgrad of the transposed conv = stride-2 conv with the same tensor
+                self.dconv[name] = _Conv(sd, name, lib.CONV_K2S2, plan.dt, plan.device, plan.tc_modes, transform=lambda w: w)
+
+    def _weights(self):
+        return self.plan._last_sd
+
+    def refresh(self):
+        sd = self._weights()
+        for c in self.dconv.values():
+            c.load(sd)
+
+    # --------------------------------------------------------------------------------------------
+    def run(self, dprobs):
+        plan, ws = self.plan, self.ws
+        B, vox, dims, dt = ws['B'], ws['vox'], ws['dims'], plan.dt
+        st = lib.stream_ptr
+        for g in self.pgrad.values():
+            g.zero_()
+        self.sums.zero_()
+        contrib = {}
+
+        def add_contrib(xv, gv):
+            """register gradient view gv (same channel span as consumer input xv) with every producer inside xv"""
+            for (bid, off), pv in self.produced.items():
+                if bid == id(xv.buf) and xv.off <= off and off + pv.C <= xv.off + xv.C:
+                    sub = _View(gv.buf, gv.off + (off - xv.off), gv.ld, pv.C)
+                    contrib.setdefault((bid, off), []).append(sub)
+
+        # ---- output block tail -----------------------------------------------------------------
+        nc = plan.out_channels
+        tail = ws['tail']
+        g1, g2 = plan.gns['out_block.gn1'], plan.gns['out_block.gn2']
+        s1 = lib.ptr(ws['stats'][plan.gn_index['out_block.gn1']])
+        s2 = lib.ptr(ws['stats2'])
+        nu = len(self.units)
+        sums2, sums1 = lib.ptr(self.sums[nu]), lib.ptr(self.sums[nu + 1])
+        pg = self.pgrad
+        dp = dprobs.contiguous().float()
+        for p in range(3):
+            lib.call('seg3d_outblock_tail_bwd', dt, p, tail['raw'].p, tail['raw'].ld, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta),
+                     lib.ptr(plan.w2), lib.ptr(plan.b2), s2, lib.ptr(g2.gamma), lib.ptr(g2.beta), GN_EPS, lib.ptr(dp),
+                     sums2, sums1, lib.ptr(pg['out_block.gn2.weight']), lib.ptr(pg['out_block.gn2.bias']),
+                     lib.ptr(pg['out_block.conv2.weight']), lib.ptr(pg['out_block.conv2.bias']),
+                     lib.ptr(pg['out_block.gn1.weight']), lib.ptr(pg['out_block.gn1.bias']), lib.ptr(pg['out_block.conv1.bias']),
+                     self.gy_tail.p, self.gy_tail.ld, B, vox[0], st())
+        x = tail['x']
+        d0 = dims[0]
+        lib.call('seg3d_conv3d_wgrad', lib.CONV_K3, dt, x.p, x.ld, x.C, self.gy_tail.p, self.gy_tail.ld, nc,
+                 lib.ptr(pg['out_block.conv1.weight']), B, d0[0], d0[1], d0[2], st())
+        dc = self.dconv['out_block.conv1']
+        lib.call('seg3d_conv3d_fwd', lib.CONV_K3, dt, dc.impl, self.gy_tail.p, self.gy_tail.ld, dc.cin, lib.ptr(dc.w), None,
+                 self.gd_tail.p, self.gd_tail.ld, dc.cout, B, d0[0], d0[1], d0[2], None, st())
+        add_contrib(x, self.gd_tail)
+
+        # ---- conv -> GN -> ReLU units in reverse ---------------------------------------------------
+        for ui in range(nu - 1, -1, -1):
+            u = self.units[ui]
+            c = plan.convs[u['conv']]
+            gsrc = contrib.get((id(u['out'].buf), u['out'].off), [])
+            assert 1 <= len(gsrc) <= 3, (u['conv'], len(gsrc))
+            gv = gsrc + [None] * (3 - len(gsrc))
+            gnp = plan.gns[u['gn']]
+            sf = lib.ptr(ws['stats'][plan.gn_index[u['gn']]])
+            gy = self.gy[u['conv']]
+            dres = self.dres.get(u['conv'])
+            nv = vox[u['lout']]
+            for p in range(2):
+                lib.call('seg3d_gn_bwd', dt, p, gv[0].p, gv[0].ld, gv[1].p if gv[1] else None, gv[1].ld if gv[1] else 0,
+                         gv[2].p if gv[2] else None, gv[2].ld if gv[2] else 0,
+                         u['out'].p, u['out'].ld, u['raw'].p, u['raw'].ld, c.cout, sf, lib.ptr(gnp.gamma), GN_EPS,
+                         lib.ptr(self.sums[ui]), lib.ptr(pg[u['gn'] + '.weight']), lib.ptr(pg[u['gn'] + '.bias']),
+                         gy.p, gy.ld, dres.p if dres else None, dres.ld if dres else 0,
+                         lib.ptr(pg[u['conv'] + '.bias']), B, nv, st())
+            if dres is not None:
+                add_contrib(u['res'], dres)
+            xd = dims[u['lin']]
+            lib.call('seg3d_conv3d_wgrad', c.mode, dt, u['x'].p, u['x'].ld, c.cin, gy.p, gy.ld, c.cout,
+                     lib.ptr(pg[u['conv'] + '.weight']), B, xd[0], xd[1], xd[2], st())
+            if u['conv'] in self.gd:
+                dcv, gd = self.dconv[u['conv']], self.gd[u['conv']]
+                od = dims[u['lout']]          # the dgrad convolution's input is dy, living at the unit's output level
+                lib.call('seg3d_conv3d_fwd', dcv.mode, dt, dcv.impl, gy.p, gy.ld, dcv.cin, lib.ptr(dcv.w), None,
+                         gd.p, gd.ld, dcv.cout, B, od[0], od[1], od[2], None, st())
+                add_contrib(u['x'], gd)
+        return self._param_grads()
+
+    def _param_grads(self):
+        """kernel-layout fp32 gradients -> the reference's parameter layouts (plumbing)."""
+        plan, out = self.plan, {}
+        for name, c in plan.convs.items():
+            g = self.pgrad[name + '.weight']
+            if c.mode == lib.CONV_T2S2:
+                out[name + '.weight'] = g.view(c.cin, 2, 2, 2, c.cout).permute(0, 4, 1, 2, 3)
+            else:
+                k = 3 if c.mode == lib.CONV_K3 else 2
+                co = c.real_cout
+                out[name + '.weight'] = g.view(k, k, k, c.cin, co).permute(4, 3, 0, 1, 2)
+            out[name + '.bias'] = self.pgrad[name + '.bias'][:c.real_cout]
+        nc = plan.out_channels
+        out['out_block.conv2.weight'] = self.pgrad['out_block.conv2.weight'].view(nc, nc, 1, 1, 1)
+        out['out_block.conv2.bias'] = self.pgrad['out_block.conv2.bias']
+        for name in plan.gns:
+            out[name + '.weight'] = self.pgrad[name + '.weight'][:nc] if name.startswith('out_block') else self.pgrad[name + '.weight']
+            out[name + '.bias'] = self.pgrad[name + '.bias'][:nc] if name.startswith('out_block') else self.pgrad[name + '.bias']
+        return out
+
+
+class _NetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, x, names, *params):
+        plan = net._current_plan()
+        B, Cin, D, H, W = x.shape
+        ws, ops = plan.plan(B, D, H, W, train=True)
+        plan.load_input(ws, x.detach().float())
+        probs = plan.run(ws, ops).clone()
+        ctx.plan, ctx.ws, ctx.names = plan, ws, names
+        return probs
+
+    @staticmethod
+    def backward(ctx, dprobs):
+        plan, ws = ctx.plan, ctx.ws
+        bw = ws.get('bwd')
+        if bw is None:
+            bw = ws['bwd'] = _Backward(plan, ws)
+        else:
+            bw.refresh()
+        grads = bw.run(dprobs)
+        return (None, None, None) + tuple(grads[n].contiguous().clone() for n in ctx.names)
+
+
+def train_forward(net, x):
+    names = [n for n, _ in net.named_parameters()]
+    params = [p for _, p in net.named_parameters()]
+    return _NetFunction.apply(net, x, names, *params)

@@ -36,8 +36,9 @@ def strip_prefix(sd):
 class _Conv(object):
     """One packed convolution.  `load` (re)packs in place so kernel-argument pointers stay valid."""
 
-    def __init__(self, sd, name, mode, dt, device, allow_tc, pad_cout=0):
-        w = sd[name + '.weight']
+    def __init__(self, sd, name, mode, dt, device, allow_tc, pad_cout=0, transform=None, pad_dim0=0):
+        self.transform, self.pad_dim0 = transform, pad_dim0
+        w = self._effective_weight(sd[name + '.weight'])
         self.name, self.mode, self.dt, self.device = name, mode, dt, device
         if mode == lib.CONV_T2S2:
             self.cin, self.cout = w.shape[0], w.shape[1]
@@ -55,9 +56,18 @@ class _Conv(object):
         self.w, self.bias = None, None
         self.load(sd)
 
+    def _effective_weight(self, w):
+        """dgrad convolutions reuse the forward kernels on a transformed view of the same parameter."""
+        w = w.detach()
+        if self.pad_dim0 and w.shape[0] < self.pad_dim0:
+            wp = torch.zeros((self.pad_dim0,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
+            wp[:w.shape[0]] = w
+            w = wp
+        return self.transform(w) if self.transform is not None else w
+
     def load(self, sd):
-        w = sd[self.name + '.weight'].detach().to(device=self.device, dtype=torch.float32)
-        b = sd.get(self.name + '.bias')
+        w = self._effective_weight(sd[self.name + '.weight']).to(device=self.device, dtype=torch.float32)
+        b = sd.get(self.name + '.bias') if self.transform is None and not self.pad_dim0 else None
         if self.cout != self.real_cout:
             wp = torch.zeros((self.cout,) + tuple(w.shape[1:]), dtype=torch.float32, device=self.device)
             wp[:self.real_cout] = w
@@ -121,6 +131,7 @@ class NetPlan(object):
         if self.device.type != 'cuda':
             raise RuntimeError('seg3d_b200 runs on CUDA devices only (no CPU fallback)')
         sd = strip_prefix(state_dict)
+        self._last_sd = sd
         self.arch = arch or detect_arch(sd)
         if tc_modes is None:
             tc_modes = () if os.environ.get('SEG3D_FORCE_SIMT') == '1' else DEFAULT_TC_MODES
@@ -160,6 +171,7 @@ class NetPlan(object):
     def refresh(self, state_dict):
         """Re-pack changed weights in place (pointers captured by cached plans stay valid)."""
         sd = strip_prefix(state_dict)
+        self._last_sd = sd
         for c in self.convs.values():
             c.load(sd)
         for g in self.gns.values():
@@ -174,7 +186,7 @@ class NetPlan(object):
             n += 1
         return n
 
-    def _build(self, B, D, H, W):
+    def _build(self, B, D, H, W, train=False):
         dev, td, dt = self.device, self.tdtype, self.dt
         assert D % 16 == 0 and H % 16 == 0 and W % 16 == 0, 'spatial dims must be multiples of max_stride=16'
         dims = [(D >> l, H >> l, W >> l) for l in range(5)]
@@ -197,8 +209,8 @@ class NetPlan(object):
             ws['T%da' % l], ws['T%db' % l] = buf(l, C), buf(l, C)
             ws['U%d' % l] = buf(l, C)                            # rblock result (up path; level 4: down_256 output)
             ws['M%da' % l], ws['M%db' % l] = buf(l, C // 4), buf(l, C // 4)   # bottleneck mids (VBNet)
-        ops, meta = [], []
-        ws['meta'] = meta
+        ops, meta, units = [], [], []
+        ws['meta'], ws['units'], ws['dims'], ws['vox'], ws['B'] = meta, units, dims, vox, B
         st = lib.stream_ptr
         raw = ws['raw']
 
@@ -229,28 +241,41 @@ class NetPlan(object):
             meta.append({'name': name, 'kind': 'gn_apply', 'flops': 0.0,
                          'bytes': esz * B * nvox * y.C * (3 if res is not None else 2)})
 
-        def rawview(C):
+        def rawview(C, l=0):
+            if train:       # training keeps every pre-GroupNorm tensor for the backward pass
+                return _View(torch.empty((B, vox[l], C), dtype=td, device=dev), 0, C, C)
             return _View(raw, 0, C, C)
 
-        def conv_gn(cname, gname, x, l, out, relu, res=None):
+        def tmpbuf(l, C, key):
+            if train:
+                return _View(torch.empty((B, vox[l], C), dtype=td, device=dev), 0, C, C)
+            return _View(ws[key], 0, C, C)
+
+        def unit(cname, gname, x, lin, lout, out, res=None):
+            """conv -> GroupNorm -> (+res) -> ReLU with the conv reading level `lin` and writing level `lout`"""
             C = self.convs[cname].cout
-            conv(cname, x, dims[l], rawview(C), gname)
-            gn(gname, rawview(C), out, vox[l], relu, res)
+            rv = rawview(C, lout)
+            conv(cname, x, dims[lin], rv, gname)
+            gn(gname, rv, out, vox[lout], True, res)
+            units.append({'conv': cname, 'gn': gname, 'x': x, 'lin': lin, 'lout': lout, 'raw': rv, 'out': out, 'res': res})
+
+        def conv_gn(cname, gname, x, l, out, relu, res=None):
+            assert relu
+            unit(cname, gname, x, l, l, out, res)
 
         def rblock(prefix, X, l, dest):
             n = self._rblock_len(prefix)
             C = X.C
             cur = X
-            tmps = [_View(ws['T%da' % l], 0, C, C), _View(ws['T%db' % l], 0, C, C)]
             for i in range(n):
                 last = i == n - 1
-                out = dest if last else tmps[i % 2]
+                out = dest if last else tmpbuf(l, C, 'T%d%s' % (l, 'ab'[i % 2]))
                 op = '%s.ops.%d' % (prefix, i)
                 if (op + '.conv') in self.convs:
                     conv_gn(op + '.conv', op + '.gn', cur, l, out, relu=True, res=X if last else None)
                 else:
-                    m1 = _View(ws['M%da' % l], 0, C // 4, C // 4)
-                    m2 = _View(ws['M%db' % l], 0, C // 4, C // 4)
+                    m1 = tmpbuf(l, C // 4, 'M%da' % l)
+                    m2 = tmpbuf(l, C // 4, 'M%db' % l)
                     conv_gn(op + '.conv1.conv', op + '.conv1.gn', cur, l, m1, relu=True)
                     conv_gn(op + '.conv2.conv', op + '.conv2.gn', m1, l, m2, relu=True)
                     conv_gn(op + '.conv3.conv', op + '.conv3.gn', m2, l, out, relu=True, res=X if last else None)
@@ -267,8 +292,7 @@ class NetPlan(object):
         for l, name in ((1, 'down_32'), (2, 'down_64'), (3, 'down_128'), (4, 'down_256')):
             C = widths[l] // 2 if l < 4 else 256
             A = _View(ws['A%d' % l], 0, C, C)
-            conv(name + '.down_conv', src, dims[l - 1], rawview(C), name + '.down_gn')
-            gn(name + '.down_gn', rawview(C), A, vox[l], relu=True)
+            unit(name + '.down_conv', name + '.down_gn', src, l - 1, l, A)
             dest = skip[l] if l < 4 else _View(ws['U4'], 0, 256, 256)
             rblock(name + '.rblock', A, l, dest)
             src = dest
@@ -276,8 +300,7 @@ class NetPlan(object):
         for l, name in ((3, 'up_256'), (2, 'up_128'), (1, 'up_64'), (0, 'up_32')):
             C = widths[l]
             up = _View(ws['cat%d' % l], 0, C, C // 2)
-            conv(name + '.up_conv', src, dims[l + 1], rawview(C // 2), name + '.up_gn')
-            gn(name + '.up_gn', rawview(C // 2), up, vox[l], relu=True)
+            unit(name + '.up_conv', name + '.up_gn', src, l + 1, l, up)
             cat = _View(ws['cat%d' % l], 0, C, C)
             dest = _View(ws['U%d' % l], 0, C, C)
             rblock(name + '.rblock', cat, l, dest)
@@ -285,7 +308,10 @@ class NetPlan(object):
         # out block: conv1 -> raw, then the fused tail
         nc = self.out_channels
         ncp = self.convs['out_block.conv1'].cout          # = nc, or 16 when padded for the tensor-core path
-        conv('out_block.conv1', src, dims[0], rawview(ncp), 'out_block.gn1')
+        rv1 = rawview(ncp, 0)
+        conv('out_block.conv1', src, dims[0], rv1, 'out_block.gn1')
+        ws['tail'] = {'x': src, 'raw': rv1, 'ncp': ncp}
+        raw = rv1.buf
         g1, g2 = self.gns['out_block.gn1'], self.gns['out_block.gn2']
         s1 = lib.ptr(ws['stats'][self.gn_index['out_block.gn1']])
         s2 = lib.ptr(ws['stats2'])
@@ -300,10 +326,10 @@ class NetPlan(object):
         ops.append(lambda a=a2: lib.call('seg3d_outblock_tail_probs', *a, st()))
         return ws, ops
 
-    def plan(self, B, D, H, W):
-        key = (B, D, H, W)
+    def plan(self, B, D, H, W, train=False):
+        key = (B, D, H, W, train)
         if key not in self._plans:
-            self._plans[key] = self._build(B, D, H, W)
+            self._plans[key] = self._build(B, D, H, W, train)
         return self._plans[key]
 
     def load_input(self, ws, x):
