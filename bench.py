@@ -163,6 +163,59 @@ def workload_config(args, size):
             'l2_policy': 'inputs larger than L2 (volume 419 MB + accumulators 839 MB per step)'}
 
 
+def run_train(args):
+    """BASELINE configs[2]: VNet, 96^3 patches, batch 8/GPU, MultiDiceLoss, Adam(lr 1e-4), data parallel."""
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = 'cuda:%d' % local
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    from segmentation3d._b200 import dist as D
+    from segmentation3d.core.seg_train import train_step
+    from segmentation3d.loss.multi_dice_loss import MultiDiceLoss
+    net = make_net(args.mode).to(dev).train()
+    D.broadcast_params(net)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.999))
+    lf = MultiDiceLoss([0.5, 0.5], 2, True)
+    B, P = args.train_batch, args.patch
+    g = torch.Generator(device=dev).manual_seed(rank)
+    crops = torch.randn((B, 1, P, P, P), generator=g, device=dev)
+    masks = torch.randint(0, 2, (B, 1, P, P, P), generator=g, device=dev).float()
+    params = list(net.parameters())
+    for _ in range(max(args.warmup, 3)):
+        loss = train_step(net, opt, lf, crops, masks, params)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = train_step(net, opt, lf, crops, masks, params)
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'train patches/s (VNet, 96^3 patches, batch %d/GPU, Dice, Adam)' % B, 'value': B * world / (ms * 1e-3),
+            'unit': 'patches/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': {'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f32'}[args.mode], 'data': 'synthetic',
+            'config': {'workload': 'VNet(1,2) training step, crops [%d,1,%d^3] per GPU, MultiDiceLoss, Adam lr 1e-4 (BASELINE configs[2])' % (B, P),
+                       'mode': args.mode, 'parallelism': 'dp%d' % world}, 'loss': float(loss.item())}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -178,9 +231,14 @@ def main():
     ap.add_argument('--ref-patches', type=int, default=4, help='patches in the bounded CPU sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--layers', action='store_true', help='print the per-kernel roofline table to stderr')
+    ap.add_argument('--task', default='infer', choices=['infer', 'train'],
+                    help="'train': secondary metric, VNet 96^3 training step (BASELINE configs[2]) in patches/s")
+    ap.add_argument('--train-batch', type=int, default=8)
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.task == 'train':
+        return run_train(args)
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
