@@ -359,9 +359,16 @@ extern "C" int seg3d_gn_bwd(int dtype, int pass, const void* g0, int ld0, const 
   return SEG3D_OK;
 }
 
+int seg3d_wgrad_tc(int dtype, const void* x, int x_ld, int Cin, const void* dy, int dy_ld, int Cout, float* dw,
+                   int N, int D, int H, int W, cudaStream_t st);
+
 extern "C" int seg3d_conv3d_wgrad(int mode, int dtype, const void* x, int x_ld, int Cin, const void* dy, int dy_ld, int Cout,
                                   float* dw, int N, int D, int H, int W, void* stream) {
   SEG3D_REQUIRE(x && dy && dw && Cin > 0 && Cout > 0 && N > 0, "conv3d_wgrad: bad arguments");
+  if (mode == SEG3D_CONV_K3) {       // tensor-core path when the shape allows it
+    const int rc = seg3d_wgrad_tc(dtype, x, x_ld, Cin, dy, dy_ld, Cout, dw, N, D, H, W, (cudaStream_t)stream);
+    if (rc != SEG3D_EUNSUPPORTED) return rc;
+  }
   WgradGeom g;
   g.mode = mode; g.N = N; g.D = D; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.x_ld = x_ld; g.dy_ld = dy_ld;
   g.Do = D; g.Ho = H; g.Wo = W;

@@ -627,6 +627,144 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Weight gradient of the k3 convolution on the tensor cores:
+//     dW[tap][ci][co] = sum over voxels v of  dy[v][co] * x[v + tap][ci]
+// is a GEMM with K = voxels.  Both operands are stored voxel-major with the channels contiguous, i.e.
+// they are MN-major UMMA operands exactly as the TMA delivers them (128B/64B/32B swizzled rows):
+//     A = dy^T : M = co (128 rows of TMEM, zero / don't-care beyond Cout), K = the 128 voxels of an 8x16 plane tile
+//     B = x    : N = ci block (<= 64), K = the same voxels shifted by (kh,kw) inside a 10x18 halo plane
+// A CTA owns one (co block, ci block, tap group) and accumulates its D_tap[co][ci] tiles in TMEM over all the
+// voxel tiles of its K split (persistent), then adds them to the fp32 gradient with coalesced atomics.
+// Tap group = one kd (9 taps) for N <= 32, one (kd,kh) (3 taps) for N = 64, so the x plane needed with dy plane z
+// is the single plane z+kd-1: a two-operand TMA pipeline, no plane ring.
+struct WgParams {
+  int Cin, Cout, nblk, mblk;            // N (ci) block width, M (co) block width (<=128)
+  int n_ci_blk, n_co_blk, ngroups, taps_per_group;
+  int D, H, W, N, ntx, nty, ntiles;     // tiles over (n, z, ty, tx)
+  int stages, a_bytes, b_bytes, a_tx, b_tx, a_atoms;
+  int b_row_bytes;
+  int tmem_cols;
+  uint32_t idesc, a_sbo, a_lbo, b_sbo, a_layout, b_layout;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(TC_THREADS)
+conv3d_k3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                          const WgParams p, float* __restrict__ dw) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + p.stages * p.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + p.stages * (p.a_bytes + p.b_bytes));
+  const uint32_t full_bar = smem_u32(bars);
+  const uint32_t empty_bar = full_bar + 8 * p.stages;
+  const uint32_t done_bar = empty_bar + 8 * p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // blockIdx.y -> (co block, ci block, tap group)
+  int c = blockIdx.y;
+  const int grp = c % p.ngroups; c /= p.ngroups;
+  const int cib = c % p.n_ci_blk; const int cob = c / p.n_ci_blk;
+  const int kd = p.taps_per_group == 9 ? grp : grp / 3;
+  const int kh0 = p.taps_per_group == 9 ? 0 : grp % 3;          // first kh of the group
+  const int ci0 = cib * p.nblk, co0 = cob * p.mblk;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int x0 = (t % p.ntx) * 8; t /= p.ntx;
+        const int y0 = (t % p.nty) * 16; t /= p.nty;
+        const int z = t % p.D; const int n = t / p.D;
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+        mbar_expect_tx(full_bar + 8 * stage, (uint32_t)(p.a_tx + p.b_tx));
+        for (int a = 0; a < p.a_atoms; ++a)
+          tma_load_5d(a_base + stage * p.a_bytes + a * 16384, &map_dy, full_bar + 8 * stage, co0 + a * 64, x0, y0, z, n);
+        tma_load_5d(b_base + stage * p.b_bytes, &map_x, full_bar + 8 * stage, ci0, x0 - 1, y0 - 1, z + kd - 1, n);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t hi_a = desc_hi(p.a_sbo, p.a_layout), hi_b = desc_hi(p.b_sbo, p.b_layout);
+      const uint32_t lbo_a = ((p.a_lbo >> 4) & 0x3FFFu) << 16;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        mbar_wait(full_bar + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t lo_a = ((a_base + stage * p.a_bytes) >> 4) | lbo_a;
+        const uint32_t b_addr = b_base + stage * p.b_bytes;
+        for (int tg = 0; tg < p.taps_per_group; ++tg) {
+          const int kh = kh0 + tg / 3, kw = tg % 3;
+          const uint32_t lo_b = (b_addr + (uint32_t)(kh * 10 + kw) * p.b_row_bytes) >> 4;
+          const uint32_t dcol = tmem_base + (uint32_t)(tg * p.nblk);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)      // 128 voxels = 8 steps of K=16 (two 8-voxel x-lines each)
+            tc_mma_f16(dcol, desc_pack(hi_a, lo_a + ((k * 2048) >> 4)), desc_pack(hi_b, lo_b + (uint32_t)((k * 2 * p.b_sbo) >> 4)),
+                       p.idesc, (!first) || (k != 0));
+        }
+        first = false;
+        tc_commit(empty_bar + 8 * stage);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(done_bar);
+    }
+  } else {
+    // epilogue (once): TMEM lane = co, column = (tap in group, ci)
+    const int q = warp & 3;
+    const int co = q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const bool has_tiles = blockIdx.x < p.ntiles;
+    if (has_tiles) {
+      for (int tg = 0; tg < p.taps_per_group; ++tg) {
+        const int tap = (kd * 3 + kh0 + tg / 3) * 3 + tg % 3;
+        for (int c0 = 0; c0 < p.nblk; c0 += 16) {
+          uint32_t v[16];
+          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tg * p.nblk + c0), v);
+          tc_wait_ld();
+          if (co < p.mblk && co0 + co < p.Cout) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const int ci = ci0 + c0 + jj;
+              if (ci < p.Cin) atomicAdd(dw + ((size_t)tap * p.Cin + ci) * p.Cout + co0 + co, __uint_as_float(v[jj]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -867,5 +1005,83 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   cudaError_t e = dtype == SEG3D_BF16 ? launch_tc<__nv_bfloat16>(persistent, grid, smem, st, map_x, map_w, p, bias, y, stats)
                                       : launch_tc<__half>(persistent, grid, smem, st, map_x, map_w, p, bias, y, stats);
   if (e != cudaSuccess) { seg3d_set_error("conv_tc kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
+  return SEG3D_OK;
+}
+
+// dW (fp32 [27][Cin][Cout], accumulated) for the k3 convolution on the tensor cores; returns SEG3D_EUNSUPPORTED
+// for shapes it does not take so the caller can use the SIMT kernel.
+int seg3d_wgrad_tc(int dtype, const void* x, int x_ld, int Cin, const void* dy, int dy_ld, int Cout, float* dw,
+                   int N, int D, int H, int W, cudaStream_t st) {
+  if (dtype != SEG3D_F16 && dtype != SEG3D_BF16) return SEG3D_EUNSUPPORTED;
+  if (Cin % 16 || Cout % 16 || x_ld % 8 || dy_ld % 8) return SEG3D_EUNSUPPORTED;
+  if (env_int("SEG3D_TC_WGRAD", 1) == 0) return SEG3D_EUNSUPPORTED;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return SEG3D_EUNSUPPORTED;
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.Cin = Cin; p.Cout = Cout; p.D = D; p.H = H; p.W = W; p.N = N;
+  p.nblk = Cin >= 64 ? 64 : Cin;                    // 16, 32 or 64 (Cin = 48 etc. not produced by the networks)
+  if (Cin % p.nblk) return SEG3D_EUNSUPPORTED;
+  p.mblk = Cout >= 128 ? 128 : Cout;
+  if (Cout % p.mblk) return SEG3D_EUNSUPPORTED;
+  p.n_ci_blk = Cin / p.nblk; p.n_co_blk = Cout / p.mblk;
+  p.taps_per_group = p.nblk <= 32 ? 9 : 3;
+  p.ngroups = 27 / p.taps_per_group;
+  p.ntx = (W + 7) / 8; p.nty = (H + 15) / 16;
+  const long long ntiles = (long long)p.ntx * p.nty * D * N;
+  if (ntiles <= 0 || ntiles >= (1ll << 31)) return SEG3D_EUNSUPPORTED;
+  p.ntiles = (int)ntiles;
+  p.a_atoms = (p.mblk + 63) / 64;
+  p.a_bytes = 2 * 16384;                            // two 64-channel atoms of 128 rows x 128 B (second may stay unloaded)
+  p.a_tx = p.a_atoms * 16384;
+  p.b_row_bytes = p.nblk * 2;
+  p.b_tx = 180 * p.b_row_bytes;
+  p.b_bytes = (p.b_tx + 1023) & ~1023;
+  p.stages = (p.a_bytes + p.b_bytes) > 50 * 1024 ? 3 : 4;
+  p.a_sbo = 1024; p.a_lbo = 16384; p.a_layout = 2;
+  p.b_sbo = 10 * p.b_row_bytes;
+  p.b_layout = p.b_row_bytes == 128 ? 2u : (p.b_row_bytes == 64 ? 4u : 6u);
+  const int cols = p.taps_per_group * p.nblk;
+  p.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
+  const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
+  // MN-major A and B (bits 15, 16), M = 128, N = ci block
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.nblk >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const CUtensorMapDataType tdt = dtype == SEG3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap map_dy, map_x;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)dy_ld * 2, (cuuint64_t)W * dy_ld * 2, (cuuint64_t)H * W * dy_ld * 2, (cuuint64_t)D * H * W * dy_ld * 2};
+    cuuint32_t box[5] = {64, 8, 16, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&map_dy, tdt, 5, const_cast<void*>(dy), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { seg3d_set_error("wgrad_tc: cuTensorMapEncodeTiled(dy) failed with %d", (int)r); return SEG3D_ECUDA; }
+  }
+  {
+    const CUtensorMapSwizzle sw = p.b_row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.b_row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2, (cuuint64_t)D * H * W * x_ld * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.nblk, 10, 18, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&map_x, tdt, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { seg3d_set_error("wgrad_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SEG3D_ECUDA; }
+  }
+  const int combos = p.n_co_blk * p.n_ci_blk * p.ngroups;
+  const int ctas_per_sm = (512 / p.tmem_cols) < 1 ? 1 : ((512 / p.tmem_cols) > 1 ? 1 : 1);   // smem ring ~170 KB: one CTA per SM
+  long long ksplit = ((long long)ctas_per_sm * seg3d_num_sms() + combos - 1) / combos;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > ntiles) ksplit = ntiles;
+  const size_t smem = 1024 + (size_t)p.stages * (p.a_bytes + p.b_bytes) + (2 * p.stages + 1) * 8 + 64;
+  dim3 grid((unsigned)ksplit, (unsigned)combos);
+  cudaError_t e;
+  if (dtype == SEG3D_BF16) {
+    e = cudaFuncSetAttribute(conv3d_k3_wgrad_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) { conv3d_k3_wgrad_tc_kernel<__nv_bfloat16><<<grid, TC_THREADS, smem, st>>>(map_dy, map_x, p, dw); e = cudaGetLastError(); }
+  } else {
+    e = cudaFuncSetAttribute(conv3d_k3_wgrad_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) { conv3d_k3_wgrad_tc_kernel<__half><<<grid, TC_THREADS, smem, st>>>(map_dy, map_x, p, dw); e = cudaGetLastError(); }
+  }
+  if (e != cudaSuccess) { seg3d_set_error("conv3d_k3_wgrad_tc_kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
   return SEG3D_OK;
 }

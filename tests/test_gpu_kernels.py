@@ -306,6 +306,49 @@ def test_forward_fp16_tcgen05_equals_simt_path(lib):
     assert (a - b).abs().max() <= 5e-3
 
 
+WG_CASES = [
+    # mode, Cin, Cout, N, D, H, W
+    ('K3', 32, 32, 2, 8, 16, 8), ('K3', 64, 64, 1, 4, 16, 16), ('K3', 16, 16, 1, 8, 8, 8), ('K3', 128, 128, 1, 4, 12, 12),
+    ('K3', 256, 256, 2, 2, 6, 6), ('K3', 32, 16, 1, 8, 16, 16), ('K3', 16, 64, 1, 4, 8, 8), ('K3', 1, 16, 1, 8, 8, 8),
+    ('K2S2', 16, 32, 1, 8, 8, 8), ('T2S2', 64, 16, 1, 4, 4, 8),
+]
+
+
+@pytest.mark.parametrize('dt_name', ['F32', 'BF16'])
+@pytest.mark.parametrize('case', WG_CASES, ids=lambda c: '-'.join(map(str, c)))
+def test_conv_wgrad_matches_torch(lib, case, dt_name):
+    L = lib
+    dt = getattr(L, dt_name)
+    tdt = L.TORCH_DTYPE[dt]
+    mname, Cin, Cout, N, D, H, W = case
+    mode = getattr(L, 'CONV_' + mname)
+    g = torch.Generator().manual_seed(Cin + 5 * Cout)
+    x = torch.randn((N, Cin, D, H, W), generator=g).to(tdt).float()
+    if mode == L.CONV_T2S2:
+        wshape, od = (Cin, Cout, 2, 2, 2), (2 * D, 2 * H, 2 * W)
+    elif mode == L.CONV_K2S2:
+        wshape, od = (Cout, Cin, 2, 2, 2), (D // 2, H // 2, W // 2)
+    else:
+        wshape, od = (Cout, Cin, 3, 3, 3), (D, H, W)
+    dy = torch.randn((N, Cout) + od, generator=g).to(tdt).float()
+    w = torch.zeros(wshape, dtype=torch.float64, requires_grad=True)
+    y = ref_conv(mode, L, x.double(), w, None)
+    (y * dy.double()).sum().backward()
+    ref = w.grad.float()
+    xd, dyd = to_ndhwc(x, tdt), to_ndhwc(dy, tdt)
+    taps = 27 if mode == L.CONV_K3 else 8
+    dw = torch.zeros((taps * Cin * Cout,), dtype=torch.float32, device='cuda')
+    L.call('seg3d_conv3d_wgrad', mode, dt, L.ptr(xd), Cin, Cin, L.ptr(dyd), Cout, Cout, L.ptr(dw), N, D, H, W, L.stream_ptr())
+    torch.cuda.synchronize()
+    if mode == L.CONV_T2S2:
+        got = dw.view(Cin, 2, 2, 2, Cout).permute(0, 4, 1, 2, 3).cpu()
+    else:
+        k = 3 if mode == L.CONV_K3 else 2
+        got = dw.view(k, k, k, Cin, Cout).permute(4, 3, 0, 1, 2).cpu()
+    err = (got - ref).abs().max() / (ref.abs().max() + 1e-12)
+    assert err <= 2e-3, float(err)
+
+
 def test_forward_batch_equals_single(lib):
     sd = oinit.init_state_dict('vnet', 1, 2, 1)
     x = seeded_input(9, (3, 1, 16, 32, 16))
