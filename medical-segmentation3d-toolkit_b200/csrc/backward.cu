@@ -331,6 +331,57 @@ int launch_tail_bwd(int C, dim3 grid, cudaStream_t st, const T* y1, int ld, cons
   return SEG3D_OK;
 }
 
+
+// ---- weight gradient of the input block (Cin == 1, Cout == 16): 27 x 16 long reductions over all voxels -------
+// thread = (tap, co); a block walks 8x8x8 voxel tiles, staging the 10^3 input halo and the 512 x 16 dy tile in
+// shared memory, and issues its 432 atomics once at the end.
+template <typename T>
+__global__ void __launch_bounds__(448)
+wgrad_cin1_kernel(const T* __restrict__ x, const T* __restrict__ dy, int dy_ld, float* __restrict__ dw,
+                  int N, int D, int H, int W, int ntx, int nty, int ntz) {
+  __shared__ float xs[10][10][10];
+  __shared__ float dys[512][16];
+  const int tid = threadIdx.x;
+  const int tap = tid >> 4, co = tid & 15;
+  const bool active = tap < 27;
+  const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+  float acc = 0.f;
+  const long long ntiles = (long long)ntx * nty * ntz * N;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long t = tile;
+    const int x0 = (int)(t % ntx) * 8; t /= ntx;
+    const int y0 = (int)(t % nty) * 8; t /= nty;
+    const int z0 = (int)(t % ntz) * 8; const int n = (int)(t / ntz);
+    const T* xn = x + (size_t)n * D * H * W;
+    const T* dn = dy + (size_t)n * D * H * W * dy_ld;
+    __syncthreads();
+    for (int i = tid; i < 1000; i += blockDim.x) {
+      const int hx = i % 10, hy = (i / 10) % 10, hz = i / 100;
+      const int gx = x0 + hx - 1, gy = y0 + hy - 1, gz = z0 + hz - 1;
+      float v = 0.f;
+      if (gx >= 0 && gx < W && gy >= 0 && gy < H && gz >= 0 && gz < D) v = to_f32<T>(xn[((size_t)gz * H + gy) * W + gx]);
+      xs[hz][hy][hx] = v;
+    }
+    for (int i = tid; i < 512 * 16; i += blockDim.x) {
+      const int c = i & 15, v = i >> 4;
+      const int lx = v & 7, ly = (v >> 3) & 7, lz = v >> 6;
+      const int gx = x0 + lx, gy = y0 + ly, gz = z0 + lz;
+      float d = 0.f;
+      if (gx < W && gy < H && gz < D) d = to_f32<T>(dn[(((size_t)gz * H + gy) * W + gx) * dy_ld + c]);
+      dys[v][c] = d;
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll 4
+      for (int v = 0; v < 512; ++v) {
+        const int lx = v & 7, ly = (v >> 3) & 7, lz = v >> 6;
+        acc = fmaf(xs[lz + kd][ly + kh][lx + kw], dys[v][co], acc);
+      }
+    }
+  }
+  if (active) atomicAdd(dw + tap * 16 + co, acc);
+}
+
 }  // namespace
 
 extern "C" int seg3d_gn_bwd(int dtype, int pass, const void* g0, int ld0, const void* g1, int ld1, const void* g2, int ld2,
@@ -365,6 +416,14 @@ int seg3d_wgrad_tc(int dtype, const void* x, int x_ld, int Cin, const void* dy, 
 extern "C" int seg3d_conv3d_wgrad(int mode, int dtype, const void* x, int x_ld, int Cin, const void* dy, int dy_ld, int Cout,
                                   float* dw, int N, int D, int H, int W, void* stream) {
   SEG3D_REQUIRE(x && dy && dw && Cin > 0 && Cout > 0 && N > 0, "conv3d_wgrad: bad arguments");
+  if (mode == SEG3D_CONV_K3 && Cin == 1 && Cout == 16 && x_ld == 1) {
+    const int ntx = (W + 7) / 8, nty = (H + 7) / 8, ntz = (D + 7) / 8;
+    const long long ntiles = (long long)ntx * nty * ntz * N;
+    const int gx = (int)(ntiles < 2LL * seg3d_num_sms() ? ntiles : 2LL * seg3d_num_sms());
+    SEG3D_DISPATCH_DTYPE(dtype, T, (wgrad_cin1_kernel<T><<<gx, 448, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)dy, dy_ld, dw, N, D, H, W, ntx, nty, ntz)));
+    SEG3D_CHECK_LAUNCH("wgrad_cin1_kernel");
+    return SEG3D_OK;
+  }
   if (mode == SEG3D_CONV_K3) {       // tensor-core path when the shape allows it
     const int rc = seg3d_wgrad_tc(dtype, x, x_ld, Cin, dy, dy_ld, Cout, dw, N, D, H, W, (cudaStream_t)stream);
     if (rc != SEG3D_EUNSUPPORTED) return rc;

@@ -649,7 +649,7 @@ struct WgParams {
   uint32_t idesc, a_sbo, a_lbo, b_sbo, a_layout, b_layout;
 };
 
-template <typename T>
+template <typename T, int NBLK, int TPG>
 __global__ void __launch_bounds__(TC_THREADS)
 conv3d_k3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                           const WgParams p, float* __restrict__ dw) {
@@ -710,22 +710,25 @@ conv3d_k3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __gr
       int stage = 0; uint32_t phase = 0;
       const uint32_t hi_a = desc_hi(p.a_sbo, p.a_layout), hi_b = desc_hi(p.b_sbo, p.b_layout);
       const uint32_t lbo_a = ((p.a_lbo >> 4) & 0x3FFFu) << 16;
-      bool first = true;
+      constexpr uint32_t RB16 = (NBLK * 2) >> 4;               // halo row bytes / 16
+      constexpr uint32_t KSTEP_B = (2 * 10 * NBLK * 2) >> 4;   // two x-lines of the halo per K=16 step
+      const uint32_t kh_off = (uint32_t)(kh0 * 10) * RB16;
+      uint32_t accumulate = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         mbar_wait(full_bar + 8 * stage, phase);
         tc_fence_after();
         const uint32_t lo_a = ((a_base + stage * p.a_bytes) >> 4) | lbo_a;
-        const uint32_t b_addr = b_base + stage * p.b_bytes;
-        for (int tg = 0; tg < p.taps_per_group; ++tg) {
-          const int kh = kh0 + tg / 3, kw = tg % 3;
-          const uint32_t lo_b = (b_addr + (uint32_t)(kh * 10 + kw) * p.b_row_bytes) >> 4;
-          const uint32_t dcol = tmem_base + (uint32_t)(tg * p.nblk);
+        const uint32_t lo_b0 = ((b_base + stage * p.b_bytes) >> 4) + kh_off;
+#pragma unroll
+        for (int tg = 0; tg < TPG; ++tg) {
+          const uint32_t lo_b = lo_b0 + (uint32_t)((tg / 3) * 10 + tg % 3) * RB16;
+          const uint32_t dcol = tmem_base + (uint32_t)(tg * NBLK);
 #pragma unroll
           for (int k = 0; k < 8; ++k)      // 128 voxels = 8 steps of K=16 (two 8-voxel x-lines each)
-            tc_mma_f16(dcol, desc_pack(hi_a, lo_a + ((k * 2048) >> 4)), desc_pack(hi_b, lo_b + (uint32_t)((k * 2 * p.b_sbo) >> 4)),
-                       p.idesc, (!first) || (k != 0));
+            tc_mma_f16(dcol, desc_pack(hi_a, lo_a + (uint32_t)((k * 2048) >> 4)), desc_pack(hi_b, lo_b + (uint32_t)k * KSTEP_B),
+                       p.idesc, k == 0 ? accumulate : 1u);
         }
-        first = false;
+        accumulate = 1;
         tc_commit(empty_bar + 8 * stage);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
@@ -1021,7 +1024,7 @@ int seg3d_wgrad_tc(int dtype, const void* x, int x_ld, int Cin, const void* dy, 
   memset(&p, 0, sizeof(p));
   p.Cin = Cin; p.Cout = Cout; p.D = D; p.H = H; p.W = W; p.N = N;
   p.nblk = Cin >= 64 ? 64 : Cin;                    // 16, 32 or 64 (Cin = 48 etc. not produced by the networks)
-  if (Cin % p.nblk) return SEG3D_EUNSUPPORTED;
+  if (Cin % p.nblk || (p.nblk != 16 && p.nblk != 32 && p.nblk != 64)) return SEG3D_EUNSUPPORTED;
   p.mblk = Cout >= 128 ? 128 : Cout;
   if (Cout % p.mblk) return SEG3D_EUNSUPPORTED;
   p.n_ci_blk = Cin / p.nblk; p.n_co_blk = Cout / p.mblk;
@@ -1032,12 +1035,14 @@ int seg3d_wgrad_tc(int dtype, const void* x, int x_ld, int Cin, const void* dy, 
   if (ntiles <= 0 || ntiles >= (1ll << 31)) return SEG3D_EUNSUPPORTED;
   p.ntiles = (int)ntiles;
   p.a_atoms = (p.mblk + 63) / 64;
-  p.a_bytes = 2 * 16384;                            // two 64-channel atoms of 128 rows x 128 B (second may stay unloaded)
+  // M = 128 always reads two 64-channel atoms (LBO = 16 KB apart); with one real atom the second read lands in the
+  // next slab of the ring (valid shared memory, values ignored: they only reach accumulator rows >= 64)
+  p.a_bytes = p.a_atoms * 16384;
   p.a_tx = p.a_atoms * 16384;
   p.b_row_bytes = p.nblk * 2;
   p.b_tx = 180 * p.b_row_bytes;
   p.b_bytes = (p.b_tx + 1023) & ~1023;
-  p.stages = (p.a_bytes + p.b_bytes) > 50 * 1024 ? 3 : 4;
+  p.stages = (200 * 1024) / (p.a_bytes + p.b_bytes); if (p.stages > 8) p.stages = 8;
   p.a_sbo = 1024; p.a_lbo = 16384; p.a_layout = 2;
   p.b_sbo = 10 * p.b_row_bytes;
   p.b_layout = p.b_row_bytes == 128 ? 2u : (p.b_row_bytes == 64 ? 4u : 6u);
@@ -1072,16 +1077,18 @@ int seg3d_wgrad_tc(int dtype, const void* x, int x_ld, int Cin, const void* dy, 
   long long ksplit = ((long long)ctas_per_sm * seg3d_num_sms() + combos - 1) / combos;
   if (ksplit < 1) ksplit = 1;
   if (ksplit > ntiles) ksplit = ntiles;
-  const size_t smem = 1024 + (size_t)p.stages * (p.a_bytes + p.b_bytes) + (2 * p.stages + 1) * 8 + 64;
+  const size_t smem = 1024 + (size_t)p.stages * (p.a_bytes + p.b_bytes) + 16384 + (2 * p.stages + 1) * 8 + 64;
   dim3 grid((unsigned)ksplit, (unsigned)combos);
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
+#define SEG3D_LAUNCH_WG(TT, NB, TP)                                                                                          \
+  { e = cudaFuncSetAttribute(conv3d_k3_wgrad_tc_kernel<TT, NB, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e == cudaSuccess) { conv3d_k3_wgrad_tc_kernel<TT, NB, TP><<<grid, TC_THREADS, smem, st>>>(map_dy, map_x, p, dw); e = cudaGetLastError(); } }
   if (dtype == SEG3D_BF16) {
-    e = cudaFuncSetAttribute(conv3d_k3_wgrad_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) { conv3d_k3_wgrad_tc_kernel<__nv_bfloat16><<<grid, TC_THREADS, smem, st>>>(map_dy, map_x, p, dw); e = cudaGetLastError(); }
+    if (p.nblk == 64) SEG3D_LAUNCH_WG(__nv_bfloat16, 64, 3) else if (p.nblk == 32) SEG3D_LAUNCH_WG(__nv_bfloat16, 32, 9) else SEG3D_LAUNCH_WG(__nv_bfloat16, 16, 9)
   } else {
-    e = cudaFuncSetAttribute(conv3d_k3_wgrad_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) { conv3d_k3_wgrad_tc_kernel<__half><<<grid, TC_THREADS, smem, st>>>(map_dy, map_x, p, dw); e = cudaGetLastError(); }
+    if (p.nblk == 64) SEG3D_LAUNCH_WG(__half, 64, 3) else if (p.nblk == 32) SEG3D_LAUNCH_WG(__half, 32, 9) else SEG3D_LAUNCH_WG(__half, 16, 9)
   }
+#undef SEG3D_LAUNCH_WG
   if (e != cudaSuccess) { seg3d_set_error("conv3d_k3_wgrad_tc_kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
   return SEG3D_OK;
 }

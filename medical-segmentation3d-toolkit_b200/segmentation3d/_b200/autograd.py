@@ -53,7 +53,9 @@ class _Backward(object):
             self.pgrad[u['gn'] + '.bias'] = torch.zeros((c.cout,), **f32)
         nc = plan.out_channels
         c1 = plan.convs['out_block.conv1']
-        self.pgrad['out_block.conv1.weight'] = torch.zeros((27 * c1.cin * nc,), **f32)
+        # when conv1 runs zero-padded to 16 output channels on the tensor cores, its weight gradient does too
+        self.conv1_co = c1.cout
+        self.pgrad['out_block.conv1.weight'] = torch.zeros((27 * c1.cin * self.conv1_co,), **f32)
         for k, n in (('out_block.conv1.bias', nc), ('out_block.gn1.weight', nc), ('out_block.gn1.bias', nc),
                      ('out_block.conv2.weight', nc * nc), ('out_block.conv2.bias', nc),
                      ('out_block.gn2.weight', nc), ('out_block.gn2.bias', nc)):
@@ -127,7 +129,7 @@ class _Backward(object):
                      self.gy_tail.p, self.gy_tail.ld, B, vox[0], st())
         x = tail['x']
         d0 = dims[0]
-        lib.call('seg3d_conv3d_wgrad', lib.CONV_K3, dt, x.p, x.ld, x.C, self.gy_tail.p, self.gy_tail.ld, nc,
+        lib.call('seg3d_conv3d_wgrad', lib.CONV_K3, dt, x.p, x.ld, x.C, self.gy_tail.p, self.gy_tail.ld, self.conv1_co,
                  lib.ptr(pg['out_block.conv1.weight']), B, d0[0], d0[1], d0[2], st())
         dc = self.dconv['out_block.conv1']
         lib.call('seg3d_conv3d_fwd', lib.CONV_K3, dt, dc.impl, self.gy_tail.p, self.gy_tail.ld, dc.cin, lib.ptr(dc.w), None,
@@ -175,8 +177,7 @@ class _Backward(object):
                 out[name + '.weight'] = g.view(c.cin, 2, 2, 2, c.cout).permute(0, 4, 1, 2, 3)
             else:
                 k = 3 if c.mode == lib.CONV_K3 else 2
-                co = c.real_cout
-                out[name + '.weight'] = g.view(k, k, k, c.cin, co).permute(4, 3, 0, 1, 2)
+                out[name + '.weight'] = g.view(k, k, k, c.cin, c.cout)[..., :c.real_cout].permute(4, 3, 0, 1, 2)
             out[name + '.bias'] = self.pgrad[name + '.bias'][:c.real_cout]
         nc = plan.out_channels
         out['out_block.conv2.weight'] = self.pgrad['out_block.conv2.weight'].view(nc, nc, 1, 1, 1)

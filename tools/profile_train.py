@@ -35,6 +35,8 @@ def timed(name, *args):
     key = name
     if name == 'seg3d_conv3d_fwd':
         key = name + ('(tc)' if args[2] == lib.IMPL_TCGEN05 else '(simt)') + ('[stats]' if args[15] else '[dgrad]')
+    if name == 'seg3d_conv3d_wgrad':
+        key = 'wgrad mode%d %dx%d D=%d' % (args[0], args[4], args[7], args[10])
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     orig(name, *args)
