@@ -23,6 +23,7 @@ extern "C" int seg3d_conv3d_fwd(int mode, int dtype, int impl, const void* x, in
     }
     return seg3d_conv_tc(mode, dtype, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, stats, st);
   }
+  SEG3D_REQUIRE(!(dtype & SEG3D_OUT_F32), "conv3d_fwd: SEG3D_OUT_F32 needs the tensor-core path");
   if (impl == SEG3D_IMPL_SIMT)
     return seg3d_conv_simt(mode, dtype, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, stats, st);
   seg3d_set_error("conv3d_fwd: unknown impl %d", impl);

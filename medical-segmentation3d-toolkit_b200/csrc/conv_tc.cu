@@ -462,6 +462,7 @@ struct ZmParams {
   int ntx, nty, nseg, lseg, nitems;
   int ring, plane_bytes, w_slab, plane_tx, w_tx;
   int acc_cols, tmem_cols;
+  int out_f32;                      // store the raw conv result as fp32 (out_block.conv1: its rounding would dominate the probability error)
   uint32_t idesc, sbo, a_sbo, layout_type;
 };
 constexpr int ZM_NB = 4;
@@ -588,6 +589,7 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         const int ocz = oc + zl, buf = ocz % ZM_NB;
         const size_t vox = (((size_t)n * p.D + (zs + zl)) * p.H + gy) * p.W + gx;
         T* yrow = y + vox * p.y_ld;
+        float* yrow32 = reinterpret_cast<float*>(y) + vox * p.y_ld;
         mbar_wait(tfull_bar + 8 * buf, (ocz / ZM_NB) & 1);
         tc_fence_after();
         const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.acc_cols);
@@ -602,8 +604,13 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             if (valid) { s += f[jj]; ss += f[jj] * f[jj]; }
           }
           if (valid) {
-            Vec8<T> o; o.set(f); o.store(yrow + c0);
-            o.set(f + 8); o.store(yrow + c0 + 8);
+            if (p.out_f32) {
+#pragma unroll
+              for (int jj = 0; jj < 16; jj += 4) *reinterpret_cast<float4*>(yrow32 + c0 + jj) = make_float4(f[jj], f[jj + 1], f[jj + 2], f[jj + 3]);
+            } else {
+              Vec8<T> o; o.set(f); o.store(yrow + c0);
+              o.set(f + 8); o.store(yrow + c0 + 8);
+            }
           }
         }
         tc_fence_before();
@@ -808,6 +815,7 @@ cudaError_t launch_tc(bool persistent, dim3 grid, size_t smem, cudaStream_t st, 
 }  // namespace
 
 int seg3d_conv_tc_supported(int mode, int dtype, int Cin, int Cout, int x_ld, int y_ld, int D, int H, int W) {
+  dtype &= ~SEG3D_OUT_F32;
   if (mode != SEG3D_CONV_K3 && mode != SEG3D_CONV_K2S2 && mode != SEG3D_CONV_T2S2) return 0;
   if (dtype != SEG3D_F16 && dtype != SEG3D_BF16) return 0;
   if (Cin % 16 || Cout % 16 || Cout > 256 || Cin > 1024) return 0;
@@ -823,11 +831,13 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   SEG3D_REQUIRE(((uintptr_t)x) % 16 == 0 && ((uintptr_t)w) % 16 == 0 && ((uintptr_t)y) % 16 == 0, "conv_tc: pointers must be 16-byte aligned");
 
   // ---- z-marching kernel for narrow k3 layers --------------------------------------------------------
+  const int out_f32 = (dtype & SEG3D_OUT_F32) ? 1 : 0;
+  dtype &= ~SEG3D_OUT_F32;
   if (mode == SEG3D_CONV_K3 && (Cin == 16 || Cin == 32 || Cin == 64) && W % 8 == 0 && D >= 4 && env_int("SEG3D_TC_ZMARCH", 1) != 0) {
     ZmParams z;
     memset(&z, 0, sizeof(z));
     z.Cout = Cout; z.KC = Cin; z.row_bytes = Cin * 2;
-    z.D = D; z.H = H; z.W = W; z.N = N; z.y_ld = y_ld;
+    z.D = D; z.H = H; z.W = W; z.N = N; z.y_ld = y_ld; z.out_f32 = out_f32;
     z.w_slab = (Cout * z.row_bytes + 1023) & ~1023;
     z.plane_tx = 180 * z.row_bytes;
     z.plane_bytes = (z.plane_tx + 1023) & ~1023;
@@ -895,6 +905,7 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
     }
   }
 
+  SEG3D_REQUIRE(!out_f32, "conv_tc: fp32 output is only available on the z-march k3 path (Cin in {16,32,64}, W %% 8 == 0)");
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.conv = mode == SEG3D_CONV_K2S2 ? 1 : (mode == SEG3D_CONV_T2S2 ? 2 : 0);

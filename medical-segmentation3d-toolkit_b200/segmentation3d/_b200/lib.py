@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.abspath(os.path.join(_HERE, '..', '..', 'lib', 'libseg3d_b200.so'))
 
 F32, F16, BF16 = 0, 1, 2
+OUT_F32 = 0x100
 CONV_K3, CONV_K2S2, CONV_T2S2, CONV_K1 = 0, 1, 2, 3
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 NORM_NONE, NORM_FIXED, NORM_ADAPTIVE = 0, 1, 2

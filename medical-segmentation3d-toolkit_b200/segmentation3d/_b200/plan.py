@@ -307,21 +307,37 @@ class NetPlan(object):
             src = dest
         # out block: conv1 -> raw, then the fused tail
         nc = self.out_channels
-        ncp = self.convs['out_block.conv1'].cout          # = nc, or 16 when padded for the tensor-core path
-        rv1 = rawview(ncp, 0)
-        conv('out_block.conv1', src, dims[0], rv1, 'out_block.gn1')
+        c1 = self.convs['out_block.conv1']
+        ncp = c1.cout                                      # = nc, or 16 when padded for the tensor-core path
+        # conv1's raw output feeds GN1 -> 1x1x1 conv -> GN2 -> softmax directly: its storage rounding would dominate
+        # the probability error, so the tensor-core path stores it in fp32 (64 B/voxel instead of 32)
+        tail_f32 = (c1.impl == lib.IMPL_TCGEN05 and src.C in (16, 32, 64) and W % 8 == 0 and not train
+                    and os.environ.get('SEG3D_TAIL_F32', '1') != '0')
+        tail_dt = lib.F32 if tail_f32 else dt
+        if tail_f32:
+            rv1 = _View(torch.empty((B, vox[0], ncp), dtype=torch.float32, device=dev), 0, ncp, ncp)
+            sp1 = lib.ptr(ws['stats'][self.gn_index['out_block.gn1']])
+            args = (c1.mode, dt | lib.OUT_F32, c1.impl, src.p, src.ld, c1.cin, lib.ptr(c1.w), lib.ptr(c1.bias), rv1.p, rv1.ld,
+                    c1.cout, B, dims[0][0], dims[0][1], dims[0][2], sp1)
+            ops.append(lambda a=args: lib.call('seg3d_conv3d_fwd', *a, st()))
+            meta.append({'name': 'out_block.conv1', 'kind': 'conv_tc_k3', 'flops': 2.0 * B * vox[0] * 27 * c1.cin * c1.cout,
+                         'bytes': 2 * B * vox[0] * c1.cin + 4 * B * vox[0] * c1.cout + c1.w.numel() * 2})
+        else:
+            rv1 = rawview(ncp, 0)
+            conv('out_block.conv1', src, dims[0], rv1, 'out_block.gn1')
         ws['tail'] = {'x': src, 'raw': rv1, 'ncp': ncp}
         raw = rv1.buf
         g1, g2 = self.gns['out_block.gn1'], self.gns['out_block.gn2']
         s1 = lib.ptr(ws['stats'][self.gn_index['out_block.gn1']])
         s2 = lib.ptr(ws['stats2'])
-        a1 = (dt, lib.ptr(raw), ncp, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),
+        a1 = (tail_dt, lib.ptr(raw), ncp, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),
               GN_EPS, s2, B, vox[0])
         ops.append(lambda a=a1: lib.call('seg3d_outblock_tail_stats', *a, st()))
         esz = 4 if dt == lib.F32 else 2
-        meta.append({'name': 'out_block.tail_stats', 'kind': 'tail', 'flops': 0.0, 'bytes': esz * B * vox[0] * nc})
-        meta.append({'name': 'out_block.tail_probs', 'kind': 'tail', 'flops': 0.0, 'bytes': (esz + 4) * B * vox[0] * nc})
-        a2 = (dt, lib.ptr(raw), ncp, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),
+        esz = 4 if tail_f32 else esz
+        meta.append({'name': 'out_block.tail_stats', 'kind': 'tail', 'flops': 0.0, 'bytes': esz * B * vox[0] * ncp})
+        meta.append({'name': 'out_block.tail_probs', 'kind': 'tail', 'flops': 0.0, 'bytes': esz * B * vox[0] * ncp + 4 * B * vox[0] * nc})
+        a2 = (tail_dt, lib.ptr(raw), ncp, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),
               s2, lib.ptr(g2.gamma), lib.ptr(g2.beta), GN_EPS, lib.ptr(ws['probs']), B, vox[0])
         ops.append(lambda a=a2: lib.call('seg3d_outblock_tail_probs', *a, st()))
         return ws, ops
