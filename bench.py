@@ -223,7 +223,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--mode', default='fp16', choices=['fp16', 'bf16', 'fp32'])
-    ap.add_argument('--batch', type=int, default=6, help='patches per network forward')
+    ap.add_argument('--batch', type=int, default=20, help='patches per network forward')
     ap.add_argument('--volume', default='512,512,400')
     ap.add_argument('--patch', type=int, default=96)
     ap.add_argument('--stride', type=int, default=96)

@@ -30,9 +30,9 @@ def axis_counts(size_xyz, starts, ends):
 
 
 class SlidingWindow(object):
-    def __init__(self, plan, batch=4):
+    def __init__(self, plan, batch=0):
         self.plan = plan
-        self.batch = int(batch)
+        self.batch = int(batch)          # 0: let the caller pick from the patch size
         self.kernel_launches = 0
 
     def accumulate(self, vol, starts, patch_xyz, normalizer, acc):
@@ -59,6 +59,8 @@ class SlidingWindow(object):
                 raise ValueError('Unsupported normalization type.')
         st = lib.stream_ptr
         C = plan.out_channels
+        if self.batch <= 0:
+            self.batch = 6
         for b0 in range(0, n, self.batch):
             nb = min(self.batch, n - b0)
             ws, ops = plan.plan(nb, pz, py, px)

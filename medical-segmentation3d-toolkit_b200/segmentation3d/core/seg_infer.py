@@ -29,7 +29,15 @@ from segmentation3d.utils.image_tools import image_partition_by_fixed_size, is_i
 from segmentation3d.utils.model_io import get_checkpoint_folder
 from segmentation3d.utils.normalizer import normalizer_from_dict
 
-DEFAULT_PATCH_BATCH = int(os.environ.get('SEG3D_PATCH_BATCH', '6'))
+DEFAULT_PATCH_BATCH = int(os.environ.get('SEG3D_PATCH_BATCH', '0'))      # 0: chosen from the patch size
+
+
+def default_patch_batch(patch_voxels):
+    """patches per network forward: as many as fit ~40 GB of fp16 workspace (~430 B/voxel), at most 20.
+    GroupNorm is per sample, so the batch size changes throughput, not results."""
+    if DEFAULT_PATCH_BATCH > 0:
+        return DEFAULT_PATCH_BATCH
+    return int(min(20, max(1, 40e9 // (430.0 * max(1, patch_voxels)))))
 
 
 # ---- test-list readers -----------------------------------------------------------------------------
@@ -87,7 +95,7 @@ def make_model(net, spacing, normalizer=None, max_stride=16, interpolation='LINE
         model.crop_normalizers = None
     else:
         model.crop_normalizers = [normalizer_from_dict(normalizer) if isinstance(normalizer, dict) else normalizer]
-    dict.__setitem__(model, 'engine', SlidingWindow(net._current_plan(), batch or DEFAULT_PATCH_BATCH))
+    dict.__setitem__(model, 'engine', SlidingWindow(net._current_plan(), batch or 0))
     return model
 
 
@@ -157,14 +165,12 @@ def _grid(model, cfg, size_xyz, spacing, bbox_start_voxel, bbox_end_voxel, use_g
 
 
 def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_start_voxel=None, bbox_end_voxel=None,
-                               use_gpu=True, spacing=None):
+                               use_gpu=True, spacing=None, z_ready=None):
     """Device-resident core of segmentation_volume: `vol` is a CUDA float32 [z,y,x] tensor already at
     the model spacing.  Returns (mean_probs [C,z,y,x] fp32, mask [z,y,x] int8) on the device.
     shard=(rank, world): this process runs patches rank::world and the accumulators are summed with
     an all-reduce over the default process group (NCCL) before the count normalisation."""
     eng = model['engine']
-    if batch:
-        eng.batch = int(batch)
     eng.plan = model['net']._current_plan()
     Z, Y, X = vol.shape
     starts, ends = _grid(model, cfg, [X, Y, Z], spacing or model['spacing'], bbox_start_voxel, bbox_end_voxel, use_gpu)
@@ -172,7 +178,22 @@ def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_sta
     patch = [ends[0][a] - starts[0][a] for a in range(3)]
     acc = torch.zeros((model['out_channels'], Z, Y, X), dtype=torch.float32, device=vol.device)
     mine = starts if shard is None else starts[shard[0]::shard[1]]
-    eng.accumulate(vol, mine, patch, norm, acc)
+    eng.batch = int(batch) if batch else (eng.batch if eng.batch > 0 else default_patch_batch(patch[0] * patch[1] * patch[2]))
+    if z_ready is None:
+        eng.accumulate(vol, mine, patch, norm, acc)
+    else:
+        # the volume is still being uploaded slab by slab (segmentation_volume_host): run the patches in order of
+        # their last z plane and make each batch wait only for the slabs it reads.  The blend is order-independent.
+        mine = sorted(mine, key=lambda s: s[2])
+        cur = torch.cuda.current_stream()
+        for b0 in range(0, len(mine), eng.batch):
+            chunk = mine[b0:b0 + eng.batch]
+            zmax = max(s[2] for s in chunk) + patch[2]
+            for z1, ev in z_ready:
+                cur.wait_event(ev)
+                if z1 >= zmax:
+                    break
+            eng.accumulate(vol, chunk, patch, norm, acc)
     if shard is not None and shard[1] > 1:
         import torch.distributed as dist
         dist.all_reduce(acc, op=dist.ReduceOp.SUM)
@@ -190,12 +211,37 @@ def segmentation_volume_host(model, cfg, host_vol, host_mask=None, batch=None, s
     on the device and are returned as a tensor.  Copies are issued on the current stream."""
     dev = next(model['net'].parameters()).device
     vol = torch.empty(host_vol.shape, dtype=torch.float32, device=dev)
-    vol.copy_(host_vol, non_blocking=True)
-    acc, mask = segmentation_volume_device(model, cfg, vol, batch=batch, shard=shard)
+    z_ready = None
+    if host_vol.is_pinned() and cfg['partition_type'] == 'SIZE' and os.environ.get('SEG3D_OVERLAP_UPLOAD', '1') != '0':
+        # upload z slabs on a side stream so the first patches start while the rest of the volume is in flight
+        side = _side_stream(dev)
+        side.wait_stream(torch.cuda.current_stream())
+        step = max(16, int(cfg['partition_size'][2] / float(model['spacing'][2]) + 0.5))
+        z_ready = []
+        with torch.cuda.stream(side):
+            for z0 in range(0, host_vol.shape[0], step):
+                z1 = min(host_vol.shape[0], z0 + step)
+                vol[z0:z1].copy_(host_vol[z0:z1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                z_ready.append((z1, ev))
+    else:
+        vol.copy_(host_vol, non_blocking=True)
+    acc, mask = segmentation_volume_device(model, cfg, vol, batch=batch, shard=shard, z_ready=z_ready)
     if host_mask is None:
         host_mask = torch.empty(mask.shape, dtype=torch.int8, pin_memory=True)
     host_mask.copy_(mask, non_blocking=True)
     return acc, host_mask
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = str(dev)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
 
 
 def _largest_cc(mask_np, labels, keep_threshold=None):
