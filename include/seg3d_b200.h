@@ -35,7 +35,8 @@ extern "C" {
 typedef enum { SEG3D_OK = 0, SEG3D_EINVAL = -1, SEG3D_ECUDA = -2, SEG3D_EUNSUPPORTED = -3 } seg3d_status;
 typedef enum { SEG3D_F32 = 0, SEG3D_F16 = 1, SEG3D_BF16 = 2 } seg3d_dtype;
 /* OR-ed into `dtype` of seg3d_conv3d_fwd: operands stay f16/bf16 but the raw result y is stored as fp32
- * (pitch y_ld in fp32 elements).  Tensor-core z-march path only (k3, Cin in {16,32,64}, W % 8 == 0). */
+ * (pitch y_ld in fp32 elements; y_ld < Cout keeps only the first y_ld channels - used to drop zero-padded output
+ * channels).  Tensor-core z-march path only (k3, Cin in {16,32,64}, W % 8 == 0). */
 #define SEG3D_OUT_F32 0x100
 typedef enum {
   SEG3D_CONV_K3 = 0,   /* k=3 s=1 p=1   nn.Conv3d          conv_gn_relu3.py:10, vnet_inblock.py:9, vnet_outblock.py:13 */

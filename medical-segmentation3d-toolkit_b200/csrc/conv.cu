@@ -12,7 +12,8 @@ extern "C" int seg3d_conv3d_fwd(int mode, int dtype, int impl, const void* x, in
                                 double* stats, void* stream) {
   SEG3D_REQUIRE(x && w && y, "conv3d_fwd: null pointer");
   SEG3D_REQUIRE(Cin > 0 && Cout > 0 && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_fwd: bad dims");
-  SEG3D_REQUIRE(x_ld >= Cin && y_ld >= Cout, "conv3d_fwd: pitch smaller than channel count");
+  // with SEG3D_OUT_F32 the fp32 result keeps only the first y_ld channels (zero-padded output channels are dropped)
+  SEG3D_REQUIRE(x_ld >= Cin && (y_ld >= Cout || ((dtype & SEG3D_OUT_F32) && y_ld > 0)), "conv3d_fwd: pitch smaller than channel count");
   cudaStream_t st = (cudaStream_t)stream;
   if (impl == SEG3D_IMPL_AUTO)
     impl = seg3d_conv_tc_supported(mode, dtype, Cin, Cout, x_ld, y_ld, D, H, W) ? SEG3D_IMPL_TCGEN05 : SEG3D_IMPL_SIMT;

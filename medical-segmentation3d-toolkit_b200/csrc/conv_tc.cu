@@ -604,9 +604,9 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             if (valid) { s += f[jj]; ss += f[jj] * f[jj]; }
           }
           if (valid) {
-            if (p.out_f32) {
+            if (p.out_f32) {           // only the first y_ld (= real) channels are kept, densely packed
 #pragma unroll
-              for (int jj = 0; jj < 16; jj += 4) *reinterpret_cast<float4*>(yrow32 + c0 + jj) = make_float4(f[jj], f[jj + 1], f[jj + 2], f[jj + 3]);
+              for (int jj = 0; jj < 16; ++jj) if (c0 + jj < p.y_ld) yrow32[c0 + jj] = f[jj];
             } else {
               Vec8<T> o; o.set(f); o.store(yrow + c0);
               o.set(f + 8); o.store(yrow + c0 + 8);
@@ -815,11 +815,13 @@ cudaError_t launch_tc(bool persistent, dim3 grid, size_t smem, cudaStream_t st, 
 }  // namespace
 
 int seg3d_conv_tc_supported(int mode, int dtype, int Cin, int Cout, int x_ld, int y_ld, int D, int H, int W) {
+  const int out_f32 = dtype & SEG3D_OUT_F32;
   dtype &= ~SEG3D_OUT_F32;
   if (mode != SEG3D_CONV_K3 && mode != SEG3D_CONV_K2S2 && mode != SEG3D_CONV_T2S2) return 0;
   if (dtype != SEG3D_F16 && dtype != SEG3D_BF16) return 0;
   if (Cin % 16 || Cout % 16 || Cout > 256 || Cin > 1024) return 0;
-  if (x_ld % 8 || y_ld % 8) return 0;
+  if (x_ld % 8 || (!out_f32 && y_ld % 8)) return 0;
+  if (out_f32 && !(mode == SEG3D_CONV_K3 && (Cin == 16 || Cin == 32 || Cin == 64) && W % 8 == 0 && D >= 4)) return 0;
   if (mode == SEG3D_CONV_K2S2 && (D % 2 || H % 2 || W % 2)) return 0;
   return 1;
 }

@@ -315,13 +315,14 @@ class NetPlan(object):
                     and os.environ.get('SEG3D_TAIL_F32', '1') != '0')
         tail_dt = lib.F32 if tail_f32 else dt
         if tail_f32:
-            rv1 = _View(torch.empty((B, vox[0], ncp), dtype=torch.float32, device=dev), 0, ncp, ncp)
+            ncp = nc                                       # the fp32 store keeps only the real channels
+            rv1 = _View(torch.empty((B, vox[0], nc), dtype=torch.float32, device=dev), 0, nc, nc)
             sp1 = lib.ptr(ws['stats'][self.gn_index['out_block.gn1']])
             args = (c1.mode, dt | lib.OUT_F32, c1.impl, src.p, src.ld, c1.cin, lib.ptr(c1.w), lib.ptr(c1.bias), rv1.p, rv1.ld,
                     c1.cout, B, dims[0][0], dims[0][1], dims[0][2], sp1)
             ops.append(lambda a=args: lib.call('seg3d_conv3d_fwd', *a, st()))
             meta.append({'name': 'out_block.conv1', 'kind': 'conv_tc_k3', 'flops': 2.0 * B * vox[0] * 27 * c1.cin * c1.cout,
-                         'bytes': 2 * B * vox[0] * c1.cin + 4 * B * vox[0] * c1.cout + c1.w.numel() * 2})
+                         'bytes': 2 * B * vox[0] * c1.cin + 4 * B * vox[0] * nc + c1.w.numel() * 2})
         else:
             rv1 = rawview(ncp, 0)
             conv('out_block.conv1', src, dims[0], rv1, 'out_block.gn1')
