@@ -412,6 +412,8 @@ extern "C" int seg3d_gn_bwd(int dtype, int pass, const void* g0, int ld0, const 
 
 int seg3d_wgrad_tc(int dtype, const void* x, int x_ld, int Cin, const void* dy, int dy_ld, int Cout, float* dw,
                    int N, int D, int H, int W, cudaStream_t st);
+int seg3d_wgrad_s2_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const void* dy, int dy_ld, int Cout, float* dw,
+                      int N, int D, int H, int W, cudaStream_t st);
 
 extern "C" int seg3d_conv3d_wgrad(int mode, int dtype, const void* x, int x_ld, int Cin, const void* dy, int dy_ld, int Cout,
                                   float* dw, int N, int D, int H, int W, void* stream) {
@@ -426,6 +428,10 @@ extern "C" int seg3d_conv3d_wgrad(int mode, int dtype, const void* x, int x_ld, 
   }
   if (mode == SEG3D_CONV_K3) {       // tensor-core path when the shape allows it
     const int rc = seg3d_wgrad_tc(dtype, x, x_ld, Cin, dy, dy_ld, Cout, dw, N, D, H, W, (cudaStream_t)stream);
+    if (rc != SEG3D_EUNSUPPORTED) return rc;
+  }
+  if (mode == SEG3D_CONV_K2S2 || mode == SEG3D_CONV_T2S2) {
+    const int rc = seg3d_wgrad_s2_tc(mode, dtype, x, x_ld, Cin, dy, dy_ld, Cout, dw, N, D, H, W, (cudaStream_t)stream);
     if (rc != SEG3D_EUNSUPPORTED) return rc;
   }
   WgradGeom g;

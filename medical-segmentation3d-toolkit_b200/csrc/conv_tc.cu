@@ -775,6 +775,142 @@ conv3d_k3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __gr
   }
 }
 
+
+// Weight gradient of the stride-2 convolutions on the tensor cores (same scheme as the k3 kernel above):
+//   MODE 1 (k2 s2 down-conv)    dW[tap][ci][co] = sum_vo x[2vo+tap][ci] * dy[vo][co]   A = dy tile, B_tap = x through the folded-stride map
+//   MODE 2 (transposed up-conv) dW[ci][tap*Cout+co] = sum_v x[v][ci] * dy[2v+tap][co]  A_tap = dy through the folded-stride map, B = x tile
+// A CTA owns (co block, ci block, (kd,kh)) and the two kw taps; K tiles are 8x16 planes of the low-resolution grid.
+struct Wg2Params {
+  int mode, Cin, Cout, nblk, mblk, n_ci_blk, n_co_blk;
+  int D, H, W, N, ntx, nty, ntiles;          // low-resolution grid (dy for MODE 1, x for MODE 2)
+  int fold_ld, foldW, foldH;                 // folded tensor: channel pitch and the low-res W, H used in the coordinate folding
+  int stages, a_bytes, b_bytes, a_slab, b_slab, tx_bytes, a_atoms, b_row_bytes, tmem_cols;
+  uint32_t idesc, b_sbo, b_layout;
+};
+
+template <typename T, int NBLK, int MODE>
+__global__ void __launch_bounds__(TC_THREADS)
+conv3d_s2_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                          const Wg2Params p, float* __restrict__ dw) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + p.stages * p.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + p.stages * (p.a_bytes + p.b_bytes) + 16384);
+  const uint32_t full_bar = smem_u32(bars);
+  const uint32_t empty_bar = full_bar + 8 * p.stages;
+  const uint32_t done_bar = empty_bar + 8 * p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int c = blockIdx.y;
+  const int grp = c & 3; c >>= 2;
+  const int cib = c % p.n_ci_blk; const int cob = c / p.n_ci_blk;
+  const int kd = grp >> 1, kh = grp & 1;
+  const int ci0 = cib * p.nblk, co0 = cob * p.mblk;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int x0 = (t % p.ntx) * 8; t /= p.ntx;
+        const int y0 = (t % p.nty) * 16; t /= p.nty;
+        const int z = t % p.D; const int n = t / p.D;
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+        const uint32_t fb = full_bar + 8 * stage, sa = a_base + stage * p.a_bytes, sb = b_base + stage * p.b_bytes;
+        mbar_expect_tx(fb, (uint32_t)p.tx_bytes);
+        if (MODE == 1) {
+          for (int a = 0; a < p.a_atoms; ++a) tma_load_5d(sa + a * 16384, &map_dy, fb, co0 + a * 64, x0, y0, z, n);
+          for (int kw = 0; kw < 2; ++kw)
+            tma_load_5d(sb + kw * p.b_slab, &map_x, fb, kw * p.fold_ld + ci0, x0 + kh * p.foldW, y0 + kd * p.foldH, z, n);
+        } else {
+          for (int kw = 0; kw < 2; ++kw)
+            for (int a = 0; a < p.a_atoms; ++a)
+              tma_load_5d(sa + kw * p.a_slab + a * 16384, &map_dy, fb, kw * p.fold_ld + co0 + a * 64, x0 + kh * p.foldW, y0 + kd * p.foldH, z, n);
+          tma_load_5d(sb, &map_x, fb, ci0, x0, y0, z, n);
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t hi_a = desc_hi(1024, 2), hi_b = desc_hi(p.b_sbo, p.b_layout);
+      const uint32_t lbo_a = ((16384u >> 4) & 0x3FFFu) << 16;
+      constexpr uint32_t KSTEP_B = (16 * NBLK * 2) >> 4;       // 16 dense rows per K=16 step
+      const uint32_t a_slab16 = (uint32_t)p.a_slab >> 4, b_slab16 = (uint32_t)p.b_slab >> 4;
+      uint32_t accumulate = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        mbar_wait(full_bar + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t lo_a0 = ((a_base + stage * p.a_bytes) >> 4) | lbo_a;
+        const uint32_t lo_b0 = (b_base + stage * p.b_bytes) >> 4;
+#pragma unroll
+        for (int kw = 0; kw < 2; ++kw) {
+          const uint32_t lo_a = lo_a0 + (MODE == 2 ? kw * a_slab16 : 0u);
+          const uint32_t lo_b = lo_b0 + (MODE == 1 ? kw * b_slab16 : 0u);
+          const uint32_t dcol = tmem_base + (uint32_t)(kw * NBLK);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            tc_mma_f16(dcol, desc_pack(hi_a, lo_a + (uint32_t)((k * 2048) >> 4)), desc_pack(hi_b, lo_b + (uint32_t)k * KSTEP_B),
+                       p.idesc, k == 0 ? accumulate : 1u);
+        }
+        accumulate = 1;
+        tc_commit(empty_bar + 8 * stage);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(done_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    for (int kw = 0; kw < 2; ++kw) {
+      const int tap = (kd * 2 + kh) * 2 + kw;
+      for (int c0 = 0; c0 < NBLK; c0 += 16) {
+        uint32_t v[16];
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kw * NBLK + c0), v);
+        tc_wait_ld();
+        if (co < p.mblk && co0 + co < p.Cout) {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const int ci = ci0 + c0 + jj;
+            if (ci < p.Cin) {
+              const size_t o = MODE == 1 ? ((size_t)tap * p.Cin + ci) * p.Cout + co0 + co : ((size_t)ci * 8 + tap) * p.Cout + co0 + co;
+              atomicAdd(dw + o, __uint_as_float(v[jj]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1103,5 +1239,93 @@ int seg3d_wgrad_tc(int dtype, const void* x, int x_ld, int Cin, const void* dy, 
   }
 #undef SEG3D_LAUNCH_WG
   if (e != cudaSuccess) { seg3d_set_error("conv3d_k3_wgrad_tc_kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
+  return SEG3D_OK;
+}
+
+// Tensor-core wgrad of the stride-2 convolutions.  mode: SEG3D_CONV_K2S2 (x dims D,H,W; dy = D/2..) or
+// SEG3D_CONV_T2S2 (x dims D,H,W; dy = 2D..).  dw in the SIMT layouts of seg3d_conv3d_fwd.
+int seg3d_wgrad_s2_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const void* dy, int dy_ld, int Cout, float* dw,
+                      int N, int D, int H, int W, cudaStream_t st) {
+  if (dtype != SEG3D_F16 && dtype != SEG3D_BF16) return SEG3D_EUNSUPPORTED;
+  if (Cin % 16 || Cout % 16 || x_ld % 8 || dy_ld % 8) return SEG3D_EUNSUPPORTED;
+  if (env_int("SEG3D_TC_WGRAD", 1) == 0) return SEG3D_EUNSUPPORTED;
+  if (mode == SEG3D_CONV_K2S2 && (D % 2 || H % 2 || W % 2)) return SEG3D_EUNSUPPORTED;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return SEG3D_EUNSUPPORTED;
+  Wg2Params p;
+  memset(&p, 0, sizeof(p));
+  p.mode = mode == SEG3D_CONV_K2S2 ? 1 : 2;
+  p.Cin = Cin; p.Cout = Cout; p.N = N;
+  p.nblk = Cin >= 64 ? 64 : Cin;
+  if (Cin % p.nblk || (p.nblk != 16 && p.nblk != 32 && p.nblk != 64)) return SEG3D_EUNSUPPORTED;
+  p.mblk = Cout >= 128 ? 128 : Cout;
+  if (Cout % p.mblk) return SEG3D_EUNSUPPORTED;
+  p.n_ci_blk = Cin / p.nblk; p.n_co_blk = Cout / p.mblk;
+  // low-resolution iteration grid
+  const int Dl = p.mode == 1 ? D / 2 : D, Hl = p.mode == 1 ? H / 2 : H, Wl = p.mode == 1 ? W / 2 : W;
+  p.D = Dl; p.H = Hl; p.W = Wl;
+  p.ntx = (Wl + 7) / 8; p.nty = (Hl + 15) / 16;
+  const long long ntiles = (long long)p.ntx * p.nty * Dl * N;
+  if (ntiles <= 0 || ntiles >= (1ll << 31)) return SEG3D_EUNSUPPORTED;
+  p.ntiles = (int)ntiles;
+  p.a_atoms = (p.mblk + 63) / 64;
+  p.a_slab = p.a_atoms * 16384;
+  p.b_row_bytes = p.nblk * 2;
+  p.b_slab = (128 * p.b_row_bytes + 1023) & ~1023;
+  p.a_bytes = p.mode == 1 ? p.a_slab : 2 * p.a_slab;
+  p.b_bytes = p.mode == 1 ? 2 * p.b_slab : p.b_slab;
+  p.tx_bytes = (p.mode == 1 ? 1 : 2) * p.a_atoms * 16384 + (p.mode == 1 ? 2 : 1) * 128 * p.b_row_bytes;
+  p.stages = (190 * 1024) / (p.a_bytes + p.b_bytes); if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) return SEG3D_EUNSUPPORTED;
+  p.b_sbo = 8 * p.b_row_bytes;
+  p.b_layout = p.b_row_bytes == 128 ? 2u : (p.b_row_bytes == 64 ? 4u : 6u);
+  const int cols = 2 * p.nblk;
+  p.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : 128);
+  const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.nblk >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const CUtensorMapDataType tdt = dtype == SEG3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle swb = p.b_row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.b_row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap map_dy, map_x;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // dense low-resolution tensor and folded high-resolution tensor
+  const void* lo_ptr = p.mode == 1 ? dy : x;   const int lo_ld = p.mode == 1 ? dy_ld : x_ld;   const int lo_C = p.mode == 1 ? Cout : Cin;
+  const void* hi_ptr = p.mode == 1 ? x : dy;   const int hi_ld = p.mode == 1 ? x_ld : dy_ld;   const int hi_C = p.mode == 1 ? Cin : Cout;
+  const int Wh = 2 * Wl, Hh = 2 * Hl, Dh = 2 * Dl;
+  p.fold_ld = hi_ld; p.foldW = Wl; p.foldH = Hl;
+  CUtensorMap map_lo, map_hi;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)lo_C, (cuuint64_t)Wl, (cuuint64_t)Hl, (cuuint64_t)Dl, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)lo_ld * 2, (cuuint64_t)Wl * lo_ld * 2, (cuuint64_t)Hl * Wl * lo_ld * 2, (cuuint64_t)Dl * Hl * Wl * lo_ld * 2};
+    cuuint32_t box[5] = {(cuuint32_t)(p.mode == 1 ? 64 : p.nblk), 8, 16, 1, 1};
+    CUresult r = encode(&map_lo, tdt, 5, const_cast<void*>(lo_ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        p.mode == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : swb, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { seg3d_set_error("wgrad_s2_tc: cuTensorMapEncodeTiled(lo) failed with %d", (int)r); return SEG3D_ECUDA; }
+  }
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)hi_ld + hi_C, (cuuint64_t)Wh, (cuuint64_t)Hh, (cuuint64_t)Dh / 2, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)2 * hi_ld * 2, (cuuint64_t)2 * Wh * hi_ld * 2, (cuuint64_t)2 * Hh * Wh * hi_ld * 2, (cuuint64_t)Dh * Hh * Wh * hi_ld * 2};
+    cuuint32_t box[5] = {(cuuint32_t)(p.mode == 1 ? p.nblk : 64), 8, 16, 1, 1};
+    CUresult r = encode(&map_hi, tdt, 5, const_cast<void*>(hi_ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        p.mode == 1 ? swb : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { seg3d_set_error("wgrad_s2_tc: cuTensorMapEncodeTiled(hi) failed with %d", (int)r); return SEG3D_ECUDA; }
+  }
+  if (p.mode == 1) { map_dy = map_lo; map_x = map_hi; } else { map_dy = map_hi; map_x = map_lo; }
+  const int combos = p.n_co_blk * p.n_ci_blk * 4;
+  long long ksplit = ((long long)seg3d_num_sms() + combos - 1) / combos;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > ntiles) ksplit = ntiles;
+  const size_t smem = 1024 + (size_t)p.stages * (p.a_bytes + p.b_bytes) + 16384 + (2 * p.stages + 1) * 8 + 64;
+  dim3 grid((unsigned)ksplit, (unsigned)combos);
+  cudaError_t e = cudaSuccess;
+#define SEG3D_LAUNCH_WG2(TT, NB, MD)                                                                                         \
+  { e = cudaFuncSetAttribute(conv3d_s2_wgrad_tc_kernel<TT, NB, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    if (e == cudaSuccess) { conv3d_s2_wgrad_tc_kernel<TT, NB, MD><<<grid, TC_THREADS, smem, st>>>(map_dy, map_x, p, dw); e = cudaGetLastError(); } }
+#define SEG3D_LAUNCH_WG2_T(TT)                                                                                               \
+  if (p.mode == 1) { if (p.nblk == 64) SEG3D_LAUNCH_WG2(TT, 64, 1) else if (p.nblk == 32) SEG3D_LAUNCH_WG2(TT, 32, 1) else SEG3D_LAUNCH_WG2(TT, 16, 1) } \
+  else             { if (p.nblk == 64) SEG3D_LAUNCH_WG2(TT, 64, 2) else if (p.nblk == 32) SEG3D_LAUNCH_WG2(TT, 32, 2) else SEG3D_LAUNCH_WG2(TT, 16, 2) }
+  if (dtype == SEG3D_BF16) { SEG3D_LAUNCH_WG2_T(__nv_bfloat16) } else { SEG3D_LAUNCH_WG2_T(__half) }
+#undef SEG3D_LAUNCH_WG2_T
+#undef SEG3D_LAUNCH_WG2
+  if (e != cudaSuccess) { seg3d_set_error("conv3d_s2_wgrad_tc_kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
   return SEG3D_OK;
 }
