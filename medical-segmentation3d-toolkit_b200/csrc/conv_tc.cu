@@ -653,7 +653,8 @@ struct WgParams {
   int stages, a_bytes, b_bytes, a_tx, b_tx, a_atoms;
   int b_row_bytes;
   int tmem_cols;
-  uint32_t idesc, a_sbo, a_lbo, b_sbo, a_layout, b_layout;
+  int merge_kw;
+  uint32_t idesc, idesc3, a_sbo, a_lbo, b_sbo, a_layout, b_layout;
 };
 
 template <typename T, int NBLK, int TPG>
@@ -726,14 +727,28 @@ conv3d_k3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __gr
         tc_fence_after();
         const uint32_t lo_a = ((a_base + stage * p.a_bytes) >> 4) | lbo_a;
         const uint32_t lo_b0 = ((b_base + stage * p.b_bytes) >> 4) + kh_off;
+        // one MMA covers the three kw taps of a kh row: N = 3*NBLK, the three N-atoms of the MN-major B operand are
+        // the same halo rows shifted by one voxel each (LBO = one row), so A is read once per kh instead of per tap
+        if (p.merge_kw) {
 #pragma unroll
-        for (int tg = 0; tg < TPG; ++tg) {
-          const uint32_t lo_b = lo_b0 + (uint32_t)((tg / 3) * 10 + tg % 3) * RB16;
-          const uint32_t dcol = tmem_base + (uint32_t)(tg * NBLK);
+          for (int khi = 0; khi < TPG / 3; ++khi) {
+            const uint32_t lo_b = (lo_b0 + (uint32_t)(khi * 10) * RB16) | (RB16 << 16);
+            const uint32_t dcol = tmem_base + (uint32_t)(khi * 3 * NBLK);
 #pragma unroll
-          for (int k = 0; k < 8; ++k)      // 128 voxels = 8 steps of K=16 (two 8-voxel x-lines each)
-            tc_mma_f16(dcol, desc_pack(hi_a, lo_a + (uint32_t)((k * 2048) >> 4)), desc_pack(hi_b, lo_b + (uint32_t)k * KSTEP_B),
-                       p.idesc, k == 0 ? accumulate : 1u);
+            for (int k = 0; k < 8; ++k)
+              tc_mma_f16(dcol, desc_pack(hi_a, lo_a + (uint32_t)((k * 2048) >> 4)), desc_pack(hi_b, lo_b + (uint32_t)k * KSTEP_B),
+                         p.idesc3, k == 0 ? accumulate : 1u);
+          }
+        } else {
+#pragma unroll
+          for (int tg = 0; tg < TPG; ++tg) {
+            const uint32_t lo_b = lo_b0 + (uint32_t)((tg / 3) * 10 + tg % 3) * RB16;
+            const uint32_t dcol = tmem_base + (uint32_t)(tg * NBLK);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)      // 128 voxels = 8 steps of K=16 (two 8-voxel x-lines each)
+              tc_mma_f16(dcol, desc_pack(hi_a, lo_a + (uint32_t)((k * 2048) >> 4)), desc_pack(hi_b, lo_b + (uint32_t)k * KSTEP_B),
+                         p.idesc, k == 0 ? accumulate : 1u);
+          }
         }
         accumulate = 1;
         tc_commit(empty_bar + 8 * stage);
@@ -1200,6 +1215,8 @@ int seg3d_wgrad_tc(int dtype, const void* x, int x_ld, int Cin, const void* dy, 
   const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
   // MN-major A and B (bits 15, 16), M = 128, N = ci block
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.nblk >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.idesc3 = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((3 * p.nblk) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.merge_kw = env_int("SEG3D_WGRAD_MERGE_KW", 1);
   const CUtensorMapDataType tdt = dtype == SEG3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap map_dy, map_x;
   {
