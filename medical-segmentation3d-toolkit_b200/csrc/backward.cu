@@ -60,6 +60,7 @@ gn_bwd_kernel(const T* __restrict__ g0, int ld0, const T* __restrict__ g1, int l
   for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
   float s1 = 0.f, s2 = 0.f;
   const size_t nb = (size_t)n * nvox;
+#pragma unroll 2
   for (long long v = (long long)blockIdx.x * (blockDim.x / cv) + threadIdx.x / cv; v < nvox; v += vstep) {
     const size_t vv = nb + v;
     float ga[8], gb[8], gc[8], o[8], yy[8];
@@ -86,11 +87,21 @@ gn_bwd_kernel(const T* __restrict__ g0, int ld0, const T* __restrict__ g1, int l
       if (dres) { w.set(dzv); w.store(dres + vv * dres_ld + c0); }
     }
   }
-  // per-channel partials: shared-memory atomics, then one global atomic per channel per block
+  // per-channel partials: lanes that own the same channel group (lane % cv) are folded with shuffles first, then
+  // one shared-memory atomic per warp and channel, then one global atomic per channel per block
+  for (int off = 16; off >= cv; off >>= 1) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sacc[c0 + j], a0[j]);
-    if (PASS == 0) atomicAdd(&sacc[C + c0 + j], a1[j]);
+    for (int j = 0; j < 8; ++j) {
+      a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], off);
+      if (PASS == 0) a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], off);
+    }
+  }
+  if ((threadIdx.x & 31) < cv) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sacc[c0 + j], a0[j]);
+      if (PASS == 0) atomicAdd(&sacc[C + c0 + j], a1[j]);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
