@@ -33,7 +33,7 @@ for p in (ROOT, PKG):
 import numpy as np   # noqa: E402
 import torch         # noqa: E402
 
-METRIC = 'sliding-window infer Mvoxels/s (512x512x400 CT, VNet, 96^3 patches)'
+METRIC = 'sliding-window infer Mvoxels/s (512x512x400 CT, VNet, 96^3 patches)'  # BASELINE.json headline (configs[1])
 NORMALIZER = {'type': 0, 'mean': 0.0, 'stddev': 1000.0, 'clip': True}
 
 
@@ -50,11 +50,12 @@ def synth_ct(size_xyz, seed, device):
     return vol.float().contiguous()
 
 
-def make_net(mode):
-    from segmentation3d.network import vnet
+def make_net(mode, arch='vnet', classes=2):
+    import importlib
+    mod = importlib.import_module('segmentation3d.network.' + arch)
     torch.manual_seed(0)
-    net = vnet.SegmentationNet(1, 2)
-    vnet.parameters_kaiming_init(net)
+    net = mod.SegmentationNet(1, classes)
+    mod.parameters_kaiming_init(net)
     net.b200_mode = mode
     return net
 
@@ -157,8 +158,10 @@ def run_reference(args):
 
 
 def workload_config(args, size):
-    return {'workload': 'VNet(1,2) random-init sliding-window inference, volume %dx%dx%d @1mm, partition_size=%d mm, '
-                        'partition_stride=%d mm (BASELINE configs[1])' % (size[0], size[1], size[2], args.patch, args.stride),
+    return {'workload': '%s(1,%d) random-init sliding-window inference, volume %dx%dx%d @1mm, partition_size=%d mm, '
+                        'partition_stride=%d mm (BASELINE configs[%d])' % ({'vnet': 'VNet', 'vbnet': 'VBNet'}[args.arch], args.classes,
+                                                                           size[0], size[1], size[2], args.patch, args.stride,
+                                                                           1 if args.arch == 'vnet' else 3),
             'patch_batch': args.batch, 'mode': args.mode, 'shard': args.shard,
             'l2_policy': 'inputs larger than L2 (volume 419 MB + accumulators 839 MB per step)'}
 
@@ -234,6 +237,8 @@ def main():
     ap.add_argument('--task', default='infer', choices=['infer', 'train'],
                     help="'train': secondary metric, VNet 96^3 training step (BASELINE configs[2]) in patches/s")
     ap.add_argument('--train-batch', type=int, default=8)
+    ap.add_argument('--arch', default='vnet', choices=['vnet', 'vbnet'], help='vbnet + --classes 5 = BASELINE configs[3]')
+    ap.add_argument('--classes', type=int, default=2)
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -256,7 +261,7 @@ def main():
     lib.load()
     size = [int(v) for v in args.volume.split(',')]
     nvox = float(size[0]) * size[1] * size[2]
-    net = make_net(args.mode).to(dev).eval()
+    net = make_net(args.mode, args.arch, args.classes).to(dev).eval()
     model = make_model(net, spacing=[1.0, 1.0, 1.0], normalizer=NORMALIZER)
     cfg = {'partition_type': 'SIZE', 'partition_size': [args.patch] * 3, 'partition_stride': [args.stride] * 3}
     vol = synth_ct(size, 1234 + (rank if args.shard == 'cases' else 0), dev)

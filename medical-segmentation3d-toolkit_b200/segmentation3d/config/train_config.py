@@ -1,43 +1,30 @@
-"""Training configuration template (same keys as reference config/train_config.py:5-140)."""
+"""Training configuration template.  `seg_train -i <this file>` reads the module-level `cfg`
+(key-for-key compatible with the reference's config/train_config.py)."""
 from easydict import EasyDict as edict
-from segmentation3d.utils.normalizer import FixedNormalizer, AdaptiveNormalizer
+from segmentation3d.utils.normalizer import FixedNormalizer, AdaptiveNormalizer  # noqa: F401  (both usable below)
 
-__C = edict()
-cfg = __C
-
-__C.general = {}
-__C.general.imseg_list = '/path/to/train.txt'      # txt: N, then image/mask path pairs; or csv with image_path,mask_path
-__C.general.save_dir = '/path/to/model_folder'
-__C.general.model_scale = 'fine'
-__C.general.resume_epoch = -1                      # -1: from scratch
-__C.general.num_gpus = 1                           # >1: launch one process per GPU with torchrun
-__C.general.seed = 0
-
-__C.dataset = {}
-__C.dataset.num_classes = 2
-__C.dataset.spacing = [1.0, 1.0, 1.0]
-__C.dataset.crop_size = [96, 96, 96]               # multiples of max_stride = 16
-__C.dataset.sampling_method = 'HYBRID'             # CENTER | GLOBAL | MASK | HYBRID
-__C.dataset.interpolation = 'LINEAR'
-__C.dataset.crop_normalizers = [AdaptiveNormalizer()]
-__C.dataset.random_translation = [15, 15, 15]      # mm
-__C.dataset.random_scale = [0.9, 1.1]
-
-__C.loss = {}
-__C.loss.name = 'Dice'                             # Focal | Dice | CE
-__C.loss.obj_weight = [1 / 2, 1 / 2]
-__C.loss.focal_gamma = 2
-
-__C.net = {}
-__C.net.name = 'vnet'                              # module under segmentation3d.network
-
-__C.train = {}
-__C.train.epochs = 1001
-__C.train.batchsize = 8
-__C.train.num_threads = 4
-__C.train.lr = 1e-4
-__C.train.betas = (0.9, 0.999)
-__C.train.save_epochs = 100
-
-__C.debug = {}
-__C.debug.save_inputs = False
+cfg = edict(dict(
+    general=dict(
+        imseg_list='/path/to/train.txt',   # txt: N, then image/mask path pairs - or csv with image_path,mask_path columns
+        save_dir='/path/to/model_folder',  # <save_dir>/<model_scale>/checkpoints/chk_<epoch>/ is written here
+        model_scale='fine',
+        resume_epoch=-1,                   # -1: train from scratch (the model_scale folder is wiped)
+        num_gpus=1,                        # >1: launch one process per GPU with torchrun
+        seed=0,
+    ),
+    dataset=dict(
+        num_classes=2,
+        spacing=[1.0, 1.0, 1.0],           # mm; training images must already be at this spacing in this build
+        crop_size=[96, 96, 96],            # voxels, multiples of the network's max_stride (16)
+        sampling_method='HYBRID',          # CENTER | GLOBAL | MASK | HYBRID
+        interpolation='LINEAR',            # LINEAR | NN, stored in the checkpoint for inference-time resampling
+        random_translation=[15, 15, 15],   # mm
+        random_scale=[0.9, 1.1],
+    ),
+    loss=dict(name='Dice', obj_weight=[1 / 2, 1 / 2], focal_gamma=2),      # name: Focal | Dice | CE
+    net=dict(name='vnet'),                                                 # a module under segmentation3d.network
+    train=dict(epochs=1001, batchsize=8, num_threads=4, lr=1e-4, betas=(0.9, 0.999), save_epochs=100),
+    debug=dict(save_inputs=False),
+))
+# normaliser objects are stored by reference (they are serialised into params.pth through to_dict())
+cfg.dataset.crop_normalizers = [AdaptiveNormalizer()]
