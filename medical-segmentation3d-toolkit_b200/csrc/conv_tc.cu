@@ -14,8 +14,9 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
-// Several CTAs are co-resident per SM (smem and TMEM columns permitting) so one tile's prologue
-// and epilogue overlap its neighbours' main loops.
+// Kernels in this file: conv3d_tc_persistent_kernel (generic k3 / k2s2 / transposed, persistent, double-buffered
+// TMEM), conv3d_k3_zmarch_kernel (narrow k3 layers, resident weights, halo-plane reuse), conv3d_k3_wgrad_tc_kernel and
+// conv3d_s2_wgrad_tc_kernel (weight gradients, MN-major operands).
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
@@ -43,7 +44,6 @@ struct TcParams {
   int kwfuse;                       // 1: one A box (tw+2 wide) per (kd,kh) serves the three kw taps via x-shifted descriptors
   int b_slab;                       // pitch of one kw weight slab inside a stage (kwfuse)
   int row_bytes;
-  int use_base_offset;
   int conv;                         // 0: k3 s1 p1, 1: k2 s2 (folded-stride tensor map), 2: transposed k2 s2
   int cout_real, npass;             // transposed conv: real Cout; GEMM N = 8*Cout split into npass passes of p.Cout columns
   int ntaps;                        // outer tap count of the K loop (27, 9 when kw-fused, 8 for k2s2)
@@ -122,149 +122,6 @@ __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo, uint32_t layout_type) 
   return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
 }
 __device__ __forceinline__ uint64_t desc_pack(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
-
-template <typename T>
-__global__ void __launch_bounds__(TC_THREADS)
-conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                    const TcParams p, const float* __restrict__ bias, T* __restrict__ y, double* __restrict__ stats) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x A][stages x B] operand ring (1024-aligned), then barriers
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t a_base = smem_base;
-  const uint32_t b_base = smem_base + p.stages * p.a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + p.stages * (p.a_bytes + p.b_bytes));
-  const uint32_t full_bar = smem_u32(bars);                  // [stages]
-  const uint32_t empty_bar = full_bar + 8 * p.stages;        // [stages]
-  const uint32_t tmem_full_bar = empty_bar + 8 * p.stages;   // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
-  float* red = reinterpret_cast<float*>(tmem_slot + 2);      // [8] epilogue partial sums
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile -> (n, z0, y0, x0)
-  int t = blockIdx.x;
-  const int tx = t % p.ntx; t /= p.ntx;
-  const int ty = t % p.nty; t /= p.nty;
-  const int tz = t % p.ntz; const int n = t / p.ntz;
-  const int x0 = tx * p.tw, y0 = ty * p.th, z0 = tz * p.td;
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    mbar_init(tmem_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int kiters = (p.kwfuse ? 9 : 27) * p.nchunk;
-
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < kiters; ++it) {
-        const int tap = it / p.nchunk, ck = it - tap * p.nchunk;
-        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-        mbar_expect_tx(full_bar + 8 * stage, (uint32_t)p.tx_bytes);
-        if (p.kwfuse) {          // tap = kd*3 + kh; the box starts one voxel to the left and is tw+2 wide
-          const int kd = tap / 3, kh = tap % 3;
-          tma_load_5d(a_base + stage * p.a_bytes, &map_x, full_bar + 8 * stage, ck * p.KC, x0 - 1, y0 + kh - 1, z0 + kd - 1, n);
-          for (int kw = 0; kw < 3; ++kw)
-            tma_load_2d(b_base + stage * p.b_bytes + kw * p.b_slab, &map_w, full_bar + 8 * stage, ck * p.KC, (tap * 3 + kw) * p.Cout);
-        } else {
-          const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-          tma_load_5d(a_base + stage * p.a_bytes, &map_x, full_bar + 8 * stage, ck * p.KC, x0 + kw - 1, y0 + kh - 1, z0 + kd - 1, n);
-          tma_load_2d(b_base + stage * p.b_bytes, &map_w, full_bar + 8 * stage, ck * p.KC, tap * p.Cout);
-        }
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      const int ksteps = p.KC / 16;
-      for (int it = 0; it < kiters; ++it) {
-        mbar_wait(full_bar + 8 * stage, phase);
-        tc_fence_after();
-        const uint32_t a_addr = a_base + stage * p.a_bytes, b_addr = b_base + stage * p.b_bytes;
-        if (p.kwfuse) {
-          for (int kw = 0; kw < 3; ++kw)
-            for (int k = 0; k < ksteps; ++k) {
-              const uint32_t sa = a_addr + kw * p.row_bytes + k * 32;
-              const uint64_t ad = make_desc(sa, p.a_sbo, p.layout_type, p.use_base_offset ? ((sa >> 7) & 7) : 0);
-              const uint64_t bd = make_desc(b_addr + kw * p.b_slab + k * 32, p.sbo, p.layout_type);
-              tc_mma_f16(tmem_base, ad, bd, p.idesc, (it | kw | k) != 0);
-            }
-        } else {
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = make_desc(a_addr + k * 32, p.a_sbo, p.layout_type);
-            const uint64_t bd = make_desc(b_addr + k * 32, p.sbo, p.layout_type);
-            tc_mma_f16(tmem_base, ad, bd, p.idesc, (it | k) != 0);
-          }
-        }
-        tc_commit(empty_bar + 8 * stage);          // frees the smem slot when these MMAs retire
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-      }
-      tc_commit(tmem_full_bar);                    // accumulator complete
-    }
-  } else {
-    // ===== epilogue: TMEM -> registers -> (+bias, stats) -> global =====
-    const int q = warp & 3;                        // TMEM lane quarter this warp may read
-    const int r = q * 32 + lane;                   // GEMM row = voxel of the tile
-    const int lx = r % p.tw, ly = (r / p.tw) % p.th, lz = r / (p.tw * p.th);
-    const int gx = x0 + lx, gy = y0 + ly, gz = z0 + lz;
-    const bool valid = (gx < p.W) && (gy < p.H) && (gz < p.D);
-    const size_t vox = (((size_t)n * p.D + gz) * p.H + gy) * p.W + gx;
-    T* yrow = y + vox * p.y_ld;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    float s = 0.f, ss = 0.f;
-    for (int c0 = 0; c0 < p.Cout; c0 += 16) {
-      uint32_t v[16];
-      tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tc_wait_ld();
-      float f[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        f[j] = __uint_as_float(v[j]) + (bias ? bias[c0 + j] : 0.f);
-        if (valid) { s += f[j]; ss += f[j] * f[j]; }
-      }
-      if (valid) {
-        Vec8<T> o; o.set(f); o.store(yrow + c0);
-        o.set(f + 8); o.store(yrow + c0 + 8);
-      }
-    }
-    if (stats) {
-      s = warp_sum(s); ss = warp_sum(ss);
-      if (lane == 0) { red[2 * q] = s; red[2 * q + 1] = ss; }
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
-      if (warp == 2 && lane == 0) {
-        const double a = (double)red[0] + (double)red[2] + (double)red[4] + (double)red[6];
-        const double b = (double)red[1] + (double)red[3] + (double)red[5] + (double)red[7];
-        atomicAdd(stats + 2 * n, a); atomicAdd(stats + 2 * n + 1, b);
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
-  }
-}
-
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -945,21 +802,15 @@ EncodeTiledFn get_encode() {
 int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 
 template <typename T>
-cudaError_t launch_tc(bool persistent, dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mx, const CUtensorMap& mw,
+cudaError_t launch_tc(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mx, const CUtensorMap& mw,
                       const TcParams& p, const float* bias, void* y, double* stats) {
   cudaError_t e;
-  if (persistent) {
 #define SEG3D_LAUNCH_P(KCV)                                                                                              \
-    e = cudaFuncSetAttribute(conv3d_tc_persistent_kernel<T, KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                                      \
-    conv3d_tc_persistent_kernel<T, KCV><<<grid, TC_THREADS, smem, st>>>(mx, mw, p, bias, (T*)y, stats);
-    if (p.KC == 64) { SEG3D_LAUNCH_P(64) } else if (p.KC == 32) { SEG3D_LAUNCH_P(32) } else { SEG3D_LAUNCH_P(16) }
+  e = cudaFuncSetAttribute(conv3d_tc_persistent_kernel<T, KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  if (e != cudaSuccess) return e;                                                                                        \
+  conv3d_tc_persistent_kernel<T, KCV><<<grid, TC_THREADS, smem, st>>>(mx, mw, p, bias, (T*)y, stats);
+  if (p.KC == 64) { SEG3D_LAUNCH_P(64) } else if (p.KC == 32) { SEG3D_LAUNCH_P(32) } else { SEG3D_LAUNCH_P(16) }
 #undef SEG3D_LAUNCH_P
-  } else {
-    e = cudaFuncSetAttribute(conv3d_k3_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    conv3d_k3_tc_kernel<T><<<grid, TC_THREADS, smem, st>>>(mx, mw, p, bias, (T*)y, stats);
-  }
   return cudaGetLastError();
 }
 
@@ -1076,7 +927,6 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   p.nchunk = Cin / p.KC;
   const int row_bytes = p.KC * 2;
   p.row_bytes = row_bytes;
-  const bool persistent = env_int("SEG3D_TC_PERSIST", 1) != 0;
 
   // kw-fused variant (k3 only): one (tw+2)-wide box per (kd,kh) serves the three kw taps through x-shifted
   // descriptors (the swizzle is a function of the absolute smem address, so any row-aligned start works).
@@ -1112,26 +962,18 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   p.sbo = 8 * row_bytes;
   p.a_sbo = p.kwfuse ? (p.tw + 2) * row_bytes : 8 * row_bytes;
   p.layout_type = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
-  p.use_base_offset = env_int("SEG3D_TC_BASEOFF", 0);
   const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 
   int stages, ctas_per_sm = 1;
-  if (persistent) {
-    p.acc_cols = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256)));
-    p.tmem_cols = 2 * p.acc_cols;
-    ctas_per_sm = 512 / p.tmem_cols; if (ctas_per_sm > 2) ctas_per_sm = 2;
-    ctas_per_sm = env_int("SEG3D_TC_CTAS_PER_SM", ctas_per_sm);
-    if (ctas_per_sm * p.tmem_cols > 512) ctas_per_sm = 512 / p.tmem_cols;
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    stages = (200 * 1024 / ctas_per_sm) / stage_bytes;
-    if (stages > 8) stages = 8;
-  } else {
-    p.tmem_cols = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256));
-    p.acc_cols = p.tmem_cols;
-    stages = 3;
-    if (3 * stage_bytes > 200 * 1024) stages = 2;
-  }
+  p.acc_cols = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256)));
+  p.tmem_cols = 2 * p.acc_cols;
+  ctas_per_sm = 512 / p.tmem_cols; if (ctas_per_sm > 2) ctas_per_sm = 2;
+  ctas_per_sm = env_int("SEG3D_TC_CTAS_PER_SM", ctas_per_sm);
+  if (ctas_per_sm * p.tmem_cols > 512) ctas_per_sm = 512 / p.tmem_cols;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  stages = (200 * 1024 / ctas_per_sm) / stage_bytes;
+  if (stages > 8) stages = 8;
   { const int e = env_int("SEG3D_TC_STAGES", 0); if (e >= 2 && e * stage_bytes <= 200 * 1024) stages = e; }
   SEG3D_REQUIRE(stages >= 2, "conv_tc: operand ring does not fit in shared memory (stage %d bytes)", stage_bytes);
   p.stages = stages;
@@ -1166,11 +1008,10 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
     if (r != CUDA_SUCCESS) { seg3d_set_error("conv_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SEG3D_ECUDA; }
   }
   const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 64;
-  SEG3D_REQUIRE(!p.conv || persistent, "conv_tc: k2s2 / transposed conv need the persistent kernel");
   const long long max_grid = (long long)ctas_per_sm * seg3d_num_sms();
-  dim3 grid((unsigned)(persistent ? (ntiles < max_grid ? ntiles : max_grid) : ntiles));
-  cudaError_t e = dtype == SEG3D_BF16 ? launch_tc<__nv_bfloat16>(persistent, grid, smem, st, map_x, map_w, p, bias, y, stats)
-                                      : launch_tc<__half>(persistent, grid, smem, st, map_x, map_w, p, bias, y, stats);
+  dim3 grid((unsigned)(ntiles < max_grid ? ntiles : max_grid));
+  cudaError_t e = dtype == SEG3D_BF16 ? launch_tc<__nv_bfloat16>(grid, smem, st, map_x, map_w, p, bias, y, stats)
+                                      : launch_tc<__half>(grid, smem, st, map_x, map_w, p, bias, y, stats);
   if (e != cudaSuccess) { seg3d_set_error("conv_tc kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
   return SEG3D_OK;
 }
