@@ -62,13 +62,25 @@ int seg3d_device_check(int device);
  *   tap = (kd*k + kh)*k + kw.
  * bias: fp32 [Cout] (may be NULL).  stats: double [N][2] accumulated (may be NULL).
  * Supported shapes: SIMT any Cin with Cin==1 or Cin%8==0; TCGEN05 needs Cin%16==0, Cout%16==0,
- * Cout<=256, dtype f16/bf16.  AUTO picks TCGEN05 when it applies and dtype != f32. */
+ * Cout<=256, dtype f16/bf16.  AUTO picks TCGEN05 when it applies and dtype != f32.
+ * Input block (K3, Cin == 1, Cout == 16, x_ld == 1): w is the fp32 SIMT layout [27][16] for both paths; AUTO with
+ * f16/bf16 storage and W % 8 == 0 runs the im2col-in-shared-memory tensor-core kernel (csrc/conv_tc_cin1.cu), which
+ * keeps the weights fp32-accurate through a hi/lo operand split. */
 int seg3d_conv3d_fwd(int mode, int dtype, int impl,
                      const void* x, int x_ld, int Cin,
                      const void* w, const float* bias,
                      void* y, int y_ld, int Cout,
                      int N, int D, int H, int W,
                      double* stats, void* stream);
+
+/* k3 s1 p1 convolution with a narrow output (Cout = classes <= 7; vnet_outblock.py:13) on the tensor cores: the nine
+ * in-plane taps are folded into the GEMM N dimension and summed in the epilogue (csrc/conv_tc_narrow.cu).
+ * x: [N,D,H,W,Cin] f16/bf16, Cin in {16,32,64}, W % 8 == 0.  w (dtype): [3 kd][NP][Cin] with row (kh*3+kw)*Cout + co,
+ * zero rows up to NP = seg3d_conv3d_k3_narrow_np(Cout) (9*Cout rounded up to 16).  y: fp32 [N,D,H,W,Cout] dense
+ * (raw conv result + bias).  stats as in seg3d_conv3d_fwd. */
+int seg3d_conv3d_k3_narrow_np(int Cout);
+int seg3d_conv3d_k3_narrow_fwd(int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
+                               float* y, int Cout, int N, int D, int H, int W, double* stats, void* stream);
 
 /* ---- GroupNorm(1,C) apply + ReLU + residual (replaces nn.GroupNorm, nn.ReLU, `input + output`,
  * torch.cat: conv_gn_relu3.py:17-19, residual_block3.py:24,46, vnet_upblock.py:20-21) ----------

@@ -5,6 +5,9 @@ int seg3d_conv_simt(int mode, int dtype, const void* x, int x_ld, int Cin, const
                     void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st);
 int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
                   void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st);
+int seg3d_conv_cin1_tc_supported(int dtype, int Cin, int Cout, int x_ld, int y_ld, int W);
+int seg3d_conv_cin1_tc(int dtype, const void* x, const void* w, const float* bias, void* y, int y_ld,
+                       int N, int D, int H, int W, double* stats, cudaStream_t st);
 int seg3d_conv_tc_supported(int mode, int dtype, int Cin, int Cout, int x_ld, int y_ld, int D, int H, int W);
 
 extern "C" int seg3d_conv3d_fwd(int mode, int dtype, int impl, const void* x, int x_ld, int Cin, const void* w,
@@ -15,6 +18,9 @@ extern "C" int seg3d_conv3d_fwd(int mode, int dtype, int impl, const void* x, in
   // with SEG3D_OUT_F32 the fp32 result keeps only the first y_ld channels (zero-padded output channels are dropped)
   SEG3D_REQUIRE(x_ld >= Cin && (y_ld >= Cout || ((dtype & SEG3D_OUT_F32) && y_ld > 0)), "conv3d_fwd: pitch smaller than channel count");
   cudaStream_t st = (cudaStream_t)stream;
+  // input block: Cin == 1, fp32 [27][16] weights (the SIMT layout) for both implementations
+  if (impl == SEG3D_IMPL_AUTO && mode == SEG3D_CONV_K3 && seg3d_conv_cin1_tc_supported(dtype, Cin, Cout, x_ld, y_ld, W))
+    return seg3d_conv_cin1_tc(dtype, x, w, bias, y, y_ld, N, D, H, W, stats, st);
   if (impl == SEG3D_IMPL_AUTO)
     impl = seg3d_conv_tc_supported(mode, dtype, Cin, Cout, x_ld, y_ld, D, H, W) ? SEG3D_IMPL_TCGEN05 : SEG3D_IMPL_SIMT;
   if (impl == SEG3D_IMPL_TCGEN05) {

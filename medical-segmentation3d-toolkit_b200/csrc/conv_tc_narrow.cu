@@ -1,0 +1,300 @@
+// conv_tc_narrow.cu - k3 s1 p1 convolution with a NARROW output (Cout = number of classes, out_block.conv1,
+// reference vnet_outblock.py:13) on the tensor cores with the nine in-plane taps folded into the GEMM N dimension.
+//
+// At M=128 the smallest UMMA N is 16 and every MMA re-reads its 128 x K A rows from shared memory, so a plain
+// implicit GEMM spends 27 * Cin/16 A-feed-bound MMAs per 128 voxels to produce 2 useful columns.  Here the GEMM is
+//
+//     P[r][(kh,kw,co)]  =  sum_kd  sum_ci  X_{z+kd-1}[r][ci] * W[kd][(kh,kw,co)][ci]
+//
+// where r runs over the FLAT rows of a 10 x 12 (x,y) halo plane (row pitch 10 voxels) and N = 9*Cout (padded to a
+// multiple of 16): 3 * Cin/16 MMAs per plane instead of 27 * Cin/16.  The epilogue finishes the convolution with
+//
+//     y[ly][lx][co]  =  sum_{kh,kw}  P[(ly+kh)*10 + lx+kw][(kh,kw,co)]
+//
+// through a shared-memory staging tile (TMEM lane = flat row, so the nine partials of one voxel sit in nine
+// different lanes).  128 flat rows hold an 8 x 10 block of outputs (rows up to (9+2)*10+7+2 = 119).
+// As in the z-march kernel a CTA walks along z, every halo plane is loaded once by TMA and feeds three output
+// planes held in four rotating TMEM accumulators.  Output: fp32 [N][D][H][W][Cout] dense + GroupNorm partial sums.
+#include "tc_ptx.cuh"
+
+namespace {
+
+struct FoldParams {
+  int C, NP, row_bytes;             // real output channels, padded GEMM N, bytes of one voxel row (Cin * 2)
+  int D, H, W, N;
+  int ntx, nty, nseg, lseg, nitems;
+  int ring, plane_bytes, w_slab, plane_tx, w_tx;
+  int acc_cols, tmem_cols, pitch;   // staging-tile pitch in floats (odd)
+  uint32_t idesc, sbo, layout_type;
+};
+constexpr int FD_NB = 4;            // rotating TMEM accumulators
+constexpr int FD_TX = 8, FD_TY = 10, FD_HX = 10, FD_HY = 12;
+
+template <typename T, int KC>
+__global__ void __launch_bounds__(TC_THREADS)
+conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                      const FoldParams p, const float* __restrict__ bias, float* __restrict__ y, double* __restrict__ stats) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t w_base = smem_base;
+  const uint32_t a_base = smem_base + 3 * p.w_slab;
+  float* stage = reinterpret_cast<float*>(smem_al + 3 * p.w_slab + p.ring * p.plane_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 128 * p.pitch);   // 512 * pitch bytes: 8-byte aligned
+  const uint32_t full_bar = smem_u32(bars);                   // [ring]
+  const uint32_t empty_bar = full_bar + 8 * p.ring;           // [ring]
+  const uint32_t tfull_bar = empty_bar + 8 * p.ring;          // [FD_NB]
+  const uint32_t tempty_bar = tfull_bar + 8 * FD_NB;          // [FD_NB]
+  const uint32_t wfull_bar = tempty_bar + 8 * FD_NB;          // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.ring + 2 * FD_NB + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < p.ring; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int b = 0; b < FD_NB; ++b) { mbar_init(tfull_bar + 8 * b, 1); mbar_init(tempty_bar + 8 * b, 4); }
+    mbar_init(wfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull_bar, (uint32_t)p.w_tx);
+      for (int kd = 0; kd < 3; ++kd) tma_load_2d(w_base + kd * p.w_slab, &map_w, wfull_bar, 0, kd * p.NP);
+      int stage_i = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        int t = item;
+        const int seg = t % p.nseg; t /= p.nseg;
+        const int x0 = (t % p.ntx) * FD_TX; t /= p.ntx;
+        const int y0 = (t % p.nty) * FD_TY; const int n = t / p.nty;
+        const int zs = seg * p.lseg;
+        const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
+        for (int ip = 0; ip < L + 2; ++ip) {
+          mbar_wait(empty_bar + 8 * stage_i, phase ^ 1);
+          mbar_expect_tx(full_bar + 8 * stage_i, (uint32_t)p.plane_tx);
+          tma_load_5d(a_base + stage_i * p.plane_bytes, &map_x, full_bar + 8 * stage_i, 0, x0 - 1, y0 - 1, zs - 1 + ip, n);
+          if (++stage_i == p.ring) { stage_i = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(wfull_bar, 0);
+      int stage_i = 0; uint32_t phase = 0; int oc = 0;
+      constexpr int KSTEPS = KC / 16;
+      const uint32_t hi = desc_hi(p.sbo, p.layout_type);
+      const uint32_t slab16 = (uint32_t)p.w_slab >> 4, w16 = w_base >> 4;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        const int seg = item % p.nseg;
+        const int zs = seg * p.lseg;
+        const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
+        for (int ip = 0; ip < L + 2; ++ip) {
+          mbar_wait(full_bar + 8 * stage_i, phase);
+          tc_fence_after();
+          const uint32_t lo_a = (a_base + stage_i * p.plane_bytes) >> 4;
+#pragma unroll
+          for (int kd = 2; kd >= 0; --kd) {
+            const int zl = ip - kd;
+            if (zl < 0 || zl >= L) continue;
+            const int ocz = oc + zl, buf = ocz % FD_NB;
+            if (kd == 0) { mbar_wait(tempty_bar + 8 * buf, ((ocz / FD_NB) & 1) ^ 1); tc_fence_after(); }
+            const uint32_t dcol = tmem_base + (uint32_t)(buf * p.acc_cols);
+            const uint32_t lo_w = w16 + (uint32_t)kd * slab16;
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+              tc_mma_f16(dcol, desc_pack(hi, lo_a + ((k * 32) >> 4)), desc_pack(hi, lo_w + ((k * 32) >> 4)), p.idesc, (kd | k) != 0);
+          }
+          tc_commit(empty_bar + 8 * stage_i);
+          if (ip >= 2) tc_commit(tfull_bar + 8 * ((oc + ip - 2) % FD_NB));
+          if (++stage_i == p.ring) { stage_i = 0; phase ^= 1; }
+        }
+        oc += L;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                  // TMEM lane = flat halo row
+    const int lx = r & 7, ly = r >> 3;            // output voxel of this thread (r < 80)
+    const bool is_out = r < FD_TX * FD_TY;
+    const int C = p.C, nine_c = 9 * p.C, pitch = p.pitch;
+    float* my_row = stage + r * pitch;
+    const float* gather = stage + (r + 2 * ly) * pitch;       // flat row of (ly, lx) at tap (0,0)
+    float s = 0.f, ss = 0.f;
+    int cur_n = -1, oc = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      int t = item;
+      const int seg = t % p.nseg; t /= p.nseg;
+      const int x0 = (t % p.ntx) * FD_TX; t /= p.ntx;
+      const int y0 = (t % p.nty) * FD_TY; const int n = t / p.nty;
+      const int zs = seg * p.lseg;
+      const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
+      if (stats && n != cur_n) {
+        if (cur_n >= 0) {
+          s = warp_sum(s); ss = warp_sum(ss);
+          if (lane == 0) { atomicAdd(stats + 2 * cur_n, (double)s); atomicAdd(stats + 2 * cur_n + 1, (double)ss); }
+        }
+        s = 0.f; ss = 0.f; cur_n = n;
+      }
+      const int gx = x0 + lx, gy = y0 + ly;
+      const bool valid = is_out && (gx < p.W) && (gy < p.H);
+      for (int zl = 0; zl < L; ++zl) {
+        const int ocz = oc + zl, buf = ocz % FD_NB;
+        mbar_wait(tfull_bar + 8 * buf, (ocz / FD_NB) & 1);
+        tc_fence_after();
+        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.acc_cols);
+        for (int c0 = 0; c0 < p.NP; c0 += 16) {
+          uint32_t v[16];
+          tc_ld16(tcol + (uint32_t)c0, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) if (c0 + jj < nine_c) my_row[c0 + jj] = __uint_as_float(v[jj]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
+        named_bar_sync(1, 128);
+        if (valid) {
+          const size_t vox = (((size_t)n * p.D + (zs + zl)) * p.H + gy) * p.W + gx;
+          float* yo = y + vox * C;
+          if (C == 2) {
+            float a0 = bias ? bias[0] : 0.f, a1 = bias ? bias[1] : 0.f;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const float* g = gather + (kh * FD_HX + kw) * pitch + (kh * 3 + kw) * 2;
+                a0 += g[0]; a1 += g[1];
+              }
+            s += a0 + a1; ss += a0 * a0 + a1 * a1;
+            *reinterpret_cast<float2*>(yo) = make_float2(a0, a1);
+          } else {
+            for (int co = 0; co < C; ++co) {
+              float a = bias ? bias[co] : 0.f;
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw)
+                  a += gather[(kh * FD_HX + kw) * pitch + (kh * 3 + kw) * C + co];
+              s += a; ss += a * a;
+              yo[co] = a;
+            }
+          }
+        }
+        named_bar_sync(1, 128);
+      }
+      oc += L;
+    }
+    if (stats && cur_n >= 0) {
+      s = warp_sum(s); ss = warp_sum(ss);
+      if (lane == 0) { atomicAdd(stats + 2 * cur_n, (double)s); atomicAdd(stats + 2 * cur_n + 1, (double)ss); }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+}  // namespace
+
+extern "C" int seg3d_conv3d_k3_narrow_np(int C) { return C >= 1 && 9 * C <= 64 ? ((9 * C + 15) / 16) * 16 : 0; }
+
+extern "C" int seg3d_conv3d_k3_narrow_fwd(int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
+                                          float* y, int C, int N, int D, int H, int W, double* stats, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SEG3D_REQUIRE(x && w && y, "conv3d_k3_narrow_fwd: null pointer");
+  SEG3D_REQUIRE(dtype == SEG3D_F16 || dtype == SEG3D_BF16, "conv3d_k3_narrow_fwd: dtype must be f16 or bf16");
+  SEG3D_REQUIRE(Cin == 16 || Cin == 32 || Cin == 64, "conv3d_k3_narrow_fwd: Cin must be 16, 32 or 64 (got %d)", Cin);
+  const int NP = seg3d_conv3d_k3_narrow_np(C);
+  SEG3D_REQUIRE(NP > 0, "conv3d_k3_narrow_fwd: 1 <= Cout <= 7 (got %d)", C);
+  SEG3D_REQUIRE(W % 8 == 0 && x_ld % 8 == 0 && N > 0 && D > 0 && H > 0, "conv3d_k3_narrow_fwd: bad dims / pitch");
+  SEG3D_REQUIRE(((uintptr_t)x) % 16 == 0 && ((uintptr_t)w) % 16 == 0 && ((uintptr_t)y) % 8 == 0, "conv3d_k3_narrow_fwd: misaligned pointer");
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { seg3d_set_error("conv3d_k3_narrow_fwd: cuTensorMapEncodeTiled entry point not available"); return SEG3D_ECUDA; }
+
+  FoldParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = C; p.NP = NP; p.row_bytes = Cin * 2;
+  p.D = D; p.H = H; p.W = W; p.N = N;
+  p.w_slab = (NP * p.row_bytes + 1023) & ~1023;
+  p.w_tx = 3 * NP * p.row_bytes;
+  p.plane_tx = FD_HX * FD_HY * p.row_bytes;
+  p.plane_bytes = (128 * p.row_bytes + 1023) & ~1023;        // the MMA reads 128 flat rows; rows 120..127 only reach unused accumulator rows
+  p.pitch = (9 * C) | 1;
+  p.ntx = W / FD_TX; p.nty = (H + FD_TY - 1) / FD_TY;
+  p.acc_cols = NP <= 32 ? 32 : 64;
+  p.tmem_cols = FD_NB * p.acc_cols;
+  int ctas_per_sm = env_int("SEG3D_FD_CTAS_PER_SM", 2);
+  if (ctas_per_sm * p.tmem_cols > 512) ctas_per_sm = 512 / p.tmem_cols;
+  const int fixed = 3 * p.w_slab + 128 * p.pitch * 4 + 1024;
+  int ring = ((200 * 1024 / ctas_per_sm) - fixed) / p.plane_bytes;
+  if (ring > 8) ring = 8;
+  { const int e = env_int("SEG3D_FD_RING", 0); if (e >= 3) ring = e; }
+  SEG3D_REQUIRE(ring >= 3, "conv3d_k3_narrow_fwd: plane ring does not fit in shared memory");
+  p.ring = ring;
+  const long long cols = (long long)N * p.ntx * p.nty;
+  const long long want = 4ll * ctas_per_sm * seg3d_num_sms();
+  int nseg = (int)((want + cols - 1) / cols);
+  if (nseg < 1) nseg = 1;
+  int lseg = (D + nseg - 1) / nseg;
+  if (lseg < 8) lseg = D < 8 ? D : 8;
+  { const int e = env_int("SEG3D_FD_LSEG", 0); if (e >= 1) lseg = e; }
+  p.lseg = lseg; p.nseg = (D + lseg - 1) / lseg;
+  const long long nitems = cols * p.nseg;
+  SEG3D_REQUIRE(nitems > 0 && nitems < (1ll << 31), "conv3d_k3_narrow_fwd: work-item count out of range");
+  p.nitems = (int)nitems;
+  p.sbo = 8 * p.row_bytes;
+  p.layout_type = p.row_bytes == 128 ? 2u : (p.row_bytes == 64 ? 4u : 6u);
+  const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+  const CUtensorMapDataType tdt = dtype == SEG3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap map_x, map_w;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2, (cuuint64_t)D * H * W * x_ld * 2};
+    cuuint32_t box[5] = {(cuuint32_t)Cin, FD_HX, FD_HY, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&map_x, tdt, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { seg3d_set_error("conv3d_k3_narrow_fwd: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SEG3D_ECUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)3 * NP};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)Cin, (cuuint32_t)NP};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&map_w, tdt, 2, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { seg3d_set_error("conv3d_k3_narrow_fwd: cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SEG3D_ECUDA; }
+  }
+  const size_t smem = 1024 + (size_t)3 * p.w_slab + (size_t)ring * p.plane_bytes + (size_t)(128 * p.pitch + 1) * 4 +
+                      (2 * ring + 2 * FD_NB + 1) * 8 + 64;
+  const long long max_grid = (long long)ctas_per_sm * seg3d_num_sms();
+  dim3 grid((unsigned)(nitems < max_grid ? nitems : max_grid));
+  cudaError_t e = cudaSuccess;
+#define SEG3D_LAUNCH_F(TT, KCV)                                                                                          \
+  { e = cudaFuncSetAttribute(conv3d_k3_fold_kernel<TT, KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    if (e == cudaSuccess) { conv3d_k3_fold_kernel<TT, KCV><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p, bias, y, stats); e = cudaGetLastError(); } }
+  if (dtype == SEG3D_BF16) {
+    if (Cin == 64) SEG3D_LAUNCH_F(__nv_bfloat16, 64) else if (Cin == 32) SEG3D_LAUNCH_F(__nv_bfloat16, 32) else SEG3D_LAUNCH_F(__nv_bfloat16, 16)
+  } else {
+    if (Cin == 64) SEG3D_LAUNCH_F(__half, 64) else if (Cin == 32) SEG3D_LAUNCH_F(__half, 32) else SEG3D_LAUNCH_F(__half, 16)
+  }
+#undef SEG3D_LAUNCH_F
+  if (e != cudaSuccess) { seg3d_set_error("conv3d_k3_fold_kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
+  return SEG3D_OK;
+}

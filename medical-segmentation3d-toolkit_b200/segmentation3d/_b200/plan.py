@@ -36,8 +36,9 @@ def strip_prefix(sd):
 class _Conv(object):
     """One packed convolution.  `load` (re)packs in place so kernel-argument pointers stay valid."""
 
-    def __init__(self, sd, name, mode, dt, device, allow_tc, pad_cout=0, transform=None, pad_dim0=0):
+    def __init__(self, sd, name, mode, dt, device, allow_tc, pad_cout=0, transform=None, pad_dim0=0, fold=False):
         self.transform, self.pad_dim0 = transform, pad_dim0
+        self.fold, self.w_fold = fold, None
         w = self._effective_weight(sd[name + '.weight'])
         self.name, self.mode, self.dt, self.device = name, mode, dt, device
         if mode == lib.CONV_T2S2:
@@ -53,6 +54,11 @@ class _Conv(object):
         tc_ok = (allow_tc and dt != lib.F32 and self.cin % 16 == 0 and self.cout % 16 == 0 and self.cout <= 256
                  and mode in allow_tc)
         self.impl = lib.IMPL_TCGEN05 if tc_ok else lib.IMPL_SIMT
+        # input block (Cin == 1): the tensor-core kernel builds its own im2col tile and takes the fp32 SIMT weight
+        # layout, so packing follows `impl` (SIMT) while the call lets the library pick (csrc/conv_tc_cin1.cu)
+        self.cin1_tc = bool(not tc_ok and allow_tc and dt != lib.F32 and mode == lib.CONV_K3 and mode in allow_tc
+                            and self.cin == 1 and self.cout == 16 and transform is None)
+        self.call_impl = lib.IMPL_AUTO if self.cin1_tc else self.impl
         self.w, self.bias = None, None
         self.load(sd)
 
@@ -88,6 +94,17 @@ class _Conv(object):
             else:                               # [taps][Cout][Cin]
                 p = w.permute(2, 3, 4, 0, 1).reshape(-1, self.cout, self.cin)
             p = p.contiguous().to(lib.TORCH_DTYPE[self.dt])
+        if self.fold:
+            # narrow-output k3 conv (seg3d_conv3d_k3_narrow_fwd): [kd][(kh,kw,co)][ci], rows zero-padded to NP
+            C = self.real_cout
+            NP = lib.load().seg3d_conv3d_k3_narrow_np(C)
+            wf = torch.zeros((3, NP, self.cin), dtype=torch.float32, device=self.device)
+            wf[:, :9 * C] = w[:C].permute(2, 3, 4, 0, 1).reshape(3, 9 * C, self.cin)
+            wf = wf.to(lib.TORCH_DTYPE[self.dt]).contiguous()
+            if self.w_fold is None:
+                self.w_fold = wf
+            else:
+                self.w_fold.copy_(wf)
         if self.w is None:
             self.w = p
             self.bias = None if b is None else b.detach().to(device=self.device, dtype=torch.float32).contiguous()
@@ -154,8 +171,11 @@ class NetPlan(object):
                     continue
                 else:
                     m = lib.CONV_K3
+                narrow = (name == 'out_block.conv1' and self.dt != lib.F32 and lib.CONV_K3 in self.tc_modes
+                          and sd[k].shape[0] <= 7 and sd[k].shape[1] in (16, 32, 64)
+                          and os.environ.get('SEG3D_NARROW', '1') != '0')
                 self.convs[name] = _Conv(sd, name, m, self.dt, self.device, self.tc_modes,
-                                         pad_cout=16 if name == 'out_block.conv1' else 0)
+                                         pad_cout=16 if name == 'out_block.conv1' else 0, fold=narrow)
             else:
                 self.gns[name] = _GN(sd, name, self.device)
         self.w2 = sd['out_block.conv2.weight'].detach().to(self.device, torch.float32).reshape(
@@ -218,15 +238,18 @@ class NetPlan(object):
             c = self.convs[name]
             assert c.cin == x.C and c.cout == y.C, (name, c.cin, x.C, c.cout, y.C)
             sp = lib.ptr(ws['stats'][self.gn_index[stats_name]]) if stats_name else None
-            args = (c.mode, dt, c.impl, x.p, x.ld, c.cin, lib.ptr(c.w), lib.ptr(c.bias), y.p, y.ld, c.cout,
+            args = (c.mode, dt, c.call_impl, x.p, x.ld, c.cin, lib.ptr(c.w), lib.ptr(c.bias), y.p, y.ld, c.cout,
                     B, xdims[0], xdims[1], xdims[2], sp)
             ops.append(lambda a=args: lib.call('seg3d_conv3d_fwd', *a, st()))
             nv_in = B * xdims[0] * xdims[1] * xdims[2]
             taps = {lib.CONV_K3: 27, lib.CONV_K2S2: 1, lib.CONV_T2S2: 8, lib.CONV_K1: 1}[c.mode]   # MACs per INPUT voxel / (cin*cout)
             nv_out = nv_in // 8 if c.mode == lib.CONV_K2S2 else (nv_in * 8 if c.mode == lib.CONV_T2S2 else nv_in)
             esz = 4 if dt == lib.F32 else 2
-            meta.append({'name': name, 'kind': ('conv_tc' if c.impl == lib.IMPL_TCGEN05 else 'conv_simt') + '_' +
-                         {lib.CONV_K3: 'k3', lib.CONV_K2S2: 'k2s2', lib.CONV_T2S2: 't2s2', lib.CONV_K1: 'k1'}[c.mode],
+            kind = ('conv_tc' if c.impl == lib.IMPL_TCGEN05 else 'conv_simt') + '_' + \
+                {lib.CONV_K3: 'k3', lib.CONV_K2S2: 'k2s2', lib.CONV_T2S2: 't2s2', lib.CONV_K1: 'k1'}[c.mode]
+            if c.cin1_tc and xdims[2] % 8 == 0:
+                kind = 'conv_tc_cin1'
+            meta.append({'name': name, 'kind': kind,
                          'flops': 2.0 * nv_in * taps * c.cin * c.cout,
                          'bytes': esz * (nv_in * c.cin + nv_out * c.cout) + c.w.numel() * c.w.element_size()})
 
@@ -314,7 +337,17 @@ class NetPlan(object):
         tail_f32 = (c1.impl == lib.IMPL_TCGEN05 and src.C in (16, 32, 64) and W % 8 == 0 and not train
                     and os.environ.get('SEG3D_TAIL_F32', '1') != '0')
         tail_dt = lib.F32 if tail_f32 else dt
-        if tail_f32:
+        if tail_f32 and c1.fold:
+            # nine in-plane taps folded into the GEMM N dimension (csrc/conv_tc_narrow.cu), fp32 result
+            ncp = nc
+            rv1 = _View(torch.empty((B, vox[0], nc), dtype=torch.float32, device=dev), 0, nc, nc)
+            sp1 = lib.ptr(ws['stats'][self.gn_index['out_block.gn1']])
+            args = (dt, src.p, src.ld, c1.cin, lib.ptr(c1.w_fold), lib.ptr(c1.bias), rv1.p, nc,
+                    B, dims[0][0], dims[0][1], dims[0][2], sp1)
+            ops.append(lambda a=args: lib.call('seg3d_conv3d_k3_narrow_fwd', *a, st()))
+            meta.append({'name': 'out_block.conv1', 'kind': 'conv_tc_narrow', 'flops': 2.0 * B * vox[0] * 27 * c1.cin * nc,
+                         'bytes': 2 * B * vox[0] * c1.cin + 4 * B * vox[0] * nc + c1.w_fold.numel() * 2})
+        elif tail_f32:
             ncp = nc                                       # the fp32 store keeps only the real channels
             rv1 = _View(torch.empty((B, vox[0], nc), dtype=torch.float32, device=dev), 0, nc, nc)
             sp1 = lib.ptr(ws['stats'][self.gn_index['out_block.gn1']])

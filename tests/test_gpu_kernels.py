@@ -357,3 +357,72 @@ def test_forward_batch_equals_single(lib):
     yb = _plan_forward(lib, sd, x, 'fp32')
     y0 = _plan_forward(lib, sd, x[1:2], 'fp32')
     assert (yb[1:2] - y0).abs().max() <= 1e-6     # GroupNorm is per sample: batching must not change results
+
+
+NARROW_CASES = [
+    # Cin, Cout, N, D, H, W  (H not a multiple of the 10-row tile, D shorter/longer than a z segment)
+    (32, 2, 2, 16, 16, 16), (32, 5, 1, 8, 24, 8), (16, 3, 1, 5, 10, 16), (64, 2, 1, 12, 32, 8), (32, 7, 3, 32, 48, 48),
+]
+
+
+@pytest.mark.parametrize('case', NARROW_CASES, ids=lambda c: '-'.join(map(str, c)))
+@pytest.mark.parametrize('dt_name', ['F16', 'BF16'])
+def test_conv_k3_narrow_matches_torch(lib, case, dt_name):
+    """seg3d_conv3d_k3_narrow_fwd (taps folded into N, epilogue gather) vs F.conv3d on the same rounded operands."""
+    L = lib
+    dt = getattr(L, dt_name)
+    tdt = L.TORCH_DTYPE[dt]
+    Cin, C, N, D, H, W = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn((N, Cin, D, H, W), generator=g).to(tdt).float()
+    w = (torch.randn((C, Cin, 3, 3, 3), generator=g) * 0.1).to(tdt).float()
+    b = torch.randn((C,), generator=g) * 0.1
+    ref = F.conv3d(x, w, b, padding=1)
+    NP = L.load().seg3d_conv3d_k3_narrow_np(C)
+    assert NP % 16 == 0 and NP >= 9 * C
+    wf = torch.zeros((3, NP, Cin))
+    wf[:, :9 * C] = w.permute(2, 3, 4, 0, 1).reshape(3, 9 * C, Cin)
+    wf = wf.to(tdt).cuda()
+    xd = to_ndhwc(x, tdt)
+    y = torch.full((N, D, H, W, C), float('nan'), dtype=torch.float32, device='cuda')
+    stats = torch.zeros((N, 2), dtype=torch.float64, device='cuda')
+    L.call('seg3d_conv3d_k3_narrow_fwd', dt, L.ptr(xd), Cin, Cin, L.ptr(wf), L.ptr(b.cuda()), L.ptr(y), C,
+           N, D, H, W, L.ptr(stats), L.stream_ptr())
+    torch.cuda.synchronize()
+    yc = from_ndhwc(y)
+    assert not torch.isnan(yc).any()
+    assert (yc - ref).abs().max() <= 2e-4 * max(1.0, float(ref.abs().max()))     # fp32 accumulate, different order
+    s_ref = torch.stack([ref.double().flatten(1).sum(1), (ref.double() ** 2).flatten(1).sum(1)], 1)
+    assert torch.allclose(stats.cpu(), s_ref, rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize('shape', [(2, 8, 12, 16), (1, 20, 32, 24), (3, 5, 16, 8), (1, 96, 96, 96)], ids=str)
+@pytest.mark.parametrize('dt_name', ['F16', 'BF16'])
+def test_conv_cin1_tensor_core_matches_torch(lib, shape, dt_name):
+    """Input block on the tensor cores (im2col tile built in shared memory, hi/lo weight split): IMPL_AUTO vs F.conv3d
+    with the input rounded to the storage type and the weights left in fp32."""
+    L = lib
+    dt = getattr(L, dt_name)
+    tdt = L.TORCH_DTYPE[dt]
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(D * 7 + W)
+    x = torch.randn((N, 1, D, H, W), generator=g).to(tdt).float()
+    w = torch.randn((16, 1, 3, 3, 3), generator=g) * 0.3
+    b = torch.randn((16,), generator=g) * 0.1
+    ref = F.conv3d(x, w, b, padding=1)
+    ld = 32                                            # written into the upper half of a 32-channel concat buffer
+    y = torch.full((N, D, H, W, ld), float('nan'), dtype=tdt, device='cuda')
+    stats = torch.zeros((N, 2), dtype=torch.float64, device='cuda')
+    xd = x.reshape(N, D, H, W).to(tdt).cuda()
+    wp = pack_simt(w, L.CONV_K3, L)
+    L.call('seg3d_conv3d_fwd', L.CONV_K3, dt, L.IMPL_AUTO, L.ptr(xd), 1, 1, L.ptr(wp), L.ptr(b.cuda()), L.ptr(y, 16), ld, 16,
+           N, D, H, W, L.ptr(stats), L.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.isnan(y[..., :16].float()).all()      # the other half of the concat buffer is untouched
+    yc = from_ndhwc(y[..., 16:])
+    assert not torch.isnan(yc).any()
+    tol_store = 2.0 ** (-11 if dt == L.F16 else -8)    # output rounding to the storage type
+    assert (yc - ref).abs().max() <= tol_store * float(ref.abs().max()) * 1.01 + 1e-5
+    s_ref = torch.stack([ref.double().flatten(1).sum(1), (ref.double() ** 2).flatten(1).sum(1)], 1)
+    rt = 1e-5 if dt == L.F16 else 2e-4                 # the sums come from the fp32 accumulators (hi+lo weights)
+    assert torch.allclose(stats.cpu(), s_ref, rtol=rt, atol=rt * float(s_ref[:, 1].max()))
