@@ -81,6 +81,25 @@ template <> struct Vec8<__nv_bfloat16> {
   __device__ __forceinline__ void zero() { v = make_uint4(0,0,0,0); }
 };
 
+// 16 consecutive channels from fp32 registers.  `wide` (pointer 32-byte aligned): one 256-bit store for the 2-byte
+// types, so a 32-byte sector is written by a single request instead of two half-sector ones.
+template <typename T>
+__device__ __forceinline__ void store16(T* dst, const float* f, bool wide) {
+  Vec8<T> a, b;
+  a.set(f); b.set(f + 8);
+  if constexpr (sizeof(T) == 2) {
+    if (wide) {
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(a.v.x), "r"(a.v.y), "r"(a.v.z), "r"(a.v.w),
+                   "r"(b.v.x), "r"(b.v.y), "r"(b.v.z), "r"(b.v.w) : "memory");
+      return;
+    }
+  }
+  a.store(dst); b.store(dst + 8);
+}
+__host__ __device__ __forceinline__ bool wide_ok(const void* base, int ld_elems, int elem_bytes) {
+  return (((uintptr_t)base) % 32 == 0) && ((ld_elems * elem_bytes) % 32 == 0);
+}
+
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }

@@ -12,8 +12,8 @@
 // warps read it back with tcgen05.ld, add the bias, take the GroupNorm partial sums from the
 // fp32 values, and store fp16/bf16 NDHWC rows with 16-byte stores.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2.. = epilogue (TMEM lane quarter =
+// warp_id % 4; the forward kernels run 8 epilogue warps, two per quarter, splitting the accumulator columns).
 // Kernels in this file: conv3d_tc_persistent_kernel (generic k3 / k2s2 / transposed, persistent, double-buffered
 // TMEM), conv3d_k3_zmarch_kernel (narrow k3 layers, resident weights, halo-plane reuse), conv3d_k3_wgrad_tc_kernel and
 // conv3d_s2_wgrad_tc_kernel (weight gradients, MN-major operands).
@@ -22,6 +22,7 @@
 namespace {
 
 constexpr int g_kwfuse_default = 1;
+constexpr int TCE_THREADS = 320;     // forward kernels: TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 
 struct TcParams {
   int Cin, Cout, KC, nchunk;        // KC = channels per K block, nchunk = Cin / KC
@@ -44,13 +45,14 @@ struct TcParams {
   int ntaps;                        // outer tap count of the K loop (27, 9 when kw-fused, 8 for k2s2)
   int x_ld, halfW, halfH;           // k2s2 coordinate folding
   int ntiles, acc_cols;             // persistent kernel: total tiles, TMEM columns per accumulator buffer
+  int wide;                         // epilogue may use 256-bit stores (32-byte aligned rows)
 };
 
 // Persistent variant: each CTA walks tiles blockIdx.x, +gridDim.x, ...; the operand ring keeps
 // streaming across tile boundaries and two TMEM accumulator buffers let the epilogue of tile i
 // overlap the MMAs of tile i+1.  GroupNorm partial sums stay in registers until the sample changes.
 template <typename T, int KC>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TCE_THREADS)
 conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                             const TcParams p, const float* __restrict__ bias, T* __restrict__ y, double* __restrict__ stats) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -65,13 +67,13 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   const uint32_t tempty_bar = tfull_bar + 16;                 // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + 8 * b, 1); mbar_init(tempty_bar + 8 * b, 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + 8 * b, 1); mbar_init(tempty_bar + 8 * b, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -81,11 +83,11 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const int kiters = p.ntaps * p.nchunk;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp, converged: see elect_one()
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         int t = tile;
@@ -96,31 +98,31 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
         for (int it = 0; it < kiters; ++it) {
           const int tap = it / p.nchunk, ck = it - tap * p.nchunk;
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          mbar_expect_tx(full_bar + 8 * stage, (uint32_t)p.tx_bytes);
+          mbar_expect_tx_e(full_bar + 8 * stage, (uint32_t)p.tx_bytes);
           const uint32_t fb = full_bar + 8 * stage, sa = a_base + stage * p.a_bytes, sb = b_base + stage * p.b_bytes;
           if (p.conv == 2) {         // transposed conv: plain GEMM rows, weight rows of this N-pass
-            tma_load_5d(sa, &map_x, fb, ck * p.KC, x0, y0, z0, n);
-            tma_load_2d(sb, &map_w, fb, ck * p.KC, pass * p.Cout);
+            tma_load_5d_e(sa, &map_x, fb, ck * p.KC, x0, y0, z0, n);
+            tma_load_2d_e(sb, &map_w, fb, ck * p.KC, pass * p.Cout);
           } else if (p.conv == 1) {  // k2 s2: tap = (kd*2+kh)*2+kw folded into the (channel, x, y) coordinates
             const int kd = tap >> 2, kh = (tap >> 1) & 1, kw = tap & 1;
-            tma_load_5d(sa, &map_x, fb, kw * p.x_ld + ck * p.KC, x0 + kh * p.halfW, y0 + kd * p.halfH, z0, n);
-            tma_load_2d(sb, &map_w, fb, ck * p.KC, tap * p.Cout);
+            tma_load_5d_e(sa, &map_x, fb, kw * p.x_ld + ck * p.KC, x0 + kh * p.halfW, y0 + kd * p.halfH, z0, n);
+            tma_load_2d_e(sb, &map_w, fb, ck * p.KC, tap * p.Cout);
           } else if (p.kwfuse) {
             const int kd = tap / 3, kh = tap % 3;
-            tma_load_5d(sa, &map_x, fb, ck * p.KC, x0 - 1, y0 + kh - 1, z0 + kd - 1, n);
+            tma_load_5d_e(sa, &map_x, fb, ck * p.KC, x0 - 1, y0 + kh - 1, z0 + kd - 1, n);
             for (int kw = 0; kw < 3; ++kw)
-              tma_load_2d(sb + kw * p.b_slab, &map_w, fb, ck * p.KC, (tap * 3 + kw) * p.Cout);
+              tma_load_2d_e(sb + kw * p.b_slab, &map_w, fb, ck * p.KC, (tap * 3 + kw) * p.Cout);
           } else {
             const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-            tma_load_5d(sa, &map_x, fb, ck * p.KC, x0 + kw - 1, y0 + kh - 1, z0 + kd - 1, n);
-            tma_load_2d(sb, &map_w, fb, ck * p.KC, tap * p.Cout);
+            tma_load_5d_e(sa, &map_x, fb, ck * p.KC, x0 + kw - 1, y0 + kh - 1, z0 + kd - 1, n);
+            tma_load_2d_e(sb, &map_w, fb, ck * p.KC, tap * p.Cout);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, converged: see elect_one()
       int stage = 0; uint32_t phase = 0; int j = 0;
       constexpr int KSTEPS = KC / 16;
       constexpr uint32_t ROWB = KC * 2;
@@ -141,25 +143,27 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
             for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k)
-                tc_mma_f16(dcol, desc_pack(hi_a, lo_a + ((kw * ROWB + k * 32) >> 4)), desc_pack(hi_b, lo_b + kw * slab16 + ((k * 32) >> 4)),
+                tc_mma_f16_e(dcol, desc_pack(hi_a, lo_a + ((kw * ROWB + k * 32) >> 4)), desc_pack(hi_b, lo_b + kw * slab16 + ((k * 32) >> 4)),
                            p.idesc, (it | kw | k) != 0);
           } else {
 #pragma unroll
             for (int k = 0; k < KSTEPS; ++k)
-              tc_mma_f16(dcol, desc_pack(hi_a, lo_a + ((k * 32) >> 4)), desc_pack(hi_b, lo_b + ((k * 32) >> 4)), p.idesc, (it | k) != 0);
+              tc_mma_f16_e(dcol, desc_pack(hi_a, lo_a + ((k * 32) >> 4)), desc_pack(hi_b, lo_b + ((k * 32) >> 4)), p.idesc, (it | k) != 0);
           }
-          tc_commit(empty_bar + 8 * stage);
+          tc_commit_e(empty_bar + 8 * stage);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull_bar + 8 * buf);
+        tc_commit_e(tfull_bar + 8 * buf);
       }
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;             // warps 2-5 take the even 16-column chunks, warps 6-9 the odd ones
     const int r = q * 32 + lane;
     const int lx = r % p.tw, ly = (r / p.tw) % p.th, lz = r / (p.tw * p.th);
     float s = 0.f, ss = 0.f;
     int cur_n = -1, j = 0;
+    const bool wide = p.wide != 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++j) {
       int t = tile;
       const int pass = t % p.npass; t /= p.npass;
@@ -181,10 +185,9 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
       mbar_wait(tfull_bar + 8 * buf, (j >> 1) & 1);
       tc_fence_after();
       const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.acc_cols);
-      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
-        uint32_t v[16];
-        tc_ld16(tcol + (uint32_t)c0, v);
-        tc_wait_ld();
+      // this warp's 16-column chunks: half, half+2, ...; the TMEM load of the next chunk is in flight while the
+      // current one is converted and stored
+      auto emit = [&](const uint32_t* v, int c0) {
         float f[16];
         int co = c0;
         T* dst = yrow + c0;
@@ -199,10 +202,21 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
           f[jj] = __uint_as_float(v[jj]) + (bias ? bias[co + jj] : 0.f);
           if (valid) { s += f[jj]; ss += f[jj] * f[jj]; }
         }
-        if (valid) {
-          Vec8<T> o; o.set(f); o.store(dst);
-          o.set(f + 8); o.store(dst + 8);
-        }
+        if (valid) store16<T>(dst, f, wide);
+      };
+      uint32_t va[16], vb[16];
+      int c0 = half * 16;
+      if (c0 < p.Cout) tc_ld16(tcol + (uint32_t)c0, va);
+      while (c0 < p.Cout) {
+        tc_wait_ld();
+        if (c0 + 32 < p.Cout) tc_ld16(tcol + (uint32_t)(c0 + 32), vb);
+        emit(va, c0);
+        c0 += 32;
+        if (c0 >= p.Cout) break;
+        tc_wait_ld();
+        if (c0 + 32 < p.Cout) tc_ld16(tcol + (uint32_t)(c0 + 32), va);
+        emit(vb, c0);
+        c0 += 32;
       }
       tc_fence_before();
       __syncwarp();
@@ -229,22 +243,28 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
 // shared memory).  A CTA owns an 8(x) x 16(y) column and walks along z: every input plane (a
 // 10 x 18 voxel halo box, one TMA load) is read from L2 exactly once and feeds the three output planes
 // z-1, z, z+1 through 27 row-shifted descriptors (the 128B/64B/32B swizzle is a function of the absolute
-// shared-memory address, so any row-aligned start address addresses the halo correctly).  Four TMEM
-// accumulators rotate: three receive MMAs while the fourth is drained by the epilogue warps.
+// shared-memory address, so any row-aligned start address addresses the halo correctly).  nb TMEM
+// accumulators rotate: three receive MMAs while the others are drained by the epilogue warps.
 // L2->SM traffic per output voxel drops from 27 (per-tap boxes) to ~1.5 voxel reads.
+// At M=128 an MMA re-reads its 128 x 16 A rows from shared memory (32 cycles) whatever N is, so N <= 32 is
+// A-feed bound at half the tensor rate.  The three output planes an input plane contributes to sit in adjacent
+// accumulators and the weight slabs are stored [(kh,kw)][kd=2,1,0][Cout][Cin], so ONE MMA with N = 3*Cout covers
+// all three kd taps of a (kh,kw) position: 9*Cin/16 MMAs per plane instead of 27*Cin/16, each math-bound.
 struct ZmParams {
   int Cout, KC, row_bytes;
   int D, H, W, N, y_ld;
   int ntx, nty, nseg, lseg, nitems;
   int ring, plane_bytes, w_slab, plane_tx, w_tx;
   int acc_cols, tmem_cols;
+  int nb, maxblk;                   // rotating TMEM accumulators; output planes one MMA may cover (N = maxblk * Cout)
+  int wide;                         // epilogue may use 256-bit stores
   int out_f32;                      // store the raw conv result as fp32 (out_block.conv1: its rounding would dominate the probability error)
-  uint32_t idesc, sbo, a_sbo, layout_type;
+  uint32_t idesc0, n8, sbo, a_sbo, layout_type;   // instruction descriptor without N; N/8 of one block (Cout >> 3)
 };
-constexpr int ZM_NB = 4;
+constexpr int ZM_MAXNB = 8;
 
 template <typename T, int KC>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TCE_THREADS)
 conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                         const ZmParams p, const float* __restrict__ bias, T* __restrict__ y, double* __restrict__ stats) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -255,17 +275,17 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + 27 * p.w_slab + p.ring * p.plane_bytes);
   const uint32_t full_bar = smem_u32(bars);                   // [ring]
   const uint32_t empty_bar = full_bar + 8 * p.ring;           // [ring]
-  const uint32_t tfull_bar = empty_bar + 8 * p.ring;          // [ZM_NB]
-  const uint32_t tempty_bar = tfull_bar + 8 * ZM_NB;          // [ZM_NB]
-  const uint32_t wfull_bar = tempty_bar + 8 * ZM_NB;          // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.ring + 2 * ZM_NB + 1);
+  const uint32_t tfull_bar = empty_bar + 8 * p.ring;          // [ZM_MAXNB]
+  const uint32_t tempty_bar = tfull_bar + 8 * ZM_MAXNB;       // [ZM_MAXNB]
+  const uint32_t wfull_bar = tempty_bar + 8 * ZM_MAXNB;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.ring + 2 * ZM_MAXNB + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     for (int s = 0; s < p.ring; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int b = 0; b < ZM_NB; ++b) { mbar_init(tfull_bar + 8 * b, 1); mbar_init(tempty_bar + 8 * b, 4); }
+    for (int b = 0; b < ZM_MAXNB; ++b) { mbar_init(tfull_bar + 8 * b, 1); mbar_init(tempty_bar + 8 * b, 8); }
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -276,12 +296,13 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(wfull_bar, (uint32_t)p.w_tx);
-      for (int tap = 0; tap < 27; ++tap) tma_load_2d(w_base + tap * p.w_slab, &map_w, wfull_bar, 0, tap * p.Cout);
+    {   // whole warp, converged: see elect_one()
+      mbar_expect_tx_e(wfull_bar, (uint32_t)p.w_tx);
+      for (int tap = 0; tap < 27; ++tap)          // smem slot order [(kh,kw)][kd = 2,1,0]
+        tma_load_2d_e(w_base + ((tap % 9) * 3 + (2 - tap / 9)) * p.w_slab, &map_w, wfull_bar, 0, tap * p.Cout);
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
         int t = item;
@@ -292,20 +313,21 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
         for (int ip = 0; ip < L + 2; ++ip) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          mbar_expect_tx(full_bar + 8 * stage, (uint32_t)p.plane_tx);
-          tma_load_5d(a_base + stage * p.plane_bytes, &map_x, full_bar + 8 * stage, 0, x0 - 1, y0 - 1, zs - 1 + ip, n);
+          mbar_expect_tx_e(full_bar + 8 * stage, (uint32_t)p.plane_tx);
+          tma_load_5d_e(a_base + stage * p.plane_bytes, &map_x, full_bar + 8 * stage, 0, x0 - 1, y0 - 1, zs - 1 + ip, n);
           if (++stage == p.ring) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                             // whole warp, converged; see elect_one()
       mbar_wait(wfull_bar, 0);
       int stage = 0; uint32_t phase = 0; int oc = 0;
       constexpr int KSTEPS = KC / 16;
       constexpr uint32_t ROWB = KC * 2;
       const uint32_t hi_a = desc_hi(p.a_sbo, p.layout_type), hi_b = desc_hi(p.sbo, p.layout_type);
       const uint32_t slab16 = (uint32_t)p.w_slab >> 4, w16 = w_base >> 4;
+      const int nb = p.nb;
       for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
         const int seg = item % p.nseg;
         const int zs = seg * p.lseg;
@@ -314,26 +336,45 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
           const uint32_t lo_a = (a_base + stage * p.plane_bytes) >> 4;
-#pragma unroll
-          for (int kd = 2; kd >= 0; --kd) {
-            const int zl = ip - kd;
-            if (zl < 0 || zl >= L) continue;
-            const int ocz = oc + zl, buf = ocz % ZM_NB;
-            if (kd == 0) { mbar_wait(tempty_bar + 8 * buf, ((ocz / ZM_NB) & 1) ^ 1); tc_fence_after(); }
-            const uint32_t dcol = tmem_base + (uint32_t)(buf * p.acc_cols);
-            const uint32_t lo_w = w16 + (uint32_t)(kd * 9) * slab16;
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-              for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-                for (int k = 0; k < KSTEPS; ++k)
-                  tc_mma_f16(dcol, desc_pack(hi_a, lo_a + (((kh * 10 + kw) * ROWB + k * 32) >> 4)),
-                             desc_pack(hi_b, lo_w + (uint32_t)(kh * 3 + kw) * slab16 + ((k * 32) >> 4)),
-                             p.idesc, (kd | kh | kw | k) != 0);
+          const int kd_hi = ip < 2 ? ip : 2;                      // kd with 0 <= ip - kd < L
+          const int kd_lo = ip - (L - 1) > 0 ? ip - (L - 1) : 0;
+          const bool fresh = kd_lo == 0;                          // output plane ip receives its first contribution
+          if (fresh) { const int ocz = oc + ip; mbar_wait(tempty_bar + 8 * (ocz % nb), ((ocz / nb) & 1) ^ 1); tc_fence_after(); }
+          // runs of adjacent accumulators (planes ip-kd for kd = hi..lo ascend; a run ends at the ring wrap or at maxblk)
+          uint32_t dA = 0, bA = 0, iA = 0, dB = 0, bB = 0, iB = 0, dC = 0, bC = 0, iC = 0; int nruns = 0;
+          for (int kd = kd_hi; kd >= kd_lo;) {
+            const int b0 = (oc + ip - kd) % nb;
+            int len = 1;
+            while (kd - len >= kd_lo && b0 + len < nb && len < p.maxblk) ++len;
+            const uint32_t d = tmem_base + (uint32_t)(b0 * p.acc_cols), bo = (uint32_t)(2 - kd) * slab16, id = p.idesc0 | ((uint32_t)len * p.n8) << 17;
+            if (nruns == 0) { dA = d; bA = bo; iA = id; } else if (nruns == 1) { dB = d; bB = bo; iB = id; } else { dC = d; bC = bo; iC = id; }
+            ++nruns;
+            kd -= len;
           }
-          tc_commit(empty_bar + 8 * stage);
-          if (ip >= 2) tc_commit(tfull_bar + 8 * ((oc + ip - 2) % ZM_NB));
+          // the very first MMA into a fresh plane must overwrite: that plane (kd = 0, the last block) is issued on its own
+          const uint32_t dF = tmem_base + (uint32_t)(((oc + ip) % nb) * p.acc_cols);
+          const uint32_t id1 = p.idesc0 | (p.n8 << 17);
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                const uint32_t da = lo_a + (((kh * 10 + kw) * ROWB + k * 32) >> 4);
+                const uint32_t db = w16 + (uint32_t)((kh * 3 + kw) * 3) * slab16 + ((k * 32) >> 4);
+                if (kh == 0 && kw == 0 && k == 0 && fresh) {
+                  tc_mma_f16_e(dF, desc_pack(hi_a, da), desc_pack(hi_b, db + 2 * slab16), id1, 0);
+                  for (int kd = kd_hi; kd >= 1; --kd)
+                    tc_mma_f16_e(tmem_base + (uint32_t)(((oc + ip - kd) % nb) * p.acc_cols), desc_pack(hi_a, da),
+                               desc_pack(hi_b, db + (uint32_t)(2 - kd) * slab16), id1, 1);
+                } else {
+                  tc_mma_f16_e(dA, desc_pack(hi_a, da), desc_pack(hi_b, db + bA), iA, 1);
+                  if (nruns > 1) tc_mma_f16_e(dB, desc_pack(hi_a, da), desc_pack(hi_b, db + bB), iB, 1);
+                  if (nruns > 2) tc_mma_f16_e(dC, desc_pack(hi_a, da), desc_pack(hi_b, db + bC), iC, 1);
+                }
+              }
+          tc_commit_e(empty_bar + 8 * stage);
+          if (ip >= 2) tc_commit_e(tfull_bar + 8 * ((oc + ip - 2) % nb));
           if (++stage == p.ring) { stage = 0; phase ^= 1; }
         }
         oc += L;
@@ -341,10 +382,12 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;             // warps 2-5: even 16-column chunks, warps 6-9: odd ones
     const int r = q * 32 + lane;
     const int lx = r & 7, ly = r >> 3;
     float s = 0.f, ss = 0.f;
     int cur_n = -1, oc = 0;
+    const bool wide = p.wide != 0;
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       int t = item;
       const int seg = t % p.nseg; t /= p.nseg;
@@ -362,14 +405,14 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       const int gx = x0 + lx, gy = y0 + ly;
       const bool valid = (gx < p.W) && (gy < p.H);
       for (int zl = 0; zl < L; ++zl) {
-        const int ocz = oc + zl, buf = ocz % ZM_NB;
+        const int ocz = oc + zl, buf = ocz % p.nb;
         const size_t vox = (((size_t)n * p.D + (zs + zl)) * p.H + gy) * p.W + gx;
         T* yrow = y + vox * p.y_ld;
         float* yrow32 = reinterpret_cast<float*>(y) + vox * p.y_ld;
-        mbar_wait(tfull_bar + 8 * buf, (ocz / ZM_NB) & 1);
+        mbar_wait(tfull_bar + 8 * buf, (ocz / p.nb) & 1);
         tc_fence_after();
         const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.acc_cols);
-        for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+        for (int c0 = half * 16; c0 < p.Cout; c0 += 32) {
           uint32_t v[16];
           tc_ld16(tcol + (uint32_t)c0, v);
           tc_wait_ld();
@@ -384,8 +427,7 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 #pragma unroll
               for (int jj = 0; jj < 16; ++jj) if (c0 + jj < p.y_ld) yrow32[c0 + jj] = f[jj];
             } else {
-              Vec8<T> o; o.set(f); o.store(yrow + c0);
-              o.set(f + 8); o.store(yrow + c0 + 8);
+              store16<T>(yrow + c0, f, wide);
             }
           }
         }
@@ -447,7 +489,7 @@ conv3d_k3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __gr
   const uint32_t empty_bar = full_bar + 8 * p.stages;
   const uint32_t done_bar = empty_bar + 8 * p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
   // blockIdx.y -> (co block, ci block, tap group)
   int c = blockIdx.y;
@@ -471,10 +513,10 @@ conv3d_k3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __gr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp, converged: see elect_one()
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         int t = tile;
@@ -482,15 +524,15 @@ conv3d_k3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __gr
         const int y0 = (t % p.nty) * 16; t /= p.nty;
         const int z = t % p.D; const int n = t / p.D;
         mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-        mbar_expect_tx(full_bar + 8 * stage, (uint32_t)(p.a_tx + p.b_tx));
+        mbar_expect_tx_e(full_bar + 8 * stage, (uint32_t)(p.a_tx + p.b_tx));
         for (int a = 0; a < p.a_atoms; ++a)
-          tma_load_5d(a_base + stage * p.a_bytes + a * 16384, &map_dy, full_bar + 8 * stage, co0 + a * 64, x0, y0, z, n);
-        tma_load_5d(b_base + stage * p.b_bytes, &map_x, full_bar + 8 * stage, ci0, x0 - 1, y0 - 1, z + kd - 1, n);
+          tma_load_5d_e(a_base + stage * p.a_bytes + a * 16384, &map_dy, full_bar + 8 * stage, co0 + a * 64, x0, y0, z, n);
+        tma_load_5d_e(b_base + stage * p.b_bytes, &map_x, full_bar + 8 * stage, ci0, x0 - 1, y0 - 1, z + kd - 1, n);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, converged: see elect_one()
       int stage = 0; uint32_t phase = 0;
       const uint32_t hi_a = desc_hi(p.a_sbo, p.a_layout), hi_b = desc_hi(p.b_sbo, p.b_layout);
       const uint32_t lbo_a = ((p.a_lbo >> 4) & 0x3FFFu) << 16;
@@ -512,7 +554,7 @@ conv3d_k3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __gr
             const uint32_t dcol = tmem_base + (uint32_t)(khi * 3 * NBLK);
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              tc_mma_f16(dcol, desc_pack(hi_a, lo_a + (uint32_t)((k * 2048) >> 4)), desc_pack(hi_b, lo_b + (uint32_t)k * KSTEP_B),
+              tc_mma_f16_e(dcol, desc_pack(hi_a, lo_a + (uint32_t)((k * 2048) >> 4)), desc_pack(hi_b, lo_b + (uint32_t)k * KSTEP_B),
                          p.idesc3, k == 0 ? accumulate : 1u);
           }
         } else {
@@ -522,15 +564,15 @@ conv3d_k3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __gr
             const uint32_t dcol = tmem_base + (uint32_t)(tg * NBLK);
 #pragma unroll
             for (int k = 0; k < 8; ++k)      // 128 voxels = 8 steps of K=16 (two 8-voxel x-lines each)
-              tc_mma_f16(dcol, desc_pack(hi_a, lo_a + (uint32_t)((k * 2048) >> 4)), desc_pack(hi_b, lo_b + (uint32_t)k * KSTEP_B),
+              tc_mma_f16_e(dcol, desc_pack(hi_a, lo_a + (uint32_t)((k * 2048) >> 4)), desc_pack(hi_b, lo_b + (uint32_t)k * KSTEP_B),
                          p.idesc, k == 0 ? accumulate : 1u);
           }
         }
         accumulate = 1;
-        tc_commit(empty_bar + 8 * stage);
+        tc_commit_e(empty_bar + 8 * stage);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      tc_commit(done_bar);
+      tc_commit_e(done_bar);
     }
   } else {
     // epilogue (once): TMEM lane = co, column = (tap in group, ci)
@@ -593,7 +635,7 @@ conv3d_s2_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __gr
   const uint32_t empty_bar = full_bar + 8 * p.stages;
   const uint32_t done_bar = empty_bar + 8 * p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   int c = blockIdx.y;
   const int grp = c & 3; c >>= 2;
   const int cib = c % p.n_ci_blk; const int cob = c / p.n_ci_blk;
@@ -614,10 +656,10 @@ conv3d_s2_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __gr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp, converged: see elect_one()
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         int t = tile;
@@ -626,22 +668,22 @@ conv3d_s2_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __gr
         const int z = t % p.D; const int n = t / p.D;
         mbar_wait(empty_bar + 8 * stage, phase ^ 1);
         const uint32_t fb = full_bar + 8 * stage, sa = a_base + stage * p.a_bytes, sb = b_base + stage * p.b_bytes;
-        mbar_expect_tx(fb, (uint32_t)p.tx_bytes);
+        mbar_expect_tx_e(fb, (uint32_t)p.tx_bytes);
         if (MODE == 1) {
-          for (int a = 0; a < p.a_atoms; ++a) tma_load_5d(sa + a * 16384, &map_dy, fb, co0 + a * 64, x0, y0, z, n);
+          for (int a = 0; a < p.a_atoms; ++a) tma_load_5d_e(sa + a * 16384, &map_dy, fb, co0 + a * 64, x0, y0, z, n);
           for (int kw = 0; kw < 2; ++kw)
-            tma_load_5d(sb + kw * p.b_slab, &map_x, fb, kw * p.fold_ld + ci0, x0 + kh * p.foldW, y0 + kd * p.foldH, z, n);
+            tma_load_5d_e(sb + kw * p.b_slab, &map_x, fb, kw * p.fold_ld + ci0, x0 + kh * p.foldW, y0 + kd * p.foldH, z, n);
         } else {
           for (int kw = 0; kw < 2; ++kw)
             for (int a = 0; a < p.a_atoms; ++a)
-              tma_load_5d(sa + kw * p.a_slab + a * 16384, &map_dy, fb, kw * p.fold_ld + co0 + a * 64, x0 + kh * p.foldW, y0 + kd * p.foldH, z, n);
-          tma_load_5d(sb, &map_x, fb, ci0, x0, y0, z, n);
+              tma_load_5d_e(sa + kw * p.a_slab + a * 16384, &map_dy, fb, kw * p.fold_ld + co0 + a * 64, x0 + kh * p.foldW, y0 + kd * p.foldH, z, n);
+          tma_load_5d_e(sb, &map_x, fb, ci0, x0, y0, z, n);
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, converged: see elect_one()
       int stage = 0; uint32_t phase = 0;
       const uint32_t hi_a = desc_hi(1024, 2), hi_b = desc_hi(p.b_sbo, p.b_layout);
       const uint32_t lbo_a = ((16384u >> 4) & 0x3FFFu) << 16;
@@ -660,14 +702,14 @@ conv3d_s2_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __gr
           const uint32_t dcol = tmem_base + (uint32_t)(kw * NBLK);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            tc_mma_f16(dcol, desc_pack(hi_a, lo_a + (uint32_t)((k * 2048) >> 4)), desc_pack(hi_b, lo_b + (uint32_t)k * KSTEP_B),
+            tc_mma_f16_e(dcol, desc_pack(hi_a, lo_a + (uint32_t)((k * 2048) >> 4)), desc_pack(hi_b, lo_b + (uint32_t)k * KSTEP_B),
                        p.idesc, k == 0 ? accumulate : 1u);
         }
         accumulate = 1;
-        tc_commit(empty_bar + 8 * stage);
+        tc_commit_e(empty_bar + 8 * stage);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      tc_commit(done_bar);
+      tc_commit_e(done_bar);
     }
   } else {
     const int q = warp & 3;
@@ -710,7 +752,7 @@ cudaError_t launch_tc(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap
 #define SEG3D_LAUNCH_P(KCV)                                                                                              \
   e = cudaFuncSetAttribute(conv3d_tc_persistent_kernel<T, KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return e;                                                                                        \
-  conv3d_tc_persistent_kernel<T, KCV><<<grid, TC_THREADS, smem, st>>>(mx, mw, p, bias, (T*)y, stats);
+  conv3d_tc_persistent_kernel<T, KCV><<<grid, TCE_THREADS, smem, st>>>(mx, mw, p, bias, (T*)y, stats);
   if (p.KC == 64) { SEG3D_LAUNCH_P(64) } else if (p.KC == 32) { SEG3D_LAUNCH_P(32) } else { SEG3D_LAUNCH_P(16) }
 #undef SEG3D_LAUNCH_P
   return cudaGetLastError();
@@ -744,6 +786,7 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
     memset(&z, 0, sizeof(z));
     z.Cout = Cout; z.KC = Cin; z.row_bytes = Cin * 2;
     z.D = D; z.H = H; z.W = W; z.N = N; z.y_ld = y_ld; z.out_f32 = out_f32;
+    z.wide = (!out_f32 && wide_ok(y, y_ld, 2) && env_int("SEG3D_WIDE_ST", 1)) ? 1 : 0;
     z.w_slab = (Cout * z.row_bytes + 1023) & ~1023;
     z.plane_tx = 180 * z.row_bytes;
     z.plane_bytes = (z.plane_tx + 1023) & ~1023;
@@ -751,7 +794,13 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
     if (27 * z.w_slab <= 112 * 1024) {
       z.ntx = W / 8; z.nty = (H + 15) / 16;
       z.acc_cols = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : 64);
-      z.tmem_cols = ZM_NB * z.acc_cols;
+      z.nb = z.acc_cols <= 32 ? 8 : 4;
+      z.tmem_cols = z.nb * z.acc_cols;
+      // one MMA may span up to three adjacent accumulators when every weight slab is a whole number of 1024-byte swizzle
+      // repeats (so the [(kh,kw)][kd] slabs are contiguous) and the accumulator pitch equals Cout
+      z.maxblk = (z.w_slab == Cout * z.row_bytes && z.acc_cols == Cout && 3 * Cout <= 256) ? env_int("SEG3D_ZM_MAXBLK", 3) : 1;
+      if (z.maxblk < 1) z.maxblk = 1;
+      if (z.maxblk > 3) z.maxblk = 3;
       int ctas_per_sm = env_int("SEG3D_ZM_CTAS_PER_SM", 2);
       if (ctas_per_sm * z.tmem_cols > 512) ctas_per_sm = 512 / z.tmem_cols;
       int ring = ((200 * 1024 / ctas_per_sm) - 27 * z.w_slab) / z.plane_bytes;
@@ -774,7 +823,8 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
         z.sbo = 8 * z.row_bytes; z.a_sbo = 10 * z.row_bytes;
         z.layout_type = z.row_bytes == 128 ? 2u : (z.row_bytes == 64 ? 4u : 6u);
         const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
-        z.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+        z.idesc0 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TILE_M >> 4) << 24);
+        z.n8 = (uint32_t)(Cout >> 3);
         const CUtensorMapDataType tdt = dtype == SEG3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
         const CUtensorMapSwizzle sw = z.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (z.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
         CUtensorMap map_x, map_w;
@@ -792,13 +842,13 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
         r = encode(&map_w, tdt, 2, const_cast<void*>(w), wdims, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { seg3d_set_error("conv_tc(zmarch): cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SEG3D_ECUDA; }
-        const size_t smem = 1024 + (size_t)27 * z.w_slab + (size_t)ring * z.plane_bytes + (2 * ring + 2 * ZM_NB + 1) * 8 + 64;
+        const size_t smem = 1024 + (size_t)27 * z.w_slab + (size_t)ring * z.plane_bytes + (2 * ring + 2 * ZM_MAXNB + 1) * 8 + 64;
         const long long max_grid = (long long)ctas_per_sm * seg3d_num_sms();
         dim3 grid((unsigned)(nitems < max_grid ? nitems : max_grid));
         cudaError_t e = cudaSuccess;
 #define SEG3D_LAUNCH_Z(TT, KCV)                                                                                             \
         { e = cudaFuncSetAttribute(conv3d_k3_zmarch_kernel<TT, KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-          if (e == cudaSuccess) { conv3d_k3_zmarch_kernel<TT, KCV><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, z, bias, (TT*)y, stats); e = cudaGetLastError(); } }
+          if (e == cudaSuccess) { conv3d_k3_zmarch_kernel<TT, KCV><<<grid, TCE_THREADS, smem, st>>>(map_x, map_w, z, bias, (TT*)y, stats); e = cudaGetLastError(); } }
         if (dtype == SEG3D_BF16) {
           if (Cin == 64) SEG3D_LAUNCH_Z(__nv_bfloat16, 64) else if (Cin == 32) SEG3D_LAUNCH_Z(__nv_bfloat16, 32) else SEG3D_LAUNCH_Z(__nv_bfloat16, 16)
         } else {
@@ -825,6 +875,7 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   }
   p.Cin = Cin; p.Cout = Cout; p.D = Do; p.H = Ho; p.W = Wo; p.N = N; p.y_ld = y_ld;
   p.x_ld = x_ld; p.halfW = W / 2; p.halfH = H / 2;
+  p.wide = (wide_ok(y, y_ld, 2) && p.cout_real % 16 == 0 && env_int("SEG3D_WIDE_ST", 1)) ? 1 : 0;
   p.KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
   p.nchunk = Cin / p.KC;
   const int row_bytes = p.KC * 2;

@@ -20,7 +20,7 @@ constexpr int C1_NB = 4;             // TMEM accumulators (32 columns each)
 
 struct Cin1Params {
   int D, H, W, N, y_ld;
-  int ntx, nty, nseg, lseg, nitems;
+  int ntx, nty, nseg, lseg, nitems, wide;
   uint32_t idesc;
 };
 
@@ -34,15 +34,15 @@ conv3d_k3_cin1_tc_kernel(const T* __restrict__ x, const float* __restrict__ w /*
   const uint32_t a_base = smem_base;                                   // [C1_STAGES][128 rows][64 B]
   const uint32_t b_base = smem_base + C1_STAGES * 8192;                // [32 rows][64 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + C1_STAGES * 8192 + 2048);
-  const uint32_t afull_bar = smem_u32(bars);                           // [C1_STAGES] 128 builder arrivals
+  const uint32_t afull_bar = smem_u32(bars);                           // [C1_STAGES] one arrival per builder warp
   const uint32_t aempty_bar = afull_bar + 8 * C1_STAGES;               // [C1_STAGES] tcgen05.commit
   const uint32_t tfull_bar = aempty_bar + 8 * C1_STAGES;               // [C1_NB]
   const uint32_t tempty_bar = tfull_bar + 8 * C1_NB;                   // [C1_NB] 4 warp arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C1_STAGES + 2 * C1_NB);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < C1_STAGES; ++s) { mbar_init(afull_bar + 8 * s, 128); mbar_init(aempty_bar + 8 * s, 1); }
+    for (int s = 0; s < C1_STAGES; ++s) { mbar_init(afull_bar + 8 * s, 4); mbar_init(aempty_bar + 8 * s, 1); }
     for (int b = 0; b < C1_NB; ++b) { mbar_init(tfull_bar + 8 * b, 1); mbar_init(tempty_bar + 8 * b, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -53,11 +53,11 @@ conv3d_k3_cin1_tc_kernel(const T* __restrict__ x, const float* __restrict__ w /*
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    {   // whole warp, converged: see elect_one()
       const uint32_t hi = desc_hi(512, 4);          // 8-row groups 512 B apart, 64B swizzle
       int stage = 0; uint32_t phase = 0; int oc = 0;
       for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
@@ -71,10 +71,10 @@ conv3d_k3_cin1_tc_kernel(const T* __restrict__ x, const float* __restrict__ w /*
           tc_fence_after();
           const uint32_t lo_a = (a_base + stage * 8192) >> 4, lo_b = b_base >> 4;
           const uint32_t dcol = tmem_base + (uint32_t)(buf * 32);
-          tc_mma_f16(dcol, desc_pack(hi, lo_a), desc_pack(hi, lo_b), p.idesc, 0);
-          tc_mma_f16(dcol, desc_pack(hi, lo_a + 2), desc_pack(hi, lo_b + 2), p.idesc, 1);
-          tc_commit(aempty_bar + 8 * stage);
-          tc_commit(tfull_bar + 8 * buf);
+          tc_mma_f16_e(dcol, desc_pack(hi, lo_a), desc_pack(hi, lo_b), p.idesc, 0);
+          tc_mma_f16_e(dcol, desc_pack(hi, lo_a + 2), desc_pack(hi, lo_b + 2), p.idesc, 1);
+          tc_commit_e(aempty_bar + 8 * stage);
+          tc_commit_e(tfull_bar + 8 * buf);
           if (++stage == C1_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -153,7 +153,8 @@ conv3d_k3_cin1_tc_kernel(const T* __restrict__ x, const float* __restrict__ w /*
               *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = v;
             }
             fence_proxy_async();
-            mbar_arrive(afull_bar + 8 * stage);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(afull_bar + 8 * stage);
             if (++stage == C1_STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
             for (int i = 0; i < 9; ++i) win[j % 3][i] = nxt[i];
@@ -171,6 +172,7 @@ conv3d_k3_cin1_tc_kernel(const T* __restrict__ x, const float* __restrict__ w /*
     for (int c = 0; c < 16; ++c) bv[c] = bias ? bias[c] : 0.f;
     float s = 0.f, ss = 0.f;
     int cur_n = -1, oc = 0;
+    const bool wide = p.wide != 0;
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       int t = item;
       const int seg = t % p.nseg; t /= p.nseg;
@@ -208,7 +210,7 @@ conv3d_k3_cin1_tc_kernel(const T* __restrict__ x, const float* __restrict__ w /*
           }
           const size_t vox = (((size_t)n * p.D + (zs + zl)) * p.H + gy) * p.W + gx;
           T* dst = y + vox * p.y_ld;
-          Vec8<T> o; o.set(f); o.store(dst); o.set(f + 8); o.store(dst + 8);
+          store16<T>(dst, f, wide);
         }
       }
     }
@@ -242,7 +244,25 @@ int seg3d_conv_cin1_tc(int dtype, const void* x, const void* w, const float* bia
   memset(&p, 0, sizeof(p));
   p.D = D; p.H = H; p.W = W; p.N = N; p.y_ld = y_ld;
   p.ntx = W / 8; p.nty = (H + 15) / 16;
-  const int ctas_per_sm = env_int("SEG3D_CIN1_CTAS_PER_SM", 3);
+  p.wide = (wide_ok(y, y_ld, 2) && env_int("SEG3D_WIDE_ST", 1)) ? 1 : 0;
+  const size_t smem = 1024 + (size_t)C1_STAGES * 8192 + 2048 + (2 * C1_STAGES + 2 * C1_NB) * 8 + 64;
+  // persistent grid = CTAs that are actually co-resident: registers (allocated per warp in units of 256) cap it at
+  // 2 per SM; forcing 3 with launch bounds spills and is 45 % slower
+  int occ = 1;
+  {
+    cudaFuncAttributes fa;
+    cudaError_t e0 = dtype == SEG3D_BF16 ? cudaFuncGetAttributes(&fa, conv3d_k3_cin1_tc_kernel<__nv_bfloat16>)
+                                         : cudaFuncGetAttributes(&fa, conv3d_k3_cin1_tc_kernel<__half>);
+    if (e0 != cudaSuccess) { seg3d_set_error("conv_cin1_tc: cudaFuncGetAttributes failed: %s", cudaGetErrorString(e0)); return SEG3D_ECUDA; }
+    const int regs_per_warp = ((fa.numRegs * 32 + 255) / 256) * 256;
+    occ = 65536 / (regs_per_warp * (C1_THREADS / 32));
+    const int by_smem = (int)((220 * 1024) / (smem + 1024));
+    if (occ > by_smem) occ = by_smem;
+    if (occ < 1) occ = 1;
+  }
+  int ctas_per_sm = env_int("SEG3D_CIN1_CTAS_PER_SM", 4);
+  if (ctas_per_sm > occ) ctas_per_sm = occ;
+  if (ctas_per_sm * C1_NB * 32 > 512) ctas_per_sm = 512 / (C1_NB * 32);
   const long long cols = (long long)N * p.ntx * p.nty;
   const long long want = 8ll * ctas_per_sm * seg3d_num_sms();
   int nseg = (int)((want + cols - 1) / cols);
@@ -255,7 +275,6 @@ int seg3d_conv_cin1_tc(int dtype, const void* x, const void* w, const float* bia
   p.nitems = (int)nitems;
   const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-  const size_t smem = 1024 + (size_t)C1_STAGES * 8192 + 2048 + (2 * C1_STAGES + 2 * C1_NB) * 8 + 64;
   const long long max_grid = (long long)ctas_per_sm * seg3d_num_sms();
   dim3 grid((unsigned)(nitems < max_grid ? nitems : max_grid));
   cudaError_t e;

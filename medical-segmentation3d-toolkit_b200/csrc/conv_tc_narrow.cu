@@ -48,7 +48,7 @@ conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   const uint32_t wfull_bar = tempty_bar + 8 * FD_NB;          // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.ring + 2 * FD_NB + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
@@ -64,12 +64,12 @@ conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(wfull_bar, (uint32_t)p.w_tx);
-      for (int kd = 0; kd < 3; ++kd) tma_load_2d(w_base + kd * p.w_slab, &map_w, wfull_bar, 0, kd * p.NP);
+    {   // whole warp, converged: see elect_one()
+      mbar_expect_tx_e(wfull_bar, (uint32_t)p.w_tx);
+      for (int kd = 0; kd < 3; ++kd) tma_load_2d_e(w_base + kd * p.w_slab, &map_w, wfull_bar, 0, kd * p.NP);
       int stage_i = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
         int t = item;
@@ -80,14 +80,14 @@ conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
         for (int ip = 0; ip < L + 2; ++ip) {
           mbar_wait(empty_bar + 8 * stage_i, phase ^ 1);
-          mbar_expect_tx(full_bar + 8 * stage_i, (uint32_t)p.plane_tx);
-          tma_load_5d(a_base + stage_i * p.plane_bytes, &map_x, full_bar + 8 * stage_i, 0, x0 - 1, y0 - 1, zs - 1 + ip, n);
+          mbar_expect_tx_e(full_bar + 8 * stage_i, (uint32_t)p.plane_tx);
+          tma_load_5d_e(a_base + stage_i * p.plane_bytes, &map_x, full_bar + 8 * stage_i, 0, x0 - 1, y0 - 1, zs - 1 + ip, n);
           if (++stage_i == p.ring) { stage_i = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, converged: see elect_one()
       mbar_wait(wfull_bar, 0);
       int stage_i = 0; uint32_t phase = 0; int oc = 0;
       constexpr int KSTEPS = KC / 16;
@@ -111,10 +111,10 @@ conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             const uint32_t lo_w = w16 + (uint32_t)kd * slab16;
 #pragma unroll
             for (int k = 0; k < KSTEPS; ++k)
-              tc_mma_f16(dcol, desc_pack(hi, lo_a + ((k * 32) >> 4)), desc_pack(hi, lo_w + ((k * 32) >> 4)), p.idesc, (kd | k) != 0);
+              tc_mma_f16_e(dcol, desc_pack(hi, lo_a + ((k * 32) >> 4)), desc_pack(hi, lo_w + ((k * 32) >> 4)), p.idesc, (kd | k) != 0);
           }
-          tc_commit(empty_bar + 8 * stage_i);
-          if (ip >= 2) tc_commit(tfull_bar + 8 * ((oc + ip - 2) % FD_NB));
+          tc_commit_e(empty_bar + 8 * stage_i);
+          if (ip >= 2) tc_commit_e(tfull_bar + 8 * ((oc + ip - 2) % FD_NB));
           if (++stage_i == p.ring) { stage_i = 0; phase ^= 1; }
         }
         oc += L;
@@ -237,10 +237,14 @@ extern "C" int seg3d_conv3d_k3_narrow_fwd(int dtype, const void* x, int x_ld, in
   p.ntx = W / FD_TX; p.nty = (H + FD_TY - 1) / FD_TY;
   p.acc_cols = NP <= 32 ? 32 : 64;
   p.tmem_cols = FD_NB * p.acc_cols;
-  int ctas_per_sm = env_int("SEG3D_FD_CTAS_PER_SM", 2);
+  int ctas_per_sm = env_int("SEG3D_FD_CTAS_PER_SM", 4);
   if (ctas_per_sm * p.tmem_cols > 512) ctas_per_sm = 512 / p.tmem_cols;
   const int fixed = 3 * p.w_slab + 128 * p.pitch * 4 + 1024;
-  int ring = ((200 * 1024 / ctas_per_sm) - fixed) / p.plane_bytes;
+  int ring = 0;
+  for (; ctas_per_sm >= 1; --ctas_per_sm) {                  // as many co-resident CTAs as leave a ring of >= 4 planes
+    ring = ((200 * 1024 / ctas_per_sm) - fixed) / p.plane_bytes;
+    if (ring >= 4 || ctas_per_sm == 1) break;
+  }
   if (ring > 8) ring = 8;
   { const int e = env_int("SEG3D_FD_RING", 0); if (e >= 3) ring = e; }
   SEG3D_REQUIRE(ring >= 3, "conv3d_k3_narrow_fwd: plane ring does not fit in shared memory");

@@ -50,6 +50,29 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One lane of a CONVERGED warp.  The MMA-issuing warp runs its loops warp-wide with uniform values and guards only the
+// tcgen05.mma / tcgen05.commit instructions with this predicate: the descriptors then live in uniform registers and each
+// MMA is a handful of uniform-datapath instructions.  Issuing from inside an `if (lane == 0)` region instead makes nvcc
+// wrap every UTCHMMA in a per-active-thread loop (ELECT / PLOP3 / BRA.U.ANY plus R2UR moves, ~15 instructions per MMA),
+// which makes the issuing thread the bottleneck.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_mma_f16_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one()) tc_mma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+}
+__device__ __forceinline__ void tc_commit_e(uint32_t bar) {
+  if (elect_one()) tc_commit(bar);
+}
+__device__ __forceinline__ void mbar_expect_tx_e(uint32_t bar, uint32_t bytes) { if (elect_one()) mbar_expect_tx(bar, bytes); }
+__device__ __forceinline__ void tma_load_5d_e(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  if (elect_one()) tma_load_5d(dst, map, bar, c0, c1, c2, c3, c4);
+}
+__device__ __forceinline__ void tma_load_2d_e(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  if (elect_one()) tma_load_2d(dst, map, bar, c0, c1);
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
