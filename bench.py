@@ -178,11 +178,11 @@ def run_train(args):
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device(dev))
     from segmentation3d._b200 import dist as D
-    from segmentation3d.core.seg_train import train_step
+    from segmentation3d.core.seg_train import make_optimizer, train_step
     from segmentation3d.loss.multi_dice_loss import MultiDiceLoss
     net = make_net(args.mode).to(dev).train()
     D.broadcast_params(net)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.999))
+    opt = make_optimizer(net, 1e-4, (0.9, 0.999))
     lf = MultiDiceLoss([0.5, 0.5], 2, True)
     B, P = args.train_batch, args.patch
     g = torch.Generator(device=dev).manual_seed(rank)

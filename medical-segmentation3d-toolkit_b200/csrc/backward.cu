@@ -17,6 +17,7 @@
 namespace {
 
 constexpr int GN_BWD_MAXC = 512;
+constexpr int GN_BWD_U = 4;
 
 template <typename T>
 __device__ __forceinline__ void load8_or_zero(const T* p, float* f) {
@@ -30,7 +31,7 @@ __device__ __forceinline__ void load8_or_zero(const T* p, float* f) {
 // PASS 0: per-sample sums S1 = sum gamma*dz, S2 = sum gamma*dz*xhat; per-channel dgamma, dbeta.
 // PASS 1: dy (+ optional dres), per-channel dbias.
 template <typename T, int PASS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 gn_bwd_kernel(const T* __restrict__ g0, int ld0, const T* __restrict__ g1, int ld1, const T* __restrict__ g2, int ld2,
               const T* __restrict__ out, int out_ld, const T* __restrict__ y, int y_ld, int C,
               const double* __restrict__ stats, const float* __restrict__ gamma, float eps,
@@ -60,31 +61,44 @@ gn_bwd_kernel(const T* __restrict__ g0, int ld0, const T* __restrict__ g1, int l
   for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
   float s1 = 0.f, s2 = 0.f;
   const size_t nb = (size_t)n * nvox;
-#pragma unroll 2
-  for (long long v = (long long)blockIdx.x * (blockDim.x / cv) + threadIdx.x / cv; v < nvox; v += vstep) {
-    const size_t vv = nb + v;
-    float ga[8], gb[8], gc[8], o[8], yy[8];
-    load8_or_zero<T>(g0 + vv * ld0 + c0, ga);
-    load8_or_zero<T>(g1 ? g1 + vv * ld1 + c0 : nullptr, gb);
-    load8_or_zero<T>(g2 ? g2 + vv * ld2 + c0 : nullptr, gc);
-    load8_or_zero<T>(out + vv * out_ld + c0, o);
-    load8_or_zero<T>(y + vv * y_ld + c0, yy);
-    float dyv[8], dzv[8];
+  // GN_BWD_U voxels per iteration with every load issued before the first use: the kernel is a pure HBM stream and
+  // needs ~100 KB of loads in flight per SM
+  for (long long v = (long long)blockIdx.x * (blockDim.x / cv) + threadIdx.x / cv; v < nvox; v += GN_BWD_U * vstep) {
+    Vec8<T> rg0[GN_BWD_U], rg1[GN_BWD_U], rg2[GN_BWD_U], ro[GN_BWD_U], ry[GN_BWD_U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float dz = o[j] > 0.f ? (ga[j] + gb[j] + gc[j]) : 0.f;
-      const float xh = (yy[j] - mean) * rstd;
-      if (PASS == 0) {
-        s1 += gam[j] * dz; s2 += gam[j] * dz * xh;
-        a0[j] += dz * xh; a1[j] += dz;
-      } else {
-        const float d = rstd * (gam[j] * dz - m1 - xh * m2);
-        dyv[j] = d; dzv[j] = dz; a0[j] += d;
-      }
+    for (int u = 0; u < GN_BWD_U; ++u) {
+      const long long vu = v + u * vstep;
+      const size_t vv = nb + (vu < nvox ? vu : v);           // clamp: the duplicate is masked below
+      rg0[u].load(g0 + vv * ld0 + c0);
+      if (g1) rg1[u].load(g1 + vv * ld1 + c0); else rg1[u].zero();
+      if (g2) rg2[u].load(g2 + vv * ld2 + c0); else rg2[u].zero();
+      ro[u].load(out + vv * out_ld + c0);
+      ry[u].load(y + vv * y_ld + c0);
     }
-    if (PASS == 1) {
-      Vec8<T> w; w.set(dyv); w.store(dy + vv * dy_ld + c0);
-      if (dres) { w.set(dzv); w.store(dres + vv * dres_ld + c0); }
+#pragma unroll
+    for (int u = 0; u < GN_BWD_U; ++u) {
+      const long long vu = v + u * vstep;
+      if (vu >= nvox) break;
+      const size_t vv = nb + vu;
+      float ga[8], gb[8], gc[8], o[8], yy[8];
+      rg0[u].get(ga); rg1[u].get(gb); rg2[u].get(gc); ro[u].get(o); ry[u].get(yy);
+      float dyv[8], dzv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dz = o[j] > 0.f ? (ga[j] + gb[j] + gc[j]) : 0.f;
+        const float xh = (yy[j] - mean) * rstd;
+        if (PASS == 0) {
+          s1 += gam[j] * dz; s2 += gam[j] * dz * xh;
+          a0[j] += dz * xh; a1[j] += dz;
+        } else {
+          const float d = rstd * (gam[j] * dz - m1 - xh * m2);
+          dyv[j] = d; dzv[j] = dz; a0[j] += d;
+        }
+      }
+      if (PASS == 1) {
+        Vec8<T> w; w.set(dyv); w.store(dy + vv * dy_ld + c0);
+        if (dres) { w.set(dzv); w.store(dres + vv * dres_ld + c0); }
+      }
     }
   }
   // per-channel partials: lanes that own the same channel group (lane % cv) are folded with shuffles first, then
@@ -343,54 +357,98 @@ int launch_tail_bwd(int C, dim3 grid, cudaStream_t st, const T* y1, int ld, cons
 }
 
 
-// ---- weight gradient of the input block (Cin == 1, Cout == 16): 27 x 16 long reductions over all voxels -------
-// thread = (tap, co); a block walks 8x8x8 voxel tiles, staging the 10^3 input halo and the 512 x 16 dy tile in
-// shared memory, and issues its 432 atomics once at the end.
+// ---- weight gradient of the input block (Cin == 1, Cout == 16): dW[tap][co] = sum_v x[v + tap] * dy[v][co] --------
+// Register-tiled: a thread owns one (x,y) column of an 8 x 8 x 12 voxel tile and four output channels, keeps its
+// 27 x 4 partial sums in registers, marches along z with the 3 x 9 input window in registers (9 shared-memory reads
+// per voxel) and reads its 4 dy channels straight from global memory (a warp covers 8 consecutive voxels x 32 B).
+// 108 independent FMAs per voxel per thread; the partial sums are folded once per block (shuffles, shared atomics,
+// 432 global atomics).
+constexpr int WC1_LZ = 12;
 template <typename T>
-__global__ void __launch_bounds__(448)
+__global__ void __launch_bounds__(256)
 wgrad_cin1_kernel(const T* __restrict__ x, const T* __restrict__ dy, int dy_ld, float* __restrict__ dw,
                   int N, int D, int H, int W, int ntx, int nty, int ntz) {
-  __shared__ float xs[10][10][10];
-  __shared__ float dys[512][16];
+  __shared__ float xs[WC1_LZ + 2][10][10];
+  __shared__ float red[27 * 16];
   const int tid = threadIdx.x;
-  const int tap = tid >> 4, co = tid & 15;
-  const bool active = tap < 27;
-  const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-  float acc = 0.f;
+  const int q = tid & 3, vox = tid >> 2, lx = vox & 7, ly = vox >> 3;
+  float acc[27][4];
+#pragma unroll
+  for (int t = 0; t < 27; ++t)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
+  for (int i = tid; i < 27 * 16; i += blockDim.x) red[i] = 0.f;
   const long long ntiles = (long long)ntx * nty * ntz * N;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     long long t = tile;
     const int x0 = (int)(t % ntx) * 8; t /= ntx;
     const int y0 = (int)(t % nty) * 8; t /= nty;
-    const int z0 = (int)(t % ntz) * 8; const int n = (int)(t / ntz);
+    const int z0 = (int)(t % ntz) * WC1_LZ; const int n = (int)(t / ntz);
     const T* xn = x + (size_t)n * D * H * W;
-    const T* dn = dy + (size_t)n * D * H * W * dy_ld;
     __syncthreads();
-    for (int i = tid; i < 1000; i += blockDim.x) {
+    for (int i = tid; i < (WC1_LZ + 2) * 100; i += blockDim.x) {
       const int hx = i % 10, hy = (i / 10) % 10, hz = i / 100;
       const int gx = x0 + hx - 1, gy = y0 + hy - 1, gz = z0 + hz - 1;
       float v = 0.f;
       if (gx >= 0 && gx < W && gy >= 0 && gy < H && gz >= 0 && gz < D) v = to_f32<T>(xn[((size_t)gz * H + gy) * W + gx]);
       xs[hz][hy][hx] = v;
     }
-    for (int i = tid; i < 512 * 16; i += blockDim.x) {
-      const int c = i & 15, v = i >> 4;
-      const int lx = v & 7, ly = (v >> 3) & 7, lz = v >> 6;
-      const int gx = x0 + lx, gy = y0 + ly, gz = z0 + lz;
-      float d = 0.f;
-      if (gx < W && gy < H && gz < D) d = to_f32<T>(dn[(((size_t)gz * H + gy) * W + gx) * dy_ld + c]);
-      dys[v][c] = d;
-    }
     __syncthreads();
-    if (active) {
-#pragma unroll 4
-      for (int v = 0; v < 512; ++v) {
-        const int lx = v & 7, ly = (v >> 3) & 7, lz = v >> 6;
-        acc = fmaf(xs[lz + kd][ly + kh][lx + kw], dys[v][co], acc);
+    const int gx = x0 + lx, gy = y0 + ly;
+    const bool inplane = gx < W && gy < H;
+    const T* dcol = dy + ((((size_t)n * D + z0) * H + gy) * W + gx) * dy_ld + q * 4;
+    const size_t zstride = (size_t)H * W * dy_ld;
+    float win[3][9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { win[0][i] = xs[0][ly + i / 3][lx + i % 3]; win[1][i] = xs[1][ly + i / 3][lx + i % 3]; }
+    // dy is read three z steps ahead as raw bits (converted at use: one block per SM, nothing else hides the latency)
+    struct Raw { uint4 v; };
+    auto load_dy = [&](int z, Raw& r) {
+      r.v = make_uint4(0u, 0u, 0u, 0u);
+      if (inplane && z < WC1_LZ && z0 + z < D) {
+        if (sizeof(T) == 2) { const uint2 t2 = *reinterpret_cast<const uint2*>(dcol + (size_t)z * zstride); r.v.x = t2.x; r.v.y = t2.y; }
+        else r.v = *reinterpret_cast<const uint4*>(dcol + (size_t)z * zstride);
+      }
+    };
+    Raw dq[3];
+    load_dy(0, dq[0]); load_dy(1, dq[1]); load_dy(2, dq[2]);
+    for (int zl = 0; zl < WC1_LZ; zl += 3) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int z = zl + j;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) win[(j + 2) % 3][i] = xs[z + 2][ly + i / 3][lx + i % 3];
+        float d[4];
+        {
+          const T* h = reinterpret_cast<const T*>(&dq[j].v);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) d[c] = to_f32<T>(h[c]);
+        }
+        load_dy(z + 3, dq[j]);
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            const float xv = win[(j + kd) % 3][i];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[kd * 9 + i][c] = fmaf(xv, d[c], acc[kd * 9 + i][c]);
+          }
       }
     }
   }
-  if (active) atomicAdd(dw + tap * 16 + co, acc);
+  // fold: lanes with the same channel quad (lane & 3), then warps through shared memory, then one atomic per weight
+#pragma unroll
+  for (int t = 0; t < 27; ++t)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v = acc[t][c];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((tid & 31) < 4) atomicAdd(&red[t * 16 + q * 4 + c], v);
+    }
+  __syncthreads();
+  for (int i = tid; i < 27 * 16; i += blockDim.x) atomicAdd(dw + i, red[i]);
 }
 
 }  // namespace
@@ -430,10 +488,11 @@ extern "C" int seg3d_conv3d_wgrad(int mode, int dtype, const void* x, int x_ld, 
                                   float* dw, int N, int D, int H, int W, void* stream) {
   SEG3D_REQUIRE(x && dy && dw && Cin > 0 && Cout > 0 && N > 0, "conv3d_wgrad: bad arguments");
   if (mode == SEG3D_CONV_K3 && Cin == 1 && Cout == 16 && x_ld == 1) {
-    const int ntx = (W + 7) / 8, nty = (H + 7) / 8, ntz = (D + 7) / 8;
+    SEG3D_REQUIRE(dy_ld % 4 == 0 && ((uintptr_t)dy) % 16 == 0, "conv3d_wgrad(cin1): dy pitch / alignment");
+    const int ntx = (W + 7) / 8, nty = (H + 7) / 8, ntz = (D + WC1_LZ - 1) / WC1_LZ;
     const long long ntiles = (long long)ntx * nty * ntz * N;
-    const int gx = (int)(ntiles < 2LL * seg3d_num_sms() ? ntiles : 2LL * seg3d_num_sms());
-    SEG3D_DISPATCH_DTYPE(dtype, T, (wgrad_cin1_kernel<T><<<gx, 448, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)dy, dy_ld, dw, N, D, H, W, ntx, nty, ntz)));
+    const int gx = (int)(ntiles < (long long)seg3d_num_sms() ? ntiles : (long long)seg3d_num_sms());   // ~200 registers: one block per SM
+    SEG3D_DISPATCH_DTYPE(dtype, T, (wgrad_cin1_kernel<T><<<gx, 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)dy, dy_ld, dw, N, D, H, W, ntx, nty, ntz)));
     SEG3D_CHECK_LAUNCH("wgrad_cin1_kernel");
     return SEG3D_OK;
   }

@@ -1034,7 +1034,9 @@ int seg3d_wgrad_tc(int dtype, const void* x, int x_ld, int Cin, const void* dy, 
   }
   const int combos = p.n_co_blk * p.n_ci_blk * p.ngroups;
   const int ctas_per_sm = (512 / p.tmem_cols) < 1 ? 1 : ((512 / p.tmem_cols) > 1 ? 1 : 1);   // smem ring ~170 KB: one CTA per SM
-  long long ksplit = ((long long)ctas_per_sm * seg3d_num_sms() + combos - 1) / combos;
+  // one CTA per SM and one wave: rounding the K split UP (e.g. 3 x 50 = 150 CTAs on 148 SMs) leaves two CTAs for a
+  // second wave that doubles the run time
+  long long ksplit = ((long long)ctas_per_sm * seg3d_num_sms()) / combos;
   if (ksplit < 1) ksplit = 1;
   if (ksplit > ntiles) ksplit = ntiles;
   const size_t smem = 1024 + (size_t)p.stages * (p.a_bytes + p.b_bytes) + 16384 + (2 * p.stages + 1) * 8 + 64;
@@ -1122,7 +1124,7 @@ int seg3d_wgrad_s2_tc(int mode, int dtype, const void* x, int x_ld, int Cin, con
   }
   if (p.mode == 1) { map_dy = map_lo; map_x = map_hi; } else { map_dy = map_hi; map_x = map_lo; }
   const int combos = p.n_co_blk * p.n_ci_blk * 4;
-  long long ksplit = ((long long)seg3d_num_sms() + combos - 1) / combos;
+  long long ksplit = (long long)seg3d_num_sms() / combos;        // one wave of one CTA per SM (see seg3d_wgrad_tc)
   if (ksplit < 1) ksplit = 1;
   if (ksplit > ntiles) ksplit = ntiles;
   const size_t smem = 1024 + (size_t)p.stages * (p.a_bytes + p.b_bytes) + 16384 + (2 * p.stages + 1) * 8 + 64;

@@ -35,8 +35,8 @@ class _Backward(object):
         self.produced = {}                    # (id(buf), off) -> producing unit's out view
         for u in self.units:
             self.produced[(id(u['out'].buf), u['out'].off)] = u['out']
-        f32 = dict(dtype=torch.float32, device=dev)
-        self.pgrad = {}                        # parameter gradients in kernel layouts (fp32, zeroed every step)
+        # parameter gradients in kernel layouts: fp32 views into ONE flat buffer, zeroed with a single memset per step
+        sizes = []
         for u in self.units:
             c = plan.convs[u['conv']]
             C = c.cout
@@ -47,19 +47,22 @@ class _Backward(object):
             if self._has_producer(u['x']):
                 self.gd[u['conv']] = _View(torch.empty((B, vox[u['lin']], u['x'].C), dtype=td, device=dev), 0, u['x'].C, u['x'].C)
             taps = {lib.CONV_K3: 27, lib.CONV_K2S2: 8, lib.CONV_T2S2: 8}[c.mode]
-            self.pgrad[u['conv'] + '.weight'] = torch.zeros((taps * c.cin * c.cout,), **f32)
-            self.pgrad[u['conv'] + '.bias'] = torch.zeros((c.cout,), **f32)
-            self.pgrad[u['gn'] + '.weight'] = torch.zeros((c.cout,), **f32)
-            self.pgrad[u['gn'] + '.bias'] = torch.zeros((c.cout,), **f32)
+            sizes += [(u['conv'] + '.weight', taps * c.cin * c.cout), (u['conv'] + '.bias', c.cout),
+                      (u['gn'] + '.weight', c.cout), (u['gn'] + '.bias', c.cout)]
         nc = plan.out_channels
         c1 = plan.convs['out_block.conv1']
         # when conv1 runs zero-padded to 16 output channels on the tensor cores, its weight gradient does too
         self.conv1_co = c1.cout
-        self.pgrad['out_block.conv1.weight'] = torch.zeros((27 * c1.cin * self.conv1_co,), **f32)
-        for k, n in (('out_block.conv1.bias', nc), ('out_block.gn1.weight', nc), ('out_block.gn1.bias', nc),
-                     ('out_block.conv2.weight', nc * nc), ('out_block.conv2.bias', nc),
-                     ('out_block.gn2.weight', nc), ('out_block.gn2.bias', nc)):
-            self.pgrad[k] = torch.zeros((n,), **f32)
+        sizes += [('out_block.conv1.weight', 27 * c1.cin * self.conv1_co),
+                  ('out_block.conv1.bias', nc), ('out_block.gn1.weight', nc), ('out_block.gn1.bias', nc),
+                  ('out_block.conv2.weight', nc * nc), ('out_block.conv2.bias', nc),
+                  ('out_block.gn2.weight', nc), ('out_block.gn2.bias', nc)]
+        total = sum((n + 3) // 4 * 4 for _, n in sizes)          # 16-byte aligned slots
+        self.pgrad_flat = torch.zeros((total,), dtype=torch.float32, device=dev)
+        self.pgrad, off = {}, 0
+        for k, n in sizes:
+            self.pgrad[k] = self.pgrad_flat[off:off + n]
+            off += (n + 3) // 4 * 4
         ncp = ws['tail']['ncp']
         self.gy_tail = _View(torch.zeros((B, vox[0], ncp), dtype=td, device=dev), 0, ncp, ncp)   # pad channels stay 0
         tx = ws['tail']['x']
@@ -98,8 +101,7 @@ class _Backward(object):
         plan, ws = self.plan, self.ws
         B, vox, dims, dt = ws['B'], ws['vox'], ws['dims'], plan.dt
         st = lib.stream_ptr
-        for g in self.pgrad.values():
-            g.zero_()
+        self.pgrad_flat.zero_()
         self.sums.zero_()
         contrib = {}
 
@@ -208,7 +210,9 @@ class _NetFunction(torch.autograd.Function):
         else:
             bw.refresh()
         grads = bw.run(dprobs)
-        return (None, None, None) + tuple(grads[n].contiguous().clone() for n in ctx.names)
+        # the slots are reused next step: hand autograd its own copy (one copy, in the reference's parameter layout)
+        return (None, None, None) + tuple(g.clone() if g.is_contiguous() else g.contiguous()
+                                          for g in (grads[n] for n in ctx.names))
 
 
 def train_forward(net, x):

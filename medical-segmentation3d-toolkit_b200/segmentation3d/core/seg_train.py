@@ -48,6 +48,13 @@ def make_loss(train_cfg, use_gpu=True):
     raise ValueError('Unknown loss function')
 
 
+def make_optimizer(net, lr, betas=(0.9, 0.999)):
+    """The reference's optim.Adam(net.parameters(), lr, betas) (core/seg_train.py:83).  `fused` keeps the update rule and
+    the state-dict layout and only changes how torch launches it (one kernel instead of ~30 multi-tensor launches)."""
+    params = list(net.parameters())
+    return optim.Adam(params, lr=lr, betas=betas, fused=all(p.is_cuda for p in params))
+
+
 def train_step(net, opt, loss_func, crops, masks, params=None):
     """core/seg_train.py:119-127 for one batch already on the device; returns the loss tensor."""
     opt.zero_grad()
@@ -114,7 +121,7 @@ def train(train_config_file):
     D.broadcast_params(net)
     assert np.all(np.array(train_cfg.dataset.crop_size) % max_stride == 0), 'crop size not divisible by max stride'
 
-    opt = optim.Adam(net.parameters(), lr=train_cfg.train.lr, betas=train_cfg.train.betas)
+    opt = make_optimizer(net, train_cfg.train.lr, train_cfg.train.betas)
     if train_cfg.general.resume_epoch >= 0:
         last_save_epoch, batch_start = load_checkpoint(train_cfg.general.resume_epoch, _StripPrefixLoader(net), opt, model_folder)
     else:

@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.join(ROOT, 'medical-segmentation3d-toolkit_b200'))
 sys.path.insert(0, ROOT)
 import torch
 from segmentation3d._b200 import lib
-from segmentation3d.core.seg_train import train_step
+from segmentation3d.core.seg_train import make_optimizer, train_step
 from segmentation3d.loss.multi_dice_loss import MultiDiceLoss
 from segmentation3d.network import vnet
 
@@ -19,7 +19,7 @@ net = vnet.SegmentationNet(1, 2)
 vnet.parameters_kaiming_init(net)
 net.b200_mode = mode
 net = net.cuda().train()
-opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+opt = make_optimizer(net, 1e-4)
 lf = MultiDiceLoss([0.5, 0.5], 2, True)
 crops = torch.randn((B, 1, 96, 96, 96), device='cuda')
 masks = torch.randint(0, 2, (B, 1, 96, 96, 96), device='cuda').float()
