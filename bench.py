@@ -337,7 +337,16 @@ def main():
         else:
             roof = {'bound': 'hbm', 'achieved': tk['bytes'] / tk['ms'] / 1e6, 'peak': hbm, 'unit': 'GB/s'}
         roof['frac'] = roof['achieved'] / roof['peak']
+        # DRAM bytes per launch of this kernel class from the committed ncu --set full capture (tools/make_profiles.py),
+        # scaled to this run's patch batch; null when no capture of this class exists
         roof['traffic'] = None
+        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+        if os.path.isfile(tpath) and args.arch == 'vnet' and args.mode == 'fp16':
+            tj = json.load(open(tpath))
+            if top[0] in tj:
+                roof['traffic'] = tj[top[0]]['dram_bytes_per_launch'] * args.batch / float(tj.get('_batch', args.batch))
+                roof['traffic_source'] = tj.get('_source')
+                roof['algorithmic_bytes_per_launch'] = tk['bytes'] / tk['n']
         roof['kernel'] = top[0]
         roof['share_of_forward'] = tk['ms'] / tot_ms
         roof['peak_source'] = which + ' (MEASURED_PEAKS.json, sustained)' if which == 'measured' else which

@@ -481,6 +481,8 @@ extern "C" int seg3d_gn_bwd(int dtype, int pass, const void* g0, int ld0, const 
 
 int seg3d_wgrad_tc(int dtype, const void* x, int x_ld, int Cin, const void* dy, int dy_ld, int Cout, float* dw,
                    int N, int D, int H, int W, cudaStream_t st);
+int seg3d_wgrad_tc9(int dtype, const void* x, int x_ld, int Cin, const void* dy, int dy_ld, int Cout, float* dw,
+                    int N, int D, int H, int W, cudaStream_t st);
 int seg3d_wgrad_s2_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const void* dy, int dy_ld, int Cout, float* dw,
                       int N, int D, int H, int W, cudaStream_t st);
 
@@ -496,7 +498,9 @@ extern "C" int seg3d_conv3d_wgrad(int mode, int dtype, const void* x, int x_ld, 
     SEG3D_CHECK_LAUNCH("wgrad_cin1_kernel");
     return SEG3D_OK;
   }
-  if (mode == SEG3D_CONV_K3) {       // tensor-core path when the shape allows it
+  if (mode == SEG3D_CONV_K3) {       // tensor-core paths when the shape allows it: nine-taps-per-MMA for narrow outputs first
+    const int rc9 = seg3d_wgrad_tc9(dtype, x, x_ld, Cin, dy, dy_ld, Cout, dw, N, D, H, W, (cudaStream_t)stream);
+    if (rc9 != SEG3D_EUNSUPPORTED) return rc9;
     const int rc = seg3d_wgrad_tc(dtype, x, x_ld, Cin, dy, dy_ld, Cout, dw, N, D, H, W, (cudaStream_t)stream);
     if (rc != SEG3D_EUNSUPPORTED) return rc;
   }

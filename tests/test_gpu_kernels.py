@@ -311,6 +311,7 @@ WG_CASES = [
     ('K3', 32, 32, 2, 8, 16, 8), ('K3', 64, 64, 1, 4, 16, 16), ('K3', 16, 16, 1, 8, 8, 8), ('K3', 128, 128, 1, 4, 12, 12),
     ('K3', 256, 256, 2, 2, 6, 6), ('K3', 32, 16, 1, 8, 16, 16), ('K3', 16, 64, 1, 4, 8, 8), ('K3', 1, 16, 1, 8, 8, 8),
     ('K2S2', 16, 32, 1, 8, 8, 8), ('T2S2', 64, 16, 1, 4, 4, 8),
+    ('K3', 64, 32, 1, 4, 24, 8), ('K3', 16, 32, 2, 5, 16, 16), ('K3', 64, 16, 1, 4, 16, 8), ('K3', 32, 32, 1, 3, 40, 24),   # nine-taps-per-MMA path
     ('K2S2', 32, 64, 2, 8, 32, 16), ('K2S2', 64, 128, 1, 4, 16, 16), ('K2S2', 128, 256, 1, 4, 12, 12),
     ('T2S2', 128, 32, 2, 4, 16, 8), ('T2S2', 256, 64, 1, 2, 12, 12), ('T2S2', 256, 128, 1, 2, 6, 6),
 ]
