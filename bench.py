@@ -33,7 +33,7 @@ for p in (ROOT, PKG):
 import numpy as np   # noqa: E402
 import torch         # noqa: E402
 
-METRIC = 'sliding-window infer Mvoxels/s (512x512x400 CT, VNet, 96^3 patches)'  # BASELINE.json headline (configs[1])
+METRIC = 'sliding-window infer Mvoxels/s (512x512x400 CT, VNet, 96^3 patches)'  # BASELINE.json headline (configs[1]); main() renames it for --arch vbnet
 NORMALIZER = {'type': 0, 'mean': 0.0, 'stddev': 1000.0, 'clip': True}
 
 
@@ -358,7 +358,7 @@ def main():
             cpu = {'value': v, 'unit': 'Mvoxels/s', 'cores': cores, 'kind': 'port',
                    'sample': '%d of %d patches (x2 forwards, reference loop incl. whole-volume numpy copies), %.1f s' % (args.ref_patches, total, dt)}
         line = {
-            'metric': METRIC, 'value': value, 'unit': 'Mvoxels/s', 'n_gpus': world, 'steps': args.steps,
+            'metric': METRIC if args.arch == 'vnet' else METRIC.replace('VNet', 'VBNet C=%d' % args.classes), 'value': value, 'unit': 'Mvoxels/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev, 'higher_is_better': True,
             'scaling': 'weak' if args.shard == 'cases' else 'strong', 'vs_baseline': None,
             'dtype': {'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f32'}[args.mode], 'data': 'synthetic',
