@@ -126,6 +126,11 @@ int seg3d_blend_accumulate(const float* probs, int N, int C, int pz, int py, int
 int seg3d_blend_finalize_argmax(float* acc, int C, int Z, int Y, int X,
                                 const int32_t* cx, const int32_t* cy, const int32_t* cz,
                                 int8_t* mask, void* stream);
+/* same on the z planes [z0, z1) only: a z slab can be finished (and its mask copied out) as soon as no remaining patch
+ * touches it, while later patches are still running */
+int seg3d_blend_finalize_argmax_z(float* acc, int C, int Z, int Y, int X, int z0, int z1,
+                                  const int32_t* cx, const int32_t* cy, const int32_t* cz,
+                                  int8_t* mask, void* stream);
 
 /* ---- losses on probabilities (loss/multi_dice_loss.py, loss/binary_dice_loss.py, loss/focal_loss.py) -
  * probs fp32 [B][C][n], target fp32 [B][n] (class index stored as float, dataloader/dataset.py:208). */

@@ -113,12 +113,13 @@ extern "C" int seg3d_blend_accumulate(const float* probs, int N, int C, int pz, 
 // ---- acc *= float32(1/count); mask = first argmax (seg_infer.py:325-327,336-338) --------------
 template <int VEC>
 __global__ void __launch_bounds__(256)
-blend_finalize_kernel(float* __restrict__ acc, int C, int Z, int Y, int X, const int32_t* __restrict__ cx,
+blend_finalize_kernel(float* __restrict__ acc, int C, int Z, int Y, int X, int z0, int z1, const int32_t* __restrict__ cx,
                       const int32_t* __restrict__ cy, const int32_t* __restrict__ cz, int8_t* __restrict__ mask) {
   const size_t vsz = (size_t)Z * Y * X;
-  const size_t nvec = vsz / VEC;
+  const size_t vbeg = (size_t)z0 * Y * X;
+  const size_t nvec = (size_t)(z1 - z0) * Y * X / VEC;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t v0 = i * VEC;
+    const size_t v0 = vbeg + i * VEC;
     const int x0 = (int)(v0 % X); const size_t t = v0 / X; const int y = (int)(t % Y), z = (int)(t / Y);
     const float cyz = (float)(cy[y] * cz[z]);
     float best[VEC]; int8_t arg[VEC];
@@ -142,16 +143,22 @@ blend_finalize_kernel(float* __restrict__ acc, int C, int Z, int Y, int X, const
   }
 }
 
-extern "C" int seg3d_blend_finalize_argmax(float* acc, int C, int Z, int Y, int X, const int32_t* cx,
-                                           const int32_t* cy, const int32_t* cz, int8_t* mask, void* stream) {
+extern "C" int seg3d_blend_finalize_argmax_z(float* acc, int C, int Z, int Y, int X, int z0, int z1, const int32_t* cx,
+                                             const int32_t* cy, const int32_t* cz, int8_t* mask, void* stream) {
   SEG3D_REQUIRE(acc && cx && cy && cz && C > 0 && C <= 127 && Z > 0 && Y > 0 && X > 0, "blend_finalize: bad arguments");
-  const size_t vsz = (size_t)Z * Y * X;
+  SEG3D_REQUIRE(0 <= z0 && z0 < z1 && z1 <= Z, "blend_finalize: bad z range [%d,%d) of %d", z0, z1, Z);
+  const size_t vsz = (size_t)(z1 - z0) * Y * X;
   const int sms = seg3d_num_sms();
   const bool v4 = (X % 4 == 0) && (((uintptr_t)acc) % 16 == 0) && (!mask || ((uintptr_t)mask) % 4 == 0);
   const size_t nvec = v4 ? vsz / 4 : vsz;
   size_t want = (nvec + 255) / 256; int gx = (int)(want > (size_t)16 * sms ? (size_t)16 * sms : (want < 1 ? 1 : want));
-  if (v4) blend_finalize_kernel<4><<<gx, 256, 0, (cudaStream_t)stream>>>(acc, C, Z, Y, X, cx, cy, cz, mask);
-  else    blend_finalize_kernel<1><<<gx, 256, 0, (cudaStream_t)stream>>>(acc, C, Z, Y, X, cx, cy, cz, mask);
+  if (v4) blend_finalize_kernel<4><<<gx, 256, 0, (cudaStream_t)stream>>>(acc, C, Z, Y, X, z0, z1, cx, cy, cz, mask);
+  else    blend_finalize_kernel<1><<<gx, 256, 0, (cudaStream_t)stream>>>(acc, C, Z, Y, X, z0, z1, cx, cy, cz, mask);
   SEG3D_CHECK_LAUNCH("blend_finalize_kernel");
   return SEG3D_OK;
+}
+
+extern "C" int seg3d_blend_finalize_argmax(float* acc, int C, int Z, int Y, int X, const int32_t* cx,
+                                           const int32_t* cy, const int32_t* cz, int8_t* mask, void* stream) {
+  return seg3d_blend_finalize_argmax_z(acc, C, Z, Y, X, 0, Z, cx, cy, cz, mask, stream);
 }

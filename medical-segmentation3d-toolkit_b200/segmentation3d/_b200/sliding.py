@@ -77,12 +77,19 @@ class SlidingWindow(object):
             lib.call('seg3d_blend_accumulate', lib.ptr(probs), nb, C, pz, py, px, sp, lib.ptr(acc), Z, Y, X, st())
             self.kernel_launches += 2 + len(ops)
 
-    def finalize(self, acc, counts, want_mask=True):
-        """acc *= 1/count in place; returns the int8 first-argmax mask [Z,Y,X]."""
+    def finalize(self, acc, counts, want_mask=True, z_range=None, mask=None):
+        """acc *= 1/count in place; returns the int8 first-argmax mask [Z,Y,X].  z_range=(z0, z1) finishes only those
+        planes (into the caller's `mask`), so a slab no remaining patch touches can be finished and copied out early."""
         C, Z, Y, X = acc.shape
-        cx, cy, cz = [torch.as_tensor(c, dtype=torch.int32, device=acc.device) for c in counts]
-        mask = torch.empty((Z, Y, X), dtype=torch.int8, device=acc.device) if want_mask else None
-        lib.call('seg3d_blend_finalize_argmax', lib.ptr(acc), C, Z, Y, X, lib.ptr(cx), lib.ptr(cy), lib.ptr(cz),
+        key = (tuple(np.asarray(c).tobytes() for c in counts), str(acc.device))
+        if getattr(self, '_counts_key', None) != key:
+            self._counts_dev = [torch.as_tensor(c, dtype=torch.int32, device=acc.device) for c in counts]
+            self._counts_key = key
+        cx, cy, cz = self._counts_dev
+        if mask is None:
+            mask = torch.empty((Z, Y, X), dtype=torch.int8, device=acc.device) if want_mask else None
+        z0, z1 = z_range if z_range is not None else (0, Z)
+        lib.call('seg3d_blend_finalize_argmax_z', lib.ptr(acc), C, Z, Y, X, int(z0), int(z1), lib.ptr(cx), lib.ptr(cy), lib.ptr(cz),
                  lib.ptr(mask), lib.stream_ptr())
         self.kernel_launches += 1
         return mask

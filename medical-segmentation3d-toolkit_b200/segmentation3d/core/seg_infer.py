@@ -165,11 +165,13 @@ def _grid(model, cfg, size_xyz, spacing, bbox_start_voxel, bbox_end_voxel, use_g
 
 
 def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_start_voxel=None, bbox_end_voxel=None,
-                               use_gpu=True, spacing=None, z_ready=None):
+                               use_gpu=True, spacing=None, z_ready=None, mask_sink=None):
     """Device-resident core of segmentation_volume: `vol` is a CUDA float32 [z,y,x] tensor already at
     the model spacing.  Returns (mean_probs [C,z,y,x] fp32, mask [z,y,x] int8) on the device.
     shard=(rank, world): this process runs patches rank::world and the accumulators are summed with
-    an all-reduce over the default process group (NCCL) before the count normalisation."""
+    an all-reduce over the default process group (NCCL) before the count normalisation.
+    mask_sink=(host_mask, stream): with z_ready, every z slab is normalised, arg-maxed and copied to the (pinned) host
+    mask on `stream` as soon as no remaining patch touches it."""
     eng = model['engine']
     eng.plan = model['net']._current_plan()
     Z, Y, X = vol.shape
@@ -179,6 +181,13 @@ def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_sta
     acc = torch.zeros((model['out_channels'], Z, Y, X), dtype=torch.float32, device=vol.device)
     mine = starts if shard is None else starts[shard[0]::shard[1]]
     eng.batch = int(batch) if batch else (eng.batch if eng.batch > 0 else default_patch_batch(patch[0] * patch[1] * patch[2]))
+    counts = axis_counts([X, Y, Z], starts, ends)
+    if bbox_start_voxel is not None:
+        # voxels outside the partitioned box have count 0: the reference divides by zero there (inf*0 = nan
+        # -> argmax 0); keep them at probability 0 / label 0 by treating the count as 1.
+        counts = [np.maximum(c, 1) for c in counts]
+    progressive = z_ready is not None and mask_sink is not None and (shard is None or shard[1] == 1)
+    mask = torch.empty((Z, Y, X), dtype=torch.int8, device=vol.device) if progressive else None
     if z_ready is None:
         eng.accumulate(vol, mine, patch, norm, acc)
     else:
@@ -186,6 +195,7 @@ def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_sta
         # their last z plane and make each batch wait only for the slabs it reads.  The blend is order-independent.
         mine = sorted(mine, key=lambda s: s[2])
         cur = torch.cuda.current_stream()
+        z_done = 0
         for b0 in range(0, len(mine), eng.batch):
             chunk = mine[b0:b0 + eng.batch]
             zmax = max(s[2] for s in chunk) + patch[2]
@@ -194,14 +204,24 @@ def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_sta
                 if z1 >= zmax:
                     break
             eng.accumulate(vol, chunk, patch, norm, acc)
+            if progressive:
+                rest = mine[b0 + eng.batch:]
+                z_final = min(s[2] for s in rest) if rest else Z     # patches are sorted by their first z plane
+                if z_final > z_done:
+                    eng.finalize(acc, counts, z_range=(z_done, z_final), mask=mask)
+                    host_mask, side = mask_sink
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    side.wait_event(ev)
+                    with torch.cuda.stream(side):
+                        host_mask[z_done:z_final].copy_(mask[z_done:z_final], non_blocking=True)
+                    z_done = z_final
+        if progressive:
+            cur.wait_stream(mask_sink[1])
+            return acc, mask
     if shard is not None and shard[1] > 1:
         import torch.distributed as dist
         dist.all_reduce(acc, op=dist.ReduceOp.SUM)
-    counts = axis_counts([X, Y, Z], starts, ends)
-    if bbox_start_voxel is not None:
-        # voxels outside the partitioned box have count 0: the reference divides by zero there (inf*0 = nan
-        # -> argmax 0); keep them at probability 0 / label 0 by treating the count as 1.
-        counts = [np.maximum(c, 1) for c in counts]
     mask = eng.finalize(acc, counts)
     return acc, mask
 
@@ -227,10 +247,12 @@ def segmentation_volume_host(model, cfg, host_vol, host_mask=None, batch=None, s
                 z_ready.append((z1, ev))
     else:
         vol.copy_(host_vol, non_blocking=True)
-    acc, mask = segmentation_volume_device(model, cfg, vol, batch=batch, shard=shard, z_ready=z_ready)
     if host_mask is None:
-        host_mask = torch.empty(mask.shape, dtype=torch.int8, pin_memory=True)
-    host_mask.copy_(mask, non_blocking=True)
+        host_mask = torch.empty(host_vol.shape, dtype=torch.int8, pin_memory=True)
+    sink = (host_mask, _side_stream(dev)) if (z_ready is not None and host_mask.is_pinned()) else None
+    acc, mask = segmentation_volume_device(model, cfg, vol, batch=batch, shard=shard, z_ready=z_ready, mask_sink=sink)
+    if sink is None or (shard is not None and shard[1] > 1):
+        host_mask.copy_(mask, non_blocking=True)
     return acc, host_mask
 
 

@@ -120,3 +120,25 @@ def test_patch_gather_normalisers_bit_exact_fixed():
     for i, s in enumerate(starts):
         ref = osw.normalize_adaptive(np.ascontiguousarray(vol.numpy()[s[2]:s[2] + 32, s[1]:s[1] + 32, s[0]:s[0] + 32]), 2.5)
         assert np.abs(out[i].cpu().numpy() - ref).max() <= 1e-5
+
+
+@pytest.mark.parametrize('size,psize,pstride', [((64, 48, 80), 32, 16), ((48, 48, 96), 32, 32)], ids=['overlap', 'tiled'])
+def test_host_path_progressive_finalize_equals_device_path(size, psize, pstride):
+    """segmentation_volume_host (slab-wise upload, z-ordered patches, slab-wise finalize + mask copy-out) must give the
+    same probabilities and the same mask as the device-resident pass: the blend is order independent only up to fp32
+    atomics, so compare with a tight tolerance, and the mask against the first-argmax of its own probabilities."""
+    from segmentation3d.core.seg_infer import segmentation_volume_device, segmentation_volume_host
+    sd = oinit.init_state_dict('vnet', 1, 2, 3)
+    model = build_model('vnet', 2, sd, 'fp32', {'type': 0, 'mean': 0.0, 'stddev': 1.0, 'clip': False})
+    cfg = {'partition_type': 'SIZE', 'partition_size': [psize] * 3, 'partition_stride': [pstride] * 3}
+    vol = seeded_input(5, (1, 1, size[2], size[1], size[0]), 'smooth')[0, 0].contiguous()
+    acc_d, mask_d = segmentation_volume_device(model, cfg, vol.cuda(), batch=3)
+    host_vol = torch.empty(vol.shape, dtype=torch.float32, pin_memory=True)
+    host_vol.copy_(vol)
+    host_mask = torch.full(vol.shape, 77, dtype=torch.int8).pin_memory()
+    acc_h, hm = segmentation_volume_host(model, cfg, host_vol, host_mask, batch=3)
+    torch.cuda.synchronize()
+    assert hm is host_mask and not (host_mask == 77).any()
+    assert (acc_h - acc_d).abs().max() <= 1e-5
+    assert np.array_equal(host_mask.numpy(), osw.argmax_first(acc_h.cpu().numpy()))
+    assert float((host_mask.cuda() == mask_d).float().mean()) >= 0.9999
