@@ -82,6 +82,14 @@ int seg3d_conv3d_k3_narrow_np(int Cout);
 int seg3d_conv3d_k3_narrow_fwd(int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
                                float* y, int Cout, int N, int D, int H, int W, double* stats, void* stream);
 
+/* conv -> GroupNorm(1,C) -> ReLU without the raw intermediate, as two launches of the same tensor-core convolution
+ * (vnet_downblock.py:19, vnet_upblock.py:19: the stride-2 / transposed convolutions are HBM-bound and cheap to run twice).
+ * pass 0: stats[n] += {sum, sum of squares} of conv + bias, nothing is stored;  pass 1: recompute and store
+ * y = relu((conv + bias - mean) * rstd * gamma + beta) from the finished statistics.  TCGEN05 shapes only. */
+int seg3d_conv3d_gn_relu_fwd(int mode, int dtype, int pass, const void* x, int x_ld, int Cin, const void* w,
+                             const float* bias, void* y, int y_ld, int Cout, int N, int D, int H, int W,
+                             double* stats, const float* gamma, const float* beta, float eps, void* stream);
+
 /* ---- GroupNorm(1,C) apply + ReLU + residual (replaces nn.GroupNorm, nn.ReLU, `input + output`,
  * torch.cat: conv_gn_relu3.py:17-19, residual_block3.py:24,46, vnet_upblock.py:20-21) ----------
  * out = [relu]( (y-mean)*rstd*gamma + beta [+ res] ), mean/rstd from stats over C*nvox elements

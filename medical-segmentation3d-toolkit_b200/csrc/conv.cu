@@ -4,7 +4,8 @@
 int seg3d_conv_simt(int mode, int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
                     void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st);
 int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
-                  void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st);
+                  void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st,
+                  int epi_mode, const double* gn_stats, const float* gn_gamma, const float* gn_beta, float gn_eps);
 int seg3d_conv_cin1_tc_supported(int dtype, int Cin, int Cout, int x_ld, int y_ld, int W);
 int seg3d_conv_cin1_tc(int dtype, const void* x, const void* w, const float* bias, void* y, int y_ld,
                        int N, int D, int H, int W, double* stats, cudaStream_t st);
@@ -28,11 +29,29 @@ extern "C" int seg3d_conv3d_fwd(int mode, int dtype, int impl, const void* x, in
       seg3d_set_error("conv3d_fwd: tcgen05 path does not take mode=%d dtype=%d Cin=%d Cout=%d", mode, dtype, Cin, Cout);
       return SEG3D_EUNSUPPORTED;
     }
-    return seg3d_conv_tc(mode, dtype, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, stats, st);
+    return seg3d_conv_tc(mode, dtype, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, stats, st, 0, nullptr, nullptr, nullptr, 0.f);
   }
   SEG3D_REQUIRE(!(dtype & SEG3D_OUT_F32), "conv3d_fwd: SEG3D_OUT_F32 needs the tensor-core path");
   if (impl == SEG3D_IMPL_SIMT)
     return seg3d_conv_simt(mode, dtype, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, stats, st);
   seg3d_set_error("conv3d_fwd: unknown impl %d", impl);
   return SEG3D_EINVAL;
+}
+
+// conv -> GroupNorm(1,C) -> ReLU in two launches of the same tensor-core convolution, for convolutions that are cheap to run
+// twice (the HBM-bound stride-2 / transposed convs: conv_gn_relu of vnet_downblock.py:19 and vnet_upblock.py:19 without the
+// raw intermediate).  pass 0: accumulate sum / sum-of-squares into `stats` (nothing is stored);  pass 1: recompute and store
+// y = relu((conv - mean) * rstd * gamma + beta) from the finished statistics.
+extern "C" int seg3d_conv3d_gn_relu_fwd(int mode, int dtype, int pass, const void* x, int x_ld, int Cin, const void* w,
+                                        const float* bias, void* y, int y_ld, int Cout, int N, int D, int H, int W,
+                                        double* stats, const float* gamma, const float* beta, float eps, void* stream) {
+  SEG3D_REQUIRE(x && w && y && stats && gamma && beta, "conv3d_gn_relu_fwd: null pointer");
+  SEG3D_REQUIRE(pass == 0 || pass == 1, "conv3d_gn_relu_fwd: pass must be 0 or 1");
+  SEG3D_REQUIRE(Cin > 0 && Cout > 0 && N > 0 && D > 0 && H > 0 && W > 0 && x_ld >= Cin && y_ld >= Cout, "conv3d_gn_relu_fwd: bad dims");
+  if (!seg3d_conv_tc_supported(mode, dtype, Cin, Cout, x_ld, y_ld, D, H, W)) {
+    seg3d_set_error("conv3d_gn_relu_fwd: tcgen05 path does not take mode=%d dtype=%d Cin=%d Cout=%d", mode, dtype, Cin, Cout);
+    return SEG3D_EUNSUPPORTED;
+  }
+  return seg3d_conv_tc(mode, dtype, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, pass == 0 ? stats : nullptr,
+                       (cudaStream_t)stream, pass == 0 ? 1 : 2, stats, gamma, beta, eps);
 }

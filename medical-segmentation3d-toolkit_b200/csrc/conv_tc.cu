@@ -46,6 +46,14 @@ struct TcParams {
   int x_ld, halfW, halfH;           // k2s2 coordinate folding
   int ntiles, acc_cols;             // persistent kernel: total tiles, TMEM columns per accumulator buffer
   int wide;                         // epilogue may use 256-bit stores (32-byte aligned rows)
+  // GroupNorm folded into the epilogue of a conv that is cheap to run twice (HBM-bound stride-2 / transposed convs):
+  // epi_mode 0: store raw + statistics; 1: statistics only, nothing stored; 2: y = relu(gn(conv)) from finished statistics
+  int epi_mode;
+  float gn_eps;
+  double gn_count;                  // elements per sample of the GroupNorm(1,C) input = real Cout * output voxels
+  const double* gn_stats;           // [N][2] finished sums (epi_mode 2)
+  const float* gn_gamma;
+  const float* gn_beta;
 };
 
 // Persistent variant: each CTA walks tiles blockIdx.x, +gridDim.x, ...; the operand ring keeps
@@ -66,8 +74,10 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   const uint32_t tfull_bar = empty_bar + 8 * p.stages;        // [2]
   const uint32_t tempty_bar = tfull_bar + 16;                 // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 4);     // [cout_real] bias (zeros when there is none), 16-byte aligned
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
+  for (int c = threadIdx.x; c < p.cout_real; c += blockDim.x) sbias[c] = bias ? bias[c] : 0.f;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -162,7 +172,8 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     const int r = q * 32 + lane;
     const int lx = r % p.tw, ly = (r / p.tw) % p.th, lz = r / (p.tw * p.th);
     float s = 0.f, ss = 0.f;
-    int cur_n = -1, j = 0;
+    int cur_n = -1, j = 0, gn_n = -1;
+    float gn_mean = 0.f, gn_rstd = 1.f;
     const bool wide = p.wide != 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++j) {
       int t = tile;
@@ -177,6 +188,7 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
         }
         s = 0.f; ss = 0.f; cur_n = n;
       }
+      if (p.epi_mode == 2 && n != gn_n) { gn_mean_rstd(p.gn_stats + 2 * n, p.gn_count, p.gn_eps, gn_mean, gn_rstd); gn_n = n; }
       const int gx = x0 + lx, gy = y0 + ly, gz = z0 + lz;
       const bool valid = (gx < p.W) && (gy < p.H) && (gz < p.D);      // W/H/D = OUTPUT dims here
       const size_t vox = (((size_t)n * p.D + gz) * p.H + gy) * p.W + gx;
@@ -187,22 +199,39 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
       const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.acc_cols);
       // this warp's 16-column chunks: half, half+2, ...; the TMEM load of the next chunk is in flight while the
       // current one is converted and stored
+      // t2s2: column -> (tap, co), output voxel (2z+kd, 2y+kh, 2x+kw): one 64-bit base per tile, 32-bit tap offsets per chunk
+      T* ybase = yrow;
+      if (p.conv == 2) {
+        const size_t ov0 = (((size_t)n * 2 * p.D + 2 * gz) * 2 * p.H + 2 * gy) * 2 * p.W + 2 * gx;
+        ybase = y + ov0 * p.y_ld;
+      }
       auto emit = [&](const uint32_t* v, int c0) {
         float f[16];
-        int co = c0;
-        T* dst = yrow + c0;
-        if (p.conv == 2) {           // column -> (tap, co); scatter to output voxel (2z+kd, 2y+kh, 2x+kw)
+        int co = c0, off = c0;
+        if (p.conv == 2) {
           const int col = pass * p.Cout + c0;
           const int tap = col / p.cout_real; co = col - tap * p.cout_real;
-          const size_t ov = (((size_t)n * 2 * p.D + 2 * gz + (tap >> 2)) * 2 * p.H + 2 * gy + ((tap >> 1) & 1)) * 2 * p.W + 2 * gx + (tap & 1);
-          dst = y + ov * p.y_ld + co;
+          off = (((tap >> 2) * 2 * p.H + ((tap >> 1) & 1)) * 2 * p.W + (tap & 1)) * p.y_ld + co;
         }
+        const float4* b4 = reinterpret_cast<const float4*>(sbias + co);
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          f[jj] = __uint_as_float(v[jj]) + (bias ? bias[co + jj] : 0.f);
-          if (valid) { s += f[jj]; ss += f[jj] * f[jj]; }
+        for (int jj = 0; jj < 16; jj += 4) {
+          const float4 bb = b4[jj >> 2];
+          f[jj] = __uint_as_float(v[jj]) + bb.x; f[jj + 1] = __uint_as_float(v[jj + 1]) + bb.y;
+          f[jj + 2] = __uint_as_float(v[jj + 2]) + bb.z; f[jj + 3] = __uint_as_float(v[jj + 3]) + bb.w;
         }
-        if (valid) store16<T>(dst, f, wide);
+        if (valid) {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) { s += f[jj]; ss = fmaf(f[jj], f[jj], ss); }
+        }
+        if (p.epi_mode == 2) {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const float a = gn_rstd * p.gn_gamma[co + jj];
+            f[jj] = fmaxf(fmaf(f[jj], a, p.gn_beta[co + jj] - gn_mean * a), 0.f);
+          }
+        }
+        if (valid && p.epi_mode != 1) store16<T>(ybase + off, f, wide);
       };
       uint32_t va[16], vb[16];
       int c0 = half * 16;
@@ -773,7 +802,8 @@ int seg3d_conv_tc_supported(int mode, int dtype, int Cin, int Cout, int x_ld, in
 }
 
 int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
-                  void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st) {
+                  void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st,
+                  int epi_mode, const double* gn_stats, const float* gn_gamma, const float* gn_beta, float gn_eps) {
   EncodeTiledFn encode = get_encode();
   if (!encode) { seg3d_set_error("conv_tc: cuTensorMapEncodeTiled entry point not available"); return SEG3D_ECUDA; }
   SEG3D_REQUIRE(((uintptr_t)x) % 16 == 0 && ((uintptr_t)w) % 16 == 0 && ((uintptr_t)y) % 16 == 0, "conv_tc: pointers must be 16-byte aligned");
@@ -781,7 +811,7 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   // ---- z-marching kernel for narrow k3 layers --------------------------------------------------------
   const int out_f32 = (dtype & SEG3D_OUT_F32) ? 1 : 0;
   dtype &= ~SEG3D_OUT_F32;
-  if (mode == SEG3D_CONV_K3 && (Cin == 16 || Cin == 32 || Cin == 64) && W % 8 == 0 && D >= 4 && env_int("SEG3D_TC_ZMARCH", 1) != 0) {
+  if (epi_mode == 0 && mode == SEG3D_CONV_K3 && (Cin == 16 || Cin == 32 || Cin == 64) && W % 8 == 0 && D >= 4 && env_int("SEG3D_TC_ZMARCH", 1) != 0) {
     ZmParams z;
     memset(&z, 0, sizeof(z));
     z.Cout = Cout; z.KC = Cin; z.row_bytes = Cin * 2;
@@ -876,6 +906,11 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   p.Cin = Cin; p.Cout = Cout; p.D = Do; p.H = Ho; p.W = Wo; p.N = N; p.y_ld = y_ld;
   p.x_ld = x_ld; p.halfW = W / 2; p.halfH = H / 2;
   p.wide = (wide_ok(y, y_ld, 2) && p.cout_real % 16 == 0 && env_int("SEG3D_WIDE_ST", 1)) ? 1 : 0;
+  p.epi_mode = epi_mode; p.gn_eps = gn_eps; p.gn_stats = gn_stats; p.gn_gamma = gn_gamma; p.gn_beta = gn_beta;
+  {
+    const long long ovox = p.conv == 1 ? (long long)(D / 2) * (H / 2) * (W / 2) : (p.conv == 2 ? 8ll * D * H * W : (long long)D * H * W);
+    p.gn_count = (double)ovox * (double)p.cout_real;
+  }
   p.KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
   p.nchunk = Cin / p.KC;
   const int row_bytes = p.KC * 2;
@@ -960,7 +995,7 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { seg3d_set_error("conv_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SEG3D_ECUDA; }
   }
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 64;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 64 + 256 * 4;
   const long long max_grid = (long long)ctas_per_sm * seg3d_num_sms();
   dim3 grid((unsigned)(ntiles < max_grid ? ntiles : max_grid));
   cudaError_t e = dtype == SEG3D_BF16 ? launch_tc<__nv_bfloat16>(grid, smem, st, map_x, map_w, p, bias, y, stats)

@@ -274,9 +274,36 @@ class NetPlan(object):
                 return _View(torch.empty((B, vox[l], C), dtype=td, device=dev), 0, C, C)
             return _View(ws[key], 0, C, C)
 
+        def conv_gn_twice(cname, gname, x, xdims, out, nvox_out):
+            """HBM-bound stride-2 / transposed conv: run it twice (statistics, then GroupNorm + ReLU in the epilogue)
+            instead of storing the raw result and streaming it through seg3d_gn_apply"""
+            c, g = self.convs[cname], self.gns[gname]
+            sp = lib.ptr(ws['stats'][self.gn_index[gname]])
+            esz = 2
+            nv_in = B * xdims[0] * xdims[1] * xdims[2]
+            taps = 1 if c.mode == lib.CONV_K2S2 else 8
+            kind = 'conv_tc_' + ('k2s2' if c.mode == lib.CONV_K2S2 else 't2s2')
+            for ps in (0, 1):
+                args = (c.mode, dt, ps, x.p, x.ld, c.cin, lib.ptr(c.w), lib.ptr(c.bias), out.p, out.ld, c.cout,
+                        B, xdims[0], xdims[1], xdims[2], sp, lib.ptr(g.gamma), lib.ptr(g.beta), GN_EPS)
+                ops.append(lambda a=args: lib.call('seg3d_conv3d_gn_relu_fwd', *a, st()))
+                meta.append({'name': cname + ('.stats' if ps == 0 else '.gn_relu'), 'kind': kind,
+                             'flops': 2.0 * nv_in * taps * c.cin * c.cout if ps == 1 else 0.0,
+                             'bytes': esz * (nv_in * c.cin + (B * nvox_out * c.cout if ps == 1 else 0)) + c.w.numel() * 2})
+
+        # measured on B200: the stride-2 convs are epilogue-bound, not HBM-bound, so running them twice costs more than the
+        # GroupNorm pass it saves (1535 vs 1640 Mvox/s); kept behind SEG3D_FUSE_S2=1
+        fuse_s2 = (not train) and dt != lib.F32 and os.environ.get('SEG3D_FUSE_S2', '0') == '1'
+
         def unit(cname, gname, x, lin, lout, out, res=None):
             """conv -> GroupNorm -> (+res) -> ReLU with the conv reading level `lin` and writing level `lout`"""
-            C = self.convs[cname].cout
+            c = self.convs[cname]
+            C = c.cout
+            if (fuse_s2 and res is None and c.impl == lib.IMPL_TCGEN05 and c.mode in (lib.CONV_K2S2, lib.CONV_T2S2)
+                    and out.ld % 8 == 0):
+                conv_gn_twice(cname, gname, x, dims[lin], out, vox[lout])
+                units.append({'conv': cname, 'gn': gname, 'x': x, 'lin': lin, 'lout': lout, 'raw': None, 'out': out, 'res': res})
+                return
             rv = rawview(C, lout)
             conv(cname, x, dims[lin], rv, gname)
             gn(gname, rv, out, vox[lout], True, res)

@@ -427,3 +427,37 @@ def test_conv_cin1_tensor_core_matches_torch(lib, shape, dt_name):
     s_ref = torch.stack([ref.double().flatten(1).sum(1), (ref.double() ** 2).flatten(1).sum(1)], 1)
     rt = 1e-5 if dt == L.F16 else 2e-4                 # the sums come from the fp32 accumulators (hi+lo weights)
     assert torch.allclose(stats.cpu(), s_ref, rtol=rt, atol=rt * float(s_ref[:, 1].max()))
+
+
+@pytest.mark.parametrize('case', [('K2S2', 16, 32, 2, 8, 12, 16), ('K2S2', 64, 128, 1, 8, 8, 8), ('T2S2', 64, 16, 2, 4, 6, 8),
+                                  ('T2S2', 256, 128, 1, 2, 4, 4)], ids=lambda c: '-'.join(map(str, c)))
+def test_conv_gn_relu_two_pass_matches_torch(lib, case):
+    """seg3d_conv3d_gn_relu_fwd (statistics pass, then GroupNorm + ReLU in the epilogue) vs relu(group_norm(conv)) in fp32
+    on the same fp16-rounded operands; the output lands in one half of a wider concat buffer."""
+    L = lib
+    dt, tdt = L.F16, torch.float16
+    mname, Cin, Cout, N, D, H, W = case
+    mode = getattr(L, 'CONV_' + mname)
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x = torch.randn((N, Cin, D, H, W), generator=g).to(tdt).float()
+    wshape = (Cin, Cout, 2, 2, 2) if mode == L.CONV_T2S2 else (Cout, Cin, 2, 2, 2)
+    w = (torch.randn(wshape, generator=g) * 0.1).to(tdt).float()
+    b = torch.randn((Cout,), generator=g) * 0.1
+    gamma = torch.rand((Cout,), generator=g) + 0.5
+    beta = torch.randn((Cout,), generator=g) * 0.2
+    ref = F.relu(F.group_norm(ref_conv(mode, L, x, w, b), 1, gamma, beta, 1e-5))
+    od = ref.shape[2:]
+    ld = 2 * Cout
+    y = torch.full((N,) + tuple(od) + (ld,), float('nan'), dtype=tdt, device='cuda')
+    stats = torch.zeros((N, 2), dtype=torch.float64, device='cuda')
+    xd, wp = to_ndhwc(x, tdt), pack_tc(w, mode, L, tdt)
+    bd, gd, btd = b.cuda(), gamma.cuda(), beta.cuda()
+    for ps in (0, 1):
+        L.call('seg3d_conv3d_gn_relu_fwd', mode, dt, ps, L.ptr(xd), Cin, Cin, L.ptr(wp), L.ptr(bd), L.ptr(y, Cout), ld, Cout,
+               N, D, H, W, L.ptr(stats), L.ptr(gd), L.ptr(btd), 1e-5, L.stream_ptr())
+        torch.cuda.synchronize()
+        if ps == 0:
+            assert torch.isnan(y.float()).all()                     # the statistics pass stores nothing
+    assert torch.isnan(y[..., :Cout].float()).all()
+    yc = from_ndhwc(y[..., Cout:])
+    assert (yc - ref).abs().max() <= 2.0 ** -10 * max(1.0, float(ref.abs().max())) + 1e-4

@@ -11,7 +11,10 @@ data = []
 for r in rows[2:]:
     if len(r) < len(hdr):
         continue
-    n = int(r[ix['# Samples']] or 0)
+    try:
+        n = int(r[ix['# Samples']] or 0)
+    except ValueError:
+        continue
     data.append((n, r))
 tot = sum(n for n, _ in data)
 print('total samples', tot)
