@@ -140,6 +140,13 @@ int seg3d_blend_finalize_argmax_z(float* acc, int C, int Z, int Y, int X, int z0
                                   const int32_t* cx, const int32_t* cy, const int32_t* cz,
                                   int8_t* mask, void* stream);
 
+/* ---- resampling either side of the path (utils/image_tools.py:329-377: sitk.Resample with an identity transform) ------
+ * src [sz][sy][sx] -> dst [dz][dy][dx], both fp32, same origin and direction: output index i reads the continuous input
+ * index i * r (r = spacing_out / spacing_in per axis, double).  linear != 0: trilinear with the upper neighbour clamped;
+ * else nearest (floor(c + 0.5)).  Voxels whose continuous index is not in [-0.5, size - 0.5) get default_value. */
+int seg3d_resample(const float* src, int sz, int sy, int sx, float* dst, int dz, int dy, int dx,
+                   double rz, double ry, double rx, int linear, float default_value, void* stream);
+
 /* ---- losses on probabilities (loss/multi_dice_loss.py, loss/binary_dice_loss.py, loss/focal_loss.py) -
  * probs fp32 [B][C][n], target fp32 [B][n] (class index stored as float, dataloader/dataset.py:208). */
 /* terms[b][c] = { sum q*t, sum q*q, sum t*t } with q = p*[p > 1/C], t = [target == c] (double) */

@@ -25,7 +25,7 @@ from segmentation3d._b200.sliding import SlidingWindow, axis_counts
 from segmentation3d.utils.attrdict import AttrDict as edict
 from segmentation3d.utils.file_io import load_config, readlines
 from segmentation3d.utils.image3d import Image3d, as_image3d, read_image, write_image
-from segmentation3d.utils.image_tools import image_partition_by_fixed_size, is_identity_resample
+from segmentation3d.utils.image_tools import image_partition_by_fixed_size, is_identity_resample, resample, resample_spacing
 from segmentation3d.utils.model_io import get_checkpoint_folder
 from segmentation3d.utils.normalizer import normalizer_from_dict
 
@@ -293,20 +293,44 @@ def segmentation_volume(model, cfg, image, bbox_start_voxel, bbox_end_voxel, use
     if not use_gpu:
         r = _cfg_get(cfg, 'cpu_model_spacing_increase_ratio', 1.0)
         model_spacing = [v * r for v in model_spacing]
-    if not is_identity_resample(image, model_spacing, model['max_stride']):
-        raise NotImplementedError('resampling to the model spacing is not built yet (SURVEY.md 8f-2): image spacing %s / '
-                                  'size %s must equal model spacing %s with size %% %d == 0'
-                                  % (image.GetSpacing(), image.GetSize(), model_spacing, model['max_stride']))
     dev = next(model['net'].parameters()).device
-    data = image.data
-    vol = (data if torch.is_tensor(data) else torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)))
-    vol = vol.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+    identity = is_identity_resample(image, model_spacing, model['max_stride'])
+    if identity:
+        iso_image = image
+        data = image.data
+        vol = (data if torch.is_tensor(data) else torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)))
+        vol = vol.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+    else:
+        # resample to the model spacing on the device (:267)
+        with torch.cuda.device(dev):
+            iso_image = resample_spacing(Image3d(image.data if not torch.is_tensor(image.data) else image.data.to(dev),
+                                                 image.GetSpacing(), image.GetOrigin(), image.GetDirection()),
+                                         model_spacing, model['max_stride'], model['interpolation'])
+        vol = iso_image.data
     if bbox_start_voxel is not None and bbox_end_voxel is not None:
-        # identity resample: the iso frame equals the image frame (:292-302)
+        # convert the bounding box to the iso image frame (:292-302)
+        if not identity:
+            bs = image.TransformContinuousIndexToPhysicalPoint([float(v) for v in bbox_start_voxel])
+            be = image.TransformContinuousIndexToPhysicalPoint([float(v) for v in bbox_end_voxel])
+            bbox_start_voxel = iso_image.TransformPhysicalPointToIndex(bs)
+            bbox_end_voxel = iso_image.TransformPhysicalPointToIndex(be)
         bbox_start_voxel = [max(0, int(v)) for v in bbox_start_voxel]
-        bbox_end_voxel = [min(int(bbox_end_voxel[a]), image.GetSize()[a]) for a in range(3)]
+        bbox_end_voxel = [min(int(bbox_end_voxel[a]), iso_image.GetSize()[a]) for a in range(3)]
     acc, mask = segmentation_volume_device(model, cfg, vol, bbox_start_voxel=bbox_start_voxel,
                                            bbox_end_voxel=bbox_end_voxel, use_gpu=use_gpu, spacing=model_spacing)
+    if not identity:
+        # resample every class map back to the scan's grid (pad 1.0 for the background class, 0.0 otherwise) and take
+        # the first-argmax there (:329-338)
+        num_classes = model['out_channels']
+        X, Y, Z = image.GetSize()
+        back = torch.empty((num_classes, Z, Y, X), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            for c in range(num_classes):
+                iso_c = Image3d(acc[c], iso_image.GetSpacing(), iso_image.GetOrigin(), iso_image.GetDirection())
+                back[c] = resample(iso_c, image, 'LINEAR', 1.0 if c == 0 else 0.0).data
+            ones = [np.ones(n, dtype=np.int32) for n in (X, Y, Z)]
+            mask = model['engine'].finalize(back, ones)
+        acc = back
     num_classes = model['out_channels']
     mean_probs = []
     for c in range(num_classes):

@@ -72,6 +72,46 @@ def is_identity_resample(image, spacing, max_stride):
     return same and resample_size(size, image.GetSpacing(), spacing, max_stride) == list(size)
 
 
+def _resample_device(src, in_spacing, out_size_xyz, out_spacing, interp_method, padding_value, device=None):
+    """fp32 [z,y,x] tensor on `in_spacing` -> CUDA fp32 [z,y,x] of out_size on out_spacing (same origin / direction)."""
+    from segmentation3d._b200 import lib
+    if interp_method not in ('LINEAR', 'NN'):
+        raise ValueError('Unsupported interpolation type.')
+    if device is None:
+        device = src.device if (torch.is_tensor(src) and src.is_cuda) else torch.device('cuda')
+    t = src if torch.is_tensor(src) else torch.from_numpy(np.ascontiguousarray(src))
+    t = t.to(device=device, dtype=torch.float32).contiguous()
+    if t.device.type != 'cuda':
+        raise RuntimeError('seg3d_b200: resampling runs on CUDA devices only (no CPU fallback)')
+    dx, dy, dz = [int(v) for v in out_size_xyz]
+    out = torch.empty((dz, dy, dx), dtype=torch.float32, device=t.device)
+    r = [float(out_spacing[a]) / float(in_spacing[a]) for a in range(3)]          # x, y, z
+    with torch.cuda.device(t.device):
+        lib.call('seg3d_resample', lib.ptr(t), t.shape[0], t.shape[1], t.shape[2], lib.ptr(out), dz, dy, dx,
+                 r[2], r[1], r[0], 1 if interp_method == 'LINEAR' else 0, float(padding_value), lib.stream_ptr())
+    return out
+
+
+def resample(image, reference, interp_method, padding_value=0.0):
+    """Resample `image` onto the grid of `reference` (utils/image_tools.py:329-343).  Both images must share origin and
+    direction, which is how the engine uses it (core/seg_infer.py:330-333)."""
+    img, ref = as_image3d(image), as_image3d(reference)
+    if (max(abs(a - b) for a, b in zip(img.GetOrigin(), ref.GetOrigin())) > 1e-6 or
+            max(abs(a - b) for a, b in zip(img.GetDirection(), ref.GetDirection())) > 1e-9):
+        raise ValueError('resample: image and reference must share origin and direction')
+    out = _resample_device(img.data, img.GetSpacing(), ref.GetSize(), ref.GetSpacing(), interp_method, padding_value)
+    return Image3d(out, ref.GetSpacing(), ref.GetOrigin(), ref.GetDirection())
+
+
+def resample_spacing(image, resampled_spacing, max_stride, interp_method):
+    """Resample to `resampled_spacing`; the output size is rounded up to a multiple of max_stride
+    (utils/image_tools.py:346-377)."""
+    img = as_image3d(image)
+    osz = resample_size(img.GetSize(), img.GetSpacing(), resampled_spacing, max_stride)
+    out = _resample_device(img.data, img.GetSpacing(), osz, resampled_spacing, interp_method, 0.0)
+    return Image3d(out, [float(v) for v in resampled_spacing], img.GetOrigin(), img.GetDirection())
+
+
 def convert_image_to_tensor(image):
     """Image (or list of images) -> float tensor [1,z,y,x] ([n,z,y,x] for a list)."""
     if isinstance(image, (list, tuple)):

@@ -192,3 +192,18 @@ def overlap_count_axes(size_xyz, starts, ends):
     for s, e in zip(starts, ends):
         cnt[s[2]:e[2], s[1]:e[1], s[0]:e[0]] += 1.0
     return cnt
+
+
+def segmentation_volume_resampled(state_dict, vol_zyx, image_spacing, model_spacing, normalizer, interpolation='LINEAR',
+                                  max_stride=16, **kw):
+    """core/seg_infer.py:262-339 for a scan whose spacing differs from the model's: resample to the model spacing (:267),
+    segment there, resample every class map back to the scan's grid with padding 1.0 for class 0 and 0.0 otherwise
+    (:329-333), first-argmax on the scan's grid (:336-338).  Returns (mean_probs [C,z,y,x], mask [z,y,x] int8)."""
+    from oracle import resample as orz
+    vol = np.asarray(vol_zyx, dtype=np.float32)
+    in_size = [vol.shape[2], vol.shape[1], vol.shape[0]]
+    iso, _ = orz.resample_spacing(vol, image_spacing, model_spacing, max_stride, interpolation)
+    probs_iso, _, _, _ = segmentation_volume(state_dict, iso, model_spacing, normalizer, max_stride=max_stride, **kw)
+    back = np.stack([orz.resample_grid(probs_iso[c], model_spacing, in_size, image_spacing, 'LINEAR', 1.0 if c == 0 else 0.0)
+                     for c in range(probs_iso.shape[0])], 0)
+    return back, argmax_first(back)

@@ -142,3 +142,52 @@ def test_host_path_progressive_finalize_equals_device_path(size, psize, pstride)
     assert (acc_h - acc_d).abs().max() <= 1e-5
     assert np.array_equal(host_mask.numpy(), osw.argmax_first(acc_h.cpu().numpy()))
     assert float((host_mask.cuda() == mask_d).float().mean()) >= 0.9999
+
+
+@pytest.mark.parametrize('interp', ['LINEAR', 'NN'])
+@pytest.mark.parametrize('case', [((40, 36, 20), (0.7, 0.8, 2.5), (1.0, 1.0, 1.0)), ((32, 32, 48), (1.0, 1.0, 1.0), (0.4, 0.6, 0.5)),
+                                  ((33, 17, 9), (1.3, 0.9, 1.1), (1.0, 1.0, 1.0))], ids=['aniso-to-iso', 'upsample', 'odd'])
+def test_resample_kernel_matches_oracle(case, interp):
+    """seg3d_resample vs the ITK-semantics restatement in oracle/resample.py (double-precision coordinates and weights on
+    both sides: the float32 results must agree to the last bit, up to the fused-multiply-add contraction of the GPU)."""
+    from oracle import resample as orz
+    from segmentation3d.utils.image3d import Image3d
+    from segmentation3d.utils.image_tools import resample, resample_spacing
+    size, sp_in, sp_out = case
+    vol = seeded_input(21, (1, 1, size[2], size[1], size[0]), 'smooth')[0, 0].numpy().astype(np.float32) * 100.0
+    ref, osz = orz.resample_spacing(vol, sp_in, sp_out, 16, interp)
+    im = resample_spacing(Image3d(vol, sp_in, (3.0, -2.0, 10.0)), sp_out, 16, interp)
+    got = im.to_numpy()
+    assert list(im.GetSize()) == osz and im.GetSpacing() == tuple(sp_out) and im.GetOrigin() == (3.0, -2.0, 10.0)
+    assert got.dtype == np.float32 and got.shape == ref.shape
+    tol = 0.0 if interp == 'NN' else 2e-5 * float(np.abs(vol).max())
+    assert np.abs(got - ref).max() <= tol
+    # and back onto the original grid with a padding value (core/seg_infer.py:330-333)
+    back_ref = orz.resample_grid(ref, sp_out, size, sp_in, 'LINEAR', 1.0)
+    back = resample(Image3d(ref, sp_out), Image3d(vol, sp_in), 'LINEAR', 1.0).to_numpy()
+    assert np.abs(back - back_ref).max() <= 2e-5 * float(np.abs(vol).max())
+
+
+def test_segmentation_volume_resamples_anisotropic_scan():
+    """Scan spacing != model spacing: resample -> segment -> resample back -> argmax, against the oracle pipeline."""
+    from segmentation3d.core.seg_infer import segmentation_volume
+    from segmentation3d.utils.image3d import Image3d
+    sd = oinit.init_state_dict('vnet', 1, 2, 4)
+    norm = {'type': 0, 'mean': 0.0, 'stddev': 1.0, 'clip': False}
+    model = build_model('vnet', 2, sd, 'fp32', norm)
+    model['spacing'] = [1.0, 1.0, 1.0]
+    size, sp = (56, 44, 20), (0.8, 0.9, 2.0)                       # -> iso 48 x 48 x 48 after rounding up to multiples of 16
+    vol = seeded_input(8, (1, 1, size[2], size[1], size[0]), 'smooth')[0, 0].numpy().astype(np.float32)
+    cfg = {'partition_type': 'SIZE', 'partition_size': [32, 32, 32], 'partition_stride': [16, 16, 16],
+           'pick_largest_cc': False, 'remove_small_cc': 0}
+    probs_im, mask_im = segmentation_volume(model, cfg, Image3d(vol, sp), None, None, True)
+    probs = np.stack([p.to_numpy() for p in probs_im], 0)
+    mask = mask_im.to_numpy()
+    ref_probs, ref_mask = osw.segmentation_volume_resampled(sd, vol, sp, [1.0, 1.0, 1.0], norm, 'LINEAR', 16,
+                                                            partition_size=[32, 32, 32], partition_stride=[16, 16, 16],
+                                                            double_forward=False, faithful_copies=False)
+    assert probs.shape == ref_probs.shape == (2,) + vol.shape and mask.shape == vol.shape and mask.dtype == np.int8
+    assert mask_im.GetSpacing() == sp and probs_im[0].GetSpacing() == sp
+    assert np.abs(probs - ref_probs).max() <= 1e-3
+    assert float((mask == ref_mask).mean()) >= 0.999
+    assert np.array_equal(mask, osw.argmax_first(probs))

@@ -163,3 +163,25 @@ def test_cal_dsc():
 def test_resample_out_size_rounding():
     assert osw.resample_out_size([512, 512, 400], [1, 1, 1], [1, 1, 1], 16) == [512, 512, 400]
     assert osw.resample_out_size([300, 300, 200], [0.5, 0.5, 1.0], [0.4, 0.4, 0.4], 16) == [384, 384, 512]
+
+
+def test_oracle_resample_restatement_known_answers():
+    """oracle/resample.py (ITK Resample semantics, parity unpinned): hand-checked 1-D cases embedded in 3-D."""
+    from oracle import resample as orz
+    line = np.array([0.0, 10.0, 20.0, 40.0], dtype=np.float32)
+    src = np.broadcast_to(line, (2, 3, 4)).copy()
+    # same spacing, same size: identity
+    assert np.array_equal(orz.resample_grid(src, [1, 1, 1], [4, 3, 2], [1, 1, 1], 'LINEAR'), src)
+    # x spacing 1 -> 0.5: c = 0, .5, 1, ..., 3.5 ; c < 3.5 is inside, c = 3.5 gets the default value
+    out = orz.resample_grid(src, [1, 1, 1], [8, 3, 2], [0.5, 1, 1], 'LINEAR', default_value=-7.0)
+    assert np.allclose(out[0, 0], [0, 5, 10, 15, 20, 30, 40, -7.0])
+    # between the last sample and the buffer edge the upper neighbour is clamped (c = 3.25 -> 40)
+    out = orz.resample_grid(src, [1, 1, 1], [14, 3, 2], [0.25, 1, 1], 'LINEAR', default_value=-7.0)
+    assert out[0, 0, 13] == 40.0 and out[1, 2, 12] == 40.0 and out[0, 0, 1] == 2.5
+    # nearest: floor(c + 0.5)
+    out = orz.resample_grid(src, [1, 1, 1], [8, 3, 2], [0.5, 1, 1], 'NN', default_value=-7.0)
+    assert np.array_equal(out[0, 0], np.array([0, 10, 10, 20, 20, 40, 40, -7.0], dtype=np.float32))
+    # output size rule of resample_spacing (image_tools.py:363-366)
+    assert orz.out_size([100, 100, 40], [0.5, 0.5, 2.0], [1, 1, 1], 16) == [64, 64, 80]
+    with pytest.raises(ValueError):
+        orz.resample_grid(src, [1, 1, 1], [4, 3, 2], [1, 1, 1], 'CUBIC')
