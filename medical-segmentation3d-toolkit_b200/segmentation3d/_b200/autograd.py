@@ -12,8 +12,11 @@ An activation can have up to three consumers (next conv, residual add, skip conn
 its contribution into its own buffer and the producer's gn_bwd sums them on the fly, so nothing is accumulated
 read-modify-write.  All arithmetic is in libseg3d_b200.so; torch only owns the buffers and the autograd node.
 """
+import os
+
 import torch
 
+from . import dist as D
 from . import lib
 from .plan import GN_EPS, _Conv, _View
 
@@ -59,10 +62,13 @@ class _Backward(object):
                   ('out_block.gn2.weight', nc), ('out_block.gn2.bias', nc)]
         total = sum((n + 3) // 4 * 4 for _, n in sizes)          # 16-byte aligned slots
         self.pgrad_flat = torch.zeros((total,), dtype=torch.float32, device=dev)
-        self.pgrad, off = {}, 0
+        self.pgrad, self.pg_off, off = {}, {}, 0
         for k, n in sizes:
             self.pgrad[k] = self.pgrad_flat[off:off + n]
+            self.pg_off[k] = off
             off += (n + 3) // 4 * 4
+        self.pg_total = off
+        self.grads_reduced = False
         ncp = ws['tail']['ncp']
         self.gy_tail = _View(torch.zeros((B, vox[0], ncp), dtype=td, device=dev), 0, ncp, ncp)   # pad channels stay 0
         tx = ws['tail']['x']
@@ -104,6 +110,19 @@ class _Backward(object):
         self.pgrad_flat.zero_()
         self.sums.zero_()
         contrib = {}
+        # data parallel: the slots are laid out in forward order and the walk below finishes them back to front, so the
+        # finished tail of the flat buffer is all-reduced (NCCL, its own stream) while the rest of the backward pass runs
+        _, world = D.world()
+        overlap = world > 1 and os.environ.get('SEG3D_OVERLAP_ALLREDUCE', '1') != '0'
+        works, sent_lo = [], self.pg_total
+        bucket = int(os.environ.get('SEG3D_ALLREDUCE_BUCKET_MB', '12')) << 18          # floats
+
+        def reduce_tail(lo, force=False):
+            nonlocal sent_lo
+            if overlap and sent_lo > lo and (force or sent_lo - lo >= bucket):
+                works.append(torch.distributed.all_reduce(self.pgrad_flat[lo:sent_lo], op=torch.distributed.ReduceOp.SUM,
+                                                          async_op=True))
+                sent_lo = lo
 
         def add_contrib(xv, gv):
             """register gradient view gv (same channel span as consumer input xv) with every producer inside xv"""
@@ -137,6 +156,7 @@ class _Backward(object):
         lib.call('seg3d_conv3d_fwd', lib.CONV_K3, dt, dc.impl, self.gy_tail.p, self.gy_tail.ld, dc.cin, lib.ptr(dc.w), None,
                  self.gd_tail.p, self.gd_tail.ld, dc.cout, B, d0[0], d0[1], d0[2], None, st())
         add_contrib(x, self.gd_tail)
+        reduce_tail(self.pg_off['out_block.conv1.weight'])
 
         # ---- conv -> GN -> ReLU units in reverse ---------------------------------------------------
         for ui in range(nu - 1, -1, -1):
@@ -168,6 +188,13 @@ class _Backward(object):
                 lib.call('seg3d_conv3d_fwd', dcv.mode, dt, dcv.impl, gy.p, gy.ld, dcv.cin, lib.ptr(dcv.w), None,
                          gd.p, gd.ld, dcv.cout, B, od[0], od[1], od[2], None, st())
                 add_contrib(u['x'], gd)
+            reduce_tail(self.pg_off[u['conv'] + '.weight'])
+        reduce_tail(0, force=True)
+        for w in works:
+            w.wait()
+        self.grads_reduced = bool(works)
+        if works:
+            self.pgrad_flat.mul_(1.0 / world)
         return self._param_grads()
 
     def _param_grads(self):
@@ -210,6 +237,7 @@ class _NetFunction(torch.autograd.Function):
         else:
             bw.refresh()
         grads = bw.run(dprobs)
+        plan.grads_reduced_in_backward = bw.grads_reduced       # train_step then skips its own all-reduce
         # the slots are reused next step: hand autograd its own copy (one copy, in the reference's parameter layout)
         return (None, None, None) + tuple(g.clone() if g.is_contiguous() else g.contiguous()
                                           for g in (grads[n] for n in ctx.names))

@@ -61,7 +61,9 @@ def train_step(net, opt, loss_func, crops, masks, params=None):
     outputs = net(crops)
     loss = loss_func(outputs, masks)
     loss.backward()
-    D.allreduce_mean_grads(params if params is not None else list(net.parameters()))
+    plan = getattr(getattr(net, 'module', net), '_plan', None)
+    if not getattr(plan, 'grads_reduced_in_backward', False):      # else: already averaged, overlapped with the backward pass
+        D.allreduce_mean_grads(params if params is not None else list(net.parameters()))
     opt.step()
     return loss
 

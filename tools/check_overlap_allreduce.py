@@ -1,0 +1,56 @@
+"""torchrun --nproc-per-node 2 tools/check_overlap_allreduce.py : two data-parallel training steps with the gradient
+all-reduce overlapped with the backward pass vs issued after it must leave identical parameters on every rank."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'medical-segmentation3d-toolkit_b200'))
+sys.path.insert(0, ROOT)
+import torch
+import torch.distributed as dist
+from segmentation3d._b200 import dist as D
+from segmentation3d.loss.multi_dice_loss import MultiDiceLoss
+from segmentation3d.network import vnet
+
+rank, local = int(os.environ['RANK']), int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(local)
+dist.init_process_group('nccl', device_id=torch.device('cuda:%d' % local))
+
+
+def run(overlap):
+    """averaged gradients of one data-parallel step (compared before Adam, which would amplify rounding noise on
+    near-zero gradients to +-lr)"""
+    os.environ['SEG3D_OVERLAP_ALLREDUCE'] = '1' if overlap else '0'
+    torch.manual_seed(0)
+    net = vnet.SegmentationNet(1, 2)
+    vnet.parameters_kaiming_init(net)
+    net.b200_mode = 'bf16'
+    net = net.cuda().train()
+    D.broadcast_params(net)
+    lf = MultiDiceLoss([0.5, 0.5], 2, True)
+    g = torch.Generator(device='cuda').manual_seed(100 + rank)
+    crops = torch.randn((2, 1, 64, 64, 64), generator=g, device='cuda')
+    masks = torch.randint(0, 2, (2, 1, 64, 64, 64), generator=g, device='cuda').float()
+    params = list(net.parameters())
+    loss = lf(net(crops), masks)
+    loss.backward()
+    reduced = net._plan.grads_reduced_in_backward
+    if not reduced:
+        D.allreduce_mean_grads(params)
+    torch.cuda.synchronize()
+    return [p.grad.detach().clone() for p in params], float(loss), reduced
+
+
+ga, la, fa = run(True)
+gb, lb, fb = run(False)
+assert fa and not fb, (fa, fb)
+worst = max(float((a - b).abs().max() / (b.abs().max() + 1e-20)) for a, b in zip(ga, gb))
+flat = torch.cat([g.reshape(-1) for g in ga])
+other = flat.clone()
+dist.broadcast(other, 0)
+same_across_ranks = bool(torch.equal(other, flat))
+print('rank %d: overlapped vs sequential all-reduce, worst per-tensor relative gradient difference %.3g, losses %.6f / %.6f, '
+      'ranks identical: %s' % (rank, worst, la, lb, same_across_ranks), flush=True)
+# wgrad accumulates with fp32 atomics (order varies run to run), so the two runs agree to rounding, not bitwise
+assert worst <= 1e-3 and same_across_ranks
+dist.destroy_process_group()
