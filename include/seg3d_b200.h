@@ -81,6 +81,14 @@ int seg3d_conv3d_fwd(int mode, int dtype, int impl,
 int seg3d_conv3d_k3_narrow_np(int Cout);
 int seg3d_conv3d_k3_narrow_fwd(int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
                                float* y, int Cout, int N, int D, int H, int W, double* stats, void* stream);
+/* the same convolution applied to x = relu(GroupNorm(raw) + res): the network's last GroupNorm + residual + ReLU
+ * (residual_block3.py:24 of up_32.rblock, whose only consumer is vnet_outblock.py:13) is formed in shared memory between
+ * the TMA loads and the MMAs, bit-identical to seg3d_gn_apply followed by seg3d_conv3d_k3_narrow_fwd.
+ * raw, res: [N,D,H,W,32] f16/bf16 (Cin must be 32); gn_stats: finished {sum, sum of squares} of raw per sample. */
+int seg3d_conv3d_k3_narrow_gn_fwd(int dtype, const void* raw, int raw_ld, const void* res, int res_ld, int Cin,
+                                  const double* gn_stats, const float* gamma, const float* beta, float eps,
+                                  const void* w, const float* bias, float* y, int Cout, int N, int D, int H, int W,
+                                  double* stats, void* stream);
 
 /* conv -> GroupNorm(1,C) -> ReLU without the raw intermediate, as two launches of the same tensor-core convolution
  * (vnet_downblock.py:19, vnet_upblock.py:19: the stride-2 / transposed convolutions are HBM-bound and cheap to run twice).

@@ -24,35 +24,48 @@ struct FoldParams {
   int D, H, W, N;
   int ntx, nty, nseg, lseg, nitems;
   int ring, plane_bytes, w_slab, plane_tx, w_tx;
-  int acc_cols, tmem_cols, pitch;   // staging-tile pitch in floats (odd)
+  int acc_cols, tmem_cols, pitch;   // staging-tile pitch in floats (odd: conflict-free scalar stores and gathers; a
+                                    // 16-byte-vector variant with an even pitch measured slower, the gather conflicts)
   uint32_t idesc, sbo, layout_type;
+  // FUSE_GN: the input is relu(gn(raw) + res) formed in shared memory from two TMA-loaded planes
+  float gn_eps;
+  double gn_count;                  // Cin * D * H * W
+  const double* gn_stats;           // [N][2] finished sums of the producing convolution
+  const float* gn_gamma;
+  const float* gn_beta;
 };
 constexpr int FD_NB = 4;            // rotating TMEM accumulators
 constexpr int FD_TX = 8, FD_TY = 10, FD_HX = 10, FD_HY = 12;
+constexpr int FDG_THREADS = 320;     // fused variant: + 4 transform warps
 
-template <typename T, int KC>
-__global__ void __launch_bounds__(TC_THREADS)
+template <typename T, int KC, bool FUSE_GN>
+__global__ void __launch_bounds__(FUSE_GN ? FDG_THREADS : TC_THREADS, FUSE_GN ? 3 : 1)
 conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                      const __grid_constant__ CUtensorMap map_r,
                       const FoldParams p, const float* __restrict__ bias, float* __restrict__ y, double* __restrict__ stats) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t w_base = smem_base;
   const uint32_t a_base = smem_base + 3 * p.w_slab;
-  float* stage = reinterpret_cast<float*>(smem_al + 3 * p.w_slab + p.ring * p.plane_bytes);
+  // one ring slot = the plane the MMA reads (+ the residual plane behind it when FUSE_GN)
+  const int slot_bytes = FUSE_GN ? 2 * p.plane_bytes : p.plane_bytes;
+  float* stage = reinterpret_cast<float*>(smem_al + 3 * p.w_slab + p.ring * slot_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 128 * p.pitch);   // 512 * pitch bytes: 8-byte aligned
   const uint32_t full_bar = smem_u32(bars);                   // [ring]
   const uint32_t empty_bar = full_bar + 8 * p.ring;           // [ring]
   const uint32_t tfull_bar = empty_bar + 8 * p.ring;          // [FD_NB]
   const uint32_t tempty_bar = tfull_bar + 8 * FD_NB;          // [FD_NB]
   const uint32_t wfull_bar = tempty_bar + 8 * FD_NB;          // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.ring + 2 * FD_NB + 1);
+  const uint32_t xf_bar = wfull_bar + 8;                      // [ring] transform done (FUSE_GN)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.ring + 2 * FD_NB + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    for (int s = 0; s < p.ring; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    if (FUSE_GN) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
+    for (int s = 0; s < p.ring; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); mbar_init(xf_bar + 8 * s, 4); }
     for (int b = 0; b < FD_NB; ++b) { mbar_init(tfull_bar + 8 * b, 1); mbar_init(tempty_bar + 8 * b, 4); }
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -80,8 +93,10 @@ conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
         for (int ip = 0; ip < L + 2; ++ip) {
           mbar_wait(empty_bar + 8 * stage_i, phase ^ 1);
-          mbar_expect_tx_e(full_bar + 8 * stage_i, (uint32_t)p.plane_tx);
-          tma_load_5d_e(a_base + stage_i * p.plane_bytes, &map_x, full_bar + 8 * stage_i, 0, x0 - 1, y0 - 1, zs - 1 + ip, n);
+          mbar_expect_tx_e(full_bar + 8 * stage_i, (uint32_t)(FUSE_GN ? 2 * p.plane_tx : p.plane_tx));
+          tma_load_5d_e(a_base + stage_i * slot_bytes, &map_x, full_bar + 8 * stage_i, 0, x0 - 1, y0 - 1, zs - 1 + ip, n);
+          if (FUSE_GN)
+            tma_load_5d_e(a_base + stage_i * slot_bytes + p.plane_bytes, &map_r, full_bar + 8 * stage_i, 0, x0 - 1, y0 - 1, zs - 1 + ip, n);
           if (++stage_i == p.ring) { stage_i = 0; phase ^= 1; }
         }
       }
@@ -98,9 +113,9 @@ conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         const int zs = seg * p.lseg;
         const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
         for (int ip = 0; ip < L + 2; ++ip) {
-          mbar_wait(full_bar + 8 * stage_i, phase);
+          mbar_wait((FUSE_GN ? xf_bar : full_bar) + 8 * stage_i, phase);
           tc_fence_after();
-          const uint32_t lo_a = (a_base + stage_i * p.plane_bytes) >> 4;
+          const uint32_t lo_a = (a_base + stage_i * slot_bytes) >> 4;
 #pragma unroll
           for (int kd = 2; kd >= 0; --kd) {
             const int zl = ip - kd;
@@ -118,6 +133,73 @@ conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           if (++stage_i == p.ring) { stage_i = 0; phase ^= 1; }
         }
         oc += L;
+      }
+    }
+  } else if (FUSE_GN && warp >= 6) {
+    // ===== transform: A = relu(gn(raw) + res), in place in the raw plane (same swizzled addresses), 64-byte rows =====
+    if constexpr (FUSE_GN) {
+      // thread t owns the 16-byte slots t, t+128, t+256, t+384 of a plane: their position inside the 64-byte row and the
+      // swizzle phase of their rows are the same, so the 8 channels (and their scale / shift) are fixed per thread
+      const int t = (warp - 6) * 32 + lane;
+      const int c8 = ((t & 3) ^ ((t >> 3) & 3)) << 3;
+      int hxk[4], hyk[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int row = (t >> 2) + 32 * k;
+        hyk[k] = row < FD_HX * FD_HY ? row / FD_HX : -1000;
+        hxk[k] = row - (row / FD_HX) * FD_HX;
+      }
+      float sa[8], sb[8];
+      int stage_i = 0; uint32_t phase = 0; int cur_n = -1;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        int tt = item;
+        const int seg = tt % p.nseg; tt /= p.nseg;
+        const int x0 = (tt % p.ntx) * FD_TX; tt /= p.ntx;
+        const int y0 = (tt % p.nty) * FD_TY; const int n = tt / p.nty;
+        const int zs = seg * p.lseg;
+        const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
+        if (n != cur_n) {
+          float mean, rstd;
+          gn_mean_rstd(p.gn_stats + 2 * n, p.gn_count, p.gn_eps, mean, rstd);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { sa[j] = rstd * p.gn_gamma[c8 + j]; sb[j] = p.gn_beta[c8 + j] - mean * sa[j]; }
+          cur_n = n;
+        }
+        bool inb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int gx = x0 - 1 + hxk[k], gy = y0 - 1 + hyk[k];
+          inb[k] = gx >= 0 && gx < p.W && gy >= 0 && gy < p.H;      // zero padding stays zero (TMA zero fill); rows >= 120 never
+        }
+        for (int ip = 0; ip < L + 2; ++ip) {
+          mbar_wait(full_bar + 8 * stage_i, phase);
+          const int gz = zs - 1 + ip;
+          if (gz >= 0 && gz < p.D) {
+            uint8_t* raw = smem_al + 3 * p.w_slab + stage_i * slot_bytes + t * 16;
+            const uint8_t* res = raw + p.plane_bytes;
+#pragma unroll
+            for (int k0 = 0; k0 < 4; k0 += 2) {               // two slots in flight (register budget: 3 CTAs of 320 threads per SM)
+              Vec8<T> a[2], r[2];
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                if (inb[k0 + k]) { a[k].load(reinterpret_cast<const T*>(raw + (k0 + k) * 2048)); r[k].load(reinterpret_cast<const T*>(res + (k0 + k) * 2048)); }
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                if (inb[k0 + k]) {
+                  float fa[8], fr[8];
+                  a[k].get(fa); r[k].get(fr);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) fa[j] = fmaxf(fmaf(fa[j], sa[j], sb[j]) + fr[j], 0.f);
+                  a[k].set(fa);
+                  a[k].store(reinterpret_cast<T*>(raw + (k0 + k) * 2048));
+                }
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(xf_bar + 8 * stage_i);
+          if (++stage_i == p.ring) { stage_i = 0; phase ^= 1; }
+        }
       }
     }
   } else {
@@ -212,9 +294,15 @@ conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 
 extern "C" int seg3d_conv3d_k3_narrow_np(int C) { return C >= 1 && 9 * C <= 64 ? ((9 * C + 15) / 16) * 16 : 0; }
 
-extern "C" int seg3d_conv3d_k3_narrow_fwd(int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
-                                          float* y, int C, int N, int D, int H, int W, double* stats, void* stream) {
+static int launch_fold(int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
+                       float* y, int C, int N, int D, int H, int W, double* stats, void* stream,
+                       const void* res, int res_ld, const double* gn_stats, const float* gn_gamma, const float* gn_beta, float gn_eps) {
   cudaStream_t st = (cudaStream_t)stream;
+  const bool fuse = res != nullptr;
+  if (fuse) {
+    SEG3D_REQUIRE(Cin == 32, "conv3d_k3_narrow_gn_fwd: Cin must be 32 (64-byte rows), got %d", Cin);
+    SEG3D_REQUIRE(gn_stats && gn_gamma && gn_beta && res_ld % 8 == 0 && ((uintptr_t)res) % 16 == 0, "conv3d_k3_narrow_gn_fwd: bad GroupNorm / residual arguments");
+  }
   SEG3D_REQUIRE(x && w && y, "conv3d_k3_narrow_fwd: null pointer");
   SEG3D_REQUIRE(dtype == SEG3D_F16 || dtype == SEG3D_BF16, "conv3d_k3_narrow_fwd: dtype must be f16 or bf16");
   SEG3D_REQUIRE(Cin == 16 || Cin == 32 || Cin == 64, "conv3d_k3_narrow_fwd: Cin must be 16, 32 or 64 (got %d)", Cin);
@@ -237,13 +325,14 @@ extern "C" int seg3d_conv3d_k3_narrow_fwd(int dtype, const void* x, int x_ld, in
   p.ntx = W / FD_TX; p.nty = (H + FD_TY - 1) / FD_TY;
   p.acc_cols = NP <= 32 ? 32 : 64;
   p.tmem_cols = FD_NB * p.acc_cols;
-  int ctas_per_sm = env_int("SEG3D_FD_CTAS_PER_SM", 4);
+  int ctas_per_sm = env_int("SEG3D_FD_CTAS_PER_SM", fuse ? 3 : 4);
   if (ctas_per_sm * p.tmem_cols > 512) ctas_per_sm = 512 / p.tmem_cols;
   const int fixed = 3 * p.w_slab + 128 * p.pitch * 4 + 1024;
   int ring = 0;
-  for (; ctas_per_sm >= 1; --ctas_per_sm) {                  // as many co-resident CTAs as leave a ring of >= 4 planes
-    ring = ((200 * 1024 / ctas_per_sm) - fixed) / p.plane_bytes;
-    if (ring >= 4 || ctas_per_sm == 1) break;
+  const int slot_bytes = fuse ? 2 * p.plane_bytes : p.plane_bytes;
+  for (; ctas_per_sm >= 1; --ctas_per_sm) {                  // as many co-resident CTAs as leave a ring of >= 4 planes (3 fused)
+    ring = ((200 * 1024 / ctas_per_sm) - fixed) / slot_bytes;
+    if (ring >= (fuse ? 3 : 4) || ctas_per_sm == 1) break;
   }
   if (ring > 8) ring = 8;
   { const int e = env_int("SEG3D_FD_RING", 0); if (e >= 3) ring = e; }
@@ -260,13 +349,14 @@ extern "C" int seg3d_conv3d_k3_narrow_fwd(int dtype, const void* x, int x_ld, in
   const long long nitems = cols * p.nseg;
   SEG3D_REQUIRE(nitems > 0 && nitems < (1ll << 31), "conv3d_k3_narrow_fwd: work-item count out of range");
   p.nitems = (int)nitems;
+  p.gn_eps = gn_eps; p.gn_count = (double)Cin * D * H * W; p.gn_stats = gn_stats; p.gn_gamma = gn_gamma; p.gn_beta = gn_beta;
   p.sbo = 8 * p.row_bytes;
   p.layout_type = p.row_bytes == 128 ? 2u : (p.row_bytes == 64 ? 4u : 6u);
   const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   const CUtensorMapDataType tdt = dtype == SEG3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  CUtensorMap map_x, map_w;
+  CUtensorMap map_x, map_w, map_r;
   {
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2, (cuuint64_t)D * H * W * x_ld * 2};
@@ -275,6 +365,13 @@ extern "C" int seg3d_conv3d_k3_narrow_fwd(int dtype, const void* x, int x_ld, in
     CUresult r = encode(&map_x, tdt, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { seg3d_set_error("conv3d_k3_narrow_fwd: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SEG3D_ECUDA; }
+    map_r = map_x;
+    if (fuse) {
+      cuuint64_t rstr[4] = {(cuuint64_t)res_ld * 2, (cuuint64_t)W * res_ld * 2, (cuuint64_t)H * W * res_ld * 2, (cuuint64_t)D * H * W * res_ld * 2};
+      r = encode(&map_r, tdt, 5, const_cast<void*>(res), dims, rstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { seg3d_set_error("conv3d_k3_narrow_gn_fwd: cuTensorMapEncodeTiled(res) failed with %d", (int)r); return SEG3D_ECUDA; }
+    }
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)3 * NP};
@@ -285,20 +382,42 @@ extern "C" int seg3d_conv3d_k3_narrow_fwd(int dtype, const void* x, int x_ld, in
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { seg3d_set_error("conv3d_k3_narrow_fwd: cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SEG3D_ECUDA; }
   }
-  const size_t smem = 1024 + (size_t)3 * p.w_slab + (size_t)ring * p.plane_bytes + (size_t)(128 * p.pitch + 1) * 4 +
-                      (2 * ring + 2 * FD_NB + 1) * 8 + 64;
+  const size_t smem = 1024 + (size_t)3 * p.w_slab + (size_t)ring * slot_bytes + (size_t)(128 * p.pitch + 1) * 4 +
+                      (3 * ring + 2 * FD_NB + 1) * 8 + 64 + 512;
   const long long max_grid = (long long)ctas_per_sm * seg3d_num_sms();
   dim3 grid((unsigned)(nitems < max_grid ? nitems : max_grid));
   cudaError_t e = cudaSuccess;
-#define SEG3D_LAUNCH_F(TT, KCV)                                                                                          \
-  { e = cudaFuncSetAttribute(conv3d_k3_fold_kernel<TT, KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    if (e == cudaSuccess) { conv3d_k3_fold_kernel<TT, KCV><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p, bias, y, stats); e = cudaGetLastError(); } }
-  if (dtype == SEG3D_BF16) {
+#define SEG3D_LAUNCH_F(TT, KCV)                                                                                                 \
+  { e = cudaFuncSetAttribute(conv3d_k3_fold_kernel<TT, KCV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    if (e == cudaSuccess) { conv3d_k3_fold_kernel<TT, KCV, false><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, map_r, p, bias, y, stats); e = cudaGetLastError(); } }
+#define SEG3D_LAUNCH_FG(TT)                                                                                                     \
+  { e = cudaFuncSetAttribute(conv3d_k3_fold_kernel<TT, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    if (e == cudaSuccess) { conv3d_k3_fold_kernel<TT, 32, true><<<grid, FDG_THREADS, smem, st>>>(map_x, map_w, map_r, p, bias, y, stats); e = cudaGetLastError(); } }
+  if (fuse) {
+    if (dtype == SEG3D_BF16) SEG3D_LAUNCH_FG(__nv_bfloat16) else SEG3D_LAUNCH_FG(__half)
+  } else if (dtype == SEG3D_BF16) {
     if (Cin == 64) SEG3D_LAUNCH_F(__nv_bfloat16, 64) else if (Cin == 32) SEG3D_LAUNCH_F(__nv_bfloat16, 32) else SEG3D_LAUNCH_F(__nv_bfloat16, 16)
   } else {
     if (Cin == 64) SEG3D_LAUNCH_F(__half, 64) else if (Cin == 32) SEG3D_LAUNCH_F(__half, 32) else SEG3D_LAUNCH_F(__half, 16)
   }
 #undef SEG3D_LAUNCH_F
+#undef SEG3D_LAUNCH_FG
   if (e != cudaSuccess) { seg3d_set_error("conv3d_k3_fold_kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
   return SEG3D_OK;
+}
+
+extern "C" int seg3d_conv3d_k3_narrow_fwd(int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
+                                          float* y, int C, int N, int D, int H, int W, double* stats, void* stream) {
+  return launch_fold(dtype, x, x_ld, Cin, w, bias, y, C, N, D, H, W, stats, stream, nullptr, 0, nullptr, nullptr, nullptr, 0.f);
+}
+
+// Same convolution on x = relu(GroupNorm(raw) + res): the last GroupNorm + residual + ReLU of the network
+// (residual_block3.py:24 of up_32.rblock) is formed in shared memory between the TMA loads and the MMAs instead of being
+// streamed through HBM by seg3d_gn_apply.  raw / res: [N,D,H,W,32] f16/bf16; gn_stats: finished sums of raw.
+extern "C" int seg3d_conv3d_k3_narrow_gn_fwd(int dtype, const void* raw, int raw_ld, const void* res, int res_ld, int Cin,
+                                             const double* gn_stats, const float* gamma, const float* beta, float eps,
+                                             const void* w, const float* bias, float* y, int C, int N, int D, int H, int W,
+                                             double* stats, void* stream) {
+  SEG3D_REQUIRE(res != nullptr, "conv3d_k3_narrow_gn_fwd: null residual");
+  return launch_fold(dtype, raw, raw_ld, Cin, w, bias, y, C, N, D, H, W, stats, stream, res, res_ld, gn_stats, gamma, beta, eps);
 }

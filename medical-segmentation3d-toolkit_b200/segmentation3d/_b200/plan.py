@@ -295,10 +295,16 @@ class NetPlan(object):
         # GroupNorm pass it saves (1535 vs 1640 Mvox/s); kept behind SEG3D_FUSE_S2=1
         fuse_s2 = (not train) and dt != lib.F32 and os.environ.get('SEG3D_FUSE_S2', '0') == '1'
 
-        def unit(cname, gname, x, lin, lout, out, res=None):
+        def unit(cname, gname, x, lin, lout, out, res=None, defer_gn=False):
             """conv -> GroupNorm -> (+res) -> ReLU with the conv reading level `lin` and writing level `lout`"""
             c = self.convs[cname]
             C = c.cout
+            if defer_gn:        # the consumer applies GroupNorm + residual + ReLU itself (seg3d_conv3d_k3_narrow_gn_fwd)
+                rv = rawview(C, lout)
+                conv(cname, x, dims[lin], rv, gname)
+                ws['deferred'] = {'raw': rv, 'res': res, 'gn': gname}
+                units.append({'conv': cname, 'gn': gname, 'x': x, 'lin': lin, 'lout': lout, 'raw': rv, 'out': out, 'res': res})
+                return
             if (fuse_s2 and res is None and c.impl == lib.IMPL_TCGEN05 and c.mode in (lib.CONV_K2S2, lib.CONV_T2S2)
                     and out.ld % 8 == 0):
                 conv_gn_twice(cname, gname, x, dims[lin], out, vox[lout])
@@ -309,11 +315,11 @@ class NetPlan(object):
             gn(gname, rv, out, vox[lout], True, res)
             units.append({'conv': cname, 'gn': gname, 'x': x, 'lin': lin, 'lout': lout, 'raw': rv, 'out': out, 'res': res})
 
-        def conv_gn(cname, gname, x, l, out, relu, res=None):
+        def conv_gn(cname, gname, x, l, out, relu, res=None, defer_gn=False):
             assert relu
-            unit(cname, gname, x, l, l, out, res)
+            unit(cname, gname, x, l, l, out, res, defer_gn)
 
-        def rblock(prefix, X, l, dest):
+        def rblock(prefix, X, l, dest, defer_last=False):
             n = self._rblock_len(prefix)
             C = X.C
             cur = X
@@ -322,7 +328,8 @@ class NetPlan(object):
                 out = dest if last else tmpbuf(l, C, 'T%d%s' % (l, 'ab'[i % 2]))
                 op = '%s.ops.%d' % (prefix, i)
                 if (op + '.conv') in self.convs:
-                    conv_gn(op + '.conv', op + '.gn', cur, l, out, relu=True, res=X if last else None)
+                    conv_gn(op + '.conv', op + '.gn', cur, l, out, relu=True, res=X if last else None,
+                            defer_gn=defer_last and last)
                 else:
                     m1 = tmpbuf(l, C // 4, 'M%da' % l)
                     m2 = tmpbuf(l, C // 4, 'M%db' % l)
@@ -332,6 +339,13 @@ class NetPlan(object):
                 cur = out
             # relu(X + ops(X)): the last apply carries relu=True with the residual (residual_block3.py:24,46);
             # for i < n-1 relu=True is ConvGnRelu3's own activation.
+
+        # the network's last GroupNorm + residual + ReLU (up_32.rblock) has a single consumer, out_block.conv1: form it in
+        # that kernel's shared memory instead of streaming it through HBM
+        c1_ = self.convs['out_block.conv1']
+        fuse_tail = (not train and c1_.fold and c1_.impl == lib.IMPL_TCGEN05 and c1_.cin == 32 and W % 8 == 0
+                     and ('up_32.rblock.ops.%d.conv' % (self._rblock_len('up_32.rblock') - 1)) in self.convs
+                     and os.environ.get('SEG3D_TAIL_F32', '1') != '0' and os.environ.get('SEG3D_FUSE_TAIL', '1') != '0')
 
         # in_block -> second half of cat0
         x_in = _View(ws['x_in'], 0, self.in_channels, self.in_channels)
@@ -353,7 +367,7 @@ class NetPlan(object):
             unit(name + '.up_conv', name + '.up_gn', src, l + 1, l, up)
             cat = _View(ws['cat%d' % l], 0, C, C)
             dest = _View(ws['U%d' % l], 0, C, C)
-            rblock(name + '.rblock', cat, l, dest)
+            rblock(name + '.rblock', cat, l, dest, defer_last=(l == 0 and fuse_tail))
             src = dest
         # out block: conv1 -> raw, then the fused tail
         nc = self.out_channels
@@ -369,11 +383,21 @@ class NetPlan(object):
             ncp = nc
             rv1 = _View(torch.empty((B, vox[0], nc), dtype=torch.float32, device=dev), 0, nc, nc)
             sp1 = lib.ptr(ws['stats'][self.gn_index['out_block.gn1']])
-            args = (dt, src.p, src.ld, c1.cin, lib.ptr(c1.w_fold), lib.ptr(c1.bias), rv1.p, nc,
-                    B, dims[0][0], dims[0][1], dims[0][2], sp1)
-            ops.append(lambda a=args: lib.call('seg3d_conv3d_k3_narrow_fwd', *a, st()))
+            dfr = ws.get('deferred')
+            if dfr is not None:
+                g0 = self.gns[dfr['gn']]
+                args = (dt, dfr['raw'].p, dfr['raw'].ld, dfr['res'].p, dfr['res'].ld, c1.cin,
+                        lib.ptr(ws['stats'][self.gn_index[dfr['gn']]]), lib.ptr(g0.gamma), lib.ptr(g0.beta), GN_EPS,
+                        lib.ptr(c1.w_fold), lib.ptr(c1.bias), rv1.p, nc, B, dims[0][0], dims[0][1], dims[0][2], sp1)
+                ops.append(lambda a=args: lib.call('seg3d_conv3d_k3_narrow_gn_fwd', *a, st()))
+                rd = 2 * (2 * B * vox[0] * c1.cin)
+            else:
+                args = (dt, src.p, src.ld, c1.cin, lib.ptr(c1.w_fold), lib.ptr(c1.bias), rv1.p, nc,
+                        B, dims[0][0], dims[0][1], dims[0][2], sp1)
+                ops.append(lambda a=args: lib.call('seg3d_conv3d_k3_narrow_fwd', *a, st()))
+                rd = 2 * B * vox[0] * c1.cin
             meta.append({'name': 'out_block.conv1', 'kind': 'conv_tc_narrow', 'flops': 2.0 * B * vox[0] * 27 * c1.cin * nc,
-                         'bytes': 2 * B * vox[0] * c1.cin + 4 * B * vox[0] * nc + c1.w_fold.numel() * 2})
+                         'bytes': rd + 4 * B * vox[0] * nc + c1.w_fold.numel() * 2})
         elif tail_f32:
             ncp = nc                                       # the fp32 store keeps only the real channels
             rv1 = _View(torch.empty((B, vox[0], nc), dtype=torch.float32, device=dev), 0, nc, nc)

@@ -461,3 +461,46 @@ def test_conv_gn_relu_two_pass_matches_torch(lib, case):
     assert torch.isnan(y[..., :Cout].float()).all()
     yc = from_ndhwc(y[..., Cout:])
     assert (yc - ref).abs().max() <= 2.0 ** -10 * max(1.0, float(ref.abs().max())) + 1e-4
+
+
+@pytest.mark.parametrize('shape', [(2, 16, 16, 16), (1, 8, 24, 8), (3, 32, 48, 48)], ids=str)
+@pytest.mark.parametrize('dt_name', ['F16', 'BF16'])
+def test_conv_k3_narrow_fused_gn_residual_equals_unfused(lib, shape, dt_name):
+    """seg3d_conv3d_k3_narrow_gn_fwd (GroupNorm + residual + ReLU formed in shared memory) must reproduce seg3d_gn_apply
+    followed by seg3d_conv3d_k3_narrow_fwd: the operand rounding point and the convolution are the same."""
+    L = lib
+    dt = getattr(L, dt_name)
+    tdt = L.TORCH_DTYPE[dt]
+    N, D, H, W = shape
+    Cin, C = 32, 2
+    g = torch.Generator().manual_seed(N * 100 + W)
+    raw = to_ndhwc(torch.randn((N, Cin, D, H, W), generator=g) * 2.0 + 0.3, tdt)
+    res = torch.full((N, D, H, W, 2 * Cin), float('nan'), dtype=tdt, device='cuda')     # residual = one half of a wider buffer
+    res[..., Cin:] = to_ndhwc(torch.randn((N, Cin, D, H, W), generator=g), tdt)
+    gamma = (torch.rand((Cin,), generator=g) + 0.5).cuda()
+    beta = (torch.randn((Cin,), generator=g) * 0.2).cuda()
+    w = (torch.randn((C, Cin, 3, 3, 3), generator=g) * 0.1)
+    b = (torch.randn((C,), generator=g) * 0.1).cuda()
+    NP = L.load().seg3d_conv3d_k3_narrow_np(C)
+    wf = torch.zeros((3, NP, Cin))
+    wf[:, :9 * C] = w.permute(2, 3, 4, 0, 1).reshape(3, 9 * C, Cin)
+    wf = wf.to(tdt).cuda()
+    rf = raw.float()
+    gstats = torch.stack([rf.double().flatten(1).sum(1), (rf.double() ** 2).flatten(1).sum(1)], 1).contiguous()
+    nvox = D * H * W
+    # unfused: gn_apply (+res, relu) -> narrow conv
+    act = torch.empty((N, D, H, W, Cin), dtype=tdt, device='cuda')
+    L.call('seg3d_gn_apply', dt, L.ptr(raw), Cin, Cin, L.ptr(gstats), L.ptr(gamma), L.ptr(beta), 1e-5, L.ptr(res, Cin), 2 * Cin,
+           L.ptr(act), Cin, 1, N, nvox, L.stream_ptr())
+    y0 = torch.full((N, D, H, W, C), float('nan'), dtype=torch.float32, device='cuda')
+    s0 = torch.zeros((N, 2), dtype=torch.float64, device='cuda')
+    L.call('seg3d_conv3d_k3_narrow_fwd', dt, L.ptr(act), Cin, Cin, L.ptr(wf), L.ptr(b), L.ptr(y0), C, N, D, H, W, L.ptr(s0), L.stream_ptr())
+    # fused
+    y1 = torch.full((N, D, H, W, C), float('nan'), dtype=torch.float32, device='cuda')
+    s1 = torch.zeros((N, 2), dtype=torch.float64, device='cuda')
+    L.call('seg3d_conv3d_k3_narrow_gn_fwd', dt, L.ptr(raw), Cin, L.ptr(res, Cin), 2 * Cin, Cin, L.ptr(gstats), L.ptr(gamma), L.ptr(beta),
+           1e-5, L.ptr(wf), L.ptr(b), L.ptr(y1), C, N, D, H, W, L.ptr(s1), L.stream_ptr())
+    torch.cuda.synchronize()
+    assert not torch.isnan(y1).any()
+    assert torch.equal(y0, y1)
+    assert torch.allclose(s0, s1, rtol=1e-9, atol=1e-6)
