@@ -155,6 +155,13 @@ int seg3d_blend_finalize_argmax_z(float* acc, int C, int Z, int Y, int X, int z0
 int seg3d_resample(const float* src, int sz, int sy, int sx, float* dst, int dz, int dy, int dx,
                    double rz, double ry, double rx, int linear, float default_value, void* stream);
 
+/* ---- connected-component post-processing (utils/image_tools.py:380-432; 26-connectivity, one label per call) ------------
+ * out[v] = label for the voxels of `label` that belong to the largest component (min_size == 0; ties: the component whose
+ * first voxel comes first in raster order) or to any component with at least min_size voxels (min_size > 0).  out is
+ * not cleared (the caller zeroes it once and calls this per label).  parent, size: int32 [Z*Y*X] scratch; best: 8 bytes. */
+int seg3d_cc_filter(const int8_t* mask, int Z, int Y, int X, int label, int min_size,
+                    int32_t* parent, int32_t* size, unsigned long long* best, int8_t* out, void* stream);
+
 /* ---- losses on probabilities (loss/multi_dice_loss.py, loss/binary_dice_loss.py, loss/focal_loss.py) -
  * probs fp32 [B][C][n], target fp32 [B][n] (class index stored as float, dataloader/dataset.py:208). */
 /* terms[b][c] = { sum q*t, sum q*q, sum t*t } with q = p*[p > 1/C], t = [target == c] (double) */

@@ -21,6 +21,7 @@ import time
 import numpy as np
 import torch
 
+from segmentation3d._b200 import lib
 from segmentation3d._b200.sliding import SlidingWindow, axis_counts
 from segmentation3d.utils.attrdict import AttrDict as edict
 from segmentation3d.utils.file_io import load_config, readlines
@@ -266,22 +267,21 @@ def _side_stream(dev):
     return _SIDE_STREAMS[key]
 
 
-def _largest_cc(mask_np, labels, keep_threshold=None):
-    """pick_largest_connected_component / remove_small_connected_component (utils/image_tools.py:380-432)
-    with 26-connectivity, on the host (post-processing, outside the hot path)."""
-    from scipy import ndimage
-    out = np.zeros_like(mask_np)
-    st = np.ones((3, 3, 3), dtype=bool)
-    for lab in labels:
-        cc, n = ndimage.label(mask_np == lab, structure=st)
-        if n == 0:
-            continue
-        sizes = np.bincount(cc.ravel())[1:]
-        if keep_threshold is None:
-            keep = [int(np.argmax(sizes)) + 1]
-        else:
-            keep = [i + 1 for i, s in enumerate(sizes) if s >= keep_threshold]
-        out[np.isin(cc, keep)] = lab
+def _cc_filter_device(mask, labels, min_size=0):
+    """pick_largest_connected_component (min_size == 0) / remove_small_connected_component (min_size = threshold)
+    (utils/image_tools.py:380-432; 26-connectivity) on the device: int8 CUDA mask [z,y,x] -> filtered int8 mask."""
+    if not (torch.is_tensor(mask) and mask.is_cuda):
+        raise RuntimeError('seg3d_b200: connected-component filtering runs on CUDA masks only (no CPU fallback)')
+    mask = mask.contiguous()
+    Z, Y, X = mask.shape
+    out = torch.zeros_like(mask)
+    parent = torch.empty((Z * Y * X,), dtype=torch.int32, device=mask.device)
+    size = torch.empty((Z * Y * X,), dtype=torch.int32, device=mask.device)
+    best = torch.empty((1,), dtype=torch.int64, device=mask.device)
+    with torch.cuda.device(mask.device):
+        for lab in labels:
+            lib.call('seg3d_cc_filter', lib.ptr(mask), Z, Y, X, int(lab), int(min_size), lib.ptr(parent), lib.ptr(size),
+                     lib.ptr(best), lib.ptr(out), lib.stream_ptr())
     return out
 
 
@@ -337,14 +337,11 @@ def segmentation_volume(model, cfg, image, bbox_start_voxel, bbox_end_voxel, use
         im = Image3d(acc[c])
         im.CopyInformation(image)
         mean_probs.append(im)
-    if _cfg_get(cfg, 'pick_largest_cc', False) or _cfg_get(cfg, 'remove_small_cc', 0) > 0:
-        m = mask.cpu().numpy()
-        labels = list(range(1, num_classes))
-        if _cfg_get(cfg, 'pick_largest_cc', False):
-            m = _largest_cc(m, labels)
-        if _cfg_get(cfg, 'remove_small_cc', 0) > 0:
-            m = _largest_cc(m, labels, keep_threshold=cfg['remove_small_cc'])
-        mask = torch.from_numpy(m.astype(np.int8))
+    labels = list(range(1, num_classes))
+    if _cfg_get(cfg, 'pick_largest_cc', False):                      # :341-342
+        mask = _cc_filter_device(mask, labels, 0)
+    if _cfg_get(cfg, 'remove_small_cc', 0) > 0:                      # :345-347
+        mask = _cc_filter_device(mask, labels, int(cfg['remove_small_cc']))
     mask_im = Image3d(mask)
     mask_im.CopyInformation(image)
     return mean_probs, mask_im

@@ -112,6 +112,24 @@ def resample_spacing(image, resampled_spacing, max_stride, interp_method):
     return Image3d(out, [float(v) for v in resampled_spacing], img.GetOrigin(), img.GetDirection())
 
 
+def pick_largest_connected_component(mask, labels):
+    """Keep, per label, the largest 26-connected component (utils/image_tools.py:380-404)."""
+    from segmentation3d.core.seg_infer import _cc_filter_device
+    img = as_image3d(mask)
+    data = img.data if torch.is_tensor(img.data) else torch.from_numpy(np.ascontiguousarray(img.data))
+    out = _cc_filter_device(data.to(device='cuda', dtype=torch.int8), list(labels), 0)
+    return Image3d(out, img.GetSpacing(), img.GetOrigin(), img.GetDirection())
+
+
+def remove_small_connected_component(mask, labels, threshold):
+    """Drop, per label, the 26-connected components smaller than `threshold` voxels (utils/image_tools.py:407-432)."""
+    from segmentation3d.core.seg_infer import _cc_filter_device
+    img = as_image3d(mask)
+    data = img.data if torch.is_tensor(img.data) else torch.from_numpy(np.ascontiguousarray(img.data))
+    out = _cc_filter_device(data.to(device='cuda', dtype=torch.int8), list(labels), int(threshold))
+    return Image3d(out, img.GetSpacing(), img.GetOrigin(), img.GetDirection())
+
+
 def convert_image_to_tensor(image):
     """Image (or list of images) -> float tensor [1,z,y,x] ([n,z,y,x] for a list)."""
     if isinstance(image, (list, tuple)):

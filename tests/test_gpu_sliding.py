@@ -191,3 +191,62 @@ def test_segmentation_volume_resamples_anisotropic_scan():
     assert np.abs(probs - ref_probs).max() <= 1e-3
     assert float((mask == ref_mask).mean()) >= 0.999
     assert np.array_equal(mask, osw.argmax_first(probs))
+
+
+def _blob_mask(seed, shape, nlabels):
+    """random multi-label mask with many components of assorted sizes (thresholded smooth noise)"""
+    g = torch.Generator().manual_seed(seed)
+    m = np.zeros(shape, dtype=np.int8)
+    for lab in range(1, nlabels + 1):
+        lo = torch.randn((1, 1) + tuple(max(2, s // 6) for s in shape), generator=g)
+        f = torch.nn.functional.interpolate(lo, size=shape, mode='trilinear', align_corners=False)[0, 0].numpy()
+        f = f + 0.35 * torch.randn(shape, generator=g).numpy()
+        m[(f > 0.9) & (m == 0)] = lab
+    return m
+
+
+@pytest.mark.parametrize('shape,nlabels', [((40, 48, 56), 1), ((64, 33, 50), 3), ((16, 16, 16), 2)], ids=['one', 'three', 'small'])
+def test_connected_component_filters_match_scipy(shape, nlabels):
+    """seg3d_cc_filter (union-find, 26-connectivity) vs the scipy restatement of pick_largest_connected_component /
+    remove_small_connected_component: exact equality of the filtered masks."""
+    from oracle import postprocess as opp
+    from segmentation3d.utils.image_tools import pick_largest_connected_component, remove_small_connected_component
+    m = _blob_mask(3, shape, nlabels)
+    labels = list(range(1, nlabels + 1))
+    assert all((m == lab).sum() > 0 for lab in labels)
+    got = pick_largest_connected_component(m, labels).to_numpy()
+    assert got.dtype == np.int8 and np.array_equal(got, opp.pick_largest_connected_component(m, labels))
+    for thr in (1, 5, 40, 10 ** 6):
+        got = remove_small_connected_component(m, labels, thr).to_numpy()
+        assert np.array_equal(got, opp.remove_small_connected_component(m, labels, thr)), thr
+    # degenerate inputs: empty label, one voxel, a full volume (one component)
+    z = np.zeros((8, 8, 8), dtype=np.int8)
+    assert not pick_largest_connected_component(z, [1]).to_numpy().any()
+    z[3, 4, 5] = 1
+    assert np.array_equal(pick_largest_connected_component(z, [1]).to_numpy(), z)
+    full = np.ones((8, 16, 24), dtype=np.int8)
+    assert np.array_equal(pick_largest_connected_component(full, [1]).to_numpy(), full)
+
+
+def test_connected_components_large_volume_timing():
+    """512 x 512 x 400 mask (the benchmark volume): one big component + specks; result checked by invariants (the kept
+    voxels are a subset of the label, the kept component is at least as large as any other run-length estimate)."""
+    from segmentation3d.core.seg_infer import _cc_filter_device
+    g = torch.Generator(device='cuda').manual_seed(0)
+    Z, Y, X = 400, 512, 512
+    lo = torch.randn((1, 1, 13, 16, 16), generator=g, device='cuda')
+    f = torch.nn.functional.interpolate(lo, size=(Z, Y, X), mode='trilinear', align_corners=False)[0, 0]
+    m = ((f > 0.5) | (torch.rand((Z, Y, X), generator=g, device='cuda') > 0.9995)).to(torch.int8)
+    del f
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = _cc_filter_device(m, [1], 0)
+    e0.record()
+    out = _cc_filter_device(m, [1], 0)
+    e1.record()
+    torch.cuda.synchronize()
+    kept, total = int(out.sum()), int(m.sum())
+    print('cc 512x512x400: %.2f ms, kept %d of %d label voxels' % (e0.elapsed_time(e1), kept, total))
+    assert 0 < kept <= total and bool(((out == 1) <= (m == 1)).all())
+    small = _cc_filter_device(m, [1], kept)            # threshold = size of the largest: only it survives
+    assert torch.equal(small, out)
