@@ -212,7 +212,7 @@ def run_train(args):
             'metric': 'train patches/s (VNet, 96^3 patches, batch %d/GPU, Dice, Adam)' % B, 'value': B * world / (ms * 1e-3),
             'unit': 'patches/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': {'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f32'}[args.mode], 'data': 'synthetic',
+            'dtype': {'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f32', 'fp32x': 'f16x2'}[args.mode], 'data': 'synthetic',
             'config': {'workload': 'VNet(1,2) training step, crops [%d,1,%d^3] per GPU, MultiDiceLoss, Adam lr 1e-4 (BASELINE configs[2])' % (B, P),
                        'mode': args.mode, 'parallelism': 'dp%d' % world}, 'loss': float(loss.item())}))
     if dist is not None:
@@ -225,7 +225,8 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--mode', default='fp16', choices=['fp16', 'bf16', 'fp32'])
+    ap.add_argument('--mode', default='fp16', choices=['fp16', 'bf16', 'fp32', 'fp32x'],
+                    help="fp32x = strict parity on the tensor cores (f16 hi/lo split operands, fp32 accumulate)")
     ap.add_argument('--batch', type=int, default=20, help='patches per network forward')
     ap.add_argument('--volume', default='512,512,400')
     ap.add_argument('--patch', type=int, default=96)
@@ -361,7 +362,7 @@ def main():
             'metric': METRIC if args.arch == 'vnet' else METRIC.replace('VNet', 'VBNet C=%d' % args.classes), 'value': value, 'unit': 'Mvoxels/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev, 'higher_is_better': True,
             'scaling': 'weak' if args.shard == 'cases' else 'strong', 'vs_baseline': None,
-            'dtype': {'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f32'}[args.mode], 'data': 'synthetic',
+            'dtype': {'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f32', 'fp32x': 'f16x2'}[args.mode], 'data': 'synthetic',
             'config': workload_config(args, size),
             'e2e': {'value': e2e, 'unit': 'Mvoxels/s', 'h2d_bytes_per_step': int(nvox * 4), 'd2h_bytes_per_step': int(nvox),
                     'ms_per_step': ms_e2e},

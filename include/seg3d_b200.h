@@ -98,6 +98,18 @@ int seg3d_conv3d_gn_relu_fwd(int mode, int dtype, int pass, const void* x, int x
                              const float* bias, void* y, int y_ld, int Cout, int N, int D, int H, int W,
                              double* stats, const float* gamma, const float* beta, float eps, void* stream);
 
+/* ---- strict-parity mode on the tensor cores: split operands -------------------------------------------------------------
+ * Activations are stored as two f16 halves per voxel row, x = hi + lo (hi at channel c, lo at channel lo_off + c; the
+ * plan uses rows [hi(Ctot) | lo(Ctot)], lo_off = Ctot, so concat-in-place still works per half).  Weights are packed
+ * [taps][Cout][whi(Cin) | wlo(Cin)] f16 (T2S2: [8*Cout][whi | wlo]).  The convolution accumulates hi*whi + lo*whi + hi*wlo
+ * in fp32 (the dropped lo*wlo term is 2^-22 relative) and writes the fp32 result + bias (pitch y_ld floats) and the
+ * GroupNorm sums; seg3d_gn_apply_split normalises it (+ReLU, + split residual) back into the split format. */
+int seg3d_conv3d_split_fwd(int mode, const void* x, int x_ld, int lo_off, int Cin, const void* w, const float* bias,
+                           float* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, void* stream);
+int seg3d_gn_apply_split(const float* y, int y_ld, int C, const double* stats, const float* gamma, const float* beta,
+                         float eps, const void* res, int res_ld, int res_lo, void* out, int out_ld, int out_lo,
+                         int relu, int N, int64_t nvox, void* stream);
+
 /* ---- GroupNorm(1,C) apply + ReLU + residual (replaces nn.GroupNorm, nn.ReLU, `input + output`,
  * torch.cat: conv_gn_relu3.py:17-19, residual_block3.py:24,46, vnet_upblock.py:20-21) ----------
  * out = [relu]( (y-mean)*rstd*gamma + beta [+ res] ), mean/rstd from stats over C*nvox elements

@@ -5,7 +5,8 @@ int seg3d_conv_simt(int mode, int dtype, const void* x, int x_ld, int Cin, const
                     void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st);
 int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
                   void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st,
-                  int epi_mode, const double* gn_stats, const float* gn_gamma, const float* gn_beta, float gn_eps);
+                  int epi_mode, const double* gn_stats, const float* gn_gamma, const float* gn_beta, float gn_eps,
+                  int split_lo_off, int out_f32_generic);
 int seg3d_conv_cin1_tc_supported(int dtype, int Cin, int Cout, int x_ld, int y_ld, int W);
 int seg3d_conv_cin1_tc(int dtype, const void* x, const void* w, const float* bias, void* y, int y_ld,
                        int N, int D, int H, int W, double* stats, cudaStream_t st);
@@ -29,7 +30,7 @@ extern "C" int seg3d_conv3d_fwd(int mode, int dtype, int impl, const void* x, in
       seg3d_set_error("conv3d_fwd: tcgen05 path does not take mode=%d dtype=%d Cin=%d Cout=%d", mode, dtype, Cin, Cout);
       return SEG3D_EUNSUPPORTED;
     }
-    return seg3d_conv_tc(mode, dtype, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, stats, st, 0, nullptr, nullptr, nullptr, 0.f);
+    return seg3d_conv_tc(mode, dtype, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, stats, st, 0, nullptr, nullptr, nullptr, 0.f, 0, 0);
   }
   SEG3D_REQUIRE(!(dtype & SEG3D_OUT_F32), "conv3d_fwd: SEG3D_OUT_F32 needs the tensor-core path");
   if (impl == SEG3D_IMPL_SIMT)
@@ -53,5 +54,23 @@ extern "C" int seg3d_conv3d_gn_relu_fwd(int mode, int dtype, int pass, const voi
     return SEG3D_EUNSUPPORTED;
   }
   return seg3d_conv_tc(mode, dtype, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, pass == 0 ? stats : nullptr,
-                       (cudaStream_t)stream, pass == 0 ? 1 : 2, stats, gamma, beta, eps);
+                       (cudaStream_t)stream, pass == 0 ? 1 : 2, stats, gamma, beta, eps, 0, 0);
+}
+
+// Strict-parity convolution on the tensor cores (split operands): x is stored as two f16 halves per voxel row,
+// x = hi + lo with hi at channel c and lo at channel lo_off + c (lo_off = x_ld / 2 for the plan's buffers); w holds
+// [taps][Cout][whi(Cin) | wlo(Cin)] (T2S2: [8*Cout][whi | wlo]).  The K loop accumulates hi*whi + lo*whi + hi*wlo in fp32
+// (the dropped lo*wlo term is 2^-22 relative), and y is the fp32 result + bias with pitch y_ld floats.
+extern "C" int seg3d_conv3d_split_fwd(int mode, const void* x, int x_ld, int lo_off, int Cin, const void* w, const float* bias,
+                                      float* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, void* stream) {
+  SEG3D_REQUIRE(x && w && y, "conv3d_split_fwd: null pointer");
+  SEG3D_REQUIRE(Cin > 0 && Cout > 0 && N > 0 && D > 0 && H > 0 && W > 0 && lo_off >= Cin && x_ld >= lo_off + Cin && y_ld >= Cout,
+                "conv3d_split_fwd: bad dims");
+  SEG3D_REQUIRE(lo_off % 8 == 0 && y_ld % 4 == 0 && ((uintptr_t)y) % 16 == 0, "conv3d_split_fwd: alignment");
+  if (!seg3d_conv_tc_supported(mode, SEG3D_F16, Cin, Cout, x_ld, 8, D, H, W)) {
+    seg3d_set_error("conv3d_split_fwd: tcgen05 path does not take mode=%d Cin=%d Cout=%d", mode, Cin, Cout);
+    return SEG3D_EUNSUPPORTED;
+  }
+  return seg3d_conv_tc(mode, SEG3D_F16, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, stats, (cudaStream_t)stream,
+                       0, nullptr, nullptr, nullptr, 0.f, lo_off, 1);
 }

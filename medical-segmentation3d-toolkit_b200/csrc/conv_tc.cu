@@ -48,6 +48,10 @@ struct TcParams {
   int wide;                         // epilogue may use 256-bit stores (32-byte aligned rows)
   // GroupNorm folded into the epilogue of a conv that is cheap to run twice (HBM-bound stride-2 / transposed convs):
   // epi_mode 0: store raw + statistics; 1: statistics only, nothing stored; 2: y = relu(gn(conv)) from finished statistics
+  // split-operand strict mode: activations are [hi | lo] f16 halves (lo_off channels apart), weights [whi | wlo]; the K loop runs
+  // the three products hi*whi, lo*whi, hi*wlo, so the fp32 accumulator carries ~22-bit operands
+  int split, lo_off, nchunk_real;
+  int out_f32;                      // store the fp32 accumulator (+bias) as float rows of pitch y_ld instead of T
   int epi_mode;
   float gn_eps;
   double gn_count;                  // elements per sample of the GroupNorm(1,C) input = real Cout * output voxels
@@ -107,25 +111,31 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
         const int z0 = (t % p.ntz) * p.td; const int n = t / p.ntz;
         for (int it = 0; it < kiters; ++it) {
           const int tap = it / p.nchunk, ck = it - tap * p.nchunk;
+          int a_c = ck * p.KC, w_c = ck * p.KC;                 // channel coordinates of this K chunk in x and in w
+          if (p.split) {
+            const int ps = ck / p.nchunk_real, c = ck - ps * p.nchunk_real;
+            a_c = c * p.KC + (ps == 1 ? p.lo_off : 0);
+            w_c = c * p.KC + (ps == 2 ? p.Cin : 0);
+          }
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           mbar_expect_tx_e(full_bar + 8 * stage, (uint32_t)p.tx_bytes);
           const uint32_t fb = full_bar + 8 * stage, sa = a_base + stage * p.a_bytes, sb = b_base + stage * p.b_bytes;
           if (p.conv == 2) {         // transposed conv: plain GEMM rows, weight rows of this N-pass
-            tma_load_5d_e(sa, &map_x, fb, ck * p.KC, x0, y0, z0, n);
-            tma_load_2d_e(sb, &map_w, fb, ck * p.KC, pass * p.Cout);
+            tma_load_5d_e(sa, &map_x, fb, a_c, x0, y0, z0, n);
+            tma_load_2d_e(sb, &map_w, fb, w_c, pass * p.Cout);
           } else if (p.conv == 1) {  // k2 s2: tap = (kd*2+kh)*2+kw folded into the (channel, x, y) coordinates
             const int kd = tap >> 2, kh = (tap >> 1) & 1, kw = tap & 1;
-            tma_load_5d_e(sa, &map_x, fb, kw * p.x_ld + ck * p.KC, x0 + kh * p.halfW, y0 + kd * p.halfH, z0, n);
-            tma_load_2d_e(sb, &map_w, fb, ck * p.KC, tap * p.Cout);
+            tma_load_5d_e(sa, &map_x, fb, kw * p.x_ld + a_c, x0 + kh * p.halfW, y0 + kd * p.halfH, z0, n);
+            tma_load_2d_e(sb, &map_w, fb, w_c, tap * p.Cout);
           } else if (p.kwfuse) {
             const int kd = tap / 3, kh = tap % 3;
-            tma_load_5d_e(sa, &map_x, fb, ck * p.KC, x0 - 1, y0 + kh - 1, z0 + kd - 1, n);
+            tma_load_5d_e(sa, &map_x, fb, a_c, x0 - 1, y0 + kh - 1, z0 + kd - 1, n);
             for (int kw = 0; kw < 3; ++kw)
-              tma_load_2d_e(sb + kw * p.b_slab, &map_w, fb, ck * p.KC, (tap * 3 + kw) * p.Cout);
+              tma_load_2d_e(sb + kw * p.b_slab, &map_w, fb, w_c, (tap * 3 + kw) * p.Cout);
           } else {
             const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-            tma_load_5d_e(sa, &map_x, fb, ck * p.KC, x0 + kw - 1, y0 + kh - 1, z0 + kd - 1, n);
-            tma_load_2d_e(sb, &map_w, fb, ck * p.KC, tap * p.Cout);
+            tma_load_5d_e(sa, &map_x, fb, a_c, x0 + kw - 1, y0 + kh - 1, z0 + kd - 1, n);
+            tma_load_2d_e(sb, &map_w, fb, w_c, tap * p.Cout);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -205,6 +215,8 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
         const size_t ov0 = (((size_t)n * 2 * p.D + 2 * gz) * 2 * p.H + 2 * gy) * 2 * p.W + 2 * gx;
         ybase = y + ov0 * p.y_ld;
       }
+      if (p.out_f32)      // the output is a float tensor: redo the row base in float elements (T is 2 bytes wide)
+        ybase = reinterpret_cast<T*>(reinterpret_cast<float*>(y) + (ybase - y));
       auto emit = [&](const uint32_t* v, int c0) {
         float f[16];
         int co = c0, off = c0;
@@ -231,7 +243,15 @@ conv3d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
             f[jj] = fmaxf(fmaf(f[jj], a, p.gn_beta[co + jj] - gn_mean * a), 0.f);
           }
         }
-        if (valid && p.epi_mode != 1) store16<T>(ybase + off, f, wide);
+        if (valid && p.epi_mode != 1) {
+          if (p.out_f32) {
+            float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ybase) + off);     // ybase / off in elements of the fp32 tensor
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4) d4[jj >> 2] = make_float4(f[jj], f[jj + 1], f[jj + 2], f[jj + 3]);
+          } else {
+            store16<T>(ybase + off, f, wide);
+          }
+        }
       };
       uint32_t va[16], vb[16];
       int c0 = half * 16;
@@ -803,7 +823,8 @@ int seg3d_conv_tc_supported(int mode, int dtype, int Cin, int Cout, int x_ld, in
 
 int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
                   void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st,
-                  int epi_mode, const double* gn_stats, const float* gn_gamma, const float* gn_beta, float gn_eps) {
+                  int epi_mode, const double* gn_stats, const float* gn_gamma, const float* gn_beta, float gn_eps,
+                  int split_lo_off, int out_f32_generic) {
   EncodeTiledFn encode = get_encode();
   if (!encode) { seg3d_set_error("conv_tc: cuTensorMapEncodeTiled entry point not available"); return SEG3D_ECUDA; }
   SEG3D_REQUIRE(((uintptr_t)x) % 16 == 0 && ((uintptr_t)w) % 16 == 0 && ((uintptr_t)y) % 16 == 0, "conv_tc: pointers must be 16-byte aligned");
@@ -811,7 +832,7 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   // ---- z-marching kernel for narrow k3 layers --------------------------------------------------------
   const int out_f32 = (dtype & SEG3D_OUT_F32) ? 1 : 0;
   dtype &= ~SEG3D_OUT_F32;
-  if (epi_mode == 0 && mode == SEG3D_CONV_K3 && (Cin == 16 || Cin == 32 || Cin == 64) && W % 8 == 0 && D >= 4 && env_int("SEG3D_TC_ZMARCH", 1) != 0) {
+  if (epi_mode == 0 && split_lo_off == 0 && !out_f32_generic && mode == SEG3D_CONV_K3 && (Cin == 16 || Cin == 32 || Cin == 64) && W % 8 == 0 && D >= 4 && env_int("SEG3D_TC_ZMARCH", 1) != 0) {
     ZmParams z;
     memset(&z, 0, sizeof(z));
     z.Cout = Cout; z.KC = Cin; z.row_bytes = Cin * 2;
@@ -891,7 +912,7 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
     }
   }
 
-  SEG3D_REQUIRE(!out_f32, "conv_tc: fp32 output is only available on the z-march k3 path (Cin in {16,32,64}, W %% 8 == 0)");
+  SEG3D_REQUIRE(!out_f32, "conv_tc: SEG3D_OUT_F32 (dense real channels) is only available on the z-march k3 path");
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.conv = mode == SEG3D_CONV_K2S2 ? 1 : (mode == SEG3D_CONV_T2S2 ? 2 : 0);
@@ -905,14 +926,16 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   }
   p.Cin = Cin; p.Cout = Cout; p.D = Do; p.H = Ho; p.W = Wo; p.N = N; p.y_ld = y_ld;
   p.x_ld = x_ld; p.halfW = W / 2; p.halfH = H / 2;
-  p.wide = (wide_ok(y, y_ld, 2) && p.cout_real % 16 == 0 && env_int("SEG3D_WIDE_ST", 1)) ? 1 : 0;
+  p.wide = (!out_f32_generic && wide_ok(y, y_ld, 2) && p.cout_real % 16 == 0 && env_int("SEG3D_WIDE_ST", 1)) ? 1 : 0;
   p.epi_mode = epi_mode; p.gn_eps = gn_eps; p.gn_stats = gn_stats; p.gn_gamma = gn_gamma; p.gn_beta = gn_beta;
   {
     const long long ovox = p.conv == 1 ? (long long)(D / 2) * (H / 2) * (W / 2) : (p.conv == 2 ? 8ll * D * H * W : (long long)D * H * W);
     p.gn_count = (double)ovox * (double)p.cout_real;
   }
   p.KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
-  p.nchunk = Cin / p.KC;
+  p.nchunk_real = Cin / p.KC;
+  p.split = split_lo_off > 0 ? 1 : 0; p.lo_off = split_lo_off; p.out_f32 = out_f32_generic;
+  p.nchunk = p.split ? 3 * p.nchunk_real : p.nchunk_real;
   const int row_bytes = p.KC * 2;
   p.row_bytes = row_bytes;
 
@@ -971,12 +994,13 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   CUtensorMap map_x, map_w;
   {
     cuuint64_t dims[5], strides[4];
+    const int cext = Cin + (p.split ? p.lo_off : 0);      // channel extent the K loop addresses (lo half = +lo_off)
     if (p.conv == 1) {   // stride-2 taps folded into the coordinates: c' = kw*ld + c, x' = x + kh*W/2, y' = y + kd*H/2
-      dims[0] = (cuuint64_t)x_ld + Cin; dims[1] = (cuuint64_t)W; dims[2] = (cuuint64_t)H; dims[3] = (cuuint64_t)D / 2; dims[4] = (cuuint64_t)N;
+      dims[0] = (cuuint64_t)x_ld + cext; dims[1] = (cuuint64_t)W; dims[2] = (cuuint64_t)H; dims[3] = (cuuint64_t)D / 2; dims[4] = (cuuint64_t)N;
       strides[0] = (cuuint64_t)2 * x_ld * 2; strides[1] = (cuuint64_t)2 * W * x_ld * 2; strides[2] = (cuuint64_t)2 * H * W * x_ld * 2;
       strides[3] = (cuuint64_t)D * H * W * x_ld * 2;
     } else {
-      dims[0] = (cuuint64_t)Cin; dims[1] = (cuuint64_t)W; dims[2] = (cuuint64_t)H; dims[3] = (cuuint64_t)D; dims[4] = (cuuint64_t)N;
+      dims[0] = (cuuint64_t)cext; dims[1] = (cuuint64_t)W; dims[2] = (cuuint64_t)H; dims[3] = (cuuint64_t)D; dims[4] = (cuuint64_t)N;
       strides[0] = (cuuint64_t)x_ld * 2; strides[1] = (cuuint64_t)W * x_ld * 2; strides[2] = (cuuint64_t)H * W * x_ld * 2;
       strides[3] = (cuuint64_t)D * H * W * x_ld * 2;
     }
@@ -987,8 +1011,9 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
     if (r != CUDA_SUCCESS) { seg3d_set_error("conv_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SEG3D_ECUDA; }
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)(p.conv == 1 ? 8 * Cout : (p.conv == 2 ? 8 * p.cout_real : 27 * Cout))};
-    cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+    const int wk = p.split ? 2 * Cin : Cin;              // weight rows hold [whi | wlo] in the split mode
+    cuuint64_t dims[2] = {(cuuint64_t)wk, (cuuint64_t)(p.conv == 1 ? 8 * Cout : (p.conv == 2 ? 8 * p.cout_real : 27 * Cout))};
+    cuuint64_t strides[1] = {(cuuint64_t)wk * 2};
     cuuint32_t box[2] = {(cuuint32_t)p.KC, (cuuint32_t)Cout};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&map_w, tdt, 2, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,

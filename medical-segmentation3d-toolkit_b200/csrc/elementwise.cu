@@ -59,6 +59,69 @@ gn_apply_kernel(const T* __restrict__ y, int y_ld, int C, const double* __restri
   }
 }
 
+// Split-operand strict mode: y is the fp32 conv result; res / out are [hi | lo] f16 rows (lo half lo_off channels after hi).
+template <bool RELU, bool RES>
+__global__ void __launch_bounds__(256)
+gn_apply_split_kernel(const float* __restrict__ y, int y_ld, int C, const double* __restrict__ stats,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                      const __half* __restrict__ res, int res_ld, int res_lo, __half* __restrict__ out, int out_ld, int out_lo,
+                      long long nvox) {
+  __shared__ float sa[GN_MAXC], sb[GN_MAXC];
+  const int n = blockIdx.y;
+  float mean, rstd;
+  gn_mean_rstd(stats + 2 * n, (double)nvox * C, eps, mean, rstd);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float a = rstd * gamma[c];
+    sa[c] = a; sb[c] = beta[c] - mean * a;
+  }
+  __syncthreads();
+  const int cv = C >> 3;
+  const long long items = nvox * cv;
+  const float* yn = y + (size_t)n * nvox * y_ld;
+  const __half* rn = RES ? res + (size_t)n * nvox * res_ld : nullptr;
+  __half* on = out + (size_t)n * nvox * out_ld;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const long long vox = it / cv; const int c0 = (int)(it - vox * cv) << 3;
+    Vec8<float> v; v.load(yn + vox * y_ld + c0);
+    float f[8]; v.get(f);
+    float rh[8], rl[8];
+    if (RES) {
+      Vec8<__half> a, b; a.load(rn + vox * res_ld + c0); b.load(rn + vox * res_ld + res_lo + c0);
+      a.get(rh); b.get(rl);
+    }
+    float hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(f[j], sa[c0 + j], sb[c0 + j]);
+      if (RES) t += rh[j] + rl[j];
+      if (RELU) t = fmaxf(t, 0.f);
+      const float h = __half2float(__float2half_rn(t));
+      hi[j] = h; lo[j] = t - h;
+    }
+    Vec8<__half> o; o.set(hi); o.store(on + vox * out_ld + c0);
+    o.set(lo); o.store(on + vox * out_ld + out_lo + c0);
+  }
+}
+
+extern "C" int seg3d_gn_apply_split(const float* y, int y_ld, int C, const double* stats, const float* gamma, const float* beta,
+                                    float eps, const void* res, int res_ld, int res_lo, void* out, int out_ld, int out_lo,
+                                    int relu, int N, int64_t nvox, void* stream) {
+  SEG3D_REQUIRE(y && stats && gamma && beta && out && C > 0 && C % 8 == 0 && C <= GN_MAXC && N > 0 && nvox > 0, "gn_apply_split: bad arguments");
+  SEG3D_REQUIRE(y_ld % 4 == 0 && out_ld % 8 == 0 && out_lo % 8 == 0 && (!res || (res_ld % 8 == 0 && res_lo % 8 == 0)), "gn_apply_split: pitches");
+  const long long items = (long long)nvox * (C / 8);
+  const int sms = seg3d_num_sms();
+  long long want = (items + 255) / 256;
+  dim3 grid((unsigned)(want > 8ll * sms ? 8ll * sms : (want < 1 ? 1 : want)), N);
+  cudaStream_t st = (cudaStream_t)stream;
+  const __half* r = (const __half*)res; __half* o = (__half*)out;
+#define SEG3D_GNS(RL, RS) gn_apply_split_kernel<RL, RS><<<grid, 256, 0, st>>>(y, y_ld, C, stats, gamma, beta, eps, r, res_ld, res_lo, o, out_ld, out_lo, nvox)
+  if (relu) { if (res) SEG3D_GNS(true, true); else SEG3D_GNS(true, false); }
+  else      { if (res) SEG3D_GNS(false, true); else SEG3D_GNS(false, false); }
+#undef SEG3D_GNS
+  SEG3D_CHECK_LAUNCH("gn_apply_split_kernel");
+  return SEG3D_OK;
+}
+
 extern "C" int seg3d_gn_apply(int dtype, const void* y, int y_ld, int C, const double* stats,
                               const float* gamma, const float* beta, float eps, const void* res, int res_ld,
                               void* out, int out_ld, int relu, int N, int64_t nvox, void* stream) {

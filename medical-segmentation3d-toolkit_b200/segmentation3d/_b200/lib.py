@@ -31,6 +31,8 @@ _SIGNATURES = {
     'seg3d_conv3d_k3_narrow_fwd': (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     'seg3d_conv3d_k3_narrow_gn_fwd': (_i, [_i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     'seg3d_conv3d_gn_relu_fwd': (_i, [_i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
+    'seg3d_conv3d_split_fwd': (_i, [_i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    'seg3d_gn_apply_split': (_i, [_vp, _i, _i, _vp, _vp, _vp, _f, _vp, _i, _i, _vp, _i, _i, _i, _i, _i64, _vp]),
     'seg3d_gn_apply': (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _f, _vp, _i, _vp, _i, _i, _i, _i64, _vp]),
     'seg3d_outblock_tail_stats': (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i64, _vp]),
     'seg3d_outblock_tail_probs': (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i64, _vp]),

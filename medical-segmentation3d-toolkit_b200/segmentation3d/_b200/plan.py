@@ -19,7 +19,8 @@ import torch
 
 from . import lib
 
-MODES = {'fp32': lib.F32, 'fp16': lib.F16, 'bf16': lib.BF16}
+# 'fp32x': strict parity on the tensor cores - f16 storage of split operands (x = hi + lo), three MMAs per product
+MODES = {'fp32': lib.F32, 'fp16': lib.F16, 'bf16': lib.BF16, 'fp32x': lib.F16}
 GN_EPS = 1e-5
 
 
@@ -36,9 +37,10 @@ def strip_prefix(sd):
 class _Conv(object):
     """One packed convolution.  `load` (re)packs in place so kernel-argument pointers stay valid."""
 
-    def __init__(self, sd, name, mode, dt, device, allow_tc, pad_cout=0, transform=None, pad_dim0=0, fold=False):
+    def __init__(self, sd, name, mode, dt, device, allow_tc, pad_cout=0, transform=None, pad_dim0=0, fold=False, split=False):
         self.transform, self.pad_dim0 = transform, pad_dim0
         self.fold, self.w_fold = fold, None
+        self.split = split          # strict mode on the tensor cores: weights packed [.. Cout][whi(Cin) | wlo(Cin)] f16
         w = self._effective_weight(sd[name + '.weight'])
         self.name, self.mode, self.dt, self.device = name, mode, dt, device
         if mode == lib.CONV_T2S2:
@@ -56,7 +58,7 @@ class _Conv(object):
         self.impl = lib.IMPL_TCGEN05 if tc_ok else lib.IMPL_SIMT
         # input block (Cin == 1): the tensor-core kernel builds its own im2col tile and takes the fp32 SIMT weight
         # layout, so packing follows `impl` (SIMT) while the call lets the library pick (csrc/conv_tc_cin1.cu)
-        self.cin1_tc = bool(not tc_ok and allow_tc and dt != lib.F32 and mode == lib.CONV_K3 and mode in allow_tc
+        self.cin1_tc = bool(not tc_ok and allow_tc and dt != lib.F32 and not split and mode == lib.CONV_K3 and mode in allow_tc
                             and self.cin == 1 and self.cout == 16 and transform is None)
         self.call_impl = lib.IMPL_AUTO if self.cin1_tc else self.impl
         self.w, self.bias = None, None
@@ -88,6 +90,14 @@ class _Conv(object):
             else:                               # [taps][Cin][Cout]
                 p = w.permute(2, 3, 4, 1, 0).reshape(-1, self.cin, self.cout)
             p = p.contiguous()
+        elif self.split:
+            if self.mode == lib.CONV_T2S2:      # [8*Cout][Cin]
+                q = w.permute(2, 3, 4, 1, 0).reshape(8 * self.cout, self.cin)
+            else:                               # [taps][Cout][Cin]
+                q = w.permute(2, 3, 4, 0, 1).reshape(-1, self.cout, self.cin)
+            hi = q.to(torch.float16)
+            lo = (q - hi.float()).to(torch.float16)
+            p = torch.cat([hi, lo], dim=-1).contiguous()
         else:
             if self.mode == lib.CONV_T2S2:      # [8*Cout][Cin]
                 p = w.permute(2, 3, 4, 1, 0).reshape(8 * self.cout, self.cin)
@@ -143,6 +153,8 @@ class NetPlan(object):
         if mode not in MODES:
             raise ValueError('mode must be one of %s' % sorted(MODES))
         self.mode, self.dt = mode, MODES[mode]
+        self.split = mode == 'fp32x'
+        self.in_dt = lib.F32 if self.split else self.dt      # storage type of the network input (patch gather output)
         self.tdtype = lib.TORCH_DTYPE[self.dt]
         self.device = torch.device(device if device is not None else 'cuda')
         if self.device.type != 'cuda':
@@ -171,11 +183,11 @@ class NetPlan(object):
                     continue
                 else:
                     m = lib.CONV_K3
-                narrow = (name == 'out_block.conv1' and self.dt != lib.F32 and lib.CONV_K3 in self.tc_modes
+                narrow = (name == 'out_block.conv1' and self.dt != lib.F32 and not self.split and lib.CONV_K3 in self.tc_modes
                           and sd[k].shape[0] <= 7 and sd[k].shape[1] in (16, 32, 64)
                           and os.environ.get('SEG3D_NARROW', '1') != '0')
                 self.convs[name] = _Conv(sd, name, m, self.dt, self.device, self.tc_modes,
-                                         pad_cout=16 if name == 'out_block.conv1' else 0, fold=narrow)
+                                         pad_cout=16 if name == 'out_block.conv1' else 0, fold=narrow, split=self.split)
             else:
                 self.gns[name] = _GN(sd, name, self.device)
         self.w2 = sd['out_block.conv2.weight'].detach().to(self.device, torch.float32).reshape(
@@ -209,15 +221,22 @@ class NetPlan(object):
     def _build(self, B, D, H, W, train=False):
         dev, td, dt = self.device, self.tdtype, self.dt
         assert D % 16 == 0 and H % 16 == 0 and W % 16 == 0, 'spatial dims must be multiples of max_stride=16'
+        split = self.split
+        if split and train:
+            raise RuntimeError("seg3d_b200: mode 'fp32x' is an inference mode (train in 'bf16' or 'fp32')")
+        cm = 2 if split else 1          # split mode: every activation row is [hi(C) | lo(C)]
         dims = [(D >> l, H >> l, W >> l) for l in range(5)]
         vox = [d[0] * d[1] * d[2] for d in dims]
 
         def buf(l, C):
-            return torch.empty((B, vox[l], C), dtype=td, device=dev)
+            return torch.empty((B, vox[l], C * cm), dtype=td, device=dev)
+
+        def V(b, off, ld, C):           # channel window of an activation buffer (ld = logical channel count of the buffer)
+            return _View(b, off, ld * cm, C)
 
         ws = {}
-        ws['x_in'] = torch.empty((B, vox[0], self.in_channels), dtype=td, device=dev)
-        ws['raw'] = torch.empty((B * vox[0] * 32,), dtype=td, device=dev)
+        ws['x_in'] = torch.empty((B, vox[0], self.in_channels), dtype=torch.float32 if split else td, device=dev)
+        ws['raw'] = torch.empty((B * vox[0] * 32,), dtype=torch.float32 if split else td, device=dev)
         ws['stats'] = torch.zeros((len(self.gn_names), B, 2), dtype=torch.float64, device=dev)
         ws['stats2'] = torch.zeros((B, 2), dtype=torch.float64, device=dev)
         ws['probs'] = torch.empty((B, self.out_channels, D, H, W), dtype=torch.float32, device=dev)
@@ -238,9 +257,19 @@ class NetPlan(object):
             c = self.convs[name]
             assert c.cin == x.C and c.cout == y.C, (name, c.cin, x.C, c.cout, y.C)
             sp = lib.ptr(ws['stats'][self.gn_index[stats_name]]) if stats_name else None
-            args = (c.mode, dt, c.call_impl, x.p, x.ld, c.cin, lib.ptr(c.w), lib.ptr(c.bias), y.p, y.ld, c.cout,
-                    B, xdims[0], xdims[1], xdims[2], sp)
-            ops.append(lambda a=args: lib.call('seg3d_conv3d_fwd', *a, st()))
+            if split and c.impl == lib.IMPL_TCGEN05:       # x: [hi | lo] f16 rows, y: fp32 raw
+                args = (c.mode, x.p, x.ld, x.ld // 2, c.cin, lib.ptr(c.w), lib.ptr(c.bias), y.p, y.ld, c.cout,
+                        B, xdims[0], xdims[1], xdims[2], sp)
+                ops.append(lambda a=args: lib.call('seg3d_conv3d_split_fwd', *a, st()))
+            elif split:                                    # input block: fp32 in, fp32 weights, fp32 out on the CUDA cores
+                assert x.buf.dtype == torch.float32 and y.buf.dtype == torch.float32
+                args = (c.mode, lib.F32, lib.IMPL_SIMT, x.p, x.ld, c.cin, lib.ptr(c.w), lib.ptr(c.bias), y.p, y.ld, c.cout,
+                        B, xdims[0], xdims[1], xdims[2], sp)
+                ops.append(lambda a=args: lib.call('seg3d_conv3d_fwd', *a, st()))
+            else:
+                args = (c.mode, dt, c.call_impl, x.p, x.ld, c.cin, lib.ptr(c.w), lib.ptr(c.bias), y.p, y.ld, c.cout,
+                        B, xdims[0], xdims[1], xdims[2], sp)
+                ops.append(lambda a=args: lib.call('seg3d_conv3d_fwd', *a, st()))
             nv_in = B * xdims[0] * xdims[1] * xdims[2]
             taps = {lib.CONV_K3: 27, lib.CONV_K2S2: 1, lib.CONV_T2S2: 8, lib.CONV_K1: 1}[c.mode]   # MACs per INPUT voxel / (cin*cout)
             nv_out = nv_in // 8 if c.mode == lib.CONV_K2S2 else (nv_in * 8 if c.mode == lib.CONV_T2S2 else nv_in)
@@ -256,10 +285,16 @@ class NetPlan(object):
         def gn(name, y, out, nvox, relu, res=None):
             g = self.gns[name]
             sp = lib.ptr(ws['stats'][self.gn_index[name]])
-            args = (dt, y.p, y.ld, y.C, sp, lib.ptr(g.gamma), lib.ptr(g.beta), GN_EPS,
-                    res.p if res is not None else None, res.ld if res is not None else 0,
-                    out.p, out.ld, 1 if relu else 0, B, nvox)
-            ops.append(lambda a=args: lib.call('seg3d_gn_apply', *a, st()))
+            if split:
+                args = (y.p, y.ld, y.C, sp, lib.ptr(g.gamma), lib.ptr(g.beta), GN_EPS,
+                        res.p if res is not None else None, res.ld if res is not None else 0, res.ld // 2 if res is not None else 0,
+                        out.p, out.ld, out.ld // 2, 1 if relu else 0, B, nvox)
+                ops.append(lambda a=args: lib.call('seg3d_gn_apply_split', *a, st()))
+            else:
+                args = (dt, y.p, y.ld, y.C, sp, lib.ptr(g.gamma), lib.ptr(g.beta), GN_EPS,
+                        res.p if res is not None else None, res.ld if res is not None else 0,
+                        out.p, out.ld, 1 if relu else 0, B, nvox)
+                ops.append(lambda a=args: lib.call('seg3d_gn_apply', *a, st()))
             esz = 4 if dt == lib.F32 else 2
             meta.append({'name': name, 'kind': 'gn_apply', 'flops': 0.0,
                          'bytes': esz * B * nvox * y.C * (3 if res is not None else 2)})
@@ -267,12 +302,12 @@ class NetPlan(object):
         def rawview(C, l=0):
             if train:       # training keeps every pre-GroupNorm tensor for the backward pass
                 return _View(torch.empty((B, vox[l], C), dtype=td, device=dev), 0, C, C)
-            return _View(raw, 0, C, C)
+            return _View(raw, 0, C, C)          # split mode: the raw scratch is fp32, one value per channel
 
         def tmpbuf(l, C, key):
             if train:
                 return _View(torch.empty((B, vox[l], C), dtype=td, device=dev), 0, C, C)
-            return _View(ws[key], 0, C, C)
+            return V(ws[key], 0, C, C)
 
         def conv_gn_twice(cname, gname, x, xdims, out, nvox_out):
             """HBM-bound stride-2 / transposed conv: run it twice (statistics, then GroupNorm + ReLU in the epilogue)
@@ -293,7 +328,7 @@ class NetPlan(object):
 
         # measured on B200: the stride-2 convs are epilogue-bound, not HBM-bound, so running them twice costs more than the
         # GroupNorm pass it saves (1535 vs 1640 Mvox/s); kept behind SEG3D_FUSE_S2=1
-        fuse_s2 = (not train) and dt != lib.F32 and os.environ.get('SEG3D_FUSE_S2', '0') == '1'
+        fuse_s2 = (not train) and dt != lib.F32 and not split and os.environ.get('SEG3D_FUSE_S2', '0') == '1'
 
         def unit(cname, gname, x, lin, lout, out, res=None, defer_gn=False):
             """conv -> GroupNorm -> (+res) -> ReLU with the conv reading level `lin` and writing level `lout`"""
@@ -343,30 +378,30 @@ class NetPlan(object):
         # the network's last GroupNorm + residual + ReLU (up_32.rblock) has a single consumer, out_block.conv1: form it in
         # that kernel's shared memory instead of streaming it through HBM
         c1_ = self.convs['out_block.conv1']
-        fuse_tail = (not train and c1_.fold and c1_.impl == lib.IMPL_TCGEN05 and c1_.cin == 32 and W % 8 == 0
+        fuse_tail = (not train and not split and c1_.fold and c1_.impl == lib.IMPL_TCGEN05 and c1_.cin == 32 and W % 8 == 0
                      and ('up_32.rblock.ops.%d.conv' % (self._rblock_len('up_32.rblock') - 1)) in self.convs
                      and os.environ.get('SEG3D_TAIL_F32', '1') != '0' and os.environ.get('SEG3D_FUSE_TAIL', '1') != '0')
 
         # in_block -> second half of cat0
         x_in = _View(ws['x_in'], 0, self.in_channels, self.in_channels)
-        skip = [_View(ws['cat%d' % l], widths[l] // 2, widths[l], widths[l] // 2) for l in range(4)]
+        skip = [V(ws['cat%d' % l], widths[l] // 2, widths[l], widths[l] // 2) for l in range(4)]
         conv_gn('in_block.conv', 'in_block.gn', x_in, 0, skip[0], relu=True)
         # down path
         src = skip[0]
         for l, name in ((1, 'down_32'), (2, 'down_64'), (3, 'down_128'), (4, 'down_256')):
             C = widths[l] // 2 if l < 4 else 256
-            A = _View(ws['A%d' % l], 0, C, C)
+            A = V(ws['A%d' % l], 0, C, C)
             unit(name + '.down_conv', name + '.down_gn', src, l - 1, l, A)
-            dest = skip[l] if l < 4 else _View(ws['U4'], 0, 256, 256)
+            dest = skip[l] if l < 4 else V(ws['U4'], 0, 256, 256)
             rblock(name + '.rblock', A, l, dest)
             src = dest
         # up path
         for l, name in ((3, 'up_256'), (2, 'up_128'), (1, 'up_64'), (0, 'up_32')):
             C = widths[l]
-            up = _View(ws['cat%d' % l], 0, C, C // 2)
+            up = V(ws['cat%d' % l], 0, C, C // 2)
             unit(name + '.up_conv', name + '.up_gn', src, l + 1, l, up)
-            cat = _View(ws['cat%d' % l], 0, C, C)
-            dest = _View(ws['U%d' % l], 0, C, C)
+            cat = V(ws['cat%d' % l], 0, C, C)
+            dest = V(ws['U%d' % l], 0, C, C)
             rblock(name + '.rblock', cat, l, dest, defer_last=(l == 0 and fuse_tail))
             src = dest
         # out block: conv1 -> raw, then the fused tail
@@ -375,9 +410,9 @@ class NetPlan(object):
         ncp = c1.cout                                      # = nc, or 16 when padded for the tensor-core path
         # conv1's raw output feeds GN1 -> 1x1x1 conv -> GN2 -> softmax directly: its storage rounding would dominate
         # the probability error, so the tensor-core path stores it in fp32 (64 B/voxel instead of 32)
-        tail_f32 = (c1.impl == lib.IMPL_TCGEN05 and src.C in (16, 32, 64) and W % 8 == 0 and not train
+        tail_f32 = (c1.impl == lib.IMPL_TCGEN05 and src.C in (16, 32, 64) and W % 8 == 0 and not train and not split
                     and os.environ.get('SEG3D_TAIL_F32', '1') != '0')
-        tail_dt = lib.F32 if tail_f32 else dt
+        tail_dt = lib.F32 if (tail_f32 or split) else dt
         if tail_f32 and c1.fold:
             # nine in-plane taps folded into the GEMM N dimension (csrc/conv_tc_narrow.cu), fp32 result
             ncp = nc
@@ -419,7 +454,7 @@ class NetPlan(object):
               GN_EPS, s2, B, vox[0])
         ops.append(lambda a=a1: lib.call('seg3d_outblock_tail_stats', *a, st()))
         esz = 4 if dt == lib.F32 else 2
-        esz = 4 if tail_f32 else esz
+        esz = 4 if (tail_f32 or split) else esz
         meta.append({'name': 'out_block.tail_stats', 'kind': 'tail', 'flops': 0.0, 'bytes': esz * B * vox[0] * ncp})
         meta.append({'name': 'out_block.tail_probs', 'kind': 'tail', 'flops': 0.0, 'bytes': esz * B * vox[0] * ncp + 4 * B * vox[0] * nc})
         a2 = (tail_dt, lib.ptr(raw), ncp, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),

@@ -72,7 +72,7 @@ class SlidingWindow(object):
                 lib.call('seg3d_patch_stats', lib.ptr(vol), Z, Y, X, sp, nb, pz, py, px, lib.ptr(pstats), st())
                 self.kernel_launches += 1
             lib.call('seg3d_patch_gather', lib.ptr(vol), Z, Y, X, sp, nb, pz, py, px, norm, mean, std, clip, lo, hi,
-                     lib.ptr(pstats), plan.dt, lib.ptr(ws['x_in']), st())
+                     lib.ptr(pstats), plan.in_dt, lib.ptr(ws['x_in']), st())
             probs = plan.run(ws, ops)
             lib.call('seg3d_blend_accumulate', lib.ptr(probs), nb, C, pz, py, px, sp, lib.ptr(acc), Z, Y, X, st())
             self.kernel_launches += 2 + len(ops)
