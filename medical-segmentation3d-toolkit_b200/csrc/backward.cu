@@ -88,8 +88,7 @@ gn_bwd_kernel(const T* __restrict__ g0, int ld0, const T* __restrict__ g1, int l
         const float dz = o[j] > 0.f ? (ga[j] + gb[j] + gc[j]) : 0.f;
         const float xh = (yy[j] - mean) * rstd;
         if (PASS == 0) {
-          s1 += gam[j] * dz; s2 += gam[j] * dz * xh;
-          a0[j] += dz * xh; a1[j] += dz;
+          a0[j] = fmaf(dz, xh, a0[j]); a1[j] += dz;        // the per-sample sums follow from these at the end (a block = one sample)
         } else {
           const float d = rstd * (gam[j] * dz - m1 - xh * m2);
           dyv[j] = d; dzv[j] = dz; a0[j] += d;
@@ -100,6 +99,10 @@ gn_bwd_kernel(const T* __restrict__ g0, int ld0, const T* __restrict__ g1, int l
         if (dres) { w.set(dzv); w.store(dres + vv * dres_ld + c0); }
       }
     }
+  }
+  if (PASS == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1 = fmaf(gam[j], a1[j], s1); s2 = fmaf(gam[j], a0[j], s2); }
   }
   // per-channel partials: lanes that own the same channel group (lane % cv) are folded with shuffles first, then
   // one shared-memory atomic per warp and channel, then one global atomic per channel per block
