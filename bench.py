@@ -162,7 +162,7 @@ def workload_config(args, size):
                         'partition_stride=%d mm (BASELINE configs[%d])' % ({'vnet': 'VNet', 'vbnet': 'VBNet'}[args.arch], args.classes,
                                                                            size[0], size[1], size[2], args.patch, args.stride,
                                                                            1 if args.arch == 'vnet' else 3),
-            'patch_batch': args.batch, 'mode': args.mode, 'shard': args.shard,
+            'patch_batch': args.batch, 'mode': args.mode, 'shard': args.shard, 'gather': args.gather if args.shard == 'patches' else None,
             'l2_policy': 'inputs larger than L2 (volume 419 MB + accumulators 839 MB per step)'}
 
 
@@ -232,6 +232,8 @@ def main():
     ap.add_argument('--patch', type=int, default=96)
     ap.add_argument('--stride', type=int, default=96)
     ap.add_argument('--shard', default='cases', choices=['cases', 'patches'])
+    ap.add_argument('--gather', default='mask', choices=['mask', 'probs'],
+                    help="--shard patches: 'mask' = reduce-scatter + slab finalize + all-gather of the int8 mask; 'probs' = all-reduce")
     ap.add_argument('--ref-patches', type=int, default=4, help='patches in the bounded CPU sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--layers', action='store_true', help='print the per-kernel roofline table to stderr')
@@ -272,10 +274,10 @@ def main():
     shard = (rank, world) if (args.shard == 'patches' and world > 1) else None
 
     def step_device():
-        return segmentation_volume_device(model, cfg, vol, batch=args.batch, shard=shard)
+        return segmentation_volume_device(model, cfg, vol, batch=args.batch, shard=shard, gather=args.gather)
 
     def step_host():
-        return segmentation_volume_host(model, cfg, host_vol, host_mask, batch=args.batch, shard=shard)
+        return segmentation_volume_host(model, cfg, host_vol, host_mask, batch=args.batch, shard=shard, gather=args.gather)
 
     def barrier():
         if dist is not None:

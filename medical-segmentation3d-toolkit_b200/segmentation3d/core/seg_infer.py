@@ -166,11 +166,14 @@ def _grid(model, cfg, size_xyz, spacing, bbox_start_voxel, bbox_end_voxel, use_g
 
 
 def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_start_voxel=None, bbox_end_voxel=None,
-                               use_gpu=True, spacing=None, z_ready=None, mask_sink=None):
+                               use_gpu=True, spacing=None, z_ready=None, mask_sink=None, gather='probs'):
     """Device-resident core of segmentation_volume: `vol` is a CUDA float32 [z,y,x] tensor already at
     the model spacing.  Returns (mean_probs [C,z,y,x] fp32, mask [z,y,x] int8) on the device.
     shard=(rank, world): this process runs patches rank::world and the accumulators are summed with
-    an all-reduce over the default process group (NCCL) before the count normalisation.
+    an all-reduce over the default process group (NCCL) before the count normalisation (gather='probs': every rank
+    returns the full probability maps).  gather='mask' (needs Z % world == 0): reduce-scatter instead - rank r receives
+    the summed z slab r, normalises and arg-maxes only that slab, and the int8 mask slabs are all-gathered; the returned
+    probabilities are then this rank's slab [C, Z/world, Y, X] only.  Half the NVLink traffic and 1/world of the finalize.
     mask_sink=(host_mask, stream): with z_ready, every z slab is normalised, arg-maxed and copied to the (pinned) host
     mask on `stream` as soon as no remaining patch touches it."""
     eng = model['engine']
@@ -222,12 +225,22 @@ def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_sta
             return acc, mask
     if shard is not None and shard[1] > 1:
         import torch.distributed as dist
+        r, w = shard
+        if gather == 'mask' and Z % w == 0:
+            C, zs = acc.shape[0], Z // w
+            send = acc.view(C, w, zs, Y, X).permute(1, 0, 2, 3, 4).contiguous()           # [world][C, zs, Y, X]
+            slab = torch.empty((C, zs, Y, X), dtype=torch.float32, device=acc.device)
+            dist.reduce_scatter_tensor(slab, send, op=dist.ReduceOp.SUM)
+            mask_slab = eng.finalize(slab, [counts[0], counts[1], np.ascontiguousarray(counts[2][r * zs:(r + 1) * zs])])
+            mask = torch.empty((Z, Y, X), dtype=torch.int8, device=acc.device)
+            dist.all_gather_into_tensor(mask, mask_slab)
+            return slab, mask
         dist.all_reduce(acc, op=dist.ReduceOp.SUM)
     mask = eng.finalize(acc, counts)
     return acc, mask
 
 
-def segmentation_volume_host(model, cfg, host_vol, host_mask=None, batch=None, shard=None):
+def segmentation_volume_host(model, cfg, host_vol, host_mask=None, batch=None, shard=None, gather='probs'):
     """End-to-end call with HOST buffers: (pinned) float32 [z,y,x] in, int8 mask out; probabilities stay
     on the device and are returned as a tensor.  Copies are issued on the current stream."""
     dev = next(model['net'].parameters()).device
@@ -251,7 +264,7 @@ def segmentation_volume_host(model, cfg, host_vol, host_mask=None, batch=None, s
     if host_mask is None:
         host_mask = torch.empty(host_vol.shape, dtype=torch.int8, pin_memory=True)
     sink = (host_mask, _side_stream(dev)) if (z_ready is not None and host_mask.is_pinned()) else None
-    acc, mask = segmentation_volume_device(model, cfg, vol, batch=batch, shard=shard, z_ready=z_ready, mask_sink=sink)
+    acc, mask = segmentation_volume_device(model, cfg, vol, batch=batch, shard=shard, z_ready=z_ready, mask_sink=sink, gather=gather)
     if sink is None or (shard is not None and shard[1] > 1):
         host_mask.copy_(mask, non_blocking=True)
     return acc, host_mask

@@ -1,0 +1,40 @@
+"""torchrun --nproc-per-node N tools/check_patch_shard.py : one volume, patches dealt rank::N.  The reduce-scatter + slab
+finalize + mask all-gather path must give the same mask as the all-reduce path and as a single-rank pass."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'medical-segmentation3d-toolkit_b200'))
+sys.path.insert(0, ROOT)
+import torch
+import torch.distributed as dist
+from segmentation3d.core.seg_infer import make_model, segmentation_volume_device
+from segmentation3d.network import vnet
+
+rank, local, world = int(os.environ['RANK']), int(os.environ['LOCAL_RANK']), int(os.environ['WORLD_SIZE'])
+torch.cuda.set_device(local)
+dist.init_process_group('nccl', device_id=torch.device('cuda:%d' % local))
+torch.manual_seed(0)
+net = vnet.SegmentationNet(1, 2)
+vnet.parameters_kaiming_init(net)
+net.b200_mode = 'fp32x'
+net = net.cuda().eval()
+model = make_model(net, spacing=[1.0, 1.0, 1.0], normalizer={'type': 0, 'mean': 0.0, 'stddev': 1.0, 'clip': False})
+cfg = {'partition_type': 'SIZE', 'partition_size': [48, 48, 48], 'partition_stride': [32, 32, 32]}
+g = torch.Generator(device='cuda').manual_seed(7)
+vol = torch.randn((64 * world // world * 2, 96, 112), generator=g, device='cuda')       # Z = 128: divisible by 2, 4, 8
+vol = torch.nn.functional.avg_pool3d(vol[None, None], 3, 1, 1)[0, 0].contiguous() * 3.0
+acc1, mask1 = segmentation_volume_device(model, cfg, vol, batch=4)
+accp, maskp = segmentation_volume_device(model, cfg, vol, batch=4, shard=(rank, world), gather='probs')
+accm, maskm = segmentation_volume_device(model, cfg, vol, batch=4, shard=(rank, world), gather='mask')
+torch.cuda.synchronize()
+zs = vol.shape[0] // world
+d_probs = float((accp - acc1).abs().max())
+d_slab = float((accm - acc1[:, rank * zs:(rank + 1) * zs]).abs().max())
+agree_p = float((maskp == mask1).float().mean())
+agree_m = float((maskm == mask1).float().mean())
+print('rank %d/%d: all-reduce max|dp| %.3g, reduce-scatter slab max|dp| %.3g, mask agreement %.6f / %.6f'
+      % (rank, world, d_probs, d_slab, agree_p, agree_m), flush=True)
+assert d_probs <= 1e-5 and d_slab <= 1e-5 and agree_p >= 0.9999 and agree_m >= 0.9999
+assert accm.shape == (2, zs) + tuple(vol.shape[1:]) and maskm.shape == vol.shape
+dist.destroy_process_group()
