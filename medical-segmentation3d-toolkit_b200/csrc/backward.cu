@@ -19,15 +19,6 @@ namespace {
 constexpr int GN_BWD_MAXC = 512;
 constexpr int GN_BWD_U = 4;
 
-template <typename T>
-__device__ __forceinline__ void load8_or_zero(const T* p, float* f) {
-  if (p) { Vec8<T> v; v.load(p); v.get(f); }
-  else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = 0.f;
-  }
-}
-
 // PASS 0: per-sample sums S1 = sum gamma*dz, S2 = sum gamma*dz*xhat; per-channel dgamma, dbeta.
 // PASS 1: dy (+ optional dres), per-channel dbias.
 template <typename T, int PASS>

@@ -82,24 +82,10 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base offset | [61,64) layout type
-// base offset: phase of the start address inside the 8 x 128 B swizzle repeat; non-zero only for the
-// x-shifted A views of the kw-fused path (PTX ISA: (start_address >> 7) & 7 when the matrix start is not
-// aligned to the repeating pattern).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint32_t layout_type, uint32_t base_offset = 0) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(base_offset & 7) << 49;
-  d |= (uint64_t)(layout_type & 7) << 61;
-  return d;
-}
-
-// The MMA-issuing thread is a single lane: every instruction between two tcgen05.mma costs issue slots
-// of that one thread, so the hot loops keep the descriptor's high word in a register and only add a
-// compile-time byte offset (>>4) to the low word.
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base offset (always 0 here: the
+// swizzle is a function of the absolute shared-memory address) | [61,64) layout type.  Built from two 32-bit halves:
+// desc_hi (SBO, version, layout) is loop invariant, the low word is start>>4 (| LBO<<16 for MN-major operands).
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo, uint32_t layout_type) {
   return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
 }
