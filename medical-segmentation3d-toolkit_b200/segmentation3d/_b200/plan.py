@@ -199,6 +199,7 @@ class NetPlan(object):
         self.gn_index = {n: i for i, n in enumerate(self.gn_names)}
         self._plans = {}
         self.launches_per_forward = 0
+        self.use_graph = os.environ.get('SEG3D_GRAPH', '0') == '1'
 
     def refresh(self, state_dict):
         """Re-pack changed weights in place (pointers captured by cached plans stay valid)."""
@@ -250,6 +251,7 @@ class NetPlan(object):
             ws['M%da' % l], ws['M%db' % l] = buf(l, C // 4), buf(l, C // 4)   # bottleneck mids (VBNet)
         ops, meta, units = [], [], []
         ws['meta'], ws['units'], ws['dims'], ws['vox'], ws['B'] = meta, units, dims, vox, B
+        ws['train'] = train
         st = lib.stream_ptr
         raw = ws['raw']
 
@@ -476,11 +478,28 @@ class NetPlan(object):
         else:
             ws['x_in'].copy_(x.reshape(B, self.in_channels, -1).permute(0, 2, 1))
 
-    def run(self, ws, ops):
+    def _run_eager(self, ws, ops):
         ws['stats'].zero_()
         ws['stats2'].zero_()
         for op in ops:
             op()
+
+    def run(self, ws, ops):
+        """One forward over the plan's workspaces.  With SEG3D_GRAPH=1 an inference plan is captured into a CUDA graph after
+        one eager run (all buffers, packed weights and tensor maps are fixed per plan) and replayed afterwards: ~60 launches
+        become one, which matters for small patch batches where the forward is launch-bound."""
+        if self.use_graph and not ws.get('train', False):
+            g = ws.get('graph')
+            if g is None:
+                self._run_eager(ws, ops)              # lazy one-time setup inside the library happens outside the capture
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_eager(ws, ops)
+                ws['graph'] = g
+            g.replay()
+        else:
+            self._run_eager(ws, ops)
         self.launches_per_forward = len(ops)
         return ws['probs']
 

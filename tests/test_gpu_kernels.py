@@ -519,3 +519,22 @@ def test_forward_split_operand_strict_mode_on_tensor_cores(lib, arch, cout, seed
     print(arch, 'fp32x', rep)
     assert rep['max_abs'] <= 1e-4, rep
     assert rep['agree'] >= 0.9999 and min(rep['dice']) >= 0.9999, rep
+
+
+def test_forward_cuda_graph_replay_equals_eager(lib):
+    """SEG3D_GRAPH=1: the captured forward must reproduce the eager one bit for bit, also after the weights changed in place."""
+    from segmentation3d._b200.plan import NetPlan
+    sd = oinit.init_state_dict('vnet', 1, 2, 2)
+    x = seeded_input(12, (1, 1, 32, 32, 32)).cuda()
+    eager = NetPlan(sd, mode='fp16', device='cuda')
+    graph = NetPlan(sd, mode='fp16', device='cuda')
+    graph.use_graph = True
+    y0 = eager.forward(x).clone()
+    y1 = graph.forward(x).clone()          # eager warm-up + capture + replay
+    y2 = graph.forward(x).clone()          # replay only
+    assert torch.equal(y0, y1) and torch.equal(y0, y2)
+    sd2 = {k: (v * 1.01 if v.dim() == 5 else v) for k, v in sd.items()}
+    eager.refresh(sd2); graph.refresh(sd2)
+    assert torch.equal(eager.forward(x), graph.forward(x))
+    x2 = seeded_input(13, (1, 1, 32, 32, 32)).cuda()
+    assert torch.equal(eager.forward(x2), graph.forward(x2))

@@ -126,8 +126,8 @@ if __name__ == '__main__':
     tag, rep, infer_csv, train_csv = sys.argv[1:5]
     os.makedirs(PROF, exist_ok=True)
     full_summary(tag, rep)
-    launch_summary(tag, 'infer', infer_csv, 1, 'Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 2400 -c 700 --csv python bench.py '
-                   '--steps 2 --warmup 3 --no-cpu-baseline` (one 512x512x400 volume = 9 forwards of 20 patches + gather / blend / finalize).')
+    launch_summary(tag, 'infer', infer_csv, 1, 'Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 1900 -c 660 --csv python bench.py '
+                   '--steps 1 --warmup 3 --no-cpu-baseline` (one 512x512x400 volume = 9 forwards of 20 patches + gather / blend / finalize).')
     launch_summary(tag, 'train', train_csv, 3, 'Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/train_one_step.py '
                    'bf16 8 3`; the launches between the last two dice_terms_kernel launches = one steady-state training step '
                    '(backward + Adam of step 2, forward of step 3; B = 8 x 96^3, bf16, Dice, Adam).', marker='dice_terms_kernel')
