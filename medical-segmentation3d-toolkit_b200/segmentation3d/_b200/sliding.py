@@ -29,6 +29,16 @@ def axis_counts(size_xyz, starts, ends):
     return out
 
 
+def batch_ranges(n, batch):
+    """(start, count) of the patch batches for n patches with at most `batch` per forward, balanced: 23 patches with
+    batch 20 run as 12 + 11, not 20 + 3 (a 3-patch forward is latency-bound and costs nearly as much as a 12-patch one)."""
+    if n <= 0:
+        return []
+    nbat = (n + batch - 1) // batch
+    per = (n + nbat - 1) // nbat
+    return [(b0, min(per, n - b0)) for b0 in range(0, n, per)]
+
+
 class SlidingWindow(object):
     def __init__(self, plan, batch=0):
         self.plan = plan
@@ -61,11 +71,7 @@ class SlidingWindow(object):
         C = plan.out_channels
         if self.batch <= 0:
             self.batch = 6
-        # balanced batches: 23 patches with batch 20 run as 12 + 11, not 20 + 3 (the tail forward would be latency-bound)
-        nbat = (n + self.batch - 1) // self.batch
-        per = (n + nbat - 1) // nbat
-        for b0 in range(0, n, per):
-            nb = min(per, n - b0)
+        for b0, nb in batch_ranges(n, self.batch):
             ws, ops = plan.plan(nb, pz, py, px)
             sp = lib.ptr(starts_dev, 3 * b0)
             pstats = None

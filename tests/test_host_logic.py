@@ -1,0 +1,77 @@
+"""CPU tests of the host-side logic added around the hot path (no GPU, no CUDA calls)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import postprocess as opp
+from oracle import resample as orz
+from segmentation3d._b200.sliding import axis_counts, batch_ranges
+from segmentation3d.utils.image3d import Image3d
+from segmentation3d.utils.image_tools import is_identity_resample, resample_size
+
+
+def test_batch_ranges_are_balanced_and_cover_everything():
+    for n in list(range(0, 50)) + [180, 181, 799, 800]:
+        for batch in (1, 3, 6, 20):
+            r = batch_ranges(n, batch)
+            assert sum(c for _, c in r) == n
+            assert all(0 < c <= batch for _, c in r)
+            assert [s for s, _ in r] == list(np.cumsum([0] + [c for _, c in r])[:-1])
+            if r:
+                assert max(c for _, c in r) - min(c for _, c in r) <= max(c for _, c in r) - 1   # no degenerate tails ...
+                assert len(r) == -(-n // batch)                                                     # ... and no extra forwards
+    assert batch_ranges(23, 20) == [(0, 12), (12, 11)]
+    assert batch_ranges(180, 20) == [(i * 20, 20) for i in range(9)]
+
+
+def test_resample_size_matches_oracle_and_reference_rule():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        size = [int(v) for v in rng.integers(8, 600, 3)]
+        sp_in = [float(v) for v in rng.uniform(0.2, 3.0, 3)]
+        sp_out = [float(v) for v in rng.uniform(0.2, 3.0, 3)]
+        assert resample_size(size, sp_in, sp_out, 16) == orz.out_size(size, sp_in, sp_out, 16)
+    assert resample_size([512, 512, 400], [0.4, 0.4, 0.4], [0.4, 0.4, 0.4], 16) == [512, 512, 400]
+    im = Image3d(np.zeros((400, 512, 512), np.float32), (1.0, 1.0, 1.0))
+    assert is_identity_resample(im, [1.0, 1.0, 1.0], 16)
+    assert not is_identity_resample(im, [1.0, 1.0, 2.0], 16)
+    assert not is_identity_resample(Image3d(np.zeros((40, 50, 64), np.float32)), [1.0, 1.0, 1.0], 16)   # 50 % 16 != 0
+
+
+def test_image3d_physical_point_round_trip():
+    im = Image3d(np.zeros((10, 12, 14), np.float32), (0.5, 0.75, 2.0), (10.0, -5.0, 3.0))
+    for idx in ([0, 0, 0], [3, 7, 9], [13, 11, 9]):
+        pt = im.TransformContinuousIndexToPhysicalPoint([float(v) for v in idx])
+        assert tuple(im.TransformPhysicalPointToIndex(pt)) == tuple(idx)
+    assert np.allclose(im.TransformContinuousIndexToPhysicalPoint([2.0, 4.0, 1.0]), [11.0, -2.0, 5.0])
+
+
+def test_axis_counts_factorise_the_overlap_count():
+    from oracle import sliding_window as osw
+    size = [80, 64, 48]
+    starts, ends = osw.partition_grid(size, [1, 1, 1], [0, 0, 0], list(size), [32, 32, 32], [16, 24, 32], 16)
+    cx, cy, cz = axis_counts(size, starts, ends)
+    cnt = osw.overlap_count_axes(size, starts, ends)
+    assert np.array_equal(cnt, (cz[:, None, None] * cy[None, :, None] * cx[None, None, :]).astype(np.float32))
+
+
+def test_oracle_connected_component_restatement():
+    m = np.zeros((6, 8, 10), np.int8)
+    m[0, 0, 0:3] = 1                 # 3 voxels
+    m[2:5, 2:5, 2:5] = 1             # 27 voxels, diagonal neighbour of nothing else
+    m[5, 5, 5] = 1                   # touches the cube only by a corner: 26-connectivity joins them (28 voxels)
+    m[0, 7, 9] = 2
+    out = opp.pick_largest_connected_component(m, [1, 2])
+    assert int((out == 1).sum()) == 28 and out[5, 5, 5] == 1 and out[0, 0, 0] == 0 and out[0, 7, 9] == 2
+    out = opp.remove_small_connected_component(m, [1, 2], 3)
+    assert int((out == 1).sum()) == 31 and out[0, 7, 9] == 0
+    assert np.array_equal(opp.remove_small_connected_component(m, [1, 2], 1), m)
+
+
+def test_make_optimizer_matches_reference_settings():
+    from segmentation3d.core.seg_train import make_optimizer
+    net = torch.nn.Linear(3, 2)
+    opt = make_optimizer(net, 1e-4, (0.9, 0.999))
+    g = opt.param_groups[0]
+    assert isinstance(opt, torch.optim.Adam) and g['lr'] == 1e-4 and tuple(g['betas']) == (0.9, 0.999)
+    assert not g.get('fused')        # fused only for CUDA parameters; the update rule is the same either way
