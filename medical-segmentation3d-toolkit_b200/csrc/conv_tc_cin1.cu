@@ -3,8 +3,8 @@
 //
 // The implicit GEMM has K = 27 taps (padded to 32): there is no channel dimension for TMA to deliver, so the
 // A tile is built in shared memory by the CTA itself.  Four builder warps own the 128 voxels of an 8 x 16
-// (x,y) plane tile and march along z: each thread keeps the 3 x 9 input window of its voxel in registers,
-// loads only the 9 values of the next plane per step, packs the 27 taps into one 64-byte K-major row and
+// (x,y) plane tile and march along z: each thread keeps the 3 x 9 input window of its voxel packed in registers, has
+// the loads of two more planes in flight, loads only the 9 values of one new plane per step, packs the 27 taps into one 64-byte K-major row and
 // stores it into the 64B-swizzled UMMA layout (fence.proxy.async, mbarrier).  One thread issues two
 // 128 x 32 x 16 MMAs per tile; four epilogue warps drain TMEM, add bias, take the GroupNorm sums, store NDHWC.
 //
@@ -129,35 +129,44 @@ conv3d_k3_cin1_tc_kernel(const T* __restrict__ x, const float* __restrict__ w /*
 #pragma unroll
         for (int i = 0; i < 9; ++i) dst[i] = (zok && ok[i]) ? (uint32_t)__ldg(pl + off[i]) : 0u;
       };
-      uint32_t win[3][9], nxt[9];
-      load_plane(zs - 1, win[0]); load_plane(zs, win[1]); load_plane(zs + 1, win[2]);
-      for (int zl = 0; zl < L; zl += 3) {
+      // Register window: the three planes a row needs are kept PACKED (nine 16-bit values in five registers), and two
+      // more planes are in flight as raw loads - plane s+1 is packed two full steps after its loads were issued, so the
+      // builder does not wait a global-load latency per plane.  Step s: pack plane s+1 (loaded at step s-2), issue the
+      // loads of plane s+3 into the buffer that just became free, build the row from planes s-1, s, s+1.
+      uint32_t wp[3][5], raw[2][9];
+      auto pack = [&](const uint32_t* r9, uint32_t* w5) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
+        for (int q = 0; q < 4; ++q) w5[q] = r9[2 * q] | (r9[2 * q + 1] << 16);
+        w5[4] = r9[8];
+      };
+      load_plane(zs - 1, raw[0]); load_plane(zs, raw[1]);
+      pack(raw[0], wp[0]); pack(raw[1], wp[1]);
+      load_plane(zs + 1, raw[1]); load_plane(zs + 2, raw[0]);
+      for (int zl = 0; zl < L; zl += 6) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
           if (zl + j < L) {
-            load_plane(zs + zl + j + 2, nxt);                     // prefetch the plane the NEXT step needs
-            uint32_t h[32];
+            pack(raw[(j + 1) % 2], wp[(j + 2) % 3]);              // plane s+1
+            load_plane(zs + zl + j + 3, raw[(j + 1) % 2]);        // plane s+3
+            uint32_t hw[16];
 #pragma unroll
-            for (int kd = 0; kd < 3; ++kd)
-#pragma unroll
-              for (int i = 0; i < 9; ++i) h[kd * 9 + i] = win[(j + kd) % 3][i];
-#pragma unroll
-            for (int k = 27; k < 32; ++k) h[k] = 0u;
+            for (int wd = 0; wd < 14; ++wd) {                      // word wd = taps (2wd, 2wd+1); tap k = plane k/9, value k%9
+              const int k0 = 2 * wd, k1 = 2 * wd + 1;
+              const uint32_t ra = wp[(j + k0 / 9) % 3][(k0 % 9) >> 1];
+              const uint32_t rb = k1 < 27 ? wp[(j + k1 / 9) % 3][(k1 % 9) >> 1] : 0u;
+              const int ha = (k0 % 9) & 1, hb = k1 < 27 ? ((k1 % 9) & 1) : 0;
+              hw[wd] = __byte_perm(ra, rb, (2 * ha) | ((2 * ha + 1) << 4) | ((4 + 2 * hb) << 8) | ((5 + 2 * hb) << 12));
+            }
+            hw[14] = 0u; hw[15] = 0u;
             mbar_wait(aempty_bar + 8 * stage, phase ^ 1);
             uint8_t* row = arow + stage * 8192;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 v;
-              v.x = h[8 * c] | (h[8 * c + 1] << 16); v.y = h[8 * c + 2] | (h[8 * c + 3] << 16);
-              v.z = h[8 * c + 4] | (h[8 * c + 5] << 16); v.w = h[8 * c + 6] | (h[8 * c + 7] << 16);
-              *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = v;
-            }
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(afull_bar + 8 * stage);
             if (++stage == C1_STAGES) { stage = 0; phase ^= 1; }
-#pragma unroll
-            for (int i = 0; i < 9; ++i) win[j % 3][i] = nxt[i];
           }
         }
       }
