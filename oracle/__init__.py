@@ -9,6 +9,8 @@ reference algorithm on the path named by BASELINE.json `north_star`:
   * patch grid, normalisers,
     sliding-window blend, argmax  -> oracle/sliding_window.py (reference: core/seg_infer.py, utils/image_tools.py)
   * Dice-ratio metric             -> oracle/metrics.py        (reference: utils/metrics.py)
+  * the same network program with the product's half-precision rounding points injected (not a restatement of the
+    reference, which is fp32: the checker for the bf16 training path)   -> oracle/reduced_precision.py
 
 The arithmetic of the reference lives in a third-party dependency, **torch**
 (reference README pins Pytorch=1.3.0; this image has torch 2.11.0+cu128): conv3d /

@@ -538,3 +538,63 @@ def test_forward_cuda_graph_replay_equals_eager(lib):
     assert torch.equal(eager.forward(x), graph.forward(x))
     x2 = seeded_input(13, (1, 1, 32, 32, 32)).cuda()
     assert torch.equal(eager.forward(x2), graph.forward(x2))
+
+
+@pytest.mark.parametrize('dt_name', ['F32', 'BF16', 'F16'])
+@pytest.mark.parametrize('C,nvox,two_grads,use_res', [(32, 1000, True, True), (16, 517, False, False), (64, 96, True, False), (256, 40, False, True)],
+                         ids=['c32', 'c16', 'c64', 'c256'])
+def test_gn_bwd_matches_closed_form(lib, dt_name, C, nvox, two_grads, use_res):
+    """seg3d_gn_bwd (both passes) against the closed-form GroupNorm(1,C)+ReLU(+residual) backward in float64, on the
+    same stored (rounded) tensors: dy, dres, dgamma, dbeta, dbias and the per-sample sums."""
+    L = lib
+    dt = getattr(L, dt_name)
+    tdt = L.TORCH_DTYPE[dt]
+    N, eps = 2, 1e-5
+    g = torch.Generator().manual_seed(C + nvox)
+    q = lambda t: t.to(tdt).cuda()                                  # noqa: E731  (stored tensors)
+    y = q(torch.randn((N, nvox, C), generator=g) * 1.5 + 0.3)
+    res = q(torch.randn((N, nvox, C), generator=g))
+    gamma, beta = torch.randn(C, generator=g).cuda() + 1.0, torch.randn(C, generator=g).cuda() * 0.3
+    g0w = q(torch.randn((N, nvox, 2 * C), generator=g) * 1e-3)       # contribution 0 lives in the upper half of a 2C-wide buffer
+    g1 = q(torch.randn((N, nvox, C), generator=g) * 1e-3)
+    yd = y.double()
+    cnt = float(nvox * C)
+    stats = torch.stack([yd.flatten(1).sum(1), (yd * yd).flatten(1).sum(1)], 1).contiguous()
+    mean = (stats[:, 0] / cnt).view(N, 1, 1)
+    var = (stats[:, 1] / cnt).view(N, 1, 1) - mean * mean
+    rstd = 1.0 / torch.sqrt(var + eps)
+    xhat = (yd - mean) * rstd
+    z = xhat * gamma.double() + beta.double() + (res.double() if use_res else 0.0)
+    out = q(torch.relu(z).float().cpu())                            # the saved post-ReLU activation, as stored
+    mask = (out.double() > 0)
+    gsum = g0w[..., C:].double() + (g1.double() if two_grads else 0.0)
+    dz = gsum * mask
+    gd = gamma.double()
+    s1 = (dz * gd).flatten(1).sum(1)
+    s2 = (dz * gd * xhat).flatten(1).sum(1)
+    dy_ref = rstd * (dz * gd - (s1 / cnt).view(N, 1, 1) - xhat * (s2 / cnt).view(N, 1, 1))
+    dgamma_ref, dbeta_ref, dbias_ref = (dz * xhat).sum((0, 1)), dz.sum((0, 1)), dy_ref.sum((0, 1))
+
+    sums = torch.zeros((N, 2), dtype=torch.float64, device='cuda')
+    dgamma = torch.zeros(C, device='cuda'); dbeta = torch.zeros(C, device='cuda'); dbias = torch.zeros(C, device='cuda')
+    dy = torch.zeros((N, nvox, 2 * C), dtype=tdt, device='cuda')     # written into the lower half of a 2C-wide buffer
+    dres = torch.zeros((N, nvox, C), dtype=tdt, device='cuda')
+    for p in range(2):
+        L.call('seg3d_gn_bwd', dt, p, L.ptr(g0w, C), 2 * C, L.ptr(g1) if two_grads else None, C if two_grads else 0, None, 0,
+               L.ptr(out), C, L.ptr(y), C, C, L.ptr(stats), L.ptr(gamma), eps, L.ptr(sums), L.ptr(dgamma), L.ptr(dbeta),
+               L.ptr(dy), 2 * C, L.ptr(dres) if use_res else None, C if use_res else 0, L.ptr(dbias), N, nvox, L.stream_ptr())
+    torch.cuda.synchronize()
+    store = {'F32': 2e-6, 'BF16': 4.5e-3, 'F16': 6e-4}[dt_name]      # half an ulp of the stored type (2^-8, 2^-11) + fp32 arithmetic
+    assert (dy[..., C:] == 0).all()
+    err = (dy[..., :C].double() - dy_ref).abs().max() / dy_ref.abs().max()
+    assert float(err) <= store + 1e-5, ('dy', float(err))
+    if use_res:
+        assert float((dres.double() - dz).abs().max() / dz.abs().max()) <= store, 'dres'
+    for name, got, ref, mag in (('S1', sums[:, 0], s1, (dz * gd).abs().flatten(1).sum(1)), ('S2', sums[:, 1], s2, (dz * gd * xhat).abs().flatten(1).sum(1))):
+        e = float(((got - ref).abs() / (mag + 1e-30)).max())
+        assert e <= 2e-5, (name, e)
+    for name, got, ref, mag in (('dgamma', dgamma, dgamma_ref, (dz * xhat).abs().sum((0, 1))), ('dbeta', dbeta, dbeta_ref, dz.abs().sum((0, 1))),
+                                ('dbias', dbias, dbias_ref, dy_ref.abs().sum((0, 1)))):
+        # fp32 accumulation of nvox*N terms per channel: compare against the sum of magnitudes; dbias sums the UNROUNDED dy
+        e = float(((got.double() - ref).abs() / (mag + 1e-30)).max())
+        assert e <= 2e-5, (name, e)

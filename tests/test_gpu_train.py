@@ -87,3 +87,59 @@ def test_two_adam_steps_match_reference_golden():
     gi = net.in_block.conv.weight.grad.cpu().numpy()
     ref = z['vnet_dice_grad_in_block']
     assert np.abs(gi - ref).max() <= 5e-2 * np.abs(ref).max()
+
+
+def _grad_agreement(ref_grads, net, tag):
+    rows = {}
+    for name, p in net.named_parameters():
+        gr = ref_grads[name].double().flatten()
+        gn = p.grad.detach().cpu().double().flatten()
+        assert torch.isfinite(gn).all(), name
+        nr = float(gr.norm())
+        if nr < 1e-10:
+            continue
+        rows[name] = (float(torch.dot(gr, gn) / (nr * float(gn.norm()) + 1e-300)), float((gr - gn).norm()) / nr)
+    worst = min(rows, key=lambda k: rows[k][0])
+    print('%s: worst cosine %.5f (%s), worst relative L2 error %.4f' % (tag, rows[worst][0], worst, max(r for _, r in rows.values())))
+    return rows
+
+
+SHALLOW = ('up_64.rblock', 'up_32', 'out_block')
+
+
+def test_bf16_training_gradients():
+    """The training bench runs in bf16 (tensor-core forward, dgrad and wgrad kernels, bf16 activations and data
+    gradients, fp32 parameter gradients).  On random-init weights the bf16-rounded program is ill-conditioned below the
+    second level: rounding flips ~1 % of the deep ReLU masks, and a 1e-6 relative change of the INPUT moves the
+    gradients of the rounded oracle (oracle/reduced_precision.py) itself by 24 % (L2, cosine 0.97) in down_64 ...
+    up_128 while the fp32 oracle does not move - measured on the CPU.  So no two bf16 implementations agree
+    there better than that; what the kernels must do is (i) reproduce the loss, (ii) stay inside that band against both
+    the fp32 oracle's autograd and the rounded oracle's, and (iii) agree tightly where the program is well conditioned:
+    the layers next to the loss and the skip path.  The backward kernels themselves are pinned per op
+    (test_gn_bwd_matches_closed_form, test_conv_wgrad_matches_torch, the dgrad = forward conv tests) and in fp32 above."""
+    from oracle import reduced_precision as orp
+    from segmentation3d.loss.multi_dice_loss import MultiDiceLoss
+    sd = oinit.randomize_affine(oinit.init_state_dict('vnet', 1, 2, 0), 5)
+    g = torch.Generator().manual_seed(33)
+    crops = torch.randn((2, 1, 32, 32, 32), generator=g)
+    masks = torch.randint(0, 2, (2, 1, 32, 32, 32), generator=g).float()
+
+    def oracle_grads(fwd):
+        params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        ref_loss = oloss.multi_dice_loss(fwd(params, crops), masks, [1.0, 1.0])
+        ref_loss.backward()
+        return float(ref_loss.detach()), {k: p.grad for k, p in params.items()}
+
+    loss32, g32 = oracle_grads(onet.forward_with_grad)
+    loss16, g16 = oracle_grads(lambda p, x: orp.forward_with_grad(p, x, torch.bfloat16))
+    net = _net('vnet', 2, sd, 'bf16')
+    loss = MultiDiceLoss([1.0, 1.0], 2, True)(net(crops.cuda()), masks.cuda())
+    loss.backward()
+    print('loss: kernels bf16 %.6f, rounded oracle %.6f, fp32 oracle %.6f' % (loss.item(), loss16, loss32))
+    assert abs(loss.item() - loss32) <= 2e-3 and abs(loss.item() - loss16) <= 2e-3
+    for tag, ref in (('vs bf16-rounded oracle autograd', g16), ('vs fp32 oracle autograd', g32)):
+        rows = _grad_agreement(ref, net, tag)
+        for name, (cos, rel) in rows.items():
+            assert cos >= 0.95 and rel <= 0.35, (tag, name, cos, rel)
+            if name.startswith(SHALLOW):
+                assert cos >= 0.99 and rel <= 0.15, (tag, name, cos, rel)

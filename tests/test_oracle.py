@@ -185,3 +185,17 @@ def test_oracle_resample_restatement_known_answers():
     assert orz.out_size([100, 100, 40], [0.5, 0.5, 2.0], [1, 1, 1], 16) == [64, 64, 80]
     with pytest.raises(ValueError):
         orz.resample_grid(src, [1, 1, 1], [4, 3, 2], [1, 1, 1], 'CUBIC')
+
+
+def test_reduced_precision_program_is_the_oracle_when_nothing_is_rounded():
+    """oracle/reduced_precision.py with every rounding point switched off (or fp32 'storage') is oracle/net.py."""
+    from oracle import reduced_precision as orp
+    for arch, cout in (('vnet', 2), ('vbnet', 3)):
+        sd = oinit.randomize_affine(oinit.init_state_dict(arch, 1, cout, 0), 2)
+        x = torch.randn((1, 1, 16, 16, 32), generator=torch.Generator().manual_seed(4))
+        ref = onet.forward(sd, x)
+        assert (orp.forward(sd, x, torch.float32) - ref).abs().max() <= 2e-6
+        everything = ('in_block', 'down_', 'up_', 'out_block')
+        assert (orp.forward(sd, x, torch.float16, exact=everything) - ref).abs().max() <= 2e-6
+        y16 = orp.forward(sd, x, torch.float16)
+        assert 0 < (y16 - ref).abs().max() <= 1e-2          # fp16 storage: inside BASELINE.json's reduced-precision bar
