@@ -77,6 +77,24 @@ def read_test_folder(folder_path, is_dicom_folder=False):
     return names, paths
 
 
+def shard_case_list(names, paths, rank, world):
+    """Batch inference over a case list shards by case (BASELINE configs[4]): rank r of a `torch.distributed.run`
+    launch segments cases r, r+world, ...; cases are independent, so there is no collective on the data path."""
+    if world <= 1:
+        return list(names), list(paths)
+    if not 0 <= rank < world:
+        raise ValueError('rank %d outside world of %d' % (rank, world))
+    return list(names[rank::world]), list(paths[rank::world])
+
+
+def launch_rank():
+    """(rank, world, local_rank) of a one-process-per-GPU launch (torchrun environment), (0, 1, None) otherwise."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world <= 1:
+        return 0, 1, None
+    return int(os.environ.get('RANK', '0')), world, int(os.environ.get('LOCAL_RANK', os.environ.get('RANK', '0')))
+
+
 # ---- model loading -----------------------------------------------------------------------------------
 def _device_for(gpu_id):
     if gpu_id is None or int(gpu_id) < 0:
@@ -374,7 +392,13 @@ def get_bounding_box(mask, selected_labels):
 
 
 def segmentation(input_path, model_folder, output_folder, seg_name, gpu_id, return_mask, save_mask, save_image, save_prob):
-    """Volumetric segmentation engine: same inputs/outputs as the reference (:353-493)."""
+    """Volumetric segmentation engine: same inputs/outputs as the reference (:353-493).
+    Launched as `python -m torch.distributed.run --nproc-per-node N -m segmentation3d.seg_infer ...`, every process takes
+    the GPU of its local rank and the cases rank::N of the list (returned masks: this rank's cases, in list order)."""
+    rank, world, local = launch_rank()
+    requested_gpu_id = gpu_id
+    if world > 1:
+        gpu_id = local
     begin = time.time()
     models = load_models(model_folder, gpu_id)
     load_model_time = time.time() - begin
@@ -396,9 +420,12 @@ def segmentation(input_path, model_folder, output_folder, seg_name, gpu_id, retu
     else:
         raise ValueError('The file {} does not exist.'.format(input_path))
 
+    file_name_list, file_path_list = shard_case_list(file_name_list, file_path_list, rank, world)
     infer_cfg = models['infer_cfg']
     scale = infer_cfg.general.single_scale
-    use_gpu = gpu_id > 0          # reference quirk kept (core/seg_infer.py:420): only selects the cpu_*_ratio knobs
+    # reference quirk kept (core/seg_infer.py:420): only selects the cpu_*_ratio knobs; every rank of a sharded launch
+    # follows the -g value the user passed, so all cases are segmented with the same partition settings
+    use_gpu = requested_gpu_id > 0
     masks, total_inference_time, num_success_case = [], 0, 0
     for i, file_path in enumerate(file_path_list):
         print('{}: {}'.format(i, file_path))

@@ -100,3 +100,16 @@ __C.debug.save_inputs = False
     print('e2e parity', rep)
     assert np.abs(probs[1] - p1).max() <= 1e-3
     assert (mask == seg).mean() >= 0.999
+    # batch inference over a txt case list, sharded by case as under `torch.distributed.run` (BASELINE configs[4]):
+    # rank 1 of 2 segments only the second case; nothing is exchanged between ranks
+    _write_cfg(str(data / 'test.txt'), '2\ncase0 %s\ncase1 %s\n' % (data / 'im0.mha', data / 'im1.mha'))
+    monkeypatch.setenv('WORLD_SIZE', '2')
+    monkeypatch.setenv('RANK', '1')
+    monkeypatch.setenv('LOCAL_RANK', '0')
+    out2 = tmp_path / 'out_sharded'
+    masks2 = segmentation(str(data / 'test.txt'), str(save_dir), str(out2), 'seg.mha', 0, True, True, False, False)
+    assert sorted(os.listdir(out2)) == ['case1'] and len(masks2) == 1
+    monkeypatch.setenv('RANK', '0')
+    masks0 = segmentation(str(data / 'test.txt'), str(save_dir), str(out2), 'seg.mha', 0, True, True, False, False)
+    assert sorted(os.listdir(out2)) == ['case0', 'case1'] and len(masks0) == 1
+    assert np.array_equal(masks0[0].to_numpy(), seg)               # case0 = im0.mha: same mask as the single-file call

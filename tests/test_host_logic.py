@@ -75,3 +75,25 @@ def test_make_optimizer_matches_reference_settings():
     g = opt.param_groups[0]
     assert isinstance(opt, torch.optim.Adam) and g['lr'] == 1e-4 and tuple(g['betas']) == (0.9, 0.999)
     assert not g.get('fused')        # fused only for CUDA parameters; the update rule is the same either way
+
+
+def test_case_list_is_dealt_round_robin_over_ranks(monkeypatch):
+    """BASELINE configs[4]: a txt case list is sharded by case over the ranks of a torchrun launch, no collective."""
+    from segmentation3d.core.seg_infer import launch_rank, shard_case_list
+    names, paths = ['c%d' % i for i in range(11)], ['/p/%d.mha' % i for i in range(11)]
+    assert shard_case_list(names, paths, 0, 1) == (names, paths)
+    seen = []
+    for r in range(4):
+        n, p = shard_case_list(names, paths, r, 4)
+        assert n == names[r::4] and p == paths[r::4]
+        assert len(n) in (2, 3)                                     # balanced to within one case
+        seen += n
+    assert sorted(seen) == sorted(names)                            # every case exactly once
+    assert shard_case_list(names[:2], paths[:2], 3, 4) == ([], [])  # more ranks than cases: idle ranks get nothing
+    with pytest.raises(ValueError):
+        shard_case_list(names, paths, 4, 4)
+    for k in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK'):
+        monkeypatch.delenv(k, raising=False)
+    assert launch_rank() == (0, 1, None)
+    monkeypatch.setenv('WORLD_SIZE', '8'); monkeypatch.setenv('RANK', '5'); monkeypatch.setenv('LOCAL_RANK', '5')
+    assert launch_rank() == (5, 8, 5)
