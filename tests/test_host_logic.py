@@ -1,4 +1,6 @@
 """CPU tests of the host-side logic added around the hot path (no GPU, no CUDA calls)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -97,3 +99,38 @@ def test_case_list_is_dealt_round_robin_over_ranks(monkeypatch):
     assert launch_rank() == (0, 1, None)
     monkeypatch.setenv('WORLD_SIZE', '8'); monkeypatch.setenv('RANK', '5'); monkeypatch.setenv('LOCAL_RANK', '5')
     assert launch_rank() == (5, 8, 5)
+
+
+def test_seg_eval_batch_dice_table(tmp_path):
+    """core/seg_eval.py::cal_dsc_batch: per-case Dice / type per label plus mean and std rows, scored like the oracle's
+    cal_dsc restatement (utils/metrics.py:22-36)."""
+    import pandas as pd
+    from oracle.metrics import cal_dsc as oracle_dsc
+    from segmentation3d.core.seg_eval import cal_dsc_batch
+    from segmentation3d.utils.image3d import write_image
+    rng = np.random.default_rng(3)
+    gts, segs, expect = [], [], []
+    for i in range(3):
+        gt = (rng.random((12, 16, 20)) > 0.6).astype(np.int8) * (1 + (rng.random((12, 16, 20)) > 0.5)).astype(np.int8)
+        seg = gt.copy()
+        seg[rng.random(gt.shape) > 0.9] = 0
+        if i == 2:
+            seg[seg == 2] = 0                                      # label 2 missed entirely -> FN
+        os.makedirs(tmp_path / ('c%d' % i))
+        g, s = str(tmp_path / ('c%d' % i) / 'gt.mha'), str(tmp_path / ('c%d' % i) / 'seg.mha')
+        write_image(Image3d(gt), g, True)
+        write_image(Image3d(seg), s, True)
+        gts.append(g); segs.append(s)
+        expect.append([oracle_dsc(gt, seg, l, 10) for l in (1, 2, 3)])
+    df = cal_dsc_batch(gts, segs, [1, 2, 3], 10, str(tmp_path / 'res.csv'))
+    back = pd.read_csv(str(tmp_path / 'res.csv'), index_col=0)
+    assert list(back.columns) == ['filename', 'label1_score', 'label1_type', 'label2_score', 'label2_type', 'label3_score', 'label3_type']
+    assert list(back['filename']) == ['gt.mha'] * 3 + ['mean', 'std']
+    for i in range(3):
+        for j, l in enumerate((1, 2, 3)):
+            assert abs(back['label%d_score' % l].iloc[i] - expect[i][j][0]) < 1e-12
+            assert back['label%d_type' % l].iloc[i] == expect[i][j][1]
+    assert back['label2_type'].iloc[2] == 'FN' and back['label3_type'].iloc[0] == 'TN'
+    assert abs(back['label1_score'].iloc[3] - np.mean([e[0][0] for e in expect])) < 1e-12
+    assert abs(back['label1_score'].iloc[4] - np.std([e[0][0] for e in expect], ddof=1)) < 1e-12
+    assert len(df) == 5
