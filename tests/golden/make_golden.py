@@ -12,6 +12,7 @@ Fixtures (all small):
   loss.npz               Dice / focal values and gradients                      (loss/*.py)
   sliding_window.npz     core.seg_infer.segmentation_volume end to end          (core/seg_infer.py:249-350)
   train_step.npz         one Adam step of the reference training loop body      (core/seg_train.py:119-127)
+  cascade.npz            segmentation_volume restricted by a bounding box       (core/seg_infer.py:292-307,428-444)
 """
 import copy
 import hashlib
@@ -234,6 +235,35 @@ def gen_sliding_window():
     np.savez_compressed(os.path.join(HERE, 'sliding_window.npz'), **out)
 
 
+def gen_cascade():
+    """core/seg_infer.py:249-339 called the way the coarse->fine cascade calls it (:428-444): a bounding box restricts
+    the patch grid.  Voxels outside the (max_stride-rounded) box are never visited: their overlap count is 0, the
+    reference multiplies 0 by 1/0 = inf there, so their probabilities are NaN and their label is 0."""
+    from easydict import EasyDict as edict
+    net = make_net('vnet', 1, 2, 2)
+    net.load_state_dict(randomize_affine(net.state_dict(), 6))
+    model = edict()
+    model.net = net
+    model.spacing, model.max_stride, model.interpolation = [1.0, 1.0, 1.0], 16, 'LINEAR'
+    model.in_channels, model.out_channels = 1, 2
+    model.crop_normalizers = [FixedNormalizer(20.0, 250.0, True)]
+    cfg = edict()
+    cfg.partition_type, cfg.partition_size, cfg.partition_stride = 'SIZE', [32, 32, 32], [16, 16, 16]
+    cfg.cpu_model_spacing_increase_ratio, cfg.cpu_partition_decrease_ratio = 1.0, 1.0
+    cfg.pick_largest_cc, cfg.remove_small_cc = False, 0
+    size, bs, be, vseed, scale = [64, 48, 64], [9, 5, 14], [49, 40, 50], 17, 300.0
+    vol = synth_volume(vseed, size, scale)
+    image = sitk.GetImageFromArray(vol)
+    with np.errstate(all='ignore'):
+        mean_probs, mask = ref_infer.segmentation_volume(model, cfg, image, list(bs), list(be), False)
+    probs = np.stack([sitk.GetArrayFromImage(p) for p in mean_probs], 0).astype(np.float32)
+    m = sitk.GetArrayFromImage(mask).astype(np.int8)
+    meta = {'arch': 'vnet', 'cout': 2, 'wseed': 2, 'aseed': 6, 'size': size, 'psize': [32, 32, 32], 'pstride': [16, 16, 16],
+            'norm': ['fixed', 20.0, 250.0, True], 'vseed': vseed, 'scale': scale, 'bbox_start': bs, 'bbox_end': be}
+    print('cascade: visited fraction', float(np.isfinite(probs[0]).mean()), 'fg frac', float((m > 0).mean()))
+    np.savez_compressed(os.path.join(HERE, 'cascade.npz'), probs=probs, mask=m, meta=np.array(json.dumps(meta)))
+
+
 def gen_train_step():
     """core/seg_train.py:83,119-127 on one synthetic batch: Adam(lr=1e-4, betas=(0.9,0.999))."""
     out = {}
@@ -265,10 +295,11 @@ def gen_train_step():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['schema', 'forward', 'grids', 'loss', 'sw', 'train']
+    which = sys.argv[1:] or ['schema', 'forward', 'grids', 'loss', 'sw', 'train', 'cascade']
     if 'schema' in which: gen_schema_and_hashes()
     if 'forward' in which: gen_forward()
     if 'grids' in which: gen_grids()
     if 'loss' in which: gen_loss()
     if 'sw' in which: gen_sliding_window()
     if 'train' in which: gen_train_step()
+    if 'cascade' in which: gen_cascade()

@@ -250,3 +250,31 @@ def test_connected_components_large_volume_timing():
     assert 0 < kept <= total and bool(((out == 1) <= (m == 1)).all())
     small = _cc_filter_device(m, [1], kept)            # threshold = size of the largest: only it survives
     assert torch.equal(small, out)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'fp16'])
+def test_segmentation_volume_with_bounding_box_matches_reference_golden(mode):
+    """The coarse->fine cascade's call (core/seg_infer.py:292-307,428-444) against the reference's own output: inside
+    the visited box probabilities and labels match; outside it the reference holds NaN (0 * 1/0) with label 0, the
+    product holds probability 0 with label 0."""
+    from segmentation3d.core.seg_infer import segmentation_volume
+    from segmentation3d.utils.image3d import Image3d
+    z = np.load(os.path.join(G, 'cascade.npz'))
+    m = json.loads(str(z['meta']))
+    sd = oinit.randomize_affine(oinit.init_state_dict(m['arch'], 1, m['cout'], m['wseed']), m['aseed'])
+    size = m['size']
+    vol = (seeded_input(m['vseed'], (1, 1, size[2], size[1], size[0]), 'smooth')[0, 0].numpy() * m['scale']).astype(np.float32)
+    nd = {'type': 0, 'mean': m['norm'][1], 'stddev': m['norm'][2], 'clip': m['norm'][3]}
+    model = build_model(m['arch'], m['cout'], sd, mode, nd)
+    cfg = {'partition_type': 'SIZE', 'partition_size': m['psize'], 'partition_stride': m['pstride'],
+           'pick_largest_cc': False, 'remove_small_cc': 0}
+    probs_im, mask_im = segmentation_volume(model, cfg, Image3d(vol), list(m['bbox_start']), list(m['bbox_end']), True)
+    probs = np.stack([p.to_numpy() for p in probs_im], 0)
+    mask = mask_im.to_numpy()
+    visited = np.isfinite(z['probs'][0])
+    err = float(np.abs(probs[:, visited] - z['probs'][:, visited]).max())
+    agree = float((mask[visited] == z['mask'][visited]).mean())
+    print('bbox', mode, 'max|dp| inside %.3g, label agreement inside %.5f' % (err, agree))
+    assert err <= (1e-3 if mode == 'fp32' else 2e-2)
+    assert agree >= (0.999 if mode == 'fp32' else 0.99)
+    assert not probs[:, ~visited].any() and not mask[~visited].any()

@@ -134,3 +134,21 @@ def test_seg_eval_batch_dice_table(tmp_path):
     assert abs(back['label1_score'].iloc[3] - np.mean([e[0][0] for e in expect])) < 1e-12
     assert abs(back['label1_score'].iloc[4] - np.std([e[0][0] for e in expect], ddof=1)) < 1e-12
     assert len(df) == 5
+
+
+def test_bounding_box_grid_and_counts_match_oracle():
+    """Host side of the cascade call (core/seg_infer.py:292-307): the product's patch grid for a bounding box equals the
+    oracle's (pinned to the reference by tests/golden/cascade.npz), and the separable per-axis overlap count equals the
+    rasterised one, 0 outside the visited box."""
+    from oracle import sliding_window as osw
+    from segmentation3d.core.seg_infer import _grid
+    size, spacing = [64, 48, 64], [1.0, 1.0, 1.0]
+    cfg = {'partition_type': 'SIZE', 'partition_size': [32, 32, 32], 'partition_stride': [16, 16, 16]}
+    for bs, be in (([9, 5, 14], [49, 40, 50]), ([0, 0, 0], [64, 48, 64]), ([40, 30, 50], [64, 48, 64]), ([3, 3, 3], [20, 19, 18])):
+        starts, ends = _grid({'max_stride': 16}, cfg, size, spacing, list(bs), list(be))
+        o_starts, o_ends = osw.partition_grid(size, spacing, list(bs), list(be), [32, 32, 32], [16, 16, 16], 16)
+        assert [list(map(int, s)) for s in starts] == [list(map(int, s)) for s in o_starts]
+        assert [list(map(int, e)) for e in ends] == [list(map(int, e)) for e in o_ends]
+        cx, cy, cz = axis_counts(size, starts, ends)
+        sep = cz[:, None, None].astype(np.float32) * cy[None, :, None] * cx[None, None, :]
+        assert np.array_equal(sep, osw.overlap_count_axes(size, o_starts, o_ends))

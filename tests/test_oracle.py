@@ -199,3 +199,27 @@ def test_reduced_precision_program_is_the_oracle_when_nothing_is_rounded():
         assert (orp.forward(sd, x, torch.float16, exact=everything) - ref).abs().max() <= 2e-6
         y16 = orp.forward(sd, x, torch.float16)
         assert 0 < (y16 - ref).abs().max() <= 1e-2          # fp16 storage: inside BASELINE.json's reduced-precision bar
+
+
+def test_sliding_window_with_bounding_box_matches_reference():
+    """The coarse->fine cascade's call (core/seg_infer.py:292-307,428-444): the box restricts the patch grid; voxels the
+    grid never visits have count 0, so the reference leaves NaN probabilities and label 0 there."""
+    z = np.load(os.path.join(G, 'cascade.npz'))
+    m = json.loads(str(z['meta']))
+    sd = oinit.randomize_affine(oinit.init_state_dict(m['arch'], 1, m['cout'], m['wseed']), m['aseed'])
+    size = m['size']
+    vol = (seeded_input(m['vseed'], (1, 1, size[2], size[1], size[0]), 'smooth')[0, 0].numpy() * m['scale']).astype(np.float32)
+    nd = {'type': 0, 'mean': m['norm'][1], 'stddev': m['norm'][2], 'clip': m['norm'][3]}
+    with np.errstate(all='ignore'):
+        probs, mask, starts, ends = osw.segmentation_volume(sd, vol, [1.0, 1.0, 1.0], nd, 'SIZE', m['psize'], m['pstride'], 16,
+                                                            bbox_start_voxel=m['bbox_start'], bbox_end_voxel=m['bbox_end'])
+    visited = np.isfinite(z['probs'][0])
+    assert 0.3 < visited.mean() < 0.8
+    assert np.array_equal(np.isfinite(probs[0]), visited)
+    assert np.abs(probs[:, visited] - z['probs'][:, visited]).max() <= 1e-6
+    assert np.array_equal(mask, z['mask']) and not mask[~visited].any()
+    # the box was rounded up to a multiple of max_stride and shifted back inside the volume (image_tools.py:179-188)
+    lo = np.min(np.array(starts), 0).tolist()
+    hi = np.max(np.array(ends), 0).tolist()
+    zz, yy, xx = np.where(visited)
+    assert lo == [int(xx.min()), int(yy.min()), int(zz.min())] and hi == [int(xx.max()) + 1, int(yy.max()) + 1, int(zz.max()) + 1]
