@@ -189,6 +189,16 @@ int seg3d_focal_fwd(const float* probs, const float* target, int B, int C, int64
 int seg3d_focal_bwd(const float* probs, const float* target, int B, int C, int64_t n,
                     const float* alpha, float gamma, float scale, float* grad, void* stream);
 
+/* cross entropy with the network output used as logits (loss/cross_entropy_loss.py:5-18 -> nn.CrossEntropyLoss):
+ * loss_i = w[t_i] * (logsumexp_c x_c - x_t), nothing for voxels whose label is ignore_index (or outside [0, C)).
+ * partial[0] += sum loss_i, partial[1] += sum w[t_i] (double; 'mean' = ratio, 'sum' = partial[0]); loss_map (fp32 [B][n],
+ * may be NULL) receives loss_i for reduction 'none'.  weight: fp32 [C] or NULL (all ones). */
+int seg3d_ce_fwd(const float* logits, const float* target, int B, int C, int64_t n, const float* weight,
+                 int ignore_index, double* partial, float* loss_map, void* stream);
+/* grad[b][c][i] = scale * g_i * w[t_i] * (softmax_c(x) - [c == t_i]); g_i = grad_map[b][i] or 1 when grad_map is NULL */
+int seg3d_ce_bwd(const float* logits, const float* target, int B, int C, int64_t n, const float* weight,
+                 int ignore_index, float scale, const float* grad_map, float* grad, void* stream);
+
 /* ---- training: backward of the conv + GroupNorm + ReLU (+ residual) unit (core/seg_train.py:124, i.e. the
  * autograd of conv_gn_relu3.py:16-20 / residual_block3.py:24) -------------------------------------------------
  * Data gradients of the convolutions reuse seg3d_conv3d_fwd with transformed weights (k3: flipped taps and

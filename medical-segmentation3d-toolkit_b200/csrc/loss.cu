@@ -125,3 +125,80 @@ extern "C" int seg3d_focal_bwd(const float* probs, const float* target, int B, i
   SEG3D_CHECK_LAUNCH("focal_bwd_kernel");
   return SEG3D_OK;
 }
+
+// ---- cross entropy on the network output (loss/cross_entropy_loss.py:5-18 -> nn.CrossEntropyLoss: the reference feeds the
+// probabilities in as logits).  loss_i = w[t_i] * (logsumexp_c x_c - x_t); voxels with t_i == ignore_index (or a label
+// outside [0, C)) contribute nothing.  partial[0] += sum loss_i, partial[1] += sum w[t_i]  (double).
+__global__ void __launch_bounds__(256)
+ce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ target, int C, long long n,
+              const float* __restrict__ weight, int ignore_index, double* __restrict__ partial, float* __restrict__ loss_map) {
+  __shared__ double red[2][8];
+  const int b = blockIdx.y;
+  const float* t = target + (size_t)b * n;
+  const float* xb = x + (size_t)b * C * n;
+  double acc = 0, wacc = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cls = (int)(long long)t[i];                    // target.long()
+    float l = 0.f;
+    if (cls != ignore_index && cls >= 0 && cls < C) {
+      float m = xb[i];
+      for (int c = 1; c < C; ++c) m = fmaxf(m, xb[(size_t)c * n + i]);
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) s += expf(xb[(size_t)c * n + i] - m);
+      const float w = weight ? weight[cls] : 1.f;
+      l = w * (m + logf(s) - xb[(size_t)cls * n + i]);
+      acc += (double)l; wacc += (double)w;
+    }
+    if (loss_map) loss_map[(size_t)b * n + i] = l;
+  }
+  acc = warp_sum(acc); wacc = warp_sum(wacc);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = acc; red[1][threadIdx.x >> 5] = wacc; }
+  __syncthreads();
+  if (threadIdx.x < 2) { double s = 0; for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w]; atomicAdd(partial + threadIdx.x, s); }
+}
+
+extern "C" int seg3d_ce_fwd(const float* logits, const float* target, int B, int C, int64_t n, const float* weight,
+                            int ignore_index, double* partial, float* loss_map, void* stream) {
+  SEG3D_REQUIRE(logits && target && partial && B > 0 && C > 0 && n > 0, "ce_fwd: bad arguments");
+  int gx = (int)((n + 256 * 8 - 1) / (256 * 8)); if (gx < 1) gx = 1; if (gx > 592) gx = 592;
+  ce_fwd_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(logits, target, C, n, weight, ignore_index, partial, loss_map);
+  SEG3D_CHECK_LAUNCH("ce_fwd_kernel");
+  return SEG3D_OK;
+}
+
+// grad[b][c][i] = scale * g_i * w[t_i] * (softmax_c(x) - [c == t_i]),  g_i = grad_map[b][i] (or 1), 0 for ignored voxels
+__global__ void __launch_bounds__(256)
+ce_bwd_kernel(const float* __restrict__ x, const float* __restrict__ target, int C, long long n,
+              const float* __restrict__ weight, int ignore_index, float scale, const float* __restrict__ grad_map,
+              float* __restrict__ grad) {
+  const int b = blockIdx.y;
+  const float* t = target + (size_t)b * n;
+  const float* xb = x + (size_t)b * C * n;
+  float* gb = grad + (size_t)b * C * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cls = (int)(long long)t[i];
+    if (cls == ignore_index || cls < 0 || cls >= C) {
+      for (int c = 0; c < C; ++c) gb[(size_t)c * n + i] = 0.f;
+      continue;
+    }
+    float m = xb[i];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, xb[(size_t)c * n + i]);
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += expf(xb[(size_t)c * n + i] - m);
+    const float k = scale * (weight ? weight[cls] : 1.f) * (grad_map ? grad_map[(size_t)b * n + i] : 1.f);
+    const float inv = 1.f / s;
+    for (int c = 0; c < C; ++c) {
+      const float p = expf(xb[(size_t)c * n + i] - m) * inv;
+      gb[(size_t)c * n + i] = k * (p - (c == cls ? 1.f : 0.f));
+    }
+  }
+}
+
+extern "C" int seg3d_ce_bwd(const float* logits, const float* target, int B, int C, int64_t n, const float* weight,
+                            int ignore_index, float scale, const float* grad_map, float* grad, void* stream) {
+  SEG3D_REQUIRE(logits && target && grad && B > 0 && C > 0 && n > 0, "ce_bwd: bad arguments");
+  int gx = (int)((n + 256 * 4 - 1) / (256 * 4)); if (gx < 1) gx = 1; if (gx > 1184) gx = 1184;
+  ce_bwd_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(logits, target, C, n, weight, ignore_index, scale, grad_map, grad);
+  SEG3D_CHECK_LAUNCH("ce_bwd_kernel");
+  return SEG3D_OK;
+}

@@ -47,6 +47,8 @@ _SIGNATURES = {
     'seg3d_dice_bwd': (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp, _vp]),
     'seg3d_focal_fwd': (_i, [_vp, _vp, _i, _i, _i64, _vp, _f, _vp, _vp]),
     'seg3d_focal_bwd': (_i, [_vp, _vp, _i, _i, _i64, _vp, _f, _f, _vp, _vp]),
+    'seg3d_ce_fwd': (_i, [_vp, _vp, _i, _i, _i64, _vp, _i, _vp, _vp, _vp]),
+    'seg3d_ce_bwd': (_i, [_vp, _vp, _i, _i, _i64, _vp, _i, _f, _vp, _vp, _vp]),
     'seg3d_gn_bwd': (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _f, _vp, _vp, _vp,
                           _vp, _i, _vp, _i, _vp, _i, _i64, _vp]),
     'seg3d_conv3d_wgrad': (_i, [_i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp]),

@@ -74,3 +74,45 @@ class FocalFunction(torch.autograd.Function):
         lib.call('seg3d_focal_bwd', lib.ptr(p), lib.ptr(t), B, C, n, lib.ptr(a), ctx.gamma, float(gout) * ctx.scale,
                  lib.ptr(grad), lib.stream_ptr())
         return grad, None, None, None, None
+
+
+class CrossEntropyFunction(torch.autograd.Function):
+    """nn.CrossEntropyLoss on [B,C,*spatial] inputs with one class index per voxel (loss/cross_entropy_loss.py:5-18):
+    w_t (logsumexp_c x_c - x_t), reduced by 'mean' (sum / sum of w_t), 'sum' or 'none'; ignore_index voxels drop out."""
+
+    @staticmethod
+    def forward(ctx, x, target, weight, ignore_index, reduction):
+        B, C, n = _check(x, target)
+        xc = x.detach().contiguous().float()
+        t = target.detach().contiguous().float()
+        w = None if weight is None else weight.to(device=xc.device, dtype=torch.float32).contiguous().view(-1)
+        if w is not None and w.numel() != C:
+            raise ValueError('weight must hold one value per class')
+        part = torch.zeros((2,), dtype=torch.float64, device=xc.device)
+        lmap = torch.empty((B,) + tuple(x.shape[2:]), dtype=torch.float32, device=xc.device) if reduction == 'none' else None
+        lib.call('seg3d_ce_fwd', lib.ptr(xc), lib.ptr(t), B, C, n, lib.ptr(w), int(ignore_index), lib.ptr(part), lib.ptr(lmap),
+                 lib.stream_ptr())
+        ctx.save_for_backward(xc, t, part)
+        ctx.w, ctx.ignore_index, ctx.reduction = w, int(ignore_index), reduction
+        if reduction == 'none':
+            return lmap
+        if reduction == 'sum':
+            return part[0].float()
+        return (part[0] / part[1]).float()
+
+    @staticmethod
+    def backward(ctx, gout):
+        xc, t, part = ctx.saved_tensors
+        B, C = xc.shape[0], xc.shape[1]
+        n = xc[0, 0].numel()
+        grad = torch.empty_like(xc)
+        gmap, scale = None, 1.0
+        if ctx.reduction == 'none':
+            gmap = gout.detach().contiguous().float()
+        elif ctx.reduction == 'sum':
+            scale = float(gout)
+        else:
+            scale = float(gout) / float(part[1])
+        lib.call('seg3d_ce_bwd', lib.ptr(xc), lib.ptr(t), B, C, n, lib.ptr(ctx.w), ctx.ignore_index, scale, lib.ptr(gmap),
+                 lib.ptr(grad), lib.stream_ptr())
+        return grad, None, None, None, None

@@ -6,6 +6,7 @@ Reference (relative to /root/reference):
   segmentation3d/loss/binary_dice_loss.py:9-36
   segmentation3d/loss/multi_dice_loss.py:9-43
   segmentation3d/loss/focal_loss.py:7-61
+  segmentation3d/loss/cross_entropy_loss.py:5-18
 """
 import torch
 
@@ -79,3 +80,11 @@ def focal_loss(probs, target, class_num, alpha=None, gamma=2, size_average=True)
     else:
         bl = -al * logp
     return bl.mean() if size_average else bl.sum()
+
+
+def cross_entropy_loss(inp, target, weight=None, ignore_index=-100, reduction='mean'):
+    """cross_entropy_loss.py:12-18: squeeze the target's channel axis, cast to long, nn.CrossEntropyLoss on the input as
+    given (the training loop feeds the network's probabilities in as logits, core/seg_train.py:98-99,122-123)."""
+    import torch.nn.functional as F
+    tgt = torch.squeeze(target, dim=1).long()
+    return F.cross_entropy(inp, tgt, weight=weight, ignore_index=ignore_index, reduction=reduction)

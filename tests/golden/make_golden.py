@@ -12,6 +12,7 @@ Fixtures (all small):
   loss.npz               Dice / focal values and gradients                      (loss/*.py)
   sliding_window.npz     core.seg_infer.segmentation_volume end to end          (core/seg_infer.py:249-350)
   train_step.npz         one Adam step of the reference training loop body      (core/seg_train.py:119-127)
+  loss_ce.npz            cross-entropy values and gradients on loss.npz's inputs (loss/cross_entropy_loss.py)
   cascade.npz            segmentation_volume restricted by a bounding box       (core/seg_infer.py:292-307,428-444)
 """
 import copy
@@ -264,6 +265,27 @@ def gen_cascade():
     np.savez_compressed(os.path.join(HERE, 'cascade.npz'), probs=probs, mask=m, meta=np.array(json.dumps(meta)))
 
 
+def gen_loss_ce():
+    """loss/cross_entropy_loss.py:5-18 (loss.name = 'CE', core/seg_train.py:98-99): the reference's wrapper applied to
+    the probabilities and targets of loss.npz - default construction, class weights, an ignored label, sum / none."""
+    from segmentation3d.loss.cross_entropy_loss import CrossEntropyLoss as RefCE
+    z = np.load(os.path.join(HERE, 'loss.npz'))
+    out = {}
+    for c in (2, 5):
+        k = 'c%d_' % c
+        probs, target = torch.from_numpy(z[k + 'probs']), torch.from_numpy(z[k + 'target'])
+        w = torch.tensor([1.0 + 0.5 * i for i in range(c)])
+        for tag, kw in (('ce', {}), ('ce_w', {'weight': w}), ('ce_ign', {'weight': w, 'ignore_index': 1}),
+                        ('ce_sum', {'reduction': 'sum'}), ('ce_none', {'weight': w, 'ignore_index': 0, 'reduction': 'none'})):
+            p = probs.clone().requires_grad_(True)
+            l = RefCE(**kw)(p, target)
+            (l if l.dim() == 0 else (l * torch.arange(l.numel(), dtype=torch.float32).view_as(l) / l.numel()).sum()).backward()
+            out[k + tag], out[k + tag + '_grad'] = l.detach().numpy(), p.grad.numpy()
+        out[k + 'weight'] = w.numpy()
+        print('ce c=%d' % c, float(out[k + 'ce']), float(out[k + 'ce_w']), float(out[k + 'ce_ign']), float(out[k + 'ce_sum']))
+    np.savez_compressed(os.path.join(HERE, 'loss_ce.npz'), **out)
+
+
 def gen_train_step():
     """core/seg_train.py:83,119-127 on one synthetic batch: Adam(lr=1e-4, betas=(0.9,0.999))."""
     out = {}
@@ -295,7 +317,7 @@ def gen_train_step():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['schema', 'forward', 'grids', 'loss', 'sw', 'train', 'cascade']
+    which = sys.argv[1:] or ['schema', 'forward', 'grids', 'loss', 'sw', 'train', 'cascade', 'ce']
     if 'schema' in which: gen_schema_and_hashes()
     if 'forward' in which: gen_forward()
     if 'grids' in which: gen_grids()
@@ -303,3 +325,4 @@ if __name__ == '__main__':
     if 'sw' in which: gen_sliding_window()
     if 'train' in which: gen_train_step()
     if 'cascade' in which: gen_cascade()
+    if 'ce' in which: gen_loss_ce()

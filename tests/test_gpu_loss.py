@@ -56,3 +56,31 @@ def test_dice_full_size_properties():
         t = (target[:, 0] == i).double().flatten(1)
         ref += 0.5 * float((1 - (2 * (q * t).sum(1) + 1e-6) / ((q * q).sum(1) + t.sum(1) + 1e-6)).mean())
     assert abs(got - ref) <= 1e-6
+
+
+def test_cross_entropy_matches_reference_golden():
+    """loss.name = 'CE' (core/seg_train.py:98-99): fused log-softmax + NLL kernels against values and gradients of the
+    reference's wrapper - default, class weights, an ignored label, 'sum' and 'none' - plus the legacy flags."""
+    from segmentation3d.loss.cross_entropy_loss import CrossEntropyLoss
+    z, zc = np.load(os.path.join(G, 'loss.npz')), np.load(os.path.join(G, 'loss_ce.npz'))
+    cases = (('ce', {}), ('ce_w', {'weight': True}), ('ce_ign', {'weight': True, 'ignore_index': 1}),
+             ('ce_sum', {'reduction': 'sum'}), ('ce_none', {'weight': True, 'ignore_index': 0, 'reduction': 'none'}))
+    for c in (2, 5):
+        k = 'c%d_' % c
+        probs, target = torch.from_numpy(z[k + 'probs']).cuda(), torch.from_numpy(z[k + 'target']).cuda()
+        for tag, kw in cases:
+            kw = dict(kw)
+            if kw.pop('weight', False):
+                kw['weight'] = torch.from_numpy(zc[k + 'weight'])
+            p = probs.clone().requires_grad_(True)
+            l = CrossEntropyLoss(**kw)(p, target)
+            assert tuple(l.shape) == tuple(zc[k + tag].shape), (k, tag)
+            (l if l.dim() == 0 else (l * torch.arange(l.numel(), dtype=torch.float32, device='cuda').view_as(l) / l.numel()).sum()).backward()
+            ref, gref = zc[k + tag], zc[k + tag + '_grad']
+            assert np.abs(l.detach().cpu().numpy() - ref).max() <= 1e-5 * max(1.0, float(np.abs(ref).max())), (k, tag)
+            assert np.abs(p.grad.cpu().numpy() - gref).max() <= 1e-7 + 1e-4 * np.abs(gref).max(), (k, tag)
+    assert CrossEntropyLoss(None, False).reduction == 'sum' and CrossEntropyLoss(None, None, -100, False).reduction == 'none'
+    x2 = torch.randn((7, 3), generator=torch.Generator().manual_seed(1))
+    t2 = torch.tensor([0, 2, 1, 1, 0, 2, 2])
+    got = CrossEntropyLoss()(x2.cuda(), t2.cuda()).item()
+    assert abs(got - float(torch.nn.functional.cross_entropy(x2, t2))) <= 1e-5

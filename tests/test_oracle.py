@@ -223,3 +223,23 @@ def test_sliding_window_with_bounding_box_matches_reference():
     hi = np.max(np.array(ends), 0).tolist()
     zz, yy, xx = np.where(visited)
     assert lo == [int(xx.min()), int(yy.min()), int(zz.min())] and hi == [int(xx.max()) + 1, int(yy.max()) + 1, int(zz.max()) + 1]
+
+
+CE_CASES = (('ce', {}), ('ce_w', {'weight': True}), ('ce_ign', {'weight': True, 'ignore_index': 1}),
+            ('ce_sum', {'reduction': 'sum'}), ('ce_none', {'weight': True, 'ignore_index': 0, 'reduction': 'none'}))
+
+
+def test_cross_entropy_matches_reference():
+    z, zc = np.load(os.path.join(G, 'loss.npz')), np.load(os.path.join(G, 'loss_ce.npz'))
+    for c in (2, 5):
+        k = 'c%d_' % c
+        probs, target = torch.from_numpy(z[k + 'probs']), torch.from_numpy(z[k + 'target'])
+        for tag, kw in CE_CASES:
+            kw = dict(kw)
+            if kw.pop('weight', False):
+                kw['weight'] = torch.from_numpy(zc[k + 'weight'])
+            p = probs.clone().requires_grad_(True)
+            l = oloss.cross_entropy_loss(p, target, **kw)
+            (l if l.dim() == 0 else (l * torch.arange(l.numel(), dtype=torch.float32).view_as(l) / l.numel()).sum()).backward()
+            assert np.abs(l.detach().numpy() - zc[k + tag]).max() <= 1e-6 * max(1.0, float(np.abs(zc[k + tag]).max())), (k, tag)
+            assert np.abs(p.grad.numpy() - zc[k + tag + '_grad']).max() <= 1e-8, (k, tag)
