@@ -1,52 +1,76 @@
-"""Training crops (reduced drop-in for reference dataloader/dataset.py:54-209).
+"""Training crops (drop-in for reference dataloader/dataset.py:12-209).
 
-Host-side data feeding is outside the accelerated path: this class keeps the
-reference's constructor and item format - (image [1,D,H,W] f32, mask [1,D,H,W] f32, frame [15], name) - and its
-CENTER / GLOBAL / MASK / HYBRID centre sampling with random translation, on images that are already at the
-training spacing (no SimpleITK resampling / random scaling in this build).
+The data loader is the caller on the near side of the training path.  Same constructor, same item format -
+(image [1,D,H,W] f32, mask [1,D,H,W] f32, frame [15] = spacing, origin, direction, case name) - and the same sampling,
+drawing from numpy's global RNG in the same order as the reference, so a seeded run picks the same crops:
+CENTER / GLOBAL / MASK / HYBRID centre (:116-173), random translation in mm (:176), random isotropic rescale of the crop
+spacing (:179), linear crop of the image and nearest-neighbour crop of the mask through `crop_image` (:182-188).
+Like the reference's SimpleITK calls, the crop runs on the host inside DataLoader workers; images are read with the
+MetaImage reader of utils/image3d.py (SimpleITK formats when that package is installed).
 """
+import os
+
 import numpy as np
-import torch
 from torch.utils.data import Dataset
 
 from segmentation3d.utils.file_io import readlines
 from segmentation3d.utils.image3d import read_image
+from segmentation3d.utils.image_tools import (convert_image_to_tensor, crop_image, get_image_frame,
+                                              select_random_voxels_in_multi_class_mask)
 
 
 def read_train_txt(imlist_file):
     """first line = N, then N (image path, mask path) line pairs (reference dataset.py:12-33)."""
     lines = readlines(imlist_file)
-    n = int(lines[0])
-    if len(lines) - 1 < 2 * n:
-        raise ValueError('too few lines in the training list')
-    return [lines[1 + 2 * i] for i in range(n)], [lines[2 + 2 * i] for i in range(n)]
+    num_cases = int(lines[0])
+    if len(lines) - 1 < num_cases * 2:
+        raise ValueError('too few lines in imlist file')
+    im_list, seg_list = [], []
+    for i in range(num_cases):
+        im_path, seg_path = lines[1 + i * 2], lines[2 + i * 2]
+        assert os.path.isfile(im_path), 'image not exist: {}'.format(im_path)
+        assert os.path.isfile(seg_path), 'mask not exist: {}'.format(seg_path)
+        im_list.append(im_path)
+        seg_list.append(seg_path)
+    return im_list, seg_list
 
 
-def read_train_csv(imlist_file):
+def read_train_csv(imlist_file, mode='train'):
+    """csv with image_name, image_path[, mask_path] columns (reference dataset.py:36-54)."""
     import pandas as pd
     df = pd.read_csv(imlist_file)
-    return df['image_path'].tolist(), df['mask_path'].tolist()
+    if mode == 'test':
+        return df['image_name'].tolist(), df['image_path'].tolist()
+    if mode in ('train', 'validation'):
+        return df['image_path'].tolist(), df['mask_path'].tolist()
+    raise ValueError('Unsupported mode type.')
 
 
 class SegmentationDataset(Dataset):
     def __init__(self, imlist_file, num_classes, spacing, crop_size, sampling_method, random_translation,
                  random_scale, interpolation, crop_normalizers):
-        if imlist_file.endswith('.txt'):
+        if imlist_file.endswith('txt'):
             self.im_list, self.seg_list = read_train_txt(imlist_file)
-        elif imlist_file.endswith('.csv'):
+        elif imlist_file.endswith('csv'):
             self.im_list, self.seg_list = read_train_csv(imlist_file)
         else:
-            raise ValueError('imseg_list must either be a txt file or a csv file')
+            raise ValueError('imseg_list must be a txt file')
         self.num_classes = num_classes
         self.spacing = np.array(spacing, dtype=np.double)
+        assert self.spacing.size == 3, 'only 3-element of spacing is supported'
         self.crop_size = np.array(crop_size, dtype=np.int32)      # x, y, z
-        assert sampling_method in ('CENTER', 'GLOBAL', 'MASK', 'HYBRID'), 'sampling_method must be CENTER, GLOBAL, MASK or HYBRID'
+        assert self.crop_size.size == 3, 'only 3-element of crop size is supported'
         self.sampling_method = sampling_method
+        assert self.sampling_method in ('CENTER', 'GLOBAL', 'MASK', 'HYBRID'), \
+            'sampling_method must be CENTER, GLOBAL, MASK or HYBRID'
         self.random_translation = np.array(random_translation, dtype=np.double)
-        self.random_scale = random_scale
-        assert interpolation in ('LINEAR', 'NN'), 'interpolation must either be a LINEAR or an NN'
+        assert self.random_translation.size == 3, 'Only 3-element of random translation is supported'
+        self.random_scale = np.array(random_scale, dtype=np.double)
+        assert self.random_scale.size == 2, 'Only 2-element of random scale is supported'
         self.interpolation = interpolation
+        assert self.interpolation in ('LINEAR', 'NN'), 'interpolation must either be a LINEAR or NN'
         self.crop_normalizers = crop_normalizers
+        assert isinstance(self.crop_normalizers, list), 'crop normalizers must be a list'
 
     def __len__(self):
         return len(self.im_list)
@@ -54,44 +78,55 @@ class SegmentationDataset(Dataset):
     def num_modality(self):
         return 1
 
-    def _centre(self, seg, size_xyz):
-        method = self.sampling_method
-        if method == 'HYBRID':
-            method = 'GLOBAL' if np.random.randint(0, 2) == 0 else 'MASK'
-        if method == 'CENTER':
-            c = np.array(size_xyz, dtype=np.double) / 2
-        elif method == 'MASK' and (seg > 0).any():
-            zyx = np.argwhere(seg > 0)
-            c = zyx[np.random.randint(0, len(zyx))][::-1].astype(np.double)
+    def global_sample(self, image):
+        """random crop centre (world) such that the crop lies inside the image where the image is larger (:108-124)."""
+        origin = image.GetOrigin()
+        im_size_mm = [image.GetSize()[idx] * image.GetSpacing()[idx] for idx in range(3)]
+        crop_size_mm = self.crop_size * self.spacing
+        sp = np.array(origin, dtype=np.double)
+        for i in range(3):
+            if im_size_mm[i] > crop_size_mm[i]:
+                sp[i] = origin[i] + np.random.uniform(0, im_size_mm[i] - crop_size_mm[i])
+        return sp + crop_size_mm / 2
+
+    def center_sample(self, image):
+        """world coordinate of the image centre (:126-138)."""
+        origin = image.GetOrigin()
+        end_point_world = image.TransformContinuousIndexToPhysicalPoint([float(image.GetSize()[idx] - 1) for idx in range(3)])
+        return np.array([(origin[idx] + end_point_world[idx]) / 2.0 for idx in range(3)], dtype=np.double)
+
+    def _mask_sample(self, seg):
+        centers = select_random_voxels_in_multi_class_mask(seg, 1, np.random.randint(1, self.num_classes))
+        if len(centers) > 0:
+            return np.array(seg.TransformContinuousIndexToPhysicalPoint([float(int(centers[0][idx])) for idx in range(3)]))
+        return self.global_sample(seg)      # no voxel of the drawn label
+
+    def sample_crop(self, index, seg):
+        """(centre [world mm], crop spacing) for item `index`: the reference's RNG call order (:156-179)."""
+        if self.sampling_method == 'CENTER':
+            center = self.center_sample(seg)
+        elif self.sampling_method == 'GLOBAL':
+            center = self.global_sample(seg)
+        elif self.sampling_method == 'MASK':
+            center = self._mask_sample(seg)
+        elif self.sampling_method == 'HYBRID':
+            center = self.global_sample(seg) if index % 2 else self._mask_sample(seg)
         else:
-            c = np.array([np.random.uniform(0, s) for s in size_xyz])
-        c += np.random.uniform(-self.random_translation, self.random_translation) / self.spacing
-        return c
+            raise ValueError('Only CENTER, GLOBAL, MASK and HYBRID are supported as sampling methods')
+        center = center + np.random.uniform(-self.random_translation, self.random_translation, size=[3])
+        crop_spacing = self.spacing * np.random.uniform(self.random_scale[0], self.random_scale[1])
+        return center, crop_spacing
 
     def __getitem__(self, index):
-        image = read_image(self.im_list[index], np.float32)
-        mask = read_image(self.seg_list[index])
-        if not np.allclose(image.GetSpacing(), self.spacing):
-            raise NotImplementedError('this build trains on images already resampled to dataset.spacing')
-        im, seg = image.to_numpy(), mask.to_numpy()
-        size = image.GetSize()
-        c = self._centre(seg, size)
-        start = [int(np.clip(round(c[a] - self.crop_size[a] / 2), 0, max(0, size[a] - self.crop_size[a]))) for a in range(3)]
-        cx, cy, cz = [int(v) for v in self.crop_size]
-        crop = np.zeros((cz, cy, cx), np.float32)
-        lab = np.zeros((cz, cy, cx), np.float32)
-        sub = im[start[2]:start[2] + cz, start[1]:start[1] + cy, start[0]:start[0] + cx]
-        crop[:sub.shape[0], :sub.shape[1], :sub.shape[2]] = sub
-        sub = seg[start[2]:start[2] + cz, start[1]:start[1] + cy, start[0]:start[0] + cx]
-        lab[:sub.shape[0], :sub.shape[1], :sub.shape[2]] = sub
-        if self.crop_normalizers is not None:
-            crop = self.crop_normalizers[0](crop_to_image(crop)).to_numpy().astype(np.float32)
-        origin = [image.GetOrigin()[a] + start[a] * self.spacing[a] for a in range(3)]
-        frame = np.array(list(origin) + list(self.spacing) + list(image.GetDirection()), dtype=np.float32)
-        name = self.im_list[index]
-        return torch.from_numpy(crop).unsqueeze(0), torch.from_numpy(lab).unsqueeze(0), torch.from_numpy(frame), name
-
-
-def crop_to_image(arr):
-    from segmentation3d.utils.image3d import Image3d
-    return Image3d(arr)
+        image_path, seg_path = self.im_list[index], self.seg_list[index]
+        case_name = os.path.basename(os.path.dirname(image_path)) + '_' + os.path.basename(image_path)
+        images = [read_image(image_path, np.float32)]
+        seg = read_image(seg_path, np.float32)
+        center, crop_spacing = self.sample_crop(index, seg)
+        for idx in range(len(images)):
+            images[idx] = crop_image(images[idx], center, self.crop_size, crop_spacing, self.interpolation)
+            if self.crop_normalizers[idx] is not None:
+                images[idx] = self.crop_normalizers[idx](images[idx])
+        seg = crop_image(seg, center, self.crop_size, crop_spacing, 'NN')
+        frame = get_image_frame(seg)
+        return convert_image_to_tensor(images), convert_image_to_tensor(seg), frame, case_name

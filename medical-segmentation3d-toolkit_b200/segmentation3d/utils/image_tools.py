@@ -112,6 +112,82 @@ def resample_spacing(image, resampled_spacing, max_stride, interp_method):
     return Image3d(out, [float(v) for v in resampled_spacing], img.GetOrigin(), img.GetDirection())
 
 
+def get_image_frame(image):
+    """[spacing(3), origin(3), direction(9)] as float32 (utils/image_tools.py:24-39)."""
+    img = as_image3d(image)
+    return np.array(list(img.GetSpacing()) + list(img.GetOrigin()) + list(img.GetDirection()), dtype=np.float32)
+
+
+def set_image_frame(image, frame):
+    """inverse of get_image_frame (utils/image_tools.py:42-59)."""
+    frame = np.asarray(frame)
+    image.SetSpacing(frame[:3].astype(np.double))
+    image.SetOrigin(frame[3:6].astype(np.double))
+    image.SetDirection(frame[6:15].astype(np.double))
+
+
+def select_random_voxels_in_multi_class_mask(mask, num_selected, selected_label):
+    """`num_selected` random [x,y,z] voxels carrying `selected_label`, with replacement; [] when the label is absent
+    (utils/image_tools.py:252-271; one np.random.randint per selected voxel)."""
+    valid = np.argwhere(as_image3d(mask).to_numpy() == selected_label)
+    selected = []
+    while len(valid) > 0 and len(selected) < num_selected:
+        selected.append(valid[np.random.randint(0, len(valid))][::-1])
+    return selected
+
+
+def crop_geometry(cropping_center, cropping_size, cropping_spacing):
+    """origin (world position of the first voxel's centre) of a crop of `cropping_size` voxels at `cropping_spacing`
+    centred on `cropping_center` - along the world axes, as the reference computes it (utils/image_tools.py:127-133)."""
+    center = [float(v) for v in cropping_center]
+    size = [int(v) for v in cropping_size]
+    spacing = [float(v) for v in cropping_spacing]
+    return [center[a] - size[a] * spacing[a] / 2.0 + spacing[a] / 2.0 for a in range(3)], size, spacing
+
+
+def crop_image(image, cropping_center, cropping_size, cropping_spacing, interp_method):
+    """Crop a patch around a world-coordinate centre at a given voxel spacing (utils/image_tools.py:111-146:
+    sitk.Resample with an identity transform onto a grid that keeps the volume's direction; pixels outside the volume
+    are 0).  ITK semantics restated: output voxel i sits at origin_crop + D (i * spacing_crop), its continuous input index
+    is c = D^-1 (p - origin) / spacing in double precision; inside means -0.5 <= c < size - 0.5 per axis; 'LINEAR' blends
+    the 8 neighbours with both neighbours clamped to the volume, 'NN' takes floor(c + 0.5).
+    Runs on the host (numpy): like the reference's SimpleITK call it executes inside DataLoader worker processes."""
+    if interp_method not in ('LINEAR', 'NN'):
+        raise ValueError('Unsupported interpolation type.')
+    img = as_image3d(image)
+    src = img.to_numpy()
+    origin_c, size, spacing_c = crop_geometry(cropping_center, cropping_size, cropping_spacing)
+    d = np.asarray(img.GetDirection(), dtype=np.float64).reshape(3, 3)
+    sp = np.asarray(img.GetSpacing(), dtype=np.float64)
+    off = np.linalg.solve(d, np.asarray(origin_c, dtype=np.float64) - np.asarray(img.GetOrigin(), dtype=np.float64)) / sp
+    n_in = [src.shape[2], src.shape[1], src.shape[0]]
+    coords = [off[a] + np.arange(size[a], dtype=np.float64) * (spacing_c[a] / sp[a]) for a in range(3)]     # x, y, z
+    ok = [(coords[a] >= -0.5) & (coords[a] < n_in[a] - 0.5) for a in range(3)]
+    inside = ok[2][:, None, None] & ok[1][None, :, None] & ok[0][None, None, :]
+    if interp_method == 'NN':
+        idx = [np.clip(np.floor(coords[a] + 0.5).astype(np.int64), 0, n_in[a] - 1) for a in range(3)]
+        val = src[np.ix_(idx[2], idx[1], idx[0])]
+    else:
+        lo, hi, w = [], [], []
+        for a in range(3):
+            f = np.floor(coords[a])
+            lo.append(np.clip(f.astype(np.int64), 0, n_in[a] - 1))
+            hi.append(np.clip(f.astype(np.int64) + 1, 0, n_in[a] - 1))
+            w.append(coords[a] - f)
+        s64 = src.astype(np.float64)
+        wx, wy, wz = w[0][None, None, :], w[1][None, :, None], w[2][:, None, None]
+
+        def corner(zi, yi, xi):
+            return s64[np.ix_(zi, yi, xi)]
+        a00 = corner(lo[2], lo[1], lo[0]) * (1 - wx) + corner(lo[2], lo[1], hi[0]) * wx
+        a01 = corner(lo[2], hi[1], lo[0]) * (1 - wx) + corner(lo[2], hi[1], hi[0]) * wx
+        a10 = corner(hi[2], lo[1], lo[0]) * (1 - wx) + corner(hi[2], lo[1], hi[0]) * wx
+        a11 = corner(hi[2], hi[1], lo[0]) * (1 - wx) + corner(hi[2], hi[1], hi[0]) * wx
+        val = (a00 * (1 - wy) + a01 * wy) * (1 - wz) + (a10 * (1 - wy) + a11 * wy) * wz
+    out = np.where(inside, val, 0).astype(src.dtype)
+    return Image3d(out, spacing_c, origin_c, img.GetDirection())
+
+
 def pick_largest_connected_component(mask, labels):
     """Keep, per label, the largest 26-connected component (utils/image_tools.py:380-404)."""
     from segmentation3d.core.seg_infer import _cc_filter_device

@@ -13,6 +13,7 @@ Fixtures (all small):
   sliding_window.npz     core.seg_infer.segmentation_volume end to end          (core/seg_infer.py:249-350)
   train_step.npz         one Adam step of the reference training loop body      (core/seg_train.py:119-127)
   loss_ce.npz            cross-entropy values and gradients on loss.npz's inputs (loss/cross_entropy_loss.py)
+  dataset_sampling.json  crops the reference's SegmentationDataset requests under a seeded RNG  (dataloader/dataset.py:140-209)
   cascade.npz            segmentation_volume restricted by a bounding box       (core/seg_infer.py:292-307,428-444)
 """
 import copy
@@ -286,6 +287,76 @@ def gen_loss_ce():
     np.savez_compressed(os.path.join(HERE, 'loss_ce.npz'), **out)
 
 
+def dataset_cases():
+    """Three synthetic (image, mask) pairs with different sizes / spacings / origins; case 1 is thinner than the crop along
+    z, case 2 has no voxel of label 2.  Duplicated in tests/test_host_logic.py (the reference package cannot be imported
+    next to the product's)."""
+    rng = np.random.RandomState(77)
+    cases = []
+    for k, (size, spacing, origin) in enumerate((((40, 36, 30), (1.0, 1.0, 1.0), (0.0, 0.0, 0.0)),
+                                                 ((48, 40, 20), (0.8, 0.8, 1.5), (-10.0, 5.0, 30.0)),
+                                                 ((30, 44, 38), (1.2, 0.9, 1.0), (3.5, -7.25, 12.0)))):
+        im = rng.standard_normal((size[2], size[1], size[0])).astype(np.float32)
+        lab = rng.randint(0, 3 if k != 2 else 2, size=(size[2], size[1], size[0])).astype(np.float32)
+        lab[rng.random_sample(lab.shape) < 0.7] = 0
+        cases.append((im, lab, spacing, origin))
+    return cases
+
+
+def gen_dataset_sampling():
+    """dataloader/dataset.py:140-209 with a recording stand-in for sitk.Resample: which crop (origin, spacing, size,
+    interpolator) the UNMODIFIED reference asks for, per sampling method, under a seeded numpy RNG - plus the frame and
+    case name it returns.  The resampling arithmetic itself (ITK) is not exercised."""
+    import tempfile
+    from segmentation3d.dataloader import dataset as ref_ds
+    cases = dataset_cases()
+    store, calls = {}, []
+    tmp = tempfile.mkdtemp()
+    lines = [str(len(cases))]
+    for k, (im, lab, spacing, origin) in enumerate(cases):
+        d = os.path.join(tmp, 'case%d' % k)
+        os.makedirs(d)
+        for name, arr in (('im.mha', im), ('seg.mha', lab)):
+            path = os.path.join(d, name)
+            open(path, 'w').close()
+            img = sitk.GetImageFromArray(arr)
+            img.SetSpacing(spacing), img.SetOrigin(origin)
+            store[path] = img
+            lines.append(path)
+    with open(os.path.join(tmp, 'train.txt'), 'w') as f:
+        f.write('\n'.join(lines) + '\n')
+
+    def read_image(path, pixel_id=None):
+        src = store[path]
+        return src._wrap(src._a.copy())
+
+    def resample(image, size, transform, interp, origin, spacing, direction):
+        calls.append({'size': [int(v) for v in size], 'origin': [float(v) for v in origin], 'spacing': [float(v) for v in spacing],
+                      'interp': 'LINEAR' if interp == sitk.sitkLinear else 'NN'})
+        out = sitk.Image([int(v) for v in size], sitk.sitkFloat32)
+        out.SetOrigin(origin), out.SetSpacing(spacing), out.SetDirection(direction)
+        return out
+
+    sitk.ReadImage, sitk.Resample = read_image, resample
+    sitk.Image.TransformIndexToPhysicalPoint = lambda self, idx: self.TransformContinuousIndexToPhysicalPoint(idx)
+    out = {}
+    for method in ('CENTER', 'GLOBAL', 'MASK', 'HYBRID'):
+        ds = ref_ds.SegmentationDataset(os.path.join(tmp, 'train.txt'), num_classes=3, spacing=[1.0, 1.0, 1.2], crop_size=[32, 32, 32],
+                                        sampling_method=method, random_translation=[5, 4, 3], random_scale=[0.9, 1.1],
+                                        interpolation='LINEAR', crop_normalizers=[None])
+        np.random.seed(1234)
+        items = []
+        for index in (0, 1, 2, 1, 0, 2, 2, 1):
+            del calls[:]
+            im_t, seg_t, frame, name = ds[index]
+            assert tuple(im_t.shape) == (1, 32, 32, 32) and tuple(seg_t.shape) == (1, 32, 32, 32)
+            items.append({'index': index, 'calls': [dict(c) for c in calls], 'frame': [float(v) for v in frame], 'name': name})
+        out[method] = items
+        print('dataset', method, items[0]['calls'][0]['origin'], items[0]['calls'][0]['spacing'])
+    with open(os.path.join(HERE, 'dataset_sampling.json'), 'w') as f:
+        json.dump(out, f)
+
+
 def gen_train_step():
     """core/seg_train.py:83,119-127 on one synthetic batch: Adam(lr=1e-4, betas=(0.9,0.999))."""
     out = {}
@@ -317,7 +388,7 @@ def gen_train_step():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['schema', 'forward', 'grids', 'loss', 'sw', 'train', 'cascade', 'ce']
+    which = sys.argv[1:] or ['schema', 'forward', 'grids', 'loss', 'sw', 'train', 'cascade', 'ce', 'dataset']
     if 'schema' in which: gen_schema_and_hashes()
     if 'forward' in which: gen_forward()
     if 'grids' in which: gen_grids()
@@ -326,3 +397,4 @@ if __name__ == '__main__':
     if 'train' in which: gen_train_step()
     if 'cascade' in which: gen_cascade()
     if 'ce' in which: gen_loss_ce()
+    if 'dataset' in which: gen_dataset_sampling()

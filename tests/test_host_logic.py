@@ -152,3 +152,137 @@ def test_bounding_box_grid_and_counts_match_oracle():
         cx, cy, cz = axis_counts(size, starts, ends)
         sep = cz[:, None, None].astype(np.float32) * cy[None, :, None] * cx[None, None, :]
         assert np.array_equal(sep, osw.overlap_count_axes(size, o_starts, o_ends))
+
+
+def _dataset_cases():
+    """same synthetic cases as tests/golden/make_golden.py::dataset_cases"""
+    rng = np.random.RandomState(77)
+    cases = []
+    for k, (size, spacing, origin) in enumerate((((40, 36, 30), (1.0, 1.0, 1.0), (0.0, 0.0, 0.0)),
+                                                 ((48, 40, 20), (0.8, 0.8, 1.5), (-10.0, 5.0, 30.0)),
+                                                 ((30, 44, 38), (1.2, 0.9, 1.0), (3.5, -7.25, 12.0)))):
+        im = rng.standard_normal((size[2], size[1], size[0])).astype(np.float32)
+        lab = rng.randint(0, 3 if k != 2 else 2, size=(size[2], size[1], size[0])).astype(np.float32)
+        lab[rng.random_sample(lab.shape) < 0.7] = 0
+        cases.append((im, lab, spacing, origin))
+    return cases
+
+
+def test_dataset_requests_the_reference_crops(tmp_path):
+    """dataloader/dataset.py:140-209: under the same numpy seed the drop-in dataset asks for exactly the crops (origin,
+    spacing, size, interpolator), frames and case names the unmodified reference asked for
+    (tests/golden/dataset_sampling.json) - all four sampling methods, images thinner than the crop, absent labels."""
+    import json
+    from segmentation3d.dataloader.dataset import SegmentationDataset
+    from segmentation3d.utils import image_tools
+    from segmentation3d.utils.image3d import write_image
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'dataset_sampling.json')))
+    lines = ['3']
+    for k, (im, lab, spacing, origin) in enumerate(_dataset_cases()):
+        d = tmp_path / ('case%d' % k)
+        os.makedirs(d)
+        write_image(Image3d(im, spacing, origin), str(d / 'im.mha'), False)
+        write_image(Image3d(lab, spacing, origin), str(d / 'seg.mha'), True)
+        lines += [str(d / 'im.mha'), str(d / 'seg.mha')]
+    with open(str(tmp_path / 'train.txt'), 'w') as f:
+        f.write('\n'.join(lines) + '\n')
+    calls = []
+    real_geometry = image_tools.crop_geometry
+
+    def recording_geometry(center, size, spacing):
+        out = real_geometry(center, size, spacing)
+        calls.append(out)
+        return out
+    image_tools.crop_geometry = recording_geometry
+    try:
+        for method, items in gold.items():
+            ds = SegmentationDataset(str(tmp_path / 'train.txt'), num_classes=3, spacing=[1.0, 1.0, 1.2], crop_size=[32, 32, 32],
+                                     sampling_method=method, random_translation=[5, 4, 3], random_scale=[0.9, 1.1],
+                                     interpolation='LINEAR', crop_normalizers=[None])
+            np.random.seed(1234)
+            for item in items:
+                del calls[:]
+                im_t, seg_t, frame, name = ds[item['index']]
+                assert tuple(im_t.shape) == (1, 32, 32, 32) and tuple(seg_t.shape) == (1, 32, 32, 32)
+                assert im_t.dtype == torch.float32 and seg_t.dtype == torch.float32
+                assert name == item['name'] and len(calls) == 2
+                for (origin, size, spacing), ref in zip(calls, item['calls']):
+                    assert size == ref['size']
+                    assert np.allclose(origin, ref['origin'], rtol=0, atol=1e-9), (method, item['index'])
+                    assert np.allclose(spacing, ref['spacing'], rtol=0, atol=1e-12)
+                assert np.allclose(frame, np.array(item['frame'], dtype=np.float32), rtol=0, atol=1e-5)
+                assert set(np.unique(seg_t.numpy())) <= {0.0, 1.0, 2.0}          # nearest-neighbour mask crop keeps labels
+    finally:
+        image_tools.crop_geometry = real_geometry
+
+
+def test_crop_image_restates_itk_resample():
+    """utils/image_tools.py:111-146 (sitk.Resample, identity transform, default pixel 0): a crop on the source lattice
+    is a copy with zeros outside the volume, a rescaled crop that starts at the volume's first voxel equals the
+    resampling restatement used for the inference side (oracle/resample.py), 'NN' keeps labels, and a rotated
+    direction matrix is honoured."""
+    from segmentation3d.utils.image_tools import crop_image
+    rng = np.random.default_rng(5)
+    src = rng.standard_normal((20, 24, 28)).astype(np.float32)                  # z, y, x
+    spacing, origin = (0.8, 1.25, 2.0), (-4.0, 10.0, 3.0)
+    img = Image3d(src, spacing, origin)
+    # (a) on-lattice crop of 16^3 voxels whose first voxel is source voxel (x=20, y=-3, z=8): copy + zero padding
+    first = np.array([20, -3, 8])
+    center = np.array(origin) + (first + 16 / 2.0 - 0.5) * np.array(spacing)
+    for interp in ('LINEAR', 'NN'):
+        out = crop_image(img, center, [16, 16, 16], spacing, interp)
+        ref = np.zeros((16, 16, 16), np.float32)
+        ref[:12, 3:, :8] = src[8:20, 0:13, 20:28]
+        assert np.abs(out.to_numpy() - ref).max() <= 1e-6, interp
+        assert np.allclose(out.GetOrigin(), np.array(origin) + first * np.array(spacing)) and np.allclose(out.GetSpacing(), spacing)
+    # (b) rescaled crop anchored at the first voxel == oracle resample_grid (same origin, ratio = crop spacing / spacing)
+    csp = (1.0, 1.0, 1.5)
+    size = [16, 24, 20]
+    center = [origin[a] + size[a] * csp[a] / 2.0 - csp[a] / 2.0 for a in range(3)]
+    for interp in ('LINEAR', 'NN'):
+        out = crop_image(img, center, size, csp, interp).to_numpy()
+        ref = orz.resample_grid(src, spacing, size, csp, interp, 0.0)
+        assert np.abs(out - ref).max() <= 1e-5, interp
+    # (c) just below the first voxel centre (continuous index in [-0.5, 0)) linear interpolation clamps to the edge value
+    out = crop_image(img, [origin[0] - 0.3 * spacing[0], origin[1], origin[2]], [1, 1, 1], spacing, 'LINEAR').to_numpy()
+    assert abs(float(out[0, 0, 0]) - float(src[0, 0, 0])) <= 1e-6
+    out = crop_image(img, [origin[0] - 0.6 * spacing[0], origin[1], origin[2]], [1, 1, 1], spacing, 'LINEAR').to_numpy()
+    assert float(out[0, 0, 0]) == 0.0
+    # (d) direction matrix: x and y axes swapped -> the crop walks the volume's own axes
+    d = (0.0, 1.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0)
+    rot = Image3d(src, (1.0, 1.0, 1.0), (0.0, 0.0, 0.0), d)
+    p = rot.TransformContinuousIndexToPhysicalPoint([5.0, 7.0, 9.0])               # world position of voxel (x=5, y=7, z=9)
+    out = crop_image(rot, p, [1, 1, 1], (1.0, 1.0, 1.0), 'NN')
+    assert float(out.to_numpy()[0, 0, 0]) == float(src[9, 7, 5])
+
+
+def test_dataset_batches_through_dataloader(tmp_path):
+    """core/seg_train.py:84-87,119: EpochConcateSampler + DataLoader collate the items into
+    (crops [B,1,D,H,W] f32, masks [B,1,D,H,W] f32, frames [B,15], names) - with worker processes too."""
+    from torch.utils.data import DataLoader
+    from segmentation3d.dataloader.dataset import SegmentationDataset
+    from segmentation3d.dataloader.sampler import EpochConcateSampler
+    from segmentation3d.utils.image3d import write_image
+    from segmentation3d.utils.normalizer import FixedNormalizer
+    lines = ['3']
+    for k, (im, lab, spacing, origin) in enumerate(_dataset_cases()):
+        d = tmp_path / ('case%d' % k)
+        os.makedirs(d)
+        write_image(Image3d(im * 100, spacing, origin), str(d / 'im.mha'), True)
+        write_image(Image3d(lab.astype(np.int8), spacing, origin), str(d / 'seg.mha'), True)
+        lines += [str(d / 'im.mha'), str(d / 'seg.mha')]
+    with open(str(tmp_path / 'train.txt'), 'w') as f:
+        f.write('\n'.join(lines) + '\n')
+    ds = SegmentationDataset(str(tmp_path / 'train.txt'), 3, [1.0, 1.0, 1.0], [32, 32, 16], 'HYBRID', [4, 4, 4], [0.9, 1.1], 'LINEAR',
+                             [FixedNormalizer(0.0, 100.0, True)])
+    for workers in (0, 2):
+        loader = DataLoader(ds, sampler=EpochConcateSampler(ds, 2), batch_size=2, num_workers=workers, pin_memory=False)
+        n = 0
+        for crops, masks, frames, names in loader:
+            assert tuple(crops.shape) == (2, 1, 16, 32, 32) and crops.dtype == torch.float32
+            assert tuple(masks.shape) == (2, 1, 16, 32, 32) and masks.dtype == torch.float32
+            assert tuple(frames.shape) == (2, 15) and len(names) == 2 and names[0].startswith('case')
+            assert float(crops.abs().max()) <= 1.0 + 1e-6                 # normaliser clip
+            assert set(np.unique(masks.numpy())) <= {0.0, 1.0, 2.0}
+            n += 1
+        assert n == 3
