@@ -171,3 +171,51 @@ def test_cal_dsc_matches_oracle_definition():
     for lab in (0, 1, 2, 5):
         for thr in (1, 400):
             assert cal_dsc(a, b, lab, thr) == ref(a, b, lab, thr)
+
+
+def _assemble_from_blocks(cin, cout, compression):
+    """the reference's SegmentationNet.__init__ (network/vnet.py:23-34, vbnet.py:24-35) written with the drop-in blocks"""
+    import torch.nn as nn
+    from segmentation3d.network.module.vnet_downblock import DownBlock
+    from segmentation3d.network.module.vnet_inblock import InputBlock
+    from segmentation3d.network.module.vnet_outblock import OutputBlock
+    from segmentation3d.network.module.vnet_upblock import UpBlock
+
+    class Net(nn.Module):
+        def __init__(self):
+            super(Net, self).__init__()
+            self.in_block = InputBlock(cin, 16)
+            self.down_32 = DownBlock(16, 1, compression=False)
+            self.down_64 = DownBlock(32, 2, compression=compression)
+            self.down_128 = DownBlock(64, 3, compression=compression)
+            self.down_256 = DownBlock(128, 3, compression=compression)
+            self.up_256 = UpBlock(256, 256, 3, compression=compression)
+            self.up_128 = UpBlock(256, 128, 3, compression=compression)
+            self.up_64 = UpBlock(128, 64, 2, compression=False)
+            self.up_32 = UpBlock(64, 32, 1, compression=False)
+            self.out_block = OutputBlock(32, cout)
+    return Net()
+
+
+def test_standalone_network_modules_keep_the_reference_schema_and_init():
+    """network/module/*.py: a network assembled from the importable blocks has the reference's state-dict keys and shapes
+    and, under the same seed, bit-identical initial weights (same construction order, same random draws)."""
+    from segmentation3d.network.module.init import kaiming_weight_init as k2
+    from segmentation3d.network.module.weight_init import gaussian_weight_init, kaiming_weight_init
+    assert k2 is kaiming_weight_init
+    schema = json.load(open(os.path.join(G, 'schema.json')))
+    hashes = json.load(open(os.path.join(G, 'weights_sha256.json')))
+    for key, ref in schema.items():
+        arch, cin, cout = key.split('_')
+        for init, tag in ((kaiming_weight_init, 'kaiming'), (gaussian_weight_init, 'gaussian')):
+            torch.manual_seed(0)
+            net = _assemble_from_blocks(int(cin), int(cout), arch == 'vbnet')
+            assert [[k, list(v.shape)] for k, v in net.state_dict().items()] == ref
+            net.apply(init)
+            assert sd_hash(net.state_dict()) == hashes['%s_seed0_%s' % (key, tag)]
+    # the blocks are device modules: a CPU tensor is refused, unsupported conv shapes too
+    from segmentation3d.network.module.conv_gn_relu3 import ConvGnRelu3
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        ConvGnRelu3(16, 16, 3, 1, 1)(torch.zeros(1, 16, 8, 8, 8))
+    with pytest.raises(NotImplementedError):
+        ConvGnRelu3(16, 16, 5, 1, 2)
