@@ -26,7 +26,8 @@ from segmentation3d._b200.sliding import SlidingWindow, axis_counts
 from segmentation3d.utils.attrdict import AttrDict as edict
 from segmentation3d.utils.file_io import load_config, readlines
 from segmentation3d.utils.image3d import Image3d, as_image3d, read_image, write_image
-from segmentation3d.utils.image_tools import image_partition_by_fixed_size, is_identity_resample, resample, resample_spacing
+from segmentation3d.utils.image_tools import (get_bounding_box, image_partition_by_fixed_size, is_identity_resample,  # noqa: F401
+                                              resample, resample_spacing)
 from segmentation3d.utils.model_io import get_checkpoint_folder
 from segmentation3d.utils.normalizer import normalizer_from_dict
 
@@ -181,6 +182,32 @@ def _grid(model, cfg, size_xyz, spacing, bbox_start_voxel, bbox_end_voxel, use_g
     frame = Image3d(np.empty((0, 0, 0), np.float32), spacing)
     frame.GetSize = lambda: tuple(int(v) for v in size_xyz)
     return image_partition_by_fixed_size(frame, bs, be, psize, pstride, model['max_stride'])
+
+
+def segmentation_voi(model, iso_image, start_voxel, end_voxel, use_gpu):
+    """Probability maps of one volume of interest [start_voxel, end_voxel) of an image already at the model spacing
+    (reference :208-246): crop -> crop normaliser -> network -> one image per class carrying the VOI's frame.  The
+    reference averages two forwards of the same tensor (:230-234), which returns the bits of one.  The sliding-window
+    engine does not come through here (it crops, normalises and blends whole patch batches on the device); this is the
+    single-VOI call kept for callers of the reference API."""
+    img = as_image3d(iso_image)
+    s, e = [int(v) for v in start_voxel], [int(v) for v in end_voxel]
+    data = img.data[s[2]:e[2], s[1]:e[1], s[0]:e[0]]
+    roi = Image3d(data, img.GetSpacing(), img.TransformContinuousIndexToPhysicalPoint([float(v) for v in s]), img.GetDirection())
+    if model['crop_normalizers'] is not None:
+        roi = model['crop_normalizers'][0](roi)
+    dev = next(model['net'].parameters()).device
+    x = roi.data if torch.is_tensor(roi.data) else torch.from_numpy(np.ascontiguousarray(roi.data))
+    x = x.to(device=dev, dtype=torch.float32).unsqueeze(0).unsqueeze(0)
+    with torch.no_grad():
+        probs = model['net'](x)
+    assert model['out_channels'] == probs.shape[1]
+    maps = []
+    for idx in range(model['out_channels']):
+        m = Image3d(probs[0][idx])
+        m.CopyInformation(roi)
+        maps.append(m)
+    return maps
 
 
 def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_start_voxel=None, bbox_end_voxel=None,
@@ -376,19 +403,6 @@ def segmentation_volume(model, cfg, image, bbox_start_voxel, bbox_end_voxel, use
     mask_im = Image3d(mask)
     mask_im.CopyInformation(image)
     return mean_probs, mask_im
-
-
-def get_bounding_box(mask, selected_labels):
-    """[x,y,z] start (inclusive) / end (exclusive) of the selected labels (utils/image_tools.py:481-510)."""
-    m = as_image3d(mask).data
-    m = m if torch.is_tensor(m) else torch.from_numpy(np.ascontiguousarray(m))
-    sel = (m > 0) if selected_labels is None else torch.isin(m, torch.tensor(list(selected_labels), device=m.device, dtype=m.dtype))
-    if not bool(sel.any()):
-        print('Fail to get the bounding box.')
-        return None, None
-    nz = sel.nonzero()
-    lo, hi = nz.min(0)[0].tolist(), nz.max(0)[0].tolist()
-    return [lo[2], lo[1], lo[0]], [hi[2] + 1, hi[1] + 1, hi[0] + 1]
 
 
 def segmentation(input_path, model_folder, output_folder, seg_name, gpu_id, return_mask, save_mask, save_image, save_prob):

@@ -23,6 +23,7 @@ from segmentation3d.loss.cross_entropy_loss import CrossEntropyLoss
 from segmentation3d.loss.focal_loss import FocalLoss
 from segmentation3d.loss.multi_dice_loss import MultiDiceLoss
 from segmentation3d.utils.file_io import load_config, setup_logger
+from segmentation3d.utils.image_tools import save_intermediate_results
 from segmentation3d.utils.model_io import load_checkpoint, save_checkpoint
 
 
@@ -55,8 +56,9 @@ def make_optimizer(net, lr, betas=(0.9, 0.999)):
     return optim.Adam(params, lr=lr, betas=betas, fused=all(p.is_cuda for p in params))
 
 
-def train_step(net, opt, loss_func, crops, masks, params=None):
-    """core/seg_train.py:119-127 for one batch already on the device; returns the loss tensor."""
+def train_step(net, opt, loss_func, crops, masks, params=None, return_outputs=False):
+    """core/seg_train.py:119-127 for one batch already on the device; returns the loss tensor (and, on request, the
+    probabilities the loss was computed from)."""
     opt.zero_grad()
     outputs = net(crops)
     loss = loss_func(outputs, masks)
@@ -65,7 +67,7 @@ def train_step(net, opt, loss_func, crops, masks, params=None):
     if not getattr(plan, 'grads_reduced_in_backward', False):      # else: already averaged, overlapped with the backward pass
         D.allreduce_mean_grads(params if params is not None else list(net.parameters()))
     opt.step()
-    return loss
+    return (loss, outputs.detach()) if return_outputs else loss
 
 
 def train(train_config_file):
@@ -109,7 +111,8 @@ def train(train_config_file):
         random_translation=train_cfg.dataset.random_translation, random_scale=train_cfg.dataset.random_scale,
         interpolation=train_cfg.dataset.interpolation, crop_normalizers=train_cfg.dataset.crop_normalizers)
     if world > 1:
-        sampler = EpochConcateDistributedSampler(dataset, train_cfg.train.epochs, rank, world, train_cfg.general.seed)
+        sampler = EpochConcateDistributedSampler(dataset, train_cfg.train.epochs, 0, rank=rank, world_size=world,
+                                                 seed=train_cfg.general.seed)
     else:
         sampler = EpochConcateSampler(dataset, train_cfg.train.epochs)
     data_loader = DataLoader(dataset, sampler=sampler, batch_size=train_cfg.train.batchsize,
@@ -144,7 +147,12 @@ def train(train_config_file):
     for crops, masks, frames, filenames in data_loader:
         begin_t = time.time()
         crops, masks = crops.cuda(non_blocking=True), masks.cuda(non_blocking=True)
-        train_loss = train_step(net, opt, loss_func, crops, masks, params)
+        if 'debug' in train_cfg and train_cfg.debug.get('save_inputs', False):       # core/seg_train.py:130-133
+            train_loss, outputs = train_step(net, opt, loss_func, crops, masks, params, return_outputs=True)
+            save_intermediate_results(list(range(crops.size(0))), crops.cpu(), masks.cpu(), outputs.cpu(), frames, filenames,
+                                      os.path.join(model_folder, 'batch_{}'.format(batch_idx - batch_start)))
+        else:
+            train_loss = train_step(net, opt, loss_func, crops, masks, params)
         epoch_idx = batch_idx * global_batch // len(dataset)
         batch_idx += 1
         loss_value = train_loss.item()

@@ -1,4 +1,4 @@
-"""Minimal 3-D image container + MetaImage (.mha/.mhd) I/O.
+"""Minimal 3-D image container + MetaImage (.mha/.mhd) and NIfTI-1 (.nii/.nii.gz) I/O.
 
 The reference uses SimpleITK images everywhere above the hot path (core/seg_infer.py:414,467-481);
 SimpleITK is not part of this image, so the engine carries its own container with the same accessor
@@ -6,7 +6,9 @@ names (GetSize/GetSpacing/GetOrigin/GetDirection/CopyInformation, sizes in x,y,z
 a numpy array in [z,y,x] order - or by a CUDA tensor when the data should stay on the device.
 `as_image3d` also accepts real SimpleITK images when that package is installed.
 """
+import gzip
 import os
+import struct
 import zlib
 
 import numpy as np
@@ -89,6 +91,8 @@ def read_image(path, dtype=None):
     """Read .mha / .mhd (MetaImage, raw or zlib-compressed).  dtype: optional numpy dtype to cast to
     (the reference reads test images as float32, core/seg_infer.py:414)."""
     low = path.lower()
+    if low.endswith('.nii') or low.endswith('.nii.gz'):
+        return read_nifti(path, dtype)
     if not (low.endswith('.mha') or low.endswith('.mhd')):
         try:
             import SimpleITK as sitk
@@ -139,8 +143,10 @@ def write_image(image, path, compress=False):
     arr = np.ascontiguousarray(image.to_numpy())
     if arr.dtype == np.bool_:
         arr = arr.astype(np.uint8)
+    if path.lower().endswith('.nii') or path.lower().endswith('.nii.gz'):
+        return write_nifti(image, path)
     if not path.lower().endswith('.mha'):
-        raise ValueError('only .mha can be written without SimpleITK: %s' % path)
+        raise ValueError('only .mha / .nii / .nii.gz can be written without SimpleITK: %s' % path)
     payload = arr.tobytes()
     if compress:
         payload = zlib.compress(payload, 1)
@@ -160,3 +166,141 @@ def write_image(image, path, compress=False):
     with open(path, 'wb') as f:
         f.write(('\n'.join(lines) + '\n').encode('ascii'))
         f.write(payload)
+
+
+# ---- NIfTI-1 (single file, "n+1"): the reference reads and writes it through ITK's NiftiImageIO --------------------------------
+# NIfTI stores its affine in RAS+ coordinates, ITK images live in LPS+: on the way in the x and y rows of the affine change
+# sign (origin and direction), on the way out they change back.  The qform (quaternion) is preferred when its code is set,
+# the sform (three affine rows) otherwise; with neither the axes are the identity scaled by pixdim.
+_NII_DT = {2: np.uint8, 4: np.int16, 8: np.int32, 16: np.float32, 64: np.float64, 256: np.int8, 512: np.uint16,
+           768: np.uint32, 1024: np.int64, 1280: np.uint64}
+_NII_DT_INV = {np.dtype(v): k for k, v in _NII_DT.items()}
+
+
+def _quatern_to_mat(b, c, d, qfac):
+    """rotation matrix of NIfTI's unit quaternion (a, b, c, d), a = sqrt(1 - b^2 - c^2 - d^2), last column times qfac"""
+    a = 1.0 - (b * b + c * c + d * d)
+    if a < 1e-7:                          # special case of nifti_quatern_to_mat44: 180 degree rotation
+        a = 1.0 / np.sqrt(b * b + c * c + d * d)
+        b, c, d, a = b * a, c * a, d * a, 0.0
+    else:
+        a = np.sqrt(a)
+    r = np.array([[a * a + b * b - c * c - d * d, 2 * b * c - 2 * a * d, 2 * b * d + 2 * a * c],
+                  [2 * b * c + 2 * a * d, a * a + c * c - b * b - d * d, 2 * c * d - 2 * a * b],
+                  [2 * b * d - 2 * a * c, 2 * c * d + 2 * a * b, a * a + d * d - c * c - b * b]], dtype=np.float64)
+    r[:, 2] *= qfac
+    return r
+
+
+def _mat_to_quatern(r):
+    """inverse of _quatern_to_mat for an orthonormal matrix: (b, c, d, qfac) (nifti_mat44_to_quatern)"""
+    r = np.array(r, dtype=np.float64)
+    qfac = 1.0
+    if np.linalg.det(r) < 0:
+        r[:, 2] = -r[:, 2]
+        qfac = -1.0
+    a = r[0, 0] + r[1, 1] + r[2, 2] + 1.0
+    if a > 0.5:
+        a = 0.5 * np.sqrt(a)
+        b, c, d = 0.25 * (r[2, 1] - r[1, 2]) / a, 0.25 * (r[0, 2] - r[2, 0]) / a, 0.25 * (r[1, 0] - r[0, 1]) / a
+    else:
+        xd, yd, zd = 1.0 + r[0, 0] - (r[1, 1] + r[2, 2]), 1.0 + r[1, 1] - (r[0, 0] + r[2, 2]), 1.0 + r[2, 2] - (r[0, 0] + r[1, 1])
+        if xd > 1.0:
+            b = 0.5 * np.sqrt(xd)
+            c, d, a = 0.25 * (r[0, 1] + r[1, 0]) / b, 0.25 * (r[0, 2] + r[2, 0]) / b, 0.25 * (r[2, 1] - r[1, 2]) / b
+        elif yd > 1.0:
+            c = 0.5 * np.sqrt(yd)
+            b, d, a = 0.25 * (r[0, 1] + r[1, 0]) / c, 0.25 * (r[1, 2] + r[2, 1]) / c, 0.25 * (r[0, 2] - r[2, 0]) / c
+        else:
+            d = 0.5 * np.sqrt(zd)
+            b, c, a = 0.25 * (r[0, 2] + r[2, 0]) / d, 0.25 * (r[1, 2] + r[2, 1]) / d, 0.25 * (r[1, 0] - r[0, 1]) / d
+        if a < 0.0:
+            b, c, d = -b, -c, -d
+    return float(b), float(c), float(d), qfac
+
+
+def read_nifti(path, dtype=None):
+    """NIfTI-1 single file (.nii / .nii.gz) -> Image3d in ITK's LPS convention."""
+    opener = gzip.open if path.lower().endswith('.gz') else open
+    with opener(path, 'rb') as f:
+        blob = f.read()
+    if len(blob) < 348:
+        raise ValueError('not a NIfTI-1 file: %s' % path)
+    end = '<' if struct.unpack('<i', blob[0:4])[0] == 348 else '>'
+    if struct.unpack(end + 'i', blob[0:4])[0] != 348 or blob[344:347] not in (b'n+1', b'ni1'):
+        raise ValueError('not a NIfTI-1 file: %s' % path)
+    if blob[344:347] == b'ni1':
+        raise ValueError('two-file NIfTI (.hdr/.img) is not supported: %s' % path)
+    dim = struct.unpack(end + '8h', blob[40:56])
+    if dim[0] < 3 or any(d != 1 for d in dim[4:1 + dim[0]]):
+        raise ValueError('only 3-D NIfTI volumes are supported (dim = %s)' % (dim,))
+    nx, ny, nz = dim[1:4]
+    datatype = struct.unpack(end + 'h', blob[70:72])[0]
+    if datatype not in _NII_DT:
+        raise ValueError('unsupported NIfTI datatype %d' % datatype)
+    pixdim = struct.unpack(end + '8f', blob[76:108])
+    vox_offset = int(struct.unpack(end + 'f', blob[108:112])[0])
+    slope, inter = struct.unpack(end + '2f', blob[112:120])
+    qform_code, sform_code = struct.unpack(end + '2h', blob[252:256])
+    np_t = np.dtype(_NII_DT[datatype]).newbyteorder(end)
+    arr = np.frombuffer(blob, dtype=np_t, count=nx * ny * nz, offset=max(vox_offset, 352)).reshape(nz, ny, nx)
+    arr = arr.astype(np_t.newbyteorder('='), copy=True)
+    if slope != 0.0 and np.isfinite(slope) and (slope != 1.0 or inter != 0.0):
+        arr = arr.astype(np.float64) * slope + inter
+    spacing = [abs(float(v)) if v != 0 else 1.0 for v in pixdim[1:4]]
+    if qform_code > 0:
+        b, c, d, qx, qy, qz = struct.unpack(end + '6f', blob[256:280])
+        rot = _quatern_to_mat(b, c, d, -1.0 if pixdim[0] < 0 else 1.0)
+        origin = np.array([qx, qy, qz], dtype=np.float64)
+    elif sform_code > 0:
+        rows = np.array(struct.unpack(end + '12f', blob[280:328]), dtype=np.float64).reshape(3, 4)
+        spacing = [float(np.linalg.norm(rows[:, a])) or 1.0 for a in range(3)]
+        rot = rows[:, :3] / np.array(spacing)
+        origin = rows[:, 3].copy()
+    else:
+        rot, origin = np.eye(3), np.zeros(3)
+    flip = np.diag([-1.0, -1.0, 1.0])                # RAS+ (NIfTI) -> LPS+ (ITK)
+    direction = flip.dot(rot)
+    origin = flip.dot(origin)
+    if dtype is not None:
+        arr = arr.astype(dtype)
+    return Image3d(arr, spacing, origin.tolist(), direction.reshape(-1).tolist())
+
+
+def write_nifti(image, path):
+    """Image3d -> NIfTI-1 single file with qform and sform set (codes 1), gzip-compressed when the name ends in .gz."""
+    image = as_image3d(image)
+    arr = np.ascontiguousarray(image.to_numpy())
+    if arr.dtype == np.bool_:
+        arr = arr.astype(np.uint8)
+    if arr.dtype not in _NII_DT_INV:
+        raise ValueError('unsupported dtype for NIfTI: %s' % arr.dtype)
+    nz, ny, nx = arr.shape
+    flip = np.diag([-1.0, -1.0, 1.0])                # LPS+ -> RAS+
+    rot = flip.dot(np.asarray(image.direction, dtype=np.float64).reshape(3, 3))
+    origin = flip.dot(np.asarray(image.origin, dtype=np.float64))
+    sp = np.asarray(image.spacing, dtype=np.float64)
+    b, c, d, qfac = _mat_to_quatern(rot)
+    hdr = bytearray(348)
+    struct.pack_into('<i', hdr, 0, 348)
+    struct.pack_into('<8h', hdr, 40, 3, nx, ny, nz, 1, 1, 1, 1)
+    struct.pack_into('<h', hdr, 70, _NII_DT_INV[arr.dtype])
+    struct.pack_into('<h', hdr, 72, arr.dtype.itemsize * 8)
+    struct.pack_into('<8f', hdr, 76, qfac, sp[0], sp[1], sp[2], 0.0, 0.0, 0.0, 0.0)
+    struct.pack_into('<f', hdr, 108, 352.0)
+    struct.pack_into('<2f', hdr, 112, 1.0, 0.0)
+    hdr[123] = 2                                      # xyzt_units: millimetres
+    struct.pack_into('<2h', hdr, 252, 1, 1)
+    struct.pack_into('<6f', hdr, 256, b, c, d, origin[0], origin[1], origin[2])
+    aff = rot * sp
+    for r in range(3):
+        struct.pack_into('<4f', hdr, 280 + 16 * r, aff[r, 0], aff[r, 1], aff[r, 2], origin[r])
+    hdr[344:348] = b'n+1\0'
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    payload = bytes(hdr) + b'\0\0\0\0' + arr.astype(arr.dtype.newbyteorder('<'), copy=False).tobytes()
+    if path.lower().endswith('.gz'):
+        with gzip.open(path, 'wb', compresslevel=1) as f:
+            f.write(payload)
+    else:
+        with open(path, 'wb') as f:
+            f.write(payload)

@@ -7,6 +7,7 @@ in this build (segmentation3d/_b200/sliding.py); the host versions below exist f
 small images and are not on the engine's path.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -186,6 +187,72 @@ def crop_image(image, cropping_center, cropping_size, cropping_spacing, interp_m
         val = (a00 * (1 - wy) + a01 * wy) * (1 - wz) + (a10 * (1 - wy) + a11 * wy) * wz
     out = np.where(inside, val, 0).astype(src.dtype)
     return Image3d(out, spacing_c, origin_c, img.GetDirection())
+
+
+def percentiles(image, percentiles):
+    """np.percentile of the voxel values (utils/image_tools.py:241-249)."""
+    return np.percentile(as_image3d(image).to_numpy(), percentiles)
+
+
+def copy_image(source_image, target_start_voxel, target_end_voxel, target_image):
+    """Paste the region of `source_image` that lies at target voxels [start, end) into a copy of `target_image`; both
+    images share their orientation (utils/image_tools.py:149-166: sitk.Paste).  The bbox lists are cast to int in place."""
+    src, tgt = as_image3d(source_image), as_image3d(target_image)
+    for idx in range(3):
+        target_start_voxel[idx] = int(target_start_voxel[idx])
+        target_end_voxel[idx] = int(target_end_voxel[idx])
+    start_world = tgt.TransformContinuousIndexToPhysicalPoint([float(v) for v in target_start_voxel])
+    s = src.TransformPhysicalPointToIndex(start_world)
+    size = [int(target_end_voxel[idx] - target_start_voxel[idx]) for idx in range(3)]
+    t = target_start_voxel
+    out = np.array(tgt.to_numpy(), copy=True)
+    out[t[2]:t[2] + size[2], t[1]:t[1] + size[1], t[0]:t[0] + size[0]] = \
+        src.to_numpy()[s[2]:s[2] + size[2], s[1]:s[1] + size[1], s[0]:s[0] + size[0]]
+    res = Image3d(out)
+    res.CopyInformation(tgt)
+    return res
+
+
+def get_bounding_box(mask, selected_labels):
+    """[x,y,z] start (inclusive) / end (exclusive) of the voxels carrying one of `selected_labels` (all non-zero labels
+    when None); (None, None) for an empty selection (utils/image_tools.py:481-510: LabelShapeStatisticsImageFilter).
+    Works on host arrays and on CUDA masks alike."""
+    m = as_image3d(mask).data
+    m = m if torch.is_tensor(m) else torch.from_numpy(np.ascontiguousarray(m))
+    sel = (m > 0) if selected_labels is None else torch.isin(m, torch.tensor(list(selected_labels), device=m.device, dtype=m.dtype))
+    if not bool(sel.any()):
+        print('Fail to get the bounding box.')
+        return None, None
+    nz = sel.nonzero()
+    lo, hi = nz.min(0)[0].tolist(), nz.max(0)[0].tolist()
+    return [lo[2], lo[1], lo[0]], [hi[2] + 1, hi[1] + 1, hi[0] + 1]
+
+
+def save_intermediate_results(idxs, crops, masks, outputs, frames, file_names, out_folder):
+    """Write the crops, masks and network outputs of the batch items `idxs` for inspection (utils/image_tools.py:62-108):
+    <out_folder>/<file_name>/batch_<i>_crop_<m>.nii.gz, batch_<i>_mask.nii.gz, batch_<i>_output_<c>.nii.gz, each with the
+    crop's frame."""
+    from segmentation3d.utils.image3d import write_image
+    if not os.path.isdir(out_folder):
+        os.makedirs(out_folder)
+    for i in idxs:
+        case_out_folder = os.path.join(out_folder, file_names[i])
+        if not os.path.isdir(case_out_folder):
+            os.makedirs(case_out_folder)
+        frame = frames[i].numpy() if torch.is_tensor(frames[i]) else np.asarray(frames[i])
+        if crops is not None:
+            for modality_idx, image in enumerate(convert_tensor_to_image(crops[i], dtype=np.float32)):
+                set_image_frame(image, frame)
+                write_image(image, os.path.join(case_out_folder, 'batch_{}_crop_{}.nii.gz'.format(i, modality_idx)))
+        if masks is not None:
+            mask = convert_tensor_to_image(masks[i, 0], dtype=np.int32)
+            set_image_frame(mask, frame)
+            write_image(mask, os.path.join(case_out_folder, 'batch_{}_mask.nii.gz'.format(i)))
+        if outputs is not None:
+            for cls in range(outputs.size()[1]):
+                output = convert_tensor_to_image(outputs[i, cls].data, dtype=np.float32)
+                set_image_frame(output, frame)
+                write_image(output, os.path.join(case_out_folder, 'batch_{}_output_{}.nii.gz'.format(i, cls)))
 
 
 def pick_largest_connected_component(mask, labels):

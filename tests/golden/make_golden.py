@@ -14,6 +14,7 @@ Fixtures (all small):
   train_step.npz         one Adam step of the reference training loop body      (core/seg_train.py:119-127)
   loss_ce.npz            cross-entropy values and gradients on loss.npz's inputs (loss/cross_entropy_loss.py)
   dataset_sampling.json  crops the reference's SegmentationDataset requests under a seeded RNG  (dataloader/dataset.py:140-209)
+  samplers.json          index streams of EpochConcateSampler / EpochConcateSamplerResume  (dataloader/sampler.py:6-53)
   cascade.npz            segmentation_volume restricted by a bounding box       (core/seg_infer.py:292-307,428-444)
 """
 import copy
@@ -357,6 +358,19 @@ def gen_dataset_sampling():
         json.dump(out, f)
 
 
+def gen_samplers():
+    """dataloader/sampler.py:6-53: the index streams of the unmodified single-process samplers under python's `random`."""
+    import random
+    from segmentation3d.dataloader import sampler as ref_sampler
+    out = {}
+    random.seed(5)
+    out['concat_n7_e3_seed5'] = list(ref_sampler.EpochConcateSampler(list(range(7)), 3))
+    out['resume_n5_e3_from2'] = list(ref_sampler.EpochConcateSamplerResume(list(range(5)), 3, 2))
+    with open(os.path.join(HERE, 'samplers.json'), 'w') as f:
+        json.dump(out, f)
+    print('samplers', out)
+
+
 def gen_train_step():
     """core/seg_train.py:83,119-127 on one synthetic batch: Adam(lr=1e-4, betas=(0.9,0.999))."""
     out = {}
@@ -388,7 +402,7 @@ def gen_train_step():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['schema', 'forward', 'grids', 'loss', 'sw', 'train', 'cascade', 'ce', 'dataset']
+    which = sys.argv[1:] or ['schema', 'forward', 'grids', 'loss', 'sw', 'train', 'cascade', 'ce', 'dataset', 'samplers']
     if 'schema' in which: gen_schema_and_hashes()
     if 'forward' in which: gen_forward()
     if 'grids' in which: gen_grids()
@@ -398,3 +412,4 @@ if __name__ == '__main__':
     if 'cascade' in which: gen_cascade()
     if 'ce' in which: gen_loss_ce()
     if 'dataset' in which: gen_dataset_sampling()
+    if 'samplers' in which: gen_samplers()

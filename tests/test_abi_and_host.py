@@ -219,3 +219,52 @@ def test_standalone_network_modules_keep_the_reference_schema_and_init():
         ConvGnRelu3(16, 16, 3, 1, 1)(torch.zeros(1, 16, 8, 8, 8))
     with pytest.raises(NotImplementedError):
         ConvGnRelu3(16, 16, 5, 1, 2)
+
+
+def test_nifti_roundtrip_and_hand_built_header(tmp_path):
+    """.nii / .nii.gz (README: supported input types): write -> read round trip of data, spacing, origin and direction in
+    ITK's LPS convention; a hand-built sform-only header (RAS affine) and a qform with a 90-degree rotation read as the
+    LPS frame ITK's NiftiImageIO reports; list readers accept the extension."""
+    import gzip
+    import struct
+    from segmentation3d.utils.image3d import Image3d, read_image, write_image
+    rng = np.random.default_rng(2)
+    for dt in (np.float32, np.int16, np.int8, np.uint8):
+        arr = (rng.standard_normal((5, 7, 9)) * 50).astype(dt)
+        d = (0.0, -1.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0)               # 90 degrees about z
+        for direction in ((1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0), d, (1.0, 0.0, 0.0, 0.0, -1.0, 0.0, 0.0, 0.0, 1.0)):
+            img = Image3d(arr, (0.5, 0.75, 2.0), (-12.5, 30.0, 7.25), direction)
+            for name in ('a.nii.gz', 'a.nii'):
+                write_image(img, str(tmp_path / name), True)
+                back = read_image(str(tmp_path / name))
+                assert back.to_numpy().dtype == dt and np.array_equal(back.to_numpy(), arr)
+                assert np.allclose(back.GetSpacing(), img.GetSpacing(), atol=1e-6)
+                assert np.allclose(back.GetOrigin(), img.GetOrigin(), atol=1e-5)
+                assert np.allclose(back.GetDirection(), direction, atol=1e-6), (direction, back.GetDirection())
+    assert read_image(str(tmp_path / 'a.nii.gz'), np.float32).to_numpy().dtype == np.float32
+    # hand-built header, sform only: RAS affine with 2 mm voxels, x axis pointing LEFT (-R), origin (90, -126, -72) RAS
+    hdr = bytearray(348)
+    struct.pack_into('<i', hdr, 0, 348)
+    struct.pack_into('<8h', hdr, 40, 3, 4, 3, 2, 1, 1, 1, 1)
+    struct.pack_into('<h', hdr, 70, 4)
+    struct.pack_into('<h', hdr, 72, 16)
+    struct.pack_into('<8f', hdr, 76, 1.0, 2.0, 2.0, 2.0, 0, 0, 0, 0)
+    struct.pack_into('<f', hdr, 108, 352.0)
+    struct.pack_into('<2h', hdr, 252, 0, 1)
+    struct.pack_into('<4f', hdr, 280, -2.0, 0.0, 0.0, 90.0)
+    struct.pack_into('<4f', hdr, 296, 0.0, 2.0, 0.0, -126.0)
+    struct.pack_into('<4f', hdr, 312, 0.0, 0.0, 2.0, -72.0)
+    hdr[344:348] = b'n+1\0'
+    vox = np.arange(24, dtype='<i2')
+    with gzip.open(str(tmp_path / 'h.nii.gz'), 'wb') as f:
+        f.write(bytes(hdr) + b'\0' * 4 + vox.tobytes())
+    im = read_image(str(tmp_path / 'h.nii.gz'))
+    assert im.GetSize() == (4, 3, 2) and im.to_numpy()[1, 2, 3] == 1 * 12 + 2 * 4 + 3
+    assert np.allclose(im.GetSpacing(), (2.0, 2.0, 2.0))
+    assert np.allclose(im.GetOrigin(), (-90.0, 126.0, -72.0))              # RAS -> LPS: x and y change sign
+    assert np.allclose(im.GetDirection(), (1.0, 0, 0, 0, -1.0, 0, 0, 0, 1.0))
+    # physical position of voxel (1, 0, 0): RAS (88, -126, -72) -> LPS (-88, 126, -72)
+    assert np.allclose(im.TransformContinuousIndexToPhysicalPoint([1.0, 0.0, 0.0]), (-88.0, 126.0, -72.0))
+    from segmentation3d.core.seg_infer import read_test_folder
+    names, paths = read_test_folder(str(tmp_path))
+    assert 'h.nii.gz' in names and 'a.nii' in names

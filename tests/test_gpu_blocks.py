@@ -83,3 +83,30 @@ def test_standalone_modules_match_oracle_blocks(monkeypatch, mode, tol):
             y = F.relu(F.group_norm(F.conv3d(x, sd['conv1.weight'], sd['conv1.bias'], padding=1), 1, sd['gn1.weight'], sd['gn1.bias'], EPS))
             y = F.softmax(F.group_norm(F.conv3d(y, sd['conv2.weight'], sd['conv2.bias']), 1, sd['gn2.weight'], sd['gn2.bias'], EPS), 1)
             close(m.cuda()(x.cuda()), y, 'OutputBlock')
+
+
+def test_segmentation_voi_and_disabled_partition_match_oracle():
+    """core/seg_infer.py:208-246 (one VOI) and partition_type = 'DISABLE' (:277-279, the whole volume as one patch)."""
+    import numpy as np
+    from oracle import init as oinit
+    from oracle import sliding_window as osw
+    from segmentation3d.core.seg_infer import make_model, segmentation_voi, segmentation_volume
+    from segmentation3d.network import vnet
+    from segmentation3d.utils.image3d import Image3d
+    sd = oinit.randomize_affine(oinit.init_state_dict('vnet', 1, 2, 0), 3)
+    net = vnet.SegmentationNet(1, 2)
+    net.load_state_dict(sd)
+    net.b200_mode = 'fp32'
+    nd = {'type': 0, 'mean': 10.0, 'stddev': 150.0, 'clip': True}
+    model = make_model(net.cuda().eval(), [1.0, 1.0, 1.0], nd)
+    vol = (torch.randn((48, 32, 64), generator=torch.Generator().manual_seed(2)) * 200).numpy().astype(np.float32)
+    probs, mask, _, _ = osw.segmentation_volume(sd, vol, [1.0, 1.0, 1.0], nd, 'DISABLE', double_forward=False, faithful_copies=False)
+    cfg = {'partition_type': 'DISABLE', 'pick_largest_cc': False, 'remove_small_cc': 0}
+    p_im, m_im = segmentation_volume(model, cfg, Image3d(vol), None, None, True)
+    got = np.stack([p.to_numpy() for p in p_im], 0)
+    assert np.abs(got - probs).max() <= 1e-3 and (m_im.to_numpy() == mask).mean() >= 0.999
+    maps = segmentation_voi(model, Image3d(vol, (1.0, 1.0, 1.0), (5.0, 6.0, 7.0)), [16, 0, 16], [48, 32, 48], True)
+    ref, _, _, _ = osw.segmentation_volume(sd, vol[16:48, 0:32, 16:48], [1.0, 1.0, 1.0], nd, 'DISABLE', double_forward=False,
+                                           faithful_copies=False)
+    assert np.abs(np.stack([m.to_numpy() for m in maps], 0) - ref).max() <= 1e-3
+    assert np.allclose(maps[0].GetOrigin(), (21.0, 6.0, 23.0)) and maps[0].GetSize() == (32, 32, 32)

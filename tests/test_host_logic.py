@@ -286,3 +286,72 @@ def test_dataset_batches_through_dataloader(tmp_path):
             assert set(np.unique(masks.numpy())) <= {0.0, 1.0, 2.0}
             n += 1
         assert n == 3
+
+
+def test_samplers_draw_the_reference_index_streams():
+    """dataloader/sampler.py:6-79: same index streams as the unmodified reference under python's `random`
+    (tests/golden/samplers.json); the distributed sampler is DistributedSampler's shuffle per epoch, rank-sharded."""
+    import json
+    import random
+    from torch.utils.data.distributed import DistributedSampler
+    from segmentation3d.dataloader.sampler import EpochConcateDistributedSampler, EpochConcateSampler, EpochConcateSamplerResume
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'samplers.json')))
+    random.seed(5)
+    s = EpochConcateSampler(list(range(7)), 3)
+    assert list(s) == gold['concat_n7_e3_seed5'] and len(s) == 21
+    s = EpochConcateSamplerResume(list(range(5)), 3, 2)
+    assert list(s) == gold['resume_n5_e3_from2'] and len(s) == 15
+    data = list(range(11))
+    streams = []
+    for r in range(2):
+        s = EpochConcateDistributedSampler(data, 3, 0, rank=r, world_size=2, seed=9)
+        got = list(s)
+        ref = []
+        base = DistributedSampler(data, num_replicas=2, rank=r, seed=9)
+        for e in range(3):
+            base.set_epoch(e)
+            ref += list(base)
+        assert got == ref and len(s) == len(got) == 18          # ceil(11 / 2) per epoch: every rank runs the same number of steps
+        streams.append(got)
+    for e in range(3):
+        both = streams[0][6 * e:6 * e + 6] + streams[1][6 * e:6 * e + 6]
+        assert set(both) == set(data)                           # every sample once per epoch (plus one padding repeat)
+
+
+def test_image_tools_helpers(tmp_path):
+    """host helpers with the reference's names: get_bounding_box, copy_image, percentiles, frames, save_intermediate_results."""
+    from segmentation3d.utils.image3d import read_image
+    from segmentation3d.utils.image_tools import (copy_image, get_bounding_box, get_image_frame, percentiles,
+                                                  save_intermediate_results, set_image_frame)
+    m = np.zeros((10, 12, 14), np.int8)
+    m[2:5, 3:9, 4:6] = 1
+    m[7, 1, 12] = 2
+    assert get_bounding_box(Image3d(m), None) == ([4, 1, 2], [13, 9, 8])
+    assert get_bounding_box(Image3d(m), [1]) == ([4, 3, 2], [6, 9, 5])
+    assert get_bounding_box(Image3d(m), [3]) == (None, None)
+    from segmentation3d.core import seg_infer
+    assert seg_infer.get_bounding_box is get_bounding_box                      # the engine's cascade uses the same function
+    rng = np.random.default_rng(0)
+    src = Image3d(rng.standard_normal((6, 6, 6)).astype(np.float32), (1.0, 1.0, 1.0), (4.0, 3.0, 2.0))
+    tgt = Image3d(np.zeros((10, 12, 14), np.float32))
+    bs, be = [5.0, 4.0, 3.0], [9, 8, 7]
+    out = copy_image(src, bs, be, tgt).to_numpy()
+    assert bs == [5, 4, 3] and isinstance(bs[0], int)
+    assert np.array_equal(out[3:7, 4:8, 5:9], src.to_numpy()[1:5, 1:5, 1:5]) and out.sum() == out[3:7, 4:8, 5:9].sum()
+    assert np.allclose(percentiles(Image3d(m), [50, 100]), np.percentile(m, [50, 100]))
+    im = Image3d(np.zeros((2, 3, 4), np.float32), (0.5, 0.6, 0.7), (1.0, 2.0, 3.0))
+    fr = get_image_frame(im)
+    assert fr.dtype == np.float32 and np.allclose(fr[:6], [0.5, 0.6, 0.7, 1.0, 2.0, 3.0])
+    im2 = Image3d(np.zeros((2, 3, 4), np.float32))
+    set_image_frame(im2, fr)
+    assert np.allclose(im2.GetSpacing(), im.GetSpacing()) and np.allclose(im2.GetOrigin(), im.GetOrigin())
+    crops, masks = torch.randn(2, 1, 4, 5, 6), torch.randint(0, 3, (2, 1, 4, 5, 6)).float()
+    outputs = torch.softmax(torch.randn(2, 3, 4, 5, 6), 1)
+    frames = torch.from_numpy(np.stack([fr, fr]))
+    save_intermediate_results([1], crops, masks, outputs, frames, ['caseA_im.mha', 'caseB_im.mha'], str(tmp_path / 'batch_0'))
+    d = tmp_path / 'batch_0' / 'caseB_im.mha'
+    assert sorted(os.listdir(d)) == ['batch_1_crop_0.nii.gz', 'batch_1_mask.nii.gz', 'batch_1_output_0.nii.gz',
+                                     'batch_1_output_1.nii.gz', 'batch_1_output_2.nii.gz']
+    back = read_image(str(d / 'batch_1_mask.nii.gz'))
+    assert back.to_numpy().dtype == np.int32 and np.array_equal(back.to_numpy(), masks[1, 0].numpy().astype(np.int32))
+    assert np.allclose(back.GetSpacing(), (0.5, 0.6, 0.7), atol=1e-6) and np.allclose(back.GetOrigin(), (1.0, 2.0, 3.0), atol=1e-5)
