@@ -25,7 +25,8 @@ from segmentation3d._b200 import lib
 from segmentation3d._b200.sliding import SlidingWindow, axis_counts
 from segmentation3d.utils.attrdict import AttrDict as edict
 from segmentation3d.utils.file_io import load_config, readlines
-from segmentation3d.utils.image3d import Image3d, as_image3d, read_image, write_image
+from segmentation3d.utils.image3d import (AsyncImageWriter, Image3d, as_image3d, io_threads, prefetch_images, read_image,  # noqa: F401
+                                          write_image)
 from segmentation3d.utils.image_tools import (get_bounding_box, image_partition_by_fixed_size, is_identity_resample,  # noqa: F401
                                               resample, resample_spacing)
 from segmentation3d.utils.model_io import get_checkpoint_folder
@@ -441,49 +442,55 @@ def segmentation(input_path, model_folder, output_folder, seg_name, gpu_id, retu
     # follows the -g value the user passed, so all cases are segmented with the same partition settings
     use_gpu = requested_gpu_id > 0
     masks, total_inference_time, num_success_case = [], 0, 0
-    for i, file_path in enumerate(file_path_list):
-        print('{}: {}'.format(i, file_path))
-        begin = time.time()
-        image = read_image(file_path, np.float32)
-        read_image_time = time.time() - begin
+    # host I/O overlaps the GPU: the next case is read while this one is segmented, results are compressed and written in
+    # the background (SEG3D_IO_THREADS=0: strictly serial, as the reference)
+    writer = AsyncImageWriter(io_threads())
+    images = prefetch_images(file_path_list, np.float32, enabled=io_threads() > 0)
+    try:
+        for i, file_path in enumerate(file_path_list):
+            print('{}: {}'.format(i, file_path))
+            image, read_image_time = next(images)
 
-        begin = time.time()
-        if scale == 'coarse':
-            mean_probs, mask = segmentation_volume(models['coarse_model'], infer_cfg.coarse, image, None, None, use_gpu)
-        elif scale == 'fine':
-            mean_probs, mask = segmentation_volume(models['fine_model'], infer_cfg.fine, image, None, None, use_gpu)
-        elif scale == 'DISABLE':
-            print('Coarse segmentation: ')
-            _, mask = segmentation_volume(models['coarse_model'], infer_cfg.coarse, image, None, None, use_gpu)
-            start_voxel, end_voxel = get_bounding_box(mask, None)
-            bbox_ratio = 100
-            for a in range(3):
-                bbox_ratio *= (end_voxel[a] - start_voxel[a]) / mask.GetSize()[a]
-            print('Fine segmentation (bbox ratio: {:.2f}%): '.format(bbox_ratio))
-            mean_probs, mask = segmentation_volume(models['fine_model'], infer_cfg.fine, image, start_voxel, end_voxel, use_gpu)
-        else:
-            raise ValueError('Unsupported scale type!')
-        torch.cuda.synchronize()
-        inference_time = time.time() - begin
-        if return_mask:
-            masks.append(mask)
+            begin = time.time()
+            if scale == 'coarse':
+                mean_probs, mask = segmentation_volume(models['coarse_model'], infer_cfg.coarse, image, None, None, use_gpu)
+            elif scale == 'fine':
+                mean_probs, mask = segmentation_volume(models['fine_model'], infer_cfg.fine, image, None, None, use_gpu)
+            elif scale == 'DISABLE':
+                print('Coarse segmentation: ')
+                _, mask = segmentation_volume(models['coarse_model'], infer_cfg.coarse, image, None, None, use_gpu)
+                start_voxel, end_voxel = get_bounding_box(mask, None)
+                bbox_ratio = 100
+                for a in range(3):
+                    bbox_ratio *= (end_voxel[a] - start_voxel[a]) / mask.GetSize()[a]
+                print('Fine segmentation (bbox ratio: {:.2f}%): '.format(bbox_ratio))
+                mean_probs, mask = segmentation_volume(models['fine_model'], infer_cfg.fine, image, start_voxel, end_voxel, use_gpu)
+            else:
+                raise ValueError('Unsupported scale type!')
+            torch.cuda.synchronize()
+            inference_time = time.time() - begin
+            if return_mask:
+                masks.append(mask)
 
-        begin = time.time()
-        case_name = file_name_list[i]
-        if save_mask or save_image or save_prob:
-            os.makedirs(os.path.join(output_folder, case_name), exist_ok=True)
-        if save_mask:
-            write_image(mask, os.path.join(output_folder, case_name, seg_name), True)
-        if save_image:
-            write_image(image, os.path.join(output_folder, case_name, 'org.mha'), True)
-        if save_prob:
-            for c, prob in enumerate(mean_probs):
-                write_image(prob, os.path.join(output_folder, case_name, 'mean_prob_{}.mha'.format(c)), True)
-        save_time = time.time() - begin
+            begin = time.time()
+            case_name = file_name_list[i]
+            if save_mask or save_image or save_prob:
+                os.makedirs(os.path.join(output_folder, case_name), exist_ok=True)
+            if save_mask:
+                writer.write(mask, os.path.join(output_folder, case_name, seg_name), True)
+            if save_image:
+                writer.write(image, os.path.join(output_folder, case_name, 'org.mha'), True)
+            if save_prob:
+                for c, prob in enumerate(mean_probs):
+                    writer.write(prob, os.path.join(output_folder, case_name, 'mean_prob_{}.mha'.format(c)), True)
+            save_time = time.time() - begin
 
-        total_test_time = load_model_time + read_image_time + inference_time + save_time
-        total_inference_time += inference_time
-        num_success_case += 1
-        print('total test time: {:.2f}, average inference time: {:.2f}'.format(
-            total_test_time, total_inference_time / num_success_case))
+            total_test_time = load_model_time + read_image_time + inference_time + save_time
+            total_inference_time += inference_time
+            num_success_case += 1
+            print('total test time: {:.2f}, average inference time: {:.2f}'.format(
+                total_test_time, total_inference_time / num_success_case))
+    finally:
+        images.close()
+        writer.close()
     return masks

@@ -168,6 +168,81 @@ def write_image(image, path, compress=False):
         f.write(payload)
 
 
+# ---- host-side I/O overlap for batch inference: the next case is read (and decompressed) while the current one is on the GPU,
+# and results are compressed and written in the background (zlib releases the GIL) --------------------------------------------
+def io_threads():
+    """worker threads for background image I/O; SEG3D_IO_THREADS=0 restores strictly serial reads and writes"""
+    try:
+        return max(0, int(os.environ.get('SEG3D_IO_THREADS', '4')))
+    except ValueError:
+        return 4
+
+
+def prefetch_images(paths, dtype=None, enabled=True, depth=None):
+    """yield (image, seconds spent waiting for it) for every path in order, with up to `depth` (default: io_threads())
+    later paths being read on worker threads.  A read error surfaces when its own case is reached, as in the serial loop."""
+    import collections
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    paths = list(paths)
+    depth = io_threads() if depth is None else depth
+    if not enabled or depth < 1 or len(paths) < 2:
+        for p in paths:
+            t0 = time.time()
+            img = read_image(p, dtype)
+            yield img, time.time() - t0
+        return
+    pool = ThreadPoolExecutor(max_workers=depth)
+    try:
+        queue, nxt = collections.deque(), 0
+        while nxt < len(paths) and len(queue) < depth:
+            queue.append(pool.submit(read_image, paths[nxt], dtype))
+            nxt += 1
+        while queue:
+            t0 = time.time()
+            img = queue.popleft().result()
+            waited = time.time() - t0
+            if nxt < len(paths):
+                queue.append(pool.submit(read_image, paths[nxt], dtype))
+                nxt += 1
+            yield img, waited
+    finally:
+        pool.shutdown(wait=False)
+
+
+class AsyncImageWriter(object):
+    """write_image in the background.  The device-to-host copy happens in `write` on the caller's thread (so it is ordered
+    with the caller's CUDA stream); only compression and the file write run on the pool.  `close` waits for every file
+    and re-raises the first error."""
+
+    def __init__(self, threads):
+        from concurrent.futures import ThreadPoolExecutor
+        self.pool = ThreadPoolExecutor(max_workers=threads) if threads > 0 else None
+        self.pending = []
+
+    def write(self, image, path, compress=False):
+        image = as_image3d(image)
+        host = Image3d(np.ascontiguousarray(image.to_numpy()), image.GetSpacing(), image.GetOrigin(), image.GetDirection())
+        if self.pool is None:
+            write_image(host, path, compress)
+        else:
+            self.pending.append(self.pool.submit(write_image, host, path, compress))
+
+    def close(self):
+        err = None
+        for f in self.pending:
+            try:
+                f.result()
+            except Exception as e:          # keep draining so no file is left half-written behind a raised error
+                err = err or e
+        self.pending = []
+        if self.pool is not None:
+            self.pool.shutdown(wait=True)
+            self.pool = None
+        if err is not None:
+            raise err
+
+
 # ---- NIfTI-1 (single file, "n+1"): the reference reads and writes it through ITK's NiftiImageIO --------------------------------
 # NIfTI stores its affine in RAS+ coordinates, ITK images live in LPS+: on the way in the x and y rows of the affine change
 # sign (origin and direction), on the way out they change back.  The qform (quaternion) is preferred when its code is set,

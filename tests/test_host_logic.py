@@ -355,3 +355,87 @@ def test_image_tools_helpers(tmp_path):
     back = read_image(str(d / 'batch_1_mask.nii.gz'))
     assert back.to_numpy().dtype == np.int32 and np.array_equal(back.to_numpy(), masks[1, 0].numpy().astype(np.int32))
     assert np.allclose(back.GetSpacing(), (0.5, 0.6, 0.7), atol=1e-6) and np.allclose(back.GetOrigin(), (1.0, 2.0, 3.0), atol=1e-5)
+
+
+def _fake_engine(monkeypatch, log):
+    """segmentation() with the GPU parts replaced by host stand-ins: the case loop, list readers, sharding, I/O overlap and
+    file layout are the code under test"""
+    from segmentation3d.core import seg_infer
+    from segmentation3d.utils.attrdict import AttrDict
+
+    def load_models(model_folder, gpu_id=0):
+        cfg = AttrDict({'general': {'single_scale': 'fine'}, 'fine': {}, 'coarse': {}})
+        m = AttrDict()
+        dict.__setitem__(m, 'infer_cfg', cfg)
+        dict.__setitem__(m, 'fine_model', {'out_channels': 2})
+        dict.__setitem__(m, 'coarse_model', None)
+        return m
+
+    def segmentation_volume(model, cfg, image, bs, be, use_gpu):
+        a = image.to_numpy()
+        log.append(float(a.flat[0]))
+        p1 = (1.0 / (1.0 + np.exp(-a))).astype(np.float32)
+        probs = []
+        for p in (1.0 - p1, p1):
+            im = Image3d(p)
+            im.CopyInformation(image)
+            probs.append(im)
+        mask = Image3d((p1 > 0.5).astype(np.int8))
+        mask.CopyInformation(image)
+        return probs, mask
+    monkeypatch.setattr(seg_infer, 'load_models', load_models)
+    monkeypatch.setattr(seg_infer, 'segmentation_volume', segmentation_volume)
+    monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
+    return seg_infer
+
+
+def test_segmentation_case_loop_with_background_io(tmp_path, monkeypatch):
+    """core/seg_infer.py:353-493: the case loop writes the same files, in the same layout, whether reads / writes overlap
+    the computation (default) or run strictly in series (SEG3D_IO_THREADS=0); a missing case raises when it is reached,
+    after the earlier cases have been written completely."""
+    from segmentation3d.utils.image3d import read_image, write_image
+    log = []
+    seg_infer = _fake_engine(monkeypatch, log)
+    rng = np.random.default_rng(1)
+    lines = ['5']
+    for k in range(5):
+        a = rng.standard_normal((6, 8, 10)).astype(np.float32)
+        a.flat[0] = k
+        write_image(Image3d(a, (1.0, 1.0, 2.0), (k, 0.0, 0.0)), str(tmp_path / ('im%d.mha' % k)), True)
+        lines.append('case%d %s' % (k, tmp_path / ('im%d.mha' % k)))
+    with open(str(tmp_path / 'test.txt'), 'w') as f:
+        f.write('\n'.join(lines) + '\n')
+    outs = {}
+    for threads in ('2', '0'):
+        monkeypatch.setenv('SEG3D_IO_THREADS', threads)
+        del log[:]
+        out = tmp_path / ('out' + threads)
+        masks = seg_infer.segmentation(str(tmp_path / 'test.txt'), str(tmp_path), str(out), 'seg.mha', 0, True, True, True, True)
+        assert log == [0.0, 1.0, 2.0, 3.0, 4.0] and len(masks) == 5                  # cases in list order
+        assert sorted(os.listdir(out)) == ['case%d' % k for k in range(5)]
+        for k in range(5):
+            d = out / ('case%d' % k)
+            assert sorted(os.listdir(d)) == ['mean_prob_0.mha', 'mean_prob_1.mha', 'org.mha', 'seg.mha']
+            seg = read_image(str(d / 'seg.mha'))
+            assert seg.to_numpy().dtype == np.int8 and np.array_equal(seg.to_numpy(), masks[k].to_numpy())
+            assert np.allclose(seg.GetOrigin(), (k, 0.0, 0.0)) and np.allclose(seg.GetSpacing(), (1.0, 1.0, 2.0))
+            outs[(threads, k)] = {n: open(str(d / n), 'rb').read() for n in os.listdir(d)}
+    for k in range(5):
+        assert outs[('2', k)] == outs[('0', k)]                                     # byte-identical files
+    # a case that cannot be read: raised at its turn, earlier cases complete on disk
+    lines[3] = 'case2 %s' % (tmp_path / 'missing.mha')
+    with open(str(tmp_path / 'bad.txt'), 'w') as f:
+        f.write('\n'.join(lines) + '\n')
+    for threads in ('2', '0'):
+        monkeypatch.setenv('SEG3D_IO_THREADS', threads)
+        out = tmp_path / ('bad' + threads)
+        with pytest.raises(FileNotFoundError):
+            seg_infer.segmentation(str(tmp_path / 'bad.txt'), str(tmp_path), str(out), 'seg.mha', 0, False, True, False, False)
+        assert sorted(os.listdir(out)) == ['case0', 'case1']
+        assert read_image(str(out / 'case1' / 'seg.mha')).GetSize() == (10, 8, 6)
+    # torchrun-style case sharding goes through the same loop
+    monkeypatch.setenv('SEG3D_IO_THREADS', '2')
+    monkeypatch.setenv('WORLD_SIZE', '2'); monkeypatch.setenv('RANK', '1'); monkeypatch.setenv('LOCAL_RANK', '1')
+    del log[:]
+    seg_infer.segmentation(str(tmp_path / 'test.txt'), str(tmp_path), str(tmp_path / 'sh'), 'seg.mha', 0, False, True, False, False)
+    assert log == [1.0, 3.0] and sorted(os.listdir(tmp_path / 'sh')) == ['case1', 'case3']
