@@ -8,6 +8,7 @@ spacing (:179), linear crop of the image and nearest-neighbour crop of the mask 
 Like the reference's SimpleITK calls, the crop runs on the host inside DataLoader workers; images are read with the
 MetaImage reader of utils/image3d.py (SimpleITK formats when that package is installed).
 """
+import collections
 import os
 
 import numpy as np
@@ -46,6 +47,32 @@ def read_train_csv(imlist_file, mode='train'):
     raise ValueError('Unsupported mode type.')
 
 
+class _ImageCache(object):
+    """decoded volumes kept per (worker) process, least recently used first out, bounded in bytes.  The reference re-reads
+    and decompresses both files for every crop; the crops drawn are the same either way."""
+
+    def __init__(self, max_bytes):
+        self.max_bytes, self.bytes, self.items = max_bytes, 0, collections.OrderedDict()
+        self.hits = self.misses = 0
+
+    def get(self, path, dtype):
+        key = (path, np.dtype(dtype).str)
+        if key in self.items:
+            self.items.move_to_end(key)
+            self.hits += 1
+            return self.items[key]
+        self.misses += 1
+        img = read_image(path, dtype)
+        n = int(img.to_numpy().nbytes)
+        if n <= self.max_bytes:
+            self.items[key] = img
+            self.bytes += n
+            while self.bytes > self.max_bytes:
+                _, old = self.items.popitem(last=False)
+                self.bytes -= int(old.to_numpy().nbytes)
+        return img
+
+
 class SegmentationDataset(Dataset):
     def __init__(self, imlist_file, num_classes, spacing, crop_size, sampling_method, random_translation,
                  random_scale, interpolation, crop_normalizers):
@@ -71,6 +98,8 @@ class SegmentationDataset(Dataset):
         assert self.interpolation in ('LINEAR', 'NN'), 'interpolation must either be a LINEAR or NN'
         self.crop_normalizers = crop_normalizers
         assert isinstance(self.crop_normalizers, list), 'crop normalizers must be a list'
+        # SEG3D_DATASET_CACHE_MB: decoded volumes kept per process (0 = re-read every item like the reference)
+        self._cache = _ImageCache(int(float(os.environ.get('SEG3D_DATASET_CACHE_MB', '2048')) * (1 << 20)))
 
     def __len__(self):
         return len(self.im_list)
@@ -120,8 +149,8 @@ class SegmentationDataset(Dataset):
     def __getitem__(self, index):
         image_path, seg_path = self.im_list[index], self.seg_list[index]
         case_name = os.path.basename(os.path.dirname(image_path)) + '_' + os.path.basename(image_path)
-        images = [read_image(image_path, np.float32)]
-        seg = read_image(seg_path, np.float32)
+        images = [self._cache.get(image_path, np.float32)]
+        seg = self._cache.get(seg_path, np.float32)
         center, crop_spacing = self.sample_crop(index, seg)
         for idx in range(len(images)):
             images[idx] = crop_image(images[idx], center, self.crop_size, crop_spacing, self.interpolation)

@@ -175,16 +175,16 @@ def crop_image(image, cropping_center, cropping_size, cropping_spacing, interp_m
             lo.append(np.clip(f.astype(np.int64), 0, n_in[a] - 1))
             hi.append(np.clip(f.astype(np.int64) + 1, 0, n_in[a] - 1))
             w.append(coords[a] - f)
-        s64 = src.astype(np.float64)
-        wx, wy, wz = w[0][None, None, :], w[1][None, :, None], w[2][:, None, None]
-
-        def corner(zi, yi, xi):
-            return s64[np.ix_(zi, yi, xi)]
-        a00 = corner(lo[2], lo[1], lo[0]) * (1 - wx) + corner(lo[2], lo[1], hi[0]) * wx
-        a01 = corner(lo[2], hi[1], lo[0]) * (1 - wx) + corner(lo[2], hi[1], hi[0]) * wx
-        a10 = corner(hi[2], lo[1], lo[0]) * (1 - wx) + corner(hi[2], lo[1], hi[0]) * wx
-        a11 = corner(hi[2], hi[1], lo[0]) * (1 - wx) + corner(hi[2], hi[1], hi[0]) * wx
-        val = (a00 * (1 - wy) + a01 * wy) * (1 - wz) + (a10 * (1 - wy) + a11 * wy) * wz
+        # only the block of the volume the crop touches is converted to float64
+        base = [int(min(lo[a].min(), hi[a].min())) for a in range(3)]
+        top = [int(max(lo[a].max(), hi[a].max())) + 1 for a in range(3)]
+        s64 = src[base[2]:top[2], base[1]:top[1], base[0]:top[0]].astype(np.float64)
+        lo = [lo[a] - base[a] for a in range(3)]
+        hi = [hi[a] - base[a] for a in range(3)]
+        # trilinear = three 1-D interpolations (x, then y, then z): same weights, a third of the gathers
+        ax = s64[:, :, lo[0]] * (1.0 - w[0])[None, None, :] + s64[:, :, hi[0]] * w[0][None, None, :]
+        ay = ax[:, lo[1], :] * (1.0 - w[1])[None, :, None] + ax[:, hi[1], :] * w[1][None, :, None]
+        val = ay[lo[2]] * (1.0 - w[2])[:, None, None] + ay[hi[2]] * w[2][:, None, None]
     out = np.where(inside, val, 0).astype(src.dtype)
     return Image3d(out, spacing_c, origin_c, img.GetDirection())
 

@@ -439,3 +439,34 @@ def test_segmentation_case_loop_with_background_io(tmp_path, monkeypatch):
     del log[:]
     seg_infer.segmentation(str(tmp_path / 'test.txt'), str(tmp_path), str(tmp_path / 'sh'), 'seg.mha', 0, False, True, False, False)
     assert log == [1.0, 3.0] and sorted(os.listdir(tmp_path / 'sh')) == ['case1', 'case3']
+
+
+def test_dataset_volume_cache_changes_nothing_but_the_reads(tmp_path, monkeypatch):
+    """SEG3D_DATASET_CACHE_MB: decoded volumes are kept per process; items are identical with and without the cache, and
+    the byte bound evicts the least recently used volume."""
+    from segmentation3d.dataloader.dataset import SegmentationDataset
+    from segmentation3d.utils.image3d import write_image
+    lines = ['3']
+    for k, (im, lab, spacing, origin) in enumerate(_dataset_cases()):
+        d = tmp_path / ('case%d' % k)
+        os.makedirs(d)
+        write_image(Image3d(im, spacing, origin), str(d / 'im.mha'), True)
+        write_image(Image3d(lab, spacing, origin), str(d / 'seg.mha'), True)
+        lines += [str(d / 'im.mha'), str(d / 'seg.mha')]
+    with open(str(tmp_path / 'train.txt'), 'w') as f:
+        f.write('\n'.join(lines) + '\n')
+    items = {}
+    for mb in ('0', '2048', '0.8'):
+        monkeypatch.setenv('SEG3D_DATASET_CACHE_MB', mb)
+        ds = SegmentationDataset(str(tmp_path / 'train.txt'), 3, [1.0, 1.0, 1.0], [16, 16, 16], 'HYBRID', [3, 3, 3], [0.9, 1.1], 'LINEAR', [None])
+        np.random.seed(3)
+        items[mb] = [ds[i] for i in (0, 1, 0, 2, 1, 0)]
+        if mb == '0':
+            assert ds._cache.hits == 0 and ds._cache.misses == 12 and not ds._cache.items
+        elif mb == '2048':
+            assert ds._cache.misses == 6 and ds._cache.hits == 6
+        else:                                   # 0.8 MB holds two cases (four 0.17 MB volumes): case 1, then case 0, get evicted
+            assert 0 < ds._cache.bytes <= 0.8 * (1 << 20) and ds._cache.misses == 10 and ds._cache.hits == 2
+    for a, b, c in zip(items['0'], items['2048'], items['0.8']):
+        for other in (b, c):
+            assert torch.equal(a[0], other[0]) and torch.equal(a[1], other[1]) and np.array_equal(a[2], other[2]) and a[3] == other[3]
