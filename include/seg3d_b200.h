@@ -167,6 +167,14 @@ int seg3d_blend_finalize_argmax_z(float* acc, int C, int Z, int Y, int X, int z0
 int seg3d_resample(const float* src, int sz, int sy, int sx, float* dst, int dz, int dy, int dx,
                    double rz, double ry, double rx, int linear, float default_value, void* stream);
 
+/* crop with resampling (utils/image_tools.py:111-146, the training data loader's call): output index i reads the continuous
+ * input index o + i * r per axis (o = (crop origin - volume origin) in input voxels, r = crop spacing / volume spacing,
+ * axes of the crop = axes of the volume).  Same ITK semantics; both neighbours of the linear interpolation are clamped to
+ * the volume, so -0.5 <= c < 0 returns the edge value.  Not yet run on a GPU (added after round 1's GPU budget was spent). */
+int seg3d_crop_resample(const float* src, int sz, int sy, int sx, float* dst, int dz, int dy, int dx,
+                        double oz, double oy, double ox, double rz, double ry, double rx,
+                        int linear, float default_value, void* stream);
+
 /* ---- connected-component post-processing (utils/image_tools.py:380-432; 26-connectivity, one label per call) ------------
  * out[v] = label for the voxels of `label` that belong to the largest component (min_size == 0; ties: the component whose
  * first voxel comes first in raster order) or to any component with at least min_size voxels (min_size > 0).  out is

@@ -42,6 +42,8 @@ _SIGNATURES = {
     'seg3d_blend_finalize_argmax': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'seg3d_blend_finalize_argmax_z': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'seg3d_resample': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, ctypes.c_double, ctypes.c_double, ctypes.c_double, _i, _f, _vp]),
+    'seg3d_crop_resample': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                 ctypes.c_double, ctypes.c_double, ctypes.c_double, _i, _f, _vp]),
     'seg3d_cc_filter': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'seg3d_dice_terms': (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp]),
     'seg3d_dice_bwd': (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp, _vp]),

@@ -115,8 +115,13 @@ def train(train_config_file):
                                                  seed=train_cfg.general.seed)
     else:
         sampler = EpochConcateSampler(dataset, train_cfg.train.epochs)
-    data_loader = DataLoader(dataset, sampler=sampler, batch_size=train_cfg.train.batchsize,
-                             num_workers=train_cfg.train.num_threads, pin_memory=True)
+    if os.environ.get('SEG3D_DEVICE_CROPS', '0') == '1':
+        # opt-in: volumes resident in HBM, crops drawn by seg3d_crop_resample (dataloader/device_loader.py)
+        from segmentation3d.dataloader.device_loader import DeviceCropLoader
+        data_loader = DeviceCropLoader(dataset, sampler, train_cfg.train.batchsize, device='cuda:%d' % local)
+    else:
+        data_loader = DataLoader(dataset, sampler=sampler, batch_size=train_cfg.train.batchsize,
+                                 num_workers=train_cfg.train.num_threads, pin_memory=True)
 
     net_module = importlib.import_module('segmentation3d.network.' + train_cfg.net.name)
     net = net_module.SegmentationNet(dataset.num_modality(), train_cfg.dataset.num_classes)

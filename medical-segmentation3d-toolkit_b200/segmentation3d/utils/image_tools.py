@@ -156,6 +156,8 @@ def crop_image(image, cropping_center, cropping_size, cropping_spacing, interp_m
     if interp_method not in ('LINEAR', 'NN'):
         raise ValueError('Unsupported interpolation type.')
     img = as_image3d(image)
+    if img.is_cuda():
+        return crop_image_device(img, cropping_center, cropping_size, cropping_spacing, interp_method)
     src = img.to_numpy()
     origin_c, size, spacing_c = crop_geometry(cropping_center, cropping_size, cropping_spacing)
     d = np.asarray(img.GetDirection(), dtype=np.float64).reshape(3, 3)
@@ -253,6 +255,34 @@ def save_intermediate_results(idxs, crops, masks, outputs, frames, file_names, o
                 output = convert_tensor_to_image(outputs[i, cls].data, dtype=np.float32)
                 set_image_frame(output, frame)
                 write_image(output, os.path.join(case_out_folder, 'batch_{}_output_{}.nii.gz'.format(i, cls)))
+
+
+def crop_image_device(image, cropping_center, cropping_size, cropping_spacing, interp_method, out=None):
+    """crop_image for a volume resident on the GPU (seg3d_crop_resample): same geometry and ITK semantics as the host
+    version above; `out` (float32 CUDA tensor [z,y,x], e.g. one item of a batch buffer) receives the crop when given.
+    Not yet run on a GPU (added after round 1's GPU budget was spent); wiring pinned in tests/test_device_crops_wiring.py."""
+    from segmentation3d._b200 import lib
+    if interp_method not in ('LINEAR', 'NN'):
+        raise ValueError('Unsupported interpolation type.')
+    img = as_image3d(image)
+    if not img.is_cuda():
+        raise RuntimeError('crop_image_device needs a CUDA-resident image (crop_image handles host images)')
+    src = img.data
+    if src.dtype != torch.float32 or not src.is_contiguous():
+        src = src.float().contiguous()
+    origin_c, size, spacing_c = crop_geometry(cropping_center, cropping_size, cropping_spacing)
+    d = np.asarray(img.GetDirection(), dtype=np.float64).reshape(3, 3)
+    sp = np.asarray(img.GetSpacing(), dtype=np.float64)
+    off = np.linalg.solve(d, np.asarray(origin_c, dtype=np.float64) - np.asarray(img.GetOrigin(), dtype=np.float64)) / sp
+    if out is None:
+        out = torch.empty((size[2], size[1], size[0]), dtype=torch.float32, device=src.device)
+    assert out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (size[2], size[1], size[0])
+    Z, Y, X = src.shape
+    with torch.cuda.device(src.device):
+        lib.call('seg3d_crop_resample', lib.ptr(src), Z, Y, X, lib.ptr(out), size[2], size[1], size[0],
+                 float(off[2]), float(off[1]), float(off[0]), float(spacing_c[2] / sp[2]), float(spacing_c[1] / sp[1]),
+                 float(spacing_c[0] / sp[0]), 1 if interp_method == 'LINEAR' else 0, 0.0, lib.stream_ptr())
+    return Image3d(out, spacing_c, origin_c, img.GetDirection())
 
 
 def pick_largest_connected_component(mask, labels):

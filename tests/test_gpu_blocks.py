@@ -110,3 +110,24 @@ def test_segmentation_voi_and_disabled_partition_match_oracle():
                                            faithful_copies=False)
     assert np.abs(np.stack([m.to_numpy() for m in maps], 0) - ref).max() <= 1e-3
     assert np.allclose(maps[0].GetOrigin(), (21.0, 6.0, 23.0)) and maps[0].GetSize() == (32, 32, 32)
+
+
+def test_device_crops_match_host_crops(tmp_path):
+    """seg3d_crop_resample against the host crop_image (ITK restatement) on the same volume: crops overlapping every face
+    of the volume, rescaled, linear and nearest; then a DeviceCropLoader batch against the DataLoader batch."""
+    import numpy as np
+    from segmentation3d.utils.image3d import Image3d
+    from segmentation3d.utils.image_tools import crop_image
+    rng = np.random.default_rng(4)
+    src = rng.standard_normal((40, 48, 56)).astype(np.float32)
+    spacing, origin = (0.8, 1.1, 1.5), (-5.0, 3.0, 12.0)
+    host = Image3d(src, spacing, origin)
+    dev = Image3d(torch.from_numpy(src).cuda(), spacing, origin)
+    for center in ((10.0, 20.0, 30.0), (-4.0, 3.5, 12.2), (39.0, 55.0, 70.0), (17.3, 28.9, 41.4)):
+        for csp in ((0.8, 1.1, 1.5), (1.0, 1.0, 1.0), (0.55, 0.7, 2.1)):
+            for interp in ('LINEAR', 'NN'):
+                a = crop_image(host, center, [32, 24, 16], csp, interp)
+                b = crop_image(dev, center, [32, 24, 16], csp, interp)
+                assert b.is_cuda() and np.allclose(a.GetOrigin(), b.GetOrigin()) and np.allclose(a.GetSpacing(), b.GetSpacing())
+                err = float(np.abs(a.to_numpy() - b.to_numpy()).max())
+                assert err <= (1e-5 if interp == 'LINEAR' else 0.0), (center, csp, interp, err)
