@@ -232,8 +232,9 @@ def main():
     ap.add_argument('--patch', type=int, default=96)
     ap.add_argument('--stride', type=int, default=96)
     ap.add_argument('--shard', default='cases', choices=['cases', 'patches'])
-    ap.add_argument('--gather', default='mask', choices=['mask', 'probs'],
-                    help="--shard patches: 'mask' = reduce-scatter + slab finalize + all-gather of the int8 mask; 'probs' = all-reduce")
+    ap.add_argument('--gather', default='mask', choices=['mask', 'probs', 'labels'],
+                    help="--shard patches: 'mask' = reduce-scatter + slab finalize + all-gather of the int8 mask; 'probs' = all-reduce; "
+                         "'labels' = local arg-max + max all-reduce of the int8 mask when patches do not overlap (not yet verified on GPUs)")
     ap.add_argument('--ref-patches', type=int, default=4, help='patches in the bounded CPU sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--layers', action='store_true', help='print the per-kernel roofline table to stderr')

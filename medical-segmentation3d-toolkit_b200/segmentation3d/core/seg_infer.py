@@ -185,6 +185,12 @@ def _grid(model, cfg, size_xyz, spacing, bbox_start_voxel, bbox_end_voxel, use_g
     return image_partition_by_fixed_size(frame, bs, be, psize, pstride, model['max_stride'])
 
 
+def labels_can_merge_by_max(counts):
+    """patch-sharded inference may exchange labels instead of probability maps when no two patches overlap: every
+    per-axis overlap count is at most 1 (partition_stride >= partition_size, or a single patch)."""
+    return all(int(np.asarray(c).max()) <= 1 for c in counts)
+
+
 def segmentation_voi(model, iso_image, start_voxel, end_voxel, use_gpu):
     """Probability maps of one volume of interest [start_voxel, end_voxel) of an image already at the model spacing
     (reference :208-246): crop -> crop normaliser -> network -> one image per class carrying the VOI's frame.  The
@@ -272,7 +278,15 @@ def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_sta
     if shard is not None and shard[1] > 1:
         import torch.distributed as dist
         r, w = shard
-        if gather == 'mask' and Z % w == 0:
+        if gather == 'labels' and labels_can_merge_by_max(counts):
+            # every voxel belongs to exactly one patch, hence to one rank: arg-max locally (voxels of other ranks' patches
+            # hold all-zero probabilities -> label 0) and merge the int8 masks with a max all-reduce - 1 byte per voxel on
+            # the wire instead of 4*C.  The returned probabilities are this rank's patches only.
+            # (opt-in; added after round 1's GPU budget was spent: not yet run on several GPUs)
+            mask = eng.finalize(acc, counts)
+            dist.all_reduce(mask, op=dist.ReduceOp.MAX)
+            return acc, mask
+        if gather in ('mask', 'labels') and Z % w == 0:
             C, zs = acc.shape[0], Z // w
             send = acc.view(C, w, zs, Y, X).permute(1, 0, 2, 3, 4).contiguous()           # [world][C, zs, Y, X]
             slab = torch.empty((C, zs, Y, X), dtype=torch.float32, device=acc.device)

@@ -83,3 +83,43 @@ def test_two_rank_sharding_and_collectives():
         assert p.exitcode == 0
     for r in res:
         assert all(r[1:]), r
+
+
+def _labels_merge_worker(rank, world, port, q):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    # a 2 x 2 x 2 grid of non-overlapping 4^3 patches dealt rank::world; labels of the patches a rank did not run are 0
+    rng = np.random.default_rng(0)
+    full = rng.integers(0, 5, size=(8, 8, 8)).astype(np.int8)
+    starts = [[x, y, z] for x in (0, 4) for y in (0, 4) for z in (0, 4)]
+    local = np.zeros_like(full)
+    for s in starts[rank::world]:
+        local[s[2]:s[2] + 4, s[1]:s[1] + 4, s[0]:s[0] + 4] = full[s[2]:s[2] + 4, s[1]:s[1] + 4, s[0]:s[0] + 4]
+    t = torch.from_numpy(local)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    q.put((rank, bool(np.array_equal(t.numpy(), full))))
+    dist.destroy_process_group()
+
+
+def test_patch_sharded_labels_merge_by_max():
+    """gather='labels' (core/seg_infer.py::segmentation_volume_device): with non-overlapping patches every voxel is
+    labelled by exactly one rank, the others hold 0 there, so a max all-reduce of the int8 masks is the full mask."""
+    import multiprocessing as mp
+    from segmentation3d._b200.sliding import axis_counts
+    from segmentation3d.core.seg_infer import labels_can_merge_by_max
+    starts = [[x, y, z] for x in (0, 4) for y in (0, 4) for z in (0, 4)]
+    assert labels_can_merge_by_max(axis_counts([8, 8, 8], starts, [[s[0] + 4, s[1] + 4, s[2] + 4] for s in starts]))
+    starts = [[x, 0, 0] for x in (0, 2, 4)]
+    assert not labels_can_merge_by_max(axis_counts([8, 4, 4], starts, [[s[0] + 4, 4, 4] for s in starts]))   # stride 2 < size 4
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_labels_merge_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
