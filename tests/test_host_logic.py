@@ -470,3 +470,40 @@ def test_dataset_volume_cache_changes_nothing_but_the_reads(tmp_path, monkeypatc
     for a, b, c in zip(items['0'], items['2048'], items['0.8']):
         for other in (b, c):
             assert torch.equal(a[0], other[0]) and torch.equal(a[1], other[1]) and np.array_equal(a[2], other[2]) and a[3] == other[3]
+
+
+def test_trilinear_restatements_agree_with_scipy_map_coordinates():
+    """SimpleITK is absent, so the ITK restatements cannot be pinned against ITK itself; scipy.ndimage.map_coordinates
+    (order=1, mode='nearest' = both neighbours clamped) is an independent implementation of the same interpolation: the
+    oracle's resample_grid (inference side) and the product's crop_image (training side) must agree with it wherever the
+    continuous index is inside the volume, and write the default value elsewhere."""
+    from scipy import ndimage
+    from segmentation3d.utils.image_tools import crop_image
+    rng = np.random.default_rng(8)
+    src = rng.standard_normal((18, 22, 26)).astype(np.float32)
+    sp_in, sp_out, size = (0.9, 1.2, 2.0), (1.3, 0.7, 1.1), [20, 30, 28]
+    cz, cy, cx = [np.arange(size[a], dtype=np.float64) * (sp_out[a] / sp_in[a]) for a in (2, 1, 0)]
+    grid = np.meshgrid(cz, cy, cx, indexing='ij')
+    ref = ndimage.map_coordinates(src.astype(np.float64), grid, order=1, mode='nearest')
+    inside = (grid[0] < 18 - 0.5) & (grid[1] < 22 - 0.5) & (grid[2] < 26 - 0.5)
+    got = orz.resample_grid(src, sp_in, size, sp_out, 'LINEAR', -7.0)
+    assert np.abs(got[inside] - ref[inside]).max() <= 1e-5 and (got[~inside] == -7.0).all() and inside.mean() > 0.3
+    nn = orz.resample_grid(src, sp_in, size, sp_out, 'NN', 0.0)
+    ref_nn = src[np.floor(grid[0] + 0.5).astype(int).clip(0, 17), np.floor(grid[1] + 0.5).astype(int).clip(0, 21),
+                 np.floor(grid[2] + 0.5).astype(int).clip(0, 25)]
+    assert np.array_equal(nn[inside], ref_nn[inside])
+    # crop with an offset origin (continuous indices below 0 and beyond the far faces)
+    origin = (4.0, -3.0, 10.0)
+    img = Image3d(src, sp_in, origin)
+    csz, csp, center = [24, 20, 16], (0.8, 1.0, 1.7), (8.0, 20.0, 40.0)
+    out = crop_image(img, center, csz, csp, 'LINEAR').to_numpy()
+    o = [center[a] - csz[a] * csp[a] / 2.0 + csp[a] / 2.0 for a in range(3)]
+    c = [(o[a] - origin[a]) / sp_in[a] + np.arange(csz[a], dtype=np.float64) * (csp[a] / sp_in[a]) for a in range(3)]
+    grid = np.meshgrid(c[2], c[1], c[0], indexing='ij')
+    ref = ndimage.map_coordinates(src.astype(np.float64), grid, order=1, mode='nearest')
+    n_in = (18, 22, 26)
+    inside = np.ones(ref.shape, bool)
+    for a in range(3):
+        inside &= (grid[a] >= -0.5) & (grid[a] < n_in[a] - 0.5)
+    assert 0.2 < inside.mean() < 0.95
+    assert np.abs(out[inside] - ref[inside]).max() <= 1e-5 and (out[~inside] == 0).all()
