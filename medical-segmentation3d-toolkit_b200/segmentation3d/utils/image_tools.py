@@ -6,7 +6,6 @@ numpy (normalise :221-238, add_image_region/add_image_value :435-469, argmax) ru
 in this build (segmentation3d/_b200/sliding.py); the host versions below exist for API parity on
 small images and are not on the engine's path.
 """
-import math
 import os
 
 import numpy as np

@@ -7,7 +7,6 @@ import collections
 import os
 import re
 import subprocess
-import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'medical-segmentation3d-toolkit_b200', 'lib', 'libseg3d_b200.so')
