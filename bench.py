@@ -15,6 +15,9 @@ accumulators with an NCCL all-reduce (strong scaling).
 `--impl reference` times the reference's own CPU path (the oracle port of
 core/seg_infer.segmentation_volume: two forwards per patch, numpy blend with the reference's
 whole-volume copies) on the host cores, on a bounded sample of patches of the same workload.
+`--task train` is the secondary metric (BASELINE configs[2], patches/s); its line carries a
+`cpu_baseline` too (one oracle training step on one crop), and `--impl reference --task train`
+prints that CPU arm on its own.
 """
 import argparse
 import json
@@ -132,9 +135,44 @@ def cpu_reference_sample(size_xyz, patch, stride, n_patches, seed):
     return vox / dt / 1e6, dt, torch.get_num_threads(), total
 
 
+def cpu_train_sample(patch, batch, steps=1):
+    """Reference CPU training step (core/seg_train.py:119-127 through the oracle's autograd program: forward, Dice loss,
+    backward, Adam) on `batch` crops of patch^3.  Returns (patches/s, seconds, cores)."""
+    from oracle import init as oinit
+    from oracle import loss as oloss
+    from oracle import net as onet
+    sd = oinit.init_state_dict('vnet', 1, 2, 0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4, betas=(0.9, 0.999))
+    g = torch.Generator().manual_seed(0)
+    crops = torch.randn((batch, 1, patch, patch, patch), generator=g)
+    masks = torch.randint(0, 2, (batch, 1, patch, patch, patch), generator=g).float()
+    t0 = time.time()
+    for _ in range(steps):
+        opt.zero_grad()
+        loss = oloss.multi_dice_loss(onet.forward_with_grad(params, crops), masks, [0.5, 0.5])
+        loss.backward()
+        opt.step()
+    dt = time.time() - t0
+    return batch * steps / dt, dt, torch.get_num_threads()
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
+        return
+    if args.task == 'train':
+        vals = [cpu_train_sample(args.patch, 1) for _ in range(args.warmup + args.steps)][args.warmup:]
+        value, dt, cores = float(np.mean([v[0] for v in vals])), float(np.mean([v[1] for v in vals])), vals[0][2]
+        sample = '1 training step on 1 crop of %d^3 per timed step (forward, Dice, backward, Adam; fp32)' % args.patch
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'train patches/s (VNet, 96^3 patches, batch %d/GPU, Dice, Adam)' % args.train_batch,
+            'value': value, 'unit': 'patches/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'VNet(1,2) training step, crops [%d,1,%d^3] per GPU, MultiDiceLoss, Adam lr 1e-4 (BASELINE configs[2])'
+                                   % (args.train_batch, args.patch), 'mode': args.mode, 'parallelism': 'dp%d' % args.gpus},
+            'cpu_baseline': {'value': value, 'unit': 'patches/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
         return
     size = [int(v) for v in args.volume.split(',')]
     vals = []
@@ -207,8 +245,14 @@ def run_train(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, cores = cpu_train_sample(P, 1)
+        cpu = {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': 'port',
+               'sample': '1 training step on 1 crop of %d^3 (forward, Dice, backward, Adam; fp32), %.1f s' % (P, dt)}
     if rank == 0:
         print(json.dumps({
+            'cpu_baseline': cpu,
             'metric': 'train patches/s (VNet, 96^3 patches, batch %d/GPU, Dice, Adam)' % B, 'value': B * world / (ms * 1e-3),
             'unit': 'patches/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
