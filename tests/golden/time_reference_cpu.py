@@ -62,3 +62,32 @@ print('volume %d^3, %d patches of %d^3, %d threads' % (size, len(starts), patch,
 print('unmodified reference %.2f s, oracle port %.2f s, port / reference = %.3f' % (t_ref, t_port, t_port / t_ref))
 print('max |dp| port vs reference %.3g, masks equal %s' % (float(np.abs(p_ref - p_port).max()),
                                                             bool(np.array_equal(sitk.GetArrayFromImage(mask).astype(np.int8), m_port))))
+
+# ---- training step: unmodified reference modules vs the oracle port bench.py --task train times ---------------------------
+from segmentation3d.loss.multi_dice_loss import MultiDiceLoss          # noqa: E402
+from oracle import loss as oloss                                       # noqa: E402
+from oracle import net as onet                                         # noqa: E402
+g = torch.Generator().manual_seed(0)
+crops = torch.randn((1, 1, patch, patch, patch), generator=g)
+masks = torch.randint(0, 2, (1, 1, patch, patch, patch), generator=g).float()
+net = ref_vnet.SegmentationNet(1, 2)
+net.load_state_dict(sd)
+net.train()
+opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.999))
+lf = MultiDiceLoss([0.5, 0.5], 2, False)
+t0 = time.time()
+opt.zero_grad()
+loss_ref = lf(net(crops), masks)
+loss_ref.backward()
+opt.step()
+t_ref = time.time() - t0
+params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+opt = torch.optim.Adam(list(params.values()), lr=1e-4, betas=(0.9, 0.999))
+t0 = time.time()
+opt.zero_grad()
+loss_port = oloss.multi_dice_loss(onet.forward_with_grad(params, crops), masks, [0.5, 0.5])
+loss_port.backward()
+opt.step()
+t_port = time.time() - t0
+print('training step on one %d^3 crop: unmodified reference %.2f s (loss %.7f), oracle port %.2f s (loss %.7f), port / reference = %.3f'
+      % (patch, t_ref, float(loss_ref), t_port, float(loss_port), t_port / t_ref))
