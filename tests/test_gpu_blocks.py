@@ -131,3 +131,48 @@ def test_device_crops_match_host_crops(tmp_path):
                 assert b.is_cuda() and np.allclose(a.GetOrigin(), b.GetOrigin()) and np.allclose(a.GetSpacing(), b.GetSpacing())
                 err = float(np.abs(a.to_numpy() - b.to_numpy()).max())
                 assert err <= (1e-5 if interp == 'LINEAR' else 0.0), (center, csp, interp, err)
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-3), ('fp16', 1e-2)])
+def test_baseline_config0_single_patch_cli_flow(tmp_path, monkeypatch, mode, tol):
+    """BASELINE.json configs[0] literally: VNet random-init (seed 0, kaiming), checkpoint written by save_checkpoint into
+    <model>/fine/checkpoints/chk_1/params.pth, infer_config with single_scale='fine' and partition_type='DISABLE', one
+    synthetic 1x1x96^3 .mha patch through `segmentation()` - against the oracle on the same weights and volume."""
+    import numpy as np
+    from oracle import init as oinit
+    from oracle import sliding_window as osw
+    from oracle.metrics import parity_report
+    from segmentation3d.core.seg_infer import segmentation
+    from segmentation3d.network import vnet
+    from segmentation3d.utils.attrdict import AttrDict
+    from segmentation3d.utils.image3d import Image3d, read_image, write_image
+    from segmentation3d.utils.model_io import save_checkpoint
+    from segmentation3d.utils.normalizer import FixedNormalizer
+    monkeypatch.setenv('SEG3D_MODE', mode)
+    torch.manual_seed(0)
+    net = vnet.SegmentationNet(1, 2)
+    vnet.parameters_kaiming_init(net)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    assert all(torch.equal(sd[k], v) for k, v in oinit.init_state_dict('vnet', 1, 2, 0).items())
+    model_dir = tmp_path / 'model'
+    cfg = AttrDict({'general': {'save_dir': str(model_dir), 'model_scale': 'fine'}, 'net': {'name': 'vnet'},
+                    'dataset': {'spacing': [1.0, 1.0, 1.0], 'interpolation': 'LINEAR', 'num_classes': 2,
+                                'crop_normalizers': [FixedNormalizer(0.0, 1.0, False)]}})
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    save_checkpoint(net, opt, 1, 1, cfg, 16, 1)
+    with open(str(model_dir / 'infer_config.py'), 'w') as f:
+        f.write("from easydict import EasyDict as edict\n__C = edict()\ncfg = __C\n__C.general = {}\n__C.general.single_scale = 'fine'\n"
+                "__C.fine = {}\n__C.fine.model_name = 'fine'\n__C.fine.pick_largest_cc = False\n__C.fine.remove_small_cc = 0\n"
+                "__C.fine.partition_type = 'DISABLE'\n__C.fine.partition_size = [96, 96, 96]\n__C.fine.partition_stride = [96, 96, 96]\n"
+                "__C.fine.cpu_model_spacing_increase_ratio = 1.0\n__C.fine.cpu_partition_decrease_ratio = 1.0\n")
+    vol = torch.randn((96, 96, 96), generator=torch.Generator().manual_seed(9)).numpy().astype(np.float32)
+    write_image(Image3d(vol), str(tmp_path / 'patch.mha'), False)
+    out = tmp_path / 'out'
+    masks = segmentation(str(tmp_path / 'patch.mha'), str(model_dir), str(out), 'seg.mha', 0, True, True, False, True)
+    probs, mask, _, _ = osw.segmentation_volume(sd, vol, [1.0, 1.0, 1.0], {'type': 0, 'mean': 0.0, 'stddev': 1.0, 'clip': False},
+                                                'DISABLE', double_forward=False, faithful_copies=False)
+    got = np.stack([read_image(str(out / 'patch.mha' / ('mean_prob_%d.mha' % c))).to_numpy() for c in range(2)], 0)
+    rep = parity_report(probs, got)
+    print('configs[0]', mode, rep)
+    assert rep['max_abs'] <= tol and rep['agree'] >= 0.999 and min(rep['dice']) >= 0.999
+    assert np.array_equal(read_image(str(out / 'patch.mha' / 'seg.mha')).to_numpy(), masks[0].to_numpy())
