@@ -171,11 +171,13 @@ def write_image(image, path, compress=False):
 # ---- host-side I/O overlap for batch inference: the next case is read (and decompressed) while the current one is on the GPU,
 # and results are compressed and written in the background (zlib releases the GIL) --------------------------------------------
 def io_threads():
-    """worker threads for background image I/O; SEG3D_IO_THREADS=0 restores strictly serial reads and writes"""
+    """worker threads for background image I/O (default: a quarter of the host cores, between 4 and 8);
+    SEG3D_IO_THREADS=0 restores strictly serial reads and writes"""
+    default = min(8, max(4, (os.cpu_count() or 4) // 4))
     try:
-        return max(0, int(os.environ.get('SEG3D_IO_THREADS', '4')))
+        return max(0, int(os.environ.get('SEG3D_IO_THREADS', default)))
     except ValueError:
-        return 4
+        return default
 
 
 def prefetch_images(paths, dtype=None, enabled=True, depth=None):
