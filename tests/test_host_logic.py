@@ -507,3 +507,37 @@ def test_trilinear_restatements_agree_with_scipy_map_coordinates():
         inside &= (grid[a] >= -0.5) & (grid[a] < n_in[a] - 0.5)
     assert 0.2 < inside.mean() < 0.95
     assert np.abs(out[inside] - ref[inside]).max() <= 1e-5 and (out[~inside] == 0).all()
+
+
+def test_patch_grid_equals_oracle_on_random_configurations():
+    """image_partition_by_fixed_size (utils/image_tools.py:163-218) against the oracle's restatement (itself pinned to 14
+    reference grids) on 400 random volumes / spacings / boxes / partition sizes and strides, in-place bbox update included."""
+    from oracle import sliding_window as osw
+    from segmentation3d.utils.image_tools import image_partition_by_fixed_size
+    rng = np.random.default_rng(2024)
+    checked = 0
+    for _ in range(400):
+        size = [int(16 * rng.integers(1, 12)) for _ in range(3)]
+        spacing = [float(rng.choice([0.4, 0.5, 0.8, 1.0, 1.25, 2.0])) for _ in range(3)]
+        if rng.random() < 0.5:
+            bs, be = [0, 0, 0], list(size)
+        else:
+            bs = [int(rng.integers(0, size[a] - 1)) for a in range(3)]
+            be = [int(rng.integers(bs[a] + 1, size[a] + 1)) for a in range(3)]
+        psize = [float(rng.choice([16, 24, 32, 48, 64, 96, 51.2, 89.6])) for _ in range(3)]
+        pstride = [float(max(4.0, psize[a] * rng.choice([0.25, 0.5, 0.75, 1.0, 1.5]))) for a in range(3)]
+        im = Image3d(np.zeros((1, 1, 1), np.float32), spacing)
+        im.GetSize = lambda s=tuple(size): s
+        b1, e1, b2, e2 = list(bs), list(be), list(bs), list(be)
+        try:
+            ref = osw.partition_grid(size, spacing, b2, e2, list(psize), list(pstride), 16)
+        except AssertionError:
+            with pytest.raises(AssertionError):
+                image_partition_by_fixed_size(im, b1, e1, list(psize), list(pstride), 16)
+            continue
+        got = image_partition_by_fixed_size(im, b1, e1, list(psize), list(pstride), 16)
+        assert [list(map(int, s)) for s in got[0]] == [list(map(int, s)) for s in ref[0]]
+        assert [list(map(int, s)) for s in got[1]] == [list(map(int, s)) for s in ref[1]]
+        assert b1 == b2 and e1 == e2
+        checked += 1
+    assert checked > 300
