@@ -353,7 +353,7 @@ def main():
         sampler.start()
     ms_dev, launches = timed(step_device, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _ = timed(step_host, max(2, args.steps // 2), 1)
+    ms_e2e, _ = timed(step_host, max(2, args.steps // 2), 3)
 
     units = nvox * (world if args.shard == 'cases' else 1)
     value = units / (ms_dev * 1e-3) / 1e6
