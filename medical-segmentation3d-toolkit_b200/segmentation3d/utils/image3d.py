@@ -20,6 +20,28 @@ _MET = {'MET_CHAR': np.int8, 'MET_UCHAR': np.uint8, 'MET_SHORT': np.int16, 'MET_
 _MET_INV = {np.dtype(v): k for k, v in _MET.items()}
 
 
+def zlib_compress(payload, level=1, chunk=4 << 20, threads=None):
+    """One valid zlib stream for `payload`.  Large buffers are deflated in independent chunks on worker threads (zlib
+    releases the GIL): every chunk is a raw deflate stream ended by a sync flush, so the pieces concatenate on byte
+    boundaries; the 2-byte zlib header goes in front and the Adler-32 of the whole buffer behind (the pigz construction).
+    Any inflater - ITK's MetaImage reader included - reads it as an ordinary stream."""
+    threads = io_threads() if threads is None else threads
+    if threads < 2 or len(payload) < 2 * chunk:
+        return zlib.compress(payload, level)
+    from concurrent.futures import ThreadPoolExecutor
+    view = memoryview(payload)
+    pieces = [view[i:i + chunk] for i in range(0, len(view), chunk)]
+
+    def deflate(args):
+        i, piece = args
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        return c.compress(piece) + c.flush(zlib.Z_FINISH if i == len(pieces) - 1 else zlib.Z_SYNC_FLUSH)
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        parts = list(pool.map(deflate, enumerate(pieces)))
+    header = b'\x78\x01'                                    # CMF = deflate / 32 KB window, FLG = fastest, check bits
+    return header + b''.join(parts) + struct.pack('>I', zlib.adler32(payload) & 0xffffffff)
+
+
 class Image3d(object):
     def __init__(self, data, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0),
                  direction=(1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)):
@@ -149,7 +171,7 @@ def write_image(image, path, compress=False):
         raise ValueError('only .mha / .nii / .nii.gz can be written without SimpleITK: %s' % path)
     payload = arr.tobytes()
     if compress:
-        payload = zlib.compress(payload, 1)
+        payload = zlib_compress(payload, 1)
     x, y, z = image.GetSize()
     tm = np.asarray(image.direction).reshape(3, 3).T.reshape(-1)
     lines = ['ObjectType = Image', 'NDims = 3', 'BinaryData = True', 'BinaryDataByteOrderMSB = False',

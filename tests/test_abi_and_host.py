@@ -268,3 +268,22 @@ def test_nifti_roundtrip_and_hand_built_header(tmp_path):
     from segmentation3d.core.seg_infer import read_test_folder
     names, paths = read_test_folder(str(tmp_path))
     assert 'h.nii.gz' in names and 'a.nii' in names
+
+
+def test_parallel_zlib_stream_is_a_plain_zlib_stream(tmp_path):
+    """utils/image3d.py::zlib_compress: chunks deflated on worker threads concatenate into one valid zlib stream (header,
+    sync-flushed raw deflate pieces, Adler-32 of the whole buffer) that zlib.decompress - hence any MetaImage reader - inflates."""
+    import zlib
+    from segmentation3d.utils.image3d import Image3d, read_image, write_image, zlib_compress
+    rng = np.random.default_rng(0)
+    data = (rng.integers(0, 4, size=3_000_001) * (rng.random(3_000_001) < 0.3)).astype(np.int8).tobytes()
+    for chunk, threads in ((1 << 20, 4), (700_001, 3), (1 << 20, 1), (8 << 20, 4)):
+        blob = zlib_compress(data, 1, chunk=chunk, threads=threads)
+        assert zlib.decompress(blob) == data
+        d = zlib.decompressobj()
+        assert d.decompress(blob) == data and d.eof and d.unused_data == b''          # exactly one stream, checksum verified
+    assert zlib_compress(b'', 1, chunk=16, threads=4) == zlib.compress(b'', 1)
+    arr = rng.standard_normal((40, 300, 300)).astype(np.float32)                          # 14 MB: takes the chunked path
+    write_image(Image3d(arr, (0.5, 0.5, 2.0)), str(tmp_path / 'big.mha'), True)
+    back = read_image(str(tmp_path / 'big.mha'))
+    assert np.array_equal(back.to_numpy(), arr) and np.allclose(back.GetSpacing(), (0.5, 0.5, 2.0))
