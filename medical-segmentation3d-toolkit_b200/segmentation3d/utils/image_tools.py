@@ -224,9 +224,14 @@ def get_bounding_box(mask, selected_labels):
     if not bool(sel.any()):
         print('Fail to get the bounding box.')
         return None, None
-    nz = sel.nonzero()
-    lo, hi = nz.min(0)[0].tolist(), nz.max(0)[0].tolist()
-    return [lo[2], lo[1], lo[0]], [hi[2] + 1, hi[1] + 1, hi[0] + 1]
+    # per-axis occupancy (three small reductions) instead of materialising the coordinates of every selected voxel
+    lo, hi = [], []
+    for axis in (2, 1, 0):                                      # x, y, z
+        other = tuple(a for a in range(3) if a != axis)
+        idx = sel.any(dim=other[1]).any(dim=other[0]).nonzero().flatten()
+        lo.append(int(idx[0]))
+        hi.append(int(idx[-1]) + 1)
+    return lo, hi
 
 
 def save_intermediate_results(idxs, crops, masks, outputs, frames, file_names, out_folder):
