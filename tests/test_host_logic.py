@@ -541,3 +541,40 @@ def test_patch_grid_equals_oracle_on_random_configurations():
         assert b1 == b2 and e1 == e2
         checked += 1
     assert checked > 300
+
+
+def test_async_writer_and_prefetch_surface_errors(tmp_path):
+    """utils/image3d.py: a failed background write is raised by close() after every other file has been written; a failed
+    read is raised when its own case is reached; both helpers degrade to serial calls with zero threads."""
+    from segmentation3d.utils.image3d import AsyncImageWriter, prefetch_images, read_image, write_image
+    a = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
+    for threads in (0, 3):
+        w = AsyncImageWriter(threads)
+        w.write(Image3d(a), str(tmp_path / ('ok%d_0.mha' % threads)), True)
+        if threads:
+            w.write(Image3d(a), str(tmp_path / 'x.tiff'), True)                  # unsupported extension -> ValueError in the worker
+        else:
+            with pytest.raises(ValueError):
+                w.write(Image3d(a), str(tmp_path / 'x.tiff'), True)
+        w.write(Image3d(a + 1), str(tmp_path / ('ok%d_1.mha' % threads)), False)
+        if threads:
+            with pytest.raises(ValueError):
+                w.close()
+        else:
+            w.close()
+        assert np.array_equal(read_image(str(tmp_path / ('ok%d_0.mha' % threads))).to_numpy(), a)
+        assert np.array_equal(read_image(str(tmp_path / ('ok%d_1.mha' % threads))).to_numpy(), a + 1)
+        w.close()                                                                 # idempotent
+    paths = []
+    for k in range(4):
+        write_image(Image3d(a + k), str(tmp_path / ('p%d.mha' % k)))
+        paths.append(str(tmp_path / ('p%d.mha' % k)))
+    paths.insert(2, str(tmp_path / 'nope.mha'))
+    for enabled, depth in ((True, 3), (True, 1), (False, 3)):
+        seen = []
+        with pytest.raises(FileNotFoundError):
+            for img, waited in prefetch_images(paths, np.float32, enabled=enabled, depth=depth):
+                seen.append(float(img.to_numpy().flat[0]))
+                assert waited >= 0.0
+        assert seen == [0.0, 1.0]
+    assert [float(i.to_numpy().flat[0]) for i, _ in prefetch_images(paths[:2] + paths[3:], np.float32, depth=2)] == [0.0, 1.0, 2.0, 3.0]
