@@ -578,3 +578,42 @@ def test_async_writer_and_prefetch_surface_errors(tmp_path):
                 assert waited >= 0.0
         assert seen == [0.0, 1.0]
     assert [float(i.to_numpy().flat[0]) for i, _ in prefetch_images(paths[:2] + paths[3:], np.float32, depth=2)] == [0.0, 1.0, 2.0, 3.0]
+
+
+def test_segmentation_cascade_orchestration(tmp_path, monkeypatch, capsys):
+    """core/seg_infer.py:428-444 (single_scale = 'DISABLE'): the coarse model sees the whole image, the bounding box of its
+    mask (all non-zero labels, end exclusive) is handed to the fine model, whose result is what gets written."""
+    from segmentation3d.core import seg_infer
+    from segmentation3d.utils.attrdict import AttrDict
+    from segmentation3d.utils.image3d import read_image, write_image
+    seen = []
+
+    def load_models(model_folder, gpu_id=0):
+        m = AttrDict()
+        dict.__setitem__(m, 'infer_cfg', AttrDict({'general': {'single_scale': 'DISABLE'}, 'fine': {'tag': 'fine'}, 'coarse': {'tag': 'coarse'}}))
+        dict.__setitem__(m, 'fine_model', {'out_channels': 2, 'tag': 'fine'})
+        dict.__setitem__(m, 'coarse_model', {'out_channels': 2, 'tag': 'coarse'})
+        return m
+
+    def segmentation_volume(model, cfg, image, bs, be, use_gpu):
+        seen.append((model['tag'], cfg['tag'], bs, be))
+        a = image.to_numpy()
+        lab = np.zeros(a.shape, np.int8)
+        if model['tag'] == 'coarse':
+            lab[3:7, 2:9, 5:11] = 1
+            lab[4, 4, 12] = 2
+        else:
+            lab[bs[2]:be[2], bs[1]:be[1], bs[0]:be[0]] = 1
+        probs = [Image3d((lab == c).astype(np.float32)) for c in range(2)]
+        mask = Image3d(lab)
+        mask.CopyInformation(image)
+        return probs, mask
+    monkeypatch.setattr(seg_infer, 'load_models', load_models)
+    monkeypatch.setattr(seg_infer, 'segmentation_volume', segmentation_volume)
+    monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
+    write_image(Image3d(np.zeros((10, 12, 16), np.float32)), str(tmp_path / 'im.mha'))
+    masks = seg_infer.segmentation(str(tmp_path / 'im.mha'), str(tmp_path), str(tmp_path / 'out'), 'seg.mha', 1, True, True, False, False)
+    assert seen == [('coarse', 'coarse', None, None), ('fine', 'fine', [5, 2, 3], [13, 9, 7])]
+    out = read_image(str(tmp_path / 'out' / 'im.mha' / 'seg.mha')).to_numpy()
+    assert out.sum() == 8 * 7 * 4 and np.array_equal(out, masks[0].to_numpy())
+    assert 'Fine segmentation (bbox ratio: %.2f%%)' % (100 * (8 / 16) * (7 / 12) * (4 / 10)) in capsys.readouterr().out
