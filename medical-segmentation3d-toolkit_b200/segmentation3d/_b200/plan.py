@@ -24,6 +24,13 @@ MODES = {'fp32': lib.F32, 'fp16': lib.F16, 'bf16': lib.BF16, 'fp32x': lib.F16}
 GN_EPS = 1e-5
 
 
+def _require_cuda(device, message):
+    """The product runs on CUDA devices only.  A function of its own so that the host-wiring tests of the CPU gate
+    (tests/test_plan_wiring.py: C-ABI calls emulated, CPU tensors) can stub it; nothing in the package does."""
+    if device.type != 'cuda':
+        raise RuntimeError(message)
+
+
 def detect_arch(sd):
     return 'vbnet' if any('.conv1.conv.weight' in k for k in sd) else 'vnet'
 
@@ -157,8 +164,7 @@ class NetPlan(object):
         self.in_dt = lib.F32 if self.split else self.dt      # storage type of the network input (patch gather output)
         self.tdtype = lib.TORCH_DTYPE[self.dt]
         self.device = torch.device(device if device is not None else 'cuda')
-        if self.device.type != 'cuda':
-            raise RuntimeError('seg3d_b200 runs on CUDA devices only (no CPU fallback)')
+        _require_cuda(self.device, 'seg3d_b200 runs on CUDA devices only (no CPU fallback)')
         sd = strip_prefix(state_dict)
         self._last_sd = sd
         self.arch = arch or detect_arch(sd)
@@ -520,8 +526,7 @@ class NetPlan(object):
 
     def forward(self, x):
         """probabilities [B,C,D,H,W] float32 (a view of the plan's output buffer; clone to keep)."""
-        if not x.is_cuda:
-            raise RuntimeError('seg3d_b200: input must be a CUDA tensor (no CPU fallback)')
+        _require_cuda(x.device, 'seg3d_b200: input must be a CUDA tensor (no CPU fallback)')
         B, Cin, D, H, W = x.shape
         assert Cin == self.in_channels
         ws, ops = self.plan(B, D, H, W)

@@ -1,0 +1,219 @@
+"""CPU check of the HOST WIRING of the whole-network kernel plan (segmentation3d/_b200/plan.py) against the oracle.
+
+Every C-ABI entry point the forward plan issues is replaced by a torch emulation of its documented semantics
+(include/seg3d_b200.h: NDHWC pitches and channel offsets, packed weight layouts of every convolution flavour, GroupNorm
+sums, in-place concat, residual / ReLU flags, the folded narrow-output layout and its fused GroupNorm input, the split
+hi/lo format of the strict mode), "device" tensors are CPU tensors and the plan's CUDA-only guard is stubbed.  What runs
+for real is the plan: buffer allocation, views and offsets, weight packing, the order of ~60 calls per forward, for VNet and
+VBNet in every execution mode.  A host-side regression in the plan then fails the CPU gate; the kernels themselves are
+pinned by the `-m gpu` tests."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import init as oinit
+from oracle import net as onet
+
+
+class _P(object):
+    def __init__(self, t, off):
+        self.t, self.off = t, off
+
+
+def _rows(p, n_rows, ld, C):
+    """[n_rows, C] view of the flat buffer behind pointer p (element offset p.off, pitch ld)"""
+    flat = p.t.reshape(-1)
+    assert p.off + (n_rows - 1) * ld + C <= flat.numel(), 'kernel argument runs past its buffer'
+    return torch.as_strided(flat, (n_rows, C), (ld, 1), p.off)
+
+
+def _stats(y):
+    return y.double().flatten(1).sum(1), (y.double() ** 2).flatten(1).sum(1)
+
+
+def _mean_rstd(stats, cnt, eps, N):
+    mean = (stats.t.reshape(-1, 2)[:N, 0] / cnt).view(N, 1, 1)
+    var = (stats.t.reshape(-1, 2)[:N, 1] / cnt).view(N, 1, 1) - mean * mean
+    return mean, 1.0 / torch.sqrt(var + eps)
+
+
+def _install(monkeypatch, calls):
+    from segmentation3d._b200 import lib, plan
+
+    def ptr(t, off=0):
+        return None if t is None else _P(t, off)
+
+    def _conv(mode, simt, xs, w, bias, Cin, Cout):
+        wp = w.t.float().reshape(-1)
+        k = {lib.CONV_K3: 3, lib.CONV_K2S2: 2, lib.CONV_T2S2: 2, lib.CONV_K1: 1}[mode]
+        b = None if bias is None else bias.t.float()[:Cout]
+        if mode == lib.CONV_T2S2:
+            wt = wp[:Cin * 8 * Cout].view(Cin, 2, 2, 2, Cout) if simt else wp[:8 * Cout * Cin].view(2, 2, 2, Cout, Cin).permute(4, 0, 1, 2, 3)
+            return F.conv_transpose3d(xs, wt.permute(0, 4, 1, 2, 3), b, stride=2)
+        n = k ** 3 * Cin * Cout
+        wt = wp[:n].view(k, k, k, Cin, Cout).permute(4, 3, 0, 1, 2) if simt else wp[:n].view(k, k, k, Cout, Cin).permute(3, 4, 0, 1, 2)
+        return F.conv3d(xs, wt, b, stride=2 if mode == lib.CONV_K2S2 else 1, padding=1 if mode == lib.CONV_K3 else 0)
+
+    def _store(r, y, y_ld, C, stats, N):
+        if stats is not None:
+            s0, s1 = _stats(r)
+            st = stats.t.reshape(-1, 2)
+            st[:N, 0] += s0
+            st[:N, 1] += s1
+        rn = r.permute(0, 2, 3, 4, 1).reshape(-1, r.shape[1])
+        dst = _rows(y, rn.shape[0], y_ld, C)
+        dst.copy_(rn[:, :C].to(dst.dtype))
+
+    def conv3d_fwd(mode, dtype, impl, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, stats, stream):
+        out_f32 = bool(dtype & lib.OUT_F32)
+        xs = _rows(x, N * D * H * W, x_ld, Cin).float().view(N, D, H, W, Cin).permute(0, 4, 1, 2, 3)
+        simt = impl == lib.IMPL_SIMT or (impl == lib.IMPL_AUTO and Cin == 1)
+        r = _conv(mode, simt, xs, w, bias, Cin, Cout)
+        if out_f32:
+            assert y.t.dtype == torch.float32
+        _store(r, y, y_ld, min(Cout, y_ld) if out_f32 else Cout, stats, N)
+        calls.append('conv')
+        return 0
+
+    def narrow_np(Cout):
+        return (9 * Cout + 15) // 16 * 16
+
+    def _narrow(xs, w, bias, Cin, Cout):
+        NP = narrow_np(Cout)
+        wf = w.t.float().view(3, NP, Cin)[:, :9 * Cout].view(3, 3, 3, Cout, Cin)            # [kd][kh][kw][co][ci]
+        return F.conv3d(xs, wf.permute(3, 4, 0, 1, 2), bias.t.float()[:Cout], padding=1)
+
+    def narrow_fwd(dtype, x, x_ld, Cin, w, bias, y, Cout, N, D, H, W, stats, stream):
+        xs = _rows(x, N * D * H * W, x_ld, Cin).float().view(N, D, H, W, Cin).permute(0, 4, 1, 2, 3)
+        _store(_narrow(xs, w, bias, Cin, Cout), y, Cout, Cout, stats, N)
+        calls.append('narrow')
+        return 0
+
+    def narrow_gn_fwd(dtype, raw, raw_ld, res, res_ld, Cin, gn_stats, gamma, beta, eps, w, bias, y, Cout, N, D, H, W, stats, stream):
+        nvox = D * H * W
+        r = _rows(raw, N * nvox, raw_ld, Cin).float().view(N, nvox, Cin)
+        mean, rstd = _mean_rstd(gn_stats, float(nvox * Cin), eps, N)
+        z = ((r.double() - mean) * rstd).float() * gamma.t.view(1, 1, Cin) + beta.t.view(1, 1, Cin)
+        z = F.relu(z + _rows(res, N * nvox, res_ld, Cin).float().view(N, nvox, Cin)).to(raw.t.dtype).float()   # stored type in smem
+        xs = z.view(N, D, H, W, Cin).permute(0, 4, 1, 2, 3)
+        _store(_narrow(xs, w, bias, Cin, Cout), y, Cout, Cout, stats, N)
+        calls.append('narrow_gn')
+        return 0
+
+    def gn_apply(dtype, y, y_ld, C, stats, gamma, beta, eps, res, res_ld, out, out_ld, relu, N, nvox, stream):
+        ys = _rows(y, N * nvox, y_ld, C).float().view(N, nvox, C)
+        mean, rstd = _mean_rstd(stats, float(nvox * C), eps, N)
+        z = ((ys.double() - mean) * rstd).float() * gamma.t.view(1, 1, C) + beta.t.view(1, 1, C)
+        if res is not None:
+            z = z + _rows(res, N * nvox, res_ld, C).float().view(N, nvox, C)
+        if relu:
+            z = F.relu(z)
+        dst = _rows(out, N * nvox, out_ld, C)
+        dst.copy_(z.reshape(-1, C).to(dst.dtype))
+        calls.append('gn')
+        return 0
+
+    def split_fwd(mode, x, x_ld, lo_off, Cin, w, bias, y, y_ld, Cout, N, D, H, W, stats, stream):
+        rows = N * D * H * W
+        xs = (_rows(x, rows, x_ld, Cin).float() + _rows(_P(x.t, x.off + lo_off), rows, x_ld, Cin).float())
+        xs = xs.view(N, D, H, W, Cin).permute(0, 4, 1, 2, 3)
+        wq = w.t.float()                                                              # [..][Cout][whi(Cin) | wlo(Cin)]
+        wsum = _P((wq[..., :Cin] + wq[..., Cin:]).contiguous(), 0)
+        _store(_conv(mode, False, xs, wsum, bias, Cin, Cout), y, y_ld, Cout, stats, N)
+        calls.append('split_conv')
+        return 0
+
+    def gn_apply_split(y, y_ld, C, stats, gamma, beta, eps, res, res_ld, res_lo, out, out_ld, out_lo, relu, N, nvox, stream):
+        ys = _rows(y, N * nvox, y_ld, C).float().view(N, nvox, C)
+        mean, rstd = _mean_rstd(stats, float(nvox * C), eps, N)
+        z = ((ys.double() - mean) * rstd).float() * gamma.t.view(1, 1, C) + beta.t.view(1, 1, C)
+        if res is not None:
+            z = z + (_rows(res, N * nvox, res_ld, C).float() + _rows(_P(res.t, res.off + res_lo), N * nvox, res_ld, C).float()).view(N, nvox, C)
+        if relu:
+            z = F.relu(z)
+        z = z.reshape(-1, C)
+        hi = z.half()
+        _rows(out, N * nvox, out_ld, C).copy_(hi)
+        _rows(_P(out.t, out.off + out_lo), N * nvox, out_ld, C).copy_((z - hi.float()).half())
+        calls.append('gn_split')
+        return 0
+
+    def _tail(y1, ld, C, stats1, g1, b1, w2, bias2, eps, N, nvox):
+        ys = _rows(y1, N * nvox, ld, C).float().view(N, nvox, C)
+        mean, rstd = _mean_rstd(stats1, float(nvox * C), eps, N)
+        a = F.relu(((ys.double() - mean) * rstd).float() * g1.t.view(1, 1, C) + b1.t.view(1, 1, C))
+        return a @ w2.t.view(C, C).t() + bias2.t.view(1, 1, C)
+
+    def tail_stats(dtype, y1, ld, C, stats1, g1, b1, w2, bias2, eps, stats2, N, nvox, stream):
+        z = _tail(y1, ld, C, stats1, g1, b1, w2, bias2, eps, N, nvox)
+        stats2.t[:, 0] += z.double().flatten(1).sum(1)
+        stats2.t[:, 1] += (z.double() ** 2).flatten(1).sum(1)
+        calls.append('tail_stats')
+        return 0
+
+    def tail_probs(dtype, y1, ld, C, stats1, g1, b1, w2, bias2, stats2, g2, b2, eps, probs, N, nvox, stream):
+        z = _tail(y1, ld, C, stats1, g1, b1, w2, bias2, eps, N, nvox)
+        mean, rstd = _mean_rstd(stats2, float(nvox * C), eps, N)
+        z = ((z.double() - mean) * rstd).float() * g2.t.view(1, 1, C) + b2.t.view(1, 1, C)
+        probs.t.copy_(F.softmax(z, 2).permute(0, 2, 1).reshape(probs.t.shape))
+        calls.append('tail_probs')
+        return 0
+
+    table = {'seg3d_conv3d_fwd': conv3d_fwd, 'seg3d_conv3d_k3_narrow_fwd': narrow_fwd, 'seg3d_conv3d_k3_narrow_gn_fwd': narrow_gn_fwd,
+             'seg3d_gn_apply': gn_apply, 'seg3d_conv3d_split_fwd': split_fwd, 'seg3d_gn_apply_split': gn_apply_split,
+             'seg3d_outblock_tail_stats': tail_stats, 'seg3d_outblock_tail_probs': tail_probs}
+    monkeypatch.setattr(lib, 'ptr', ptr)
+    monkeypatch.setattr(lib, 'call', lambda name, *a: table[name](*a))
+    monkeypatch.setattr(lib, 'stream_ptr', lambda: 0)
+    monkeypatch.setattr(plan, '_require_cuda', lambda device, message: None)         # the test stubs the guard, the package never does
+    return plan
+
+
+@pytest.mark.parametrize('arch,cout', [('vnet', 2), ('vbnet', 5)])
+@pytest.mark.parametrize('mode,tol', [('fp32', 2e-5), ('fp16', 2e-2), ('bf16', 1.5e-1), ('fp32x', 1e-4)])
+def test_plan_issues_the_reference_network(monkeypatch, arch, cout, mode, tol):
+    calls = []
+    plan = _install(monkeypatch, calls)
+    sd = oinit.randomize_affine(oinit.init_state_dict(arch, 1, cout, 0), 7)
+    x = torch.randn((2, 1, 16, 32, 16), generator=torch.Generator().manual_seed(3))
+    ref = onet.forward(sd, x)
+    p = plan.NetPlan(sd, mode=mode, device='cpu')
+    got = p.forward(x).clone()
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    err = float((got - ref).abs().max())
+    assert err <= tol, (arch, mode, err)
+    assert float((got.sum(1) - 1).abs().max()) <= 1e-5
+    n_convs = sum(1 for k, v in sd.items() if k.endswith('.weight') and v.dim() == 5) - 1          # out_block.conv2 lives in the tail
+    assert sum(c in ('conv', 'narrow', 'narrow_gn', 'split_conv') for c in calls) == n_convs
+    if mode in ('fp16', 'bf16'):
+        assert 'narrow_gn' in calls                                                   # fused last GroupNorm + narrow-output conv is the default
+    if mode == 'fp32x':
+        assert 'split_conv' in calls and 'gn_split' in calls
+    # a second forward through the cached plan, and after an in-place weight refresh, stays correct
+    sd2 = {k: (v * 1.01 if k.endswith('conv.weight') else v) for k, v in sd.items()}
+    p.refresh(sd2)
+    err = float((p.forward(x) - onet.forward(sd2, x)).abs().max())
+    assert err <= tol, (arch, mode, 'refresh', err)
+
+
+def test_plan_without_the_fused_tail_and_with_batches(monkeypatch):
+    calls = []
+    plan = _install(monkeypatch, calls)
+    sd = oinit.randomize_affine(oinit.init_state_dict('vnet', 1, 2, 1), 2)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((3, 1, 16, 16, 32), generator=g)
+    ref = onet.forward(sd, x)
+    for env in ({'SEG3D_FUSE_TAIL': '0'}, {'SEG3D_NARROW': '0'}, {'SEG3D_TAIL_F32': '0'}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        del calls[:]
+        got = plan.NetPlan(sd, mode='fp16', device='cpu').forward(x)
+        assert float((got - ref).abs().max()) <= 2e-2, env
+        assert 'narrow_gn' not in calls
+        for k in env:
+            monkeypatch.delenv(k)
+    # GroupNorm is per sample: a batch equals its items run one by one
+    p = plan.NetPlan(sd, mode='fp32', device='cpu')
+    whole = p.forward(x).clone()
+    for i in range(3):
+        assert float((p.forward(x[i:i + 1]) - whole[i:i + 1]).abs().max()) <= 1e-5
