@@ -13,6 +13,7 @@ import os
 import torch
 import torch.nn as nn
 
+from segmentation3d._b200 import plan as _plan
 from segmentation3d._b200.plan import NetPlan
 
 
@@ -123,8 +124,7 @@ class VShapedNet(nn.Module):
     def _current_plan(self):
         params = list(self.parameters())
         dev = params[0].device
-        if dev.type != 'cuda':
-            raise RuntimeError('segmentation3d (B200 build) has no CPU path: move the network to a CUDA device')
+        _plan._require_cuda(dev, 'segmentation3d (B200 build) has no CPU path: move the network to a CUDA device')
         key = (self.b200_mode, str(dev), tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
         if self._plan is None or self._plan_key != key:
             if self._plan is not None and self._plan_key[:2] == key[:2]:
@@ -135,8 +135,7 @@ class VShapedNet(nn.Module):
         return self._plan
 
     def forward(self, input):
-        if not input.is_cuda:
-            raise RuntimeError('segmentation3d (B200 build) has no CPU path: pass a CUDA tensor')
+        _plan._require_cuda(input.device, 'segmentation3d (B200 build) has no CPU path: pass a CUDA tensor')
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from segmentation3d._b200.autograd import train_forward
             return train_forward(self, input)
