@@ -123,3 +123,60 @@ def test_patch_sharded_labels_merge_by_max():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+class _Patch(object):
+    """minimal stand-in for pytest's monkeypatch inside spawned workers"""
+
+    def setattr(self, obj, name, value):
+        setattr(obj, name, value)
+
+
+def _sharded_engine_worker(rank, world, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (os.path.join(root, 'medical-segmentation3d-toolkit_b200'), root, os.path.join(root, 'tests')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    import test_sliding_wiring as tsw
+    from oracle import init as oinit
+    from segmentation3d.core.seg_infer import segmentation_volume_device
+    lib = tsw._install(_Patch(), [])
+    sd = oinit.randomize_affine(oinit.init_state_dict('vnet', 1, 2, 3), 4)
+    vol = (tsw._seeded(5, (1, 1, 32, 64, 32))[0, 0].numpy() * 100).astype(np.float32)
+    nd = {'type': 0, 'mean': 0.0, 'stddev': 100.0, 'clip': False}
+    out = {}
+    for name, cfg, gather in (('tiled_labels', {'partition_type': 'SIZE', 'partition_size': [32, 32, 32], 'partition_stride': [32, 32, 32]}, 'labels'),
+                              ('tiled_probs', {'partition_type': 'SIZE', 'partition_size': [32, 32, 32], 'partition_stride': [32, 32, 32]}, 'probs'),
+                              ('overlap_probs', {'partition_type': 'SIZE', 'partition_size': [32, 32, 32], 'partition_stride': [16, 16, 16]}, 'probs')):
+        model, _ = tsw._model(sd, 2, nd, lib, batch=1)
+        single_acc, single_mask = segmentation_volume_device(model, cfg, torch.from_numpy(vol))
+        model, plan = tsw._model(sd, 2, nd, lib, batch=1)          # one patch per forward on both sides: identical arithmetic
+        acc, mask = segmentation_volume_device(model, cfg, torch.from_numpy(vol), shard=(rank, world), gather=gather)
+        ok = bool(torch.equal(mask, single_mask))
+        if gather == 'probs':
+            ok = ok and float((acc - single_acc).abs().max()) <= 1e-6
+        out[name] = (ok, sum(plan.forwards))
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_patch_sharded_engine_under_gloo_equals_single_process():
+    """segmentation_volume_device(shard=(rank, world)) with the kernels emulated (tests/test_sliding_wiring.py) and a real
+    2-rank gloo group: the 'probs' exchange (all-reduce of the accumulators) and the 'labels' exchange (local arg-max + max
+    all-reduce, non-overlapping patches) both return the single-process mask on every rank, each rank having run only its
+    share of the patches."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_engine_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for r in range(2):
+        assert res[r]['tiled_labels'] == (True, 1) and res[r]['tiled_probs'] == (True, 1)         # 2 patches, one per rank
+        assert res[r]['overlap_probs'][0] is True
+    assert res[0]['overlap_probs'][1] + res[1]['overlap_probs'][1] == 3                            # 3 overlapping patches in all
