@@ -180,3 +180,61 @@ def test_patch_sharded_engine_under_gloo_equals_single_process():
         assert res[r]['tiled_labels'] == (True, 1) and res[r]['tiled_probs'] == (True, 1)         # 2 patches, one per rank
         assert res[r]['overlap_probs'][0] is True
     assert res[0]['overlap_probs'][1] + res[1]['overlap_probs'][1] == 3                            # 3 overlapping patches in all
+
+
+def _ddp_train_worker(rank, world, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (os.path.join(root, 'medical-segmentation3d-toolkit_b200'), root, os.path.join(root, 'tests')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    import test_autograd_wiring as taw
+    from oracle import init as oinit
+    from oracle import loss as oloss
+    from oracle import net as onet
+    from segmentation3d.core.seg_train import make_optimizer, train_step
+    from segmentation3d.loss.multi_dice_loss import MultiDiceLoss
+    from segmentation3d.network import vnet
+    os.environ['SEG3D_ALLREDUCE_BUCKET_MB'] = '1'                    # several overlapped all-reduces per backward pass
+    taw._install(_Patch(), [])
+    sd = oinit.randomize_affine(oinit.init_state_dict('vnet', 1, 2, 0), 5)
+    g = torch.Generator().manual_seed(21)
+    crops = torch.randn((2, 1, 16, 16, 32), generator=g)
+    masks = torch.randint(0, 2, (2, 1, 16, 16, 32), generator=g).float()
+    # oracle: the reference's single-process step on the global batch of two crops
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref_loss = oloss.multi_dice_loss(onet.forward_with_grad(params, crops), masks, [1.0, 1.0])
+    ref_loss.backward()
+    net = vnet.SegmentationNet(1, 2)
+    net.load_state_dict(sd)
+    net.b200_mode = 'fp32'
+    net.train()
+    opt = make_optimizer(net, 1e-4)
+    lf = MultiDiceLoss([1.0, 1.0], 2, False)
+    loss = train_step(net, opt, lf, crops[rank:rank + 1], masks[rank:rank + 1])        # this rank's crop only
+    reduced = bool(getattr(net._plan, 'grads_reduced_in_backward', False))
+    worst = 0.0
+    for name, p in net.named_parameters():
+        gr = params[name].grad
+        worst = max(worst, float((p.grad - gr).abs().max()) / (float(gr.abs().max()) + 1e-12))
+    q.put((rank, worst, reduced, float(loss.detach())))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_step_under_gloo_equals_the_global_batch_gradient():
+    """core/seg_train.py::train_step on two gloo ranks (one crop each, kernels emulated as in tests/test_autograd_wiring.py):
+    the gradient all-reduce issued from inside the backward pass leaves, on every rank, the gradient of the reference's
+    single-process step on the global batch."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for rank, worst, reduced, loss in res:
+        assert reduced, 'the overlapped all-reduce did not run'
+        assert worst <= 1e-2, (rank, worst)
