@@ -1,22 +1,28 @@
 """conv -> GroupNorm(1,C) [-> ReLU] units (drop-in for reference network/module/conv_gn_relu3.py:4-34): same constructors,
 attribute names and state-dict keys; forward runs the C-ABI convolution + GroupNorm-apply kernels
-(segmentation3d/_b200/blocks.py).  Only the shape the reference instantiates is built: ksize 3, stride 1, padding 1."""
+(segmentation3d/_b200/blocks.py).  Built for the convolution shapes the library has kernels for: ksize 3 / stride 1 /
+padding 1 (every use in the reference networks), ksize 2 / stride 2 / padding 0 (the second case of the reference's own
+conv_gn_relu3_test.py) and ksize 1 / stride 1 / padding 0."""
 import torch.nn as nn
 
 from segmentation3d._b200 import blocks, lib
 from segmentation3d.network._graph import Conv3dParams, GroupNormParams
 
 
-def _check_k3(ksize, stride, padding):
-    if (ksize, stride, padding) != (3, 1, 1):
-        raise NotImplementedError('B200 build: ConvGnRelu3 is built for ksize=3, stride=1, padding=1 (the only instantiation in the '
-                                  'reference networks), got ksize=%r stride=%r padding=%r' % (ksize, stride, padding))
+_CONV_MODES = {(3, 1, 1): lib.CONV_K3, (2, 2, 0): lib.CONV_K2S2, (1, 1, 0): lib.CONV_K1}
+
+
+def _conv_mode(ksize, stride, padding):
+    if (ksize, stride, padding) not in _CONV_MODES:
+        raise NotImplementedError('B200 build: ConvGnRelu3 has kernels for (ksize, stride, padding) in %s, got (%r, %r, %r)'
+                                  % (sorted(_CONV_MODES), ksize, stride, padding))
+    return _CONV_MODES[(ksize, stride, padding)]
 
 
 class ConvGnRelu3(nn.Module):
     def __init__(self, in_channels, out_channels, ksize, stride, padding, do_act=True, bias=True):
         super(ConvGnRelu3, self).__init__()
-        _check_k3(ksize, stride, padding)
+        self._conv_mode = _conv_mode(ksize, stride, padding)
         self.conv = Conv3dParams(in_channels, out_channels, ksize)
         if not bias:
             self.conv.bias = None
@@ -26,7 +32,7 @@ class ConvGnRelu3(nn.Module):
             self.act = nn.ReLU(inplace=True)          # kept for the module tree; the ReLU runs inside the GroupNorm-apply kernel
 
     def _run(self, x_nd, dt, res=None, relu=None):
-        return blocks.conv_gn(x_nd, self.conv, self.gn, lib.CONV_K3, dt, self.do_act if relu is None else relu, res)
+        return blocks.conv_gn(x_nd, self.conv, self.gn, self._conv_mode, dt, self.do_act if relu is None else relu, res)
 
     def forward(self, input):
         blocks.check_input(input, self.conv.in_channels)

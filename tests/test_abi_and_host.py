@@ -219,6 +219,7 @@ def test_standalone_network_modules_keep_the_reference_schema_and_init():
         ConvGnRelu3(16, 16, 3, 1, 1)(torch.zeros(1, 16, 8, 8, 8))
     with pytest.raises(NotImplementedError):
         ConvGnRelu3(16, 16, 5, 1, 2)
+    ConvGnRelu3(1, 16, ksize=2, stride=2, padding=0)              # the second model of the reference's conv_gn_relu3_test.py
 
 
 def test_nifti_roundtrip_and_hand_built_header(tmp_path):

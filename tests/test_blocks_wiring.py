@@ -193,3 +193,28 @@ def test_standalone_modules_wire_the_kernels_like_the_reference_blocks(monkeypat
             close(p, y, 'OutputBlock')
             assert float((p.sum(1) - 1).abs().max()) <= 1e-5
     assert {'conv0', 'conv1', 'conv2', 'gn', 'tail_stats', 'tail_probs'} <= set(calls)
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 2e-5), ('fp16', 3e-2)])
+def test_conv_gn_relu3_output_size_like_the_reference_test(monkeypatch, mode, tol):
+    """network/module/conv_gn_relu3_test.py:8-43 (the reference's own test of this module): a k3 s1 p1 and a k2 s2 p0
+    ConvGnRelu3 from 1 to 16 channels on a [4, 1, 48, 32, 16] batch keep / halve the spatial size - plus the values, against
+    torch's functional ops."""
+    _install(monkeypatch)
+    monkeypatch.setenv('SEG3D_MODE', mode)
+    from segmentation3d.network.module.conv_gn_relu3 import ConvGnRelu3
+    in_channels, out_channels = 1, 16
+    model1 = ConvGnRelu3(in_channels, out_channels, ksize=3, stride=1, padding=1, do_act=True)
+    model2 = ConvGnRelu3(in_channels, out_channels, ksize=2, stride=2, padding=0, do_act=True)
+    assert sum(p.numel() for p in model1.parameters()) == 16 * 27 + 16 + 32
+    assert sum(p.numel() for p in model2.parameters()) == 16 * 8 + 16 + 32
+    batch_size, (dim_x, dim_y, dim_z) = 4, (16, 32, 48)
+    inputs = torch.rand([batch_size, in_channels, dim_z, dim_y, dim_x], generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        outputs1, outputs2 = model1(inputs), model2(inputs)
+        ref1 = F.relu(F.group_norm(F.conv3d(inputs, model1.conv.weight, model1.conv.bias, padding=1), 1, model1.gn.weight, model1.gn.bias, EPS))
+        ref2 = F.relu(F.group_norm(F.conv3d(inputs, model2.conv.weight, model2.conv.bias, stride=2), 1, model2.gn.weight, model2.gn.bias, EPS))
+    assert tuple(outputs1.size()) == (batch_size, out_channels, dim_z, dim_y, dim_x)
+    assert tuple(outputs2.size()) == (batch_size, out_channels, dim_z // 2, dim_y // 2, dim_x // 2)
+    assert float((outputs1 - ref1).abs().max()) <= tol * max(1.0, float(ref1.abs().max()))
+    assert float((outputs2 - ref2).abs().max()) <= tol * max(1.0, float(ref2.abs().max()))

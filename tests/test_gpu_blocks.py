@@ -176,3 +176,22 @@ def test_baseline_config0_single_patch_cli_flow(tmp_path, monkeypatch, mode, tol
     print('configs[0]', mode, rep)
     assert rep['max_abs'] <= tol and rep['agree'] >= 0.999 and min(rep['dice']) >= 0.999
     assert np.array_equal(read_image(str(out / 'patch.mha' / 'seg.mha')).to_numpy(), masks[0].to_numpy())
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('fp16', 2e-2)])
+def test_conv_gn_relu3_output_size_like_the_reference_test(monkeypatch, mode, tol):
+    """network/module/conv_gn_relu3_test.py:8-43 on the GPU: k3 s1 p1 and k2 s2 p0 units from 1 to 16 channels on a
+    [4, 1, 48, 32, 16] batch - the reference's shape assertions plus the values against torch's functional ops."""
+    monkeypatch.setenv('SEG3D_MODE', mode)
+    from segmentation3d.network.module.conv_gn_relu3 import ConvGnRelu3
+    model1 = ConvGnRelu3(1, 16, ksize=3, stride=1, padding=1, do_act=True).cuda()
+    model2 = ConvGnRelu3(1, 16, ksize=2, stride=2, padding=0, do_act=True).cuda()
+    inputs = torch.rand([4, 1, 48, 32, 16], generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        outputs1, outputs2 = model1(inputs.cuda()).cpu(), model2(inputs.cuda()).cpu()
+        sd1, sd2 = _sd(model1), _sd(model2)
+        ref1 = F.relu(F.group_norm(F.conv3d(inputs, sd1['conv.weight'], sd1['conv.bias'], padding=1), 1, sd1['gn.weight'], sd1['gn.bias'], EPS))
+        ref2 = F.relu(F.group_norm(F.conv3d(inputs, sd2['conv.weight'], sd2['conv.bias'], stride=2), 1, sd2['gn.weight'], sd2['gn.bias'], EPS))
+    assert tuple(outputs1.size()) == (4, 16, 48, 32, 16) and tuple(outputs2.size()) == (4, 16, 24, 16, 8)
+    assert float((outputs1 - ref1).abs().max()) <= tol * max(1.0, float(ref1.abs().max()))
+    assert float((outputs2 - ref2).abs().max()) <= tol * max(1.0, float(ref2.abs().max()))
