@@ -37,4 +37,17 @@ print('rank %d/%d: all-reduce max|dp| %.3g, reduce-scatter slab max|dp| %.3g, ma
       % (rank, world, d_probs, d_slab, agree_p, agree_m), flush=True)
 assert d_probs <= 1e-5 and d_slab <= 1e-5 and agree_p >= 0.9999 and agree_m >= 0.9999
 assert accm.shape == (2, zs) + tuple(vol.shape[1:]) and maskm.shape == vol.shape
+# label exchange (gather='labels'): non-overlapping patches, local arg-max + max all-reduce of the int8 mask
+from segmentation3d.core.seg_infer import _grid, labels_can_merge_by_max
+from segmentation3d._b200.sliding import axis_counts
+cfg_t = {'partition_type': 'SIZE', 'partition_size': [48, 48, 48], 'partition_stride': [48, 48, 48]}
+vol_t = vol[:96, :96, :96].contiguous()
+st, en = _grid(model, cfg_t, [96, 96, 96], [1.0, 1.0, 1.0], None, None)
+assert labels_can_merge_by_max(axis_counts([96, 96, 96], st, en)) and len(st) == 8
+_, mask_t1 = segmentation_volume_device(model, cfg_t, vol_t, batch=4)
+_, mask_tl = segmentation_volume_device(model, cfg_t, vol_t, batch=4, shard=(rank, world), gather='labels')
+torch.cuda.synchronize()
+agree_l = float((mask_tl == mask_t1).float().mean())
+print('rank %d/%d: label exchange mask agreement %.6f' % (rank, world, agree_l), flush=True)
+assert agree_l >= 0.9999
 dist.destroy_process_group()
