@@ -22,7 +22,9 @@ class _MP(object):
 class Plugin(object):
     @pytest.fixture(autouse=True)
     def _emulate(self, monkeypatch):
-        import test_plan_wiring as tpw, test_sliding_wiring as tsw, test_device_crops_wiring as tdc
+        import test_autograd_wiring as taw
+        import test_device_crops_wiring as tdc
+        import test_sliding_wiring as tsw
         from segmentation3d._b200 import lib, blocks
         from segmentation3d.utils import image3d
         tables = []
@@ -30,7 +32,7 @@ class Plugin(object):
         def grab(install, *a):
             install(monkeypatch, *a)
             tables.append(lib.call)
-        grab(tpw._install, [])
+        grab(taw._install, [])          # forward + backward entry points of the network, loss reductions
         grab(tsw._install, [])
         grab(tdc._install)
         def call(name, *a):
@@ -53,7 +55,17 @@ class Plugin(object):
         monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
         monkeypatch.setattr(torch.cuda, 'is_available', lambda: True)
         monkeypatch.setattr(torch.cuda, 'device_count', lambda: 1)
+        for name in ('set_device', 'manual_seed', 'manual_seed_all'):
+            monkeypatch.setattr(torch.cuda, name, lambda *a, **k: None)
+        monkeypatch.setattr(torch.cuda, 'current_device', lambda: 0)
+        monkeypatch.setattr(torch.cuda, 'is_current_stream_capturing', lambda: False)
+        monkeypatch.setattr(torch.Tensor, 'pin_memory', lambda self, *a, **k: self)
+        monkeypatch.setattr(torch.Tensor, 'is_pinned', lambda self, *a, **k: False)
         from segmentation3d.core import seg_infer
+        from segmentation3d.dataloader import device_loader
+        real_init = device_loader.DeviceCropLoader.__init__
+        monkeypatch.setattr(device_loader.DeviceCropLoader, '__init__',
+                            lambda self, dataset, sampler, batch_size, device=None, cache_gb=None: real_init(self, dataset, sampler, batch_size, 'cpu', cache_gb))
         monkeypatch.setattr(seg_infer, '_device_for', lambda gpu_id: torch.device('cpu'))
         yield
 
