@@ -191,7 +191,9 @@ int seg3d_dice_terms(const float* probs, const float* target, int B, int C, int6
  * from the terms (closed form of d loss / d p). */
 int seg3d_dice_bwd(const float* probs, const float* target, int B, int C, int64_t n,
                    const float* coef, float* grad, void* stream);
-/* focal: partial[0] += sum_i -alpha[t_i] * (1-p_t)^gamma * log(p_t + 1e-10) (double) */
+/* focal: partial[0] += sum_i -alpha[t_i] * (1-p_t)^gamma * log(p_t + 1e-10) (double);
+ * partial[1] += number of voxels whose label lies outside [0, C) - they contribute nothing and the caller raises (the
+ * reference's one-hot gather, loss/focal_loss.py:46-48, raises an index error).  partial holds two doubles. */
 int seg3d_focal_fwd(const float* probs, const float* target, int B, int C, int64_t n,
                     const float* alpha, float gamma, double* partial, void* stream);
 int seg3d_focal_bwd(const float* probs, const float* target, int B, int C, int64_t n,

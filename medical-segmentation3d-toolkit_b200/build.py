@@ -31,6 +31,15 @@ def _digest():
     return h.hexdigest()
 
 
+def _file_digest(src):
+    """one object file depends on its source, every header, and the flags"""
+    h = hashlib.sha256()
+    for f in [src] + sorted(glob.glob(os.path.join(CSRC, '*.cuh'))) + [os.path.join(HERE, '..', 'include', 'seg3d_b200.h')]:
+        h.update(open(f, 'rb').read())
+    h.update(' '.join(FLAGS).encode())
+    return h.hexdigest()
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, 'build.sha256')
@@ -41,14 +50,19 @@ def build(force=False, verbose=False):
     procs = []
     for src in _sources():
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + '.o')
-        cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
+        fd, fstamp = _file_digest(src), obj + '.sha256'
+        if not force and not verbose and os.path.isfile(obj) and os.path.isfile(fstamp) and open(fstamp).read().strip() == fd:
+            continue                                  # unchanged translation unit: keep its object file
+        cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+        procs.append((src, fstamp, fd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
-    for src, p in procs:
+    for src, fstamp, fd, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0 or verbose:
             sys.stderr.write('== %s ==\n%s\n' % (os.path.basename(src), out))
+        if p.returncode == 0:
+            open(fstamp, 'w').write(fd)
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed')

@@ -343,7 +343,8 @@ int launch_tail_bwd(int C, dim3 grid, cudaStream_t st, const T* y1, int ld, cons
 #define TB_CASE(CC) case CC: tail_bwd_kernel<T, CC, PASS><<<grid, 256, 0, st>>>(y1, ld, a, dy1, dy_ld, nvox); break;
   switch (C) {
     TB_CASE(1) TB_CASE(2) TB_CASE(3) TB_CASE(4) TB_CASE(5) TB_CASE(6) TB_CASE(7) TB_CASE(8)
-    default: seg3d_set_error("tail backward: C=%d not in 1..8", C); return SEG3D_EUNSUPPORTED;
+    TB_CASE(9) TB_CASE(10) TB_CASE(11) TB_CASE(12) TB_CASE(13) TB_CASE(14) TB_CASE(15) TB_CASE(16)
+    default: seg3d_set_error("tail backward: C=%d not in 1..16", C); return SEG3D_EUNSUPPORTED;
   }
 #undef TB_CASE
   SEG3D_CHECK_LAUNCH("tail_bwd_kernel");

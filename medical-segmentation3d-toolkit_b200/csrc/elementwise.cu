@@ -147,8 +147,9 @@ extern "C" int seg3d_gn_apply(int dtype, const void* y, int y_ld, int C, const d
 }
 
 // ---------------------------------------------------------------------------------------------
-// Output-block tail.  C <= 8 classes; one thread per voxel keeps the C-vector in registers.
-constexpr int TAIL_MAXC = 8;
+// Output-block tail.  C <= 16 classes (the reference's own network/vbnet_test.py builds 16); one thread per voxel keeps the
+// C-vector in registers.
+constexpr int TAIL_MAXC = 16;
 
 struct TailParams {
   float a1[TAIL_MAXC], b1[TAIL_MAXC];        // GN1 folded scale/shift (filled per sample in-kernel)
@@ -223,7 +224,8 @@ static int launch_tail(int C, dim3 grid, cudaStream_t st, const T* y1, int ld, c
 #define TAIL_CASE(CC) case CC: outblock_tail_kernel<T, CC, PROBS><<<grid, 256, 0, st>>>(y1, ld, stats1, g1, b1, w2, bias2, eps, s2o, s2i, g2, b2, probs, nvox); break;
   switch (C) {
     TAIL_CASE(1) TAIL_CASE(2) TAIL_CASE(3) TAIL_CASE(4) TAIL_CASE(5) TAIL_CASE(6) TAIL_CASE(7) TAIL_CASE(8)
-    default: seg3d_set_error("outblock tail: C=%d not in 1..8", C); return SEG3D_EUNSUPPORTED;
+    TAIL_CASE(9) TAIL_CASE(10) TAIL_CASE(11) TAIL_CASE(12) TAIL_CASE(13) TAIL_CASE(14) TAIL_CASE(15) TAIL_CASE(16)
+    default: seg3d_set_error("outblock tail: C=%d not in 1..16", C); return SEG3D_EUNSUPPORTED;
   }
 #undef TAIL_CASE
   SEG3D_CHECK_LAUNCH("outblock_tail_kernel");

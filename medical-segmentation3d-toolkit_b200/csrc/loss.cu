@@ -67,6 +67,7 @@ extern "C" int seg3d_dice_bwd(const float* probs, const float* target, int B, in
 }
 
 // focal_loss.py:45-59: p_t = p[target] + 1e-10; loss_i = -alpha[t] (1-p_t)^gamma log p_t
+// partial[0] += sum loss_i;  partial[1] += number of voxels whose label lies outside [0, C) (they contribute nothing)
 __global__ void __launch_bounds__(256)
 focal_fwd_kernel(const float* __restrict__ probs, const float* __restrict__ target, int C, long long n,
                  const float* __restrict__ alpha, float gamma, double* __restrict__ partial) {
@@ -74,8 +75,10 @@ focal_fwd_kernel(const float* __restrict__ probs, const float* __restrict__ targ
   const int b = blockIdx.y;
   const float* t = target + (size_t)b * n;
   double acc = 0;
+  int bad = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int cls = (int)(long long)t[i];                    // target.long()
+    if (cls < 0 || cls >= C) { ++bad; continue; }            // the reference's one-hot gather raises here: counted, reported by the caller
     const float pt = probs[((size_t)b * C + cls) * n + i] + 1e-10f;
     const float lg = logf(pt);
     const float w = gamma > 0.f ? powf(1.f - pt, gamma) : 1.f;
@@ -85,6 +88,7 @@ focal_fwd_kernel(const float* __restrict__ probs, const float* __restrict__ targ
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < 8; ++w) s += red[w]; atomicAdd(partial, s); }
+  if (bad) atomicAdd(partial + 1, (double)bad);
 }
 
 extern "C" int seg3d_focal_fwd(const float* probs, const float* target, int B, int C, int64_t n,
@@ -103,7 +107,7 @@ focal_bwd_kernel(const float* __restrict__ probs, const float* __restrict__ targ
   const int b = blockIdx.y;
   const float* t = target + (size_t)b * n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int cls = (int)(long long)t[i];
+    const int cls = (int)(long long)t[i];                    // a label outside [0, C) matches no class: zero gradient
     for (int c = 0; c < C; ++c) {
       float g = 0.f;
       if (c == cls) {

@@ -57,7 +57,9 @@ crop_resample_kernel(const float* __restrict__ src, int sz, int sy, int sx, floa
   const size_t total = (size_t)dz * dy * dx;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % dx); const size_t t = i / dx; const int y = (int)(t % dy), z = (int)(t / dy);
-    const double cx = ox + x * rx, cy = oy + y * ry, cz = oz + z * rz;
+    // product and sum rounded separately (no FMA contraction): the host restatement computes o + i * r in two double
+    // operations, and at an exact half-voxel tie a fused product would pick the other nearest neighbour
+    const double cx = __dadd_rn(ox, __dmul_rn((double)x, rx)), cy = __dadd_rn(oy, __dmul_rn((double)y, ry)), cz = __dadd_rn(oz, __dmul_rn((double)z, rz));
     float out = dflt;
     if (cx >= -0.5 && cy >= -0.5 && cz >= -0.5 && cx < sx - 0.5 && cy < sy - 0.5 && cz < sz - 0.5) {
       if (LINEAR) {

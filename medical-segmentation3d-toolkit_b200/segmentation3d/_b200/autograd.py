@@ -220,17 +220,24 @@ class _Backward(object):
 class _NetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, x, names, *params):
-        plan = net._current_plan()
+        plan = net._current_plan(train=True)
         B, Cin, D, H, W = x.shape
         ws, ops = plan.plan(B, D, H, W, train=True)
         plan.load_input(ws, x.detach().float())
         probs = plan.run(ws, ops).clone()
-        ctx.plan, ctx.ws, ctx.names = plan, ws, names
+        # the saved activations live in the plan's workspace, shared by every forward of this shape: stamp the forward so
+        # that a backward after a LATER forward of the same shape (gradient accumulation over two crops, two forwards
+        # before one backward) fails loudly instead of differentiating the wrong activations
+        ws['generation'] = ws.get('generation', 0) + 1
+        ctx.plan, ctx.ws, ctx.names, ctx.generation = plan, ws, names, ws['generation']
         return probs
 
     @staticmethod
     def backward(ctx, dprobs):
         plan, ws = ctx.plan, ctx.ws
+        if ws.get('generation') != ctx.generation:
+            raise RuntimeError('seg3d_b200: the activations of this forward were overwritten by a later forward of the same '
+                               'shape; call backward() before the next forward (one forward per backward)')
         bw = ws.get('bwd')
         if bw is None:
             bw = ws['bwd'] = _Backward(plan, ws)

@@ -173,8 +173,8 @@ class NetPlan(object):
         self.tc_modes = tuple(tc_modes)
         self.in_channels = sd['in_block.conv.weight'].shape[1]
         self.out_channels = sd['out_block.conv2.weight'].shape[0]
-        if self.out_channels > 8:
-            raise RuntimeError('seg3d_b200: at most 8 output classes are supported by the out-block tail')
+        if self.out_channels > 16:
+            raise RuntimeError('seg3d_b200: at most 16 output classes are supported by the out-block tail kernels')
         self.convs, self.gns = {}, {}
         for k in sd:
             if not k.endswith('.weight'):
@@ -471,10 +471,18 @@ class NetPlan(object):
         return ws, ops
 
     def plan(self, B, D, H, W, train=False):
+        """(workspaces, launch list) for one input shape.  The cache is a small LRU (SEG3D_PLAN_CACHE shapes, default 4):
+        whole-volume forwards (partition_type 'DISABLE') have a different shape per case, and an unbounded cache would
+        keep ~430 B/voxel of workspace alive for every case ever seen."""
         key = (B, D, H, W, train)
-        if key not in self._plans:
-            self._plans[key] = self._build(B, D, H, W, train)
-        return self._plans[key]
+        hit = self._plans.pop(key, None)
+        if hit is None:
+            limit = max(1, int(os.environ.get('SEG3D_PLAN_CACHE', '4')))
+            while len(self._plans) >= limit:
+                self._plans.pop(next(iter(self._plans)))          # least recently used: dicts keep insertion order
+            hit = self._build(B, D, H, W, train)
+        self._plans[key] = hit
+        return hit
 
     def load_input(self, ws, x):
         """x: [B,Cin,D,H,W] float32 CUDA tensor -> NDHWC storage dtype."""

@@ -44,38 +44,54 @@ def default_patch_batch(patch_voxels):
 
 
 # ---- test-list readers -----------------------------------------------------------------------------
+IMAGE_SUFFIXES = ('.mhd', '.nii', '.hdr', '.nii.gz', '.mha', '.image3d')      # search order of the reference (:81)
+
+
 def read_test_txt(txt_file):
-    """First line = number of cases, then one '<case_name> <path>' line per case."""
+    """First line = number of cases, then exactly that many '<case_name> <path>' lines (:23-46); every path must exist."""
     lines = readlines(txt_file)
     case_num = int(lines[0])
-    if len(lines) - 1 < case_num:
-        raise ValueError('case num cannot be greater than path num!')
+    if len(lines) - 1 != case_num:
+        raise ValueError('case num do not equal path num!')
     names, paths = [], []
-    for i in range(case_num):
-        tokens = lines[1 + i].split()
-        if len(tokens) != 2:
-            raise ValueError('invalid line: %s' % lines[1 + i])
+    for line in lines[1:1 + case_num]:
+        tokens = line.strip().split()
+        if len(tokens) < 2:
+            raise ValueError('invalid line: %s' % line)
+        if not os.path.isfile(tokens[1]):
+            raise ValueError('image not exist: {}'.format(tokens[1]))
         names.append(tokens[0])
         paths.append(tokens[1])
     return names, paths
 
 
-def read_test_csv(csv_file):
-    """csv with columns image_name,image_path."""
+def read_test_csv(csv_file, mode='test'):
+    """csv with columns image_name,image_path[,mask_path] (:49-67)."""
     import pandas as pd
     df = pd.read_csv(csv_file)
-    return df['image_name'].tolist(), df['image_path'].tolist()
+    if mode == 'test':
+        return df['image_name'].tolist(), df['image_path'].tolist()
+    if mode in ('train', 'validation'):
+        return df['image_path'].tolist(), df['mask_path'].tolist()
+    raise ValueError('Unsupported mode type.')
 
 
 def read_test_folder(folder_path, is_dicom_folder=False):
-    """Every .mha/.mhd/.nii/.nii.gz/.hdr/.image3d file (or the folder itself for a DICOM series)."""
+    """Every image file of the folder, all suffixes sorted TOGETHER by path; the case name is the file name cut at the first
+    known suffix found in it ('case1.mha' -> 'case1', 'case2.nii.gz' -> 'case2'), as the reference does (:70-96), so results
+    land in <out>/case1/.  A DICOM folder is one case named after the folder."""
     if is_dicom_folder:
-        return [os.path.basename(os.path.normpath(folder_path))], [folder_path]
+        return [os.path.split(folder_path)[1]], [folder_path]
+    found = []
+    for suf in IMAGE_SUFFIXES:
+        found.extend(glob.glob(os.path.join(folder_path, '*' + suf)))
     names, paths = [], []
-    for ext in ('*.mha', '*.mhd', '*.nii.gz', '*.nii', '*.hdr', '*.image3d'):
-        for p in sorted(glob.glob(os.path.join(folder_path, ext))):
-            names.append(os.path.basename(p))
-            paths.append(p)
+    for path in sorted(found):
+        name = os.path.basename(path)
+        cuts = [name.find(suf) for suf in IMAGE_SUFFIXES]
+        hit = next((c for c in cuts if c != -1), -1)
+        names.append(name[:hit] if hit != -1 else name)
+        paths.append(path)
     return names, paths
 
 
@@ -217,32 +233,87 @@ def segmentation_voi(model, iso_image, start_voxel, end_voxel, use_gpu):
     return maps
 
 
+def deal_patches(starts, rank, world):
+    """Patches of ONE volume for rank `rank` of `world`: the reference list (x outer, z inner; utils/image_tools.py:202-204)
+    re-ordered by first z plane and cut into `world` contiguous runs whose lengths differ by at most one.  A rank's patches
+    then span one or two z layers of the lattice, so it reads, accumulates and finishes only that z range of the volume."""
+    order = sorted(range(len(starts)), key=lambda i: (starts[i][2], starts[i][1], starts[i][0]))
+    n = len(order)
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    return [starts[i] for i in order[lo:hi]]
+
+
+def shard_plan(model, cfg, shape_zyx, shard, bbox_start_voxel=None, bbox_end_voxel=None, use_gpu=True, spacing=None):
+    """Grid of a volume [Z,Y,X] and this rank's part of it: (starts, ends, mine, (z_lo, z_hi)).  z range = the planes this
+    rank's patches read and write ((0, Z) without sharding)."""
+    Z, Y, X = [int(v) for v in shape_zyx]
+    starts, ends = _grid(model, cfg, [X, Y, Z], spacing or model['spacing'], bbox_start_voxel, bbox_end_voxel, use_gpu)
+    if shard is None or shard[1] <= 1:
+        return starts, ends, starts, (0, Z)
+    mine = deal_patches(starts, shard[0], shard[1])
+    pz = ends[0][2] - starts[0][2]
+    if not mine:
+        return starts, ends, mine, (0, 0)
+    return starts, ends, mine, (min(s[2] for s in mine), max(s[2] for s in mine) + pz)
+
+
 def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_start_voxel=None, bbox_end_voxel=None,
                                use_gpu=True, spacing=None, z_ready=None, mask_sink=None, gather='probs'):
     """Device-resident core of segmentation_volume: `vol` is a CUDA float32 [z,y,x] tensor already at
     the model spacing.  Returns (mean_probs [C,z,y,x] fp32, mask [z,y,x] int8) on the device.
-    shard=(rank, world): this process runs patches rank::world and the accumulators are summed with
-    an all-reduce over the default process group (NCCL) before the count normalisation (gather='probs': every rank
-    returns the full probability maps).  gather='mask' (needs Z % world == 0): reduce-scatter instead - rank r receives
-    the summed z slab r, normalises and arg-maxes only that slab, and the int8 mask slabs are all-gathered; the returned
-    probabilities are then this rank's slab [C, Z/world, Y, X] only.  Half the NVLink traffic and 1/world of the finalize.
+    shard=(rank, world): the patches of this ONE volume are dealt over the ranks of the default process group (NCCL) in
+    contiguous z runs (`deal_patches`); every rank touches only the z range of its patches.  The exchange step:
+      gather='labels' (taken when no two patches overlap, i.e. partition_stride >= partition_size - the BASELINE configs):
+          every voxel belongs to exactly one patch, hence to one rank: count-normalise + arg-max the local z range and merge
+          the int8 masks with ONE max all-reduce (1 byte per voxel on the wire).  Returned probabilities: this rank's z range.
+      gather='mask' (needs Z % world == 0; also what 'labels' falls back to when patches overlap): per-class reduce-scatter
+          of z slabs of the fp32 accumulators, count normalisation + arg-max on the local slab, all-gather of the int8 mask;
+          the returned probabilities are this rank's slab [C, Z/world, Y, X].
+      gather='probs': all-reduce of the full maps; every rank returns the full probability maps.
     mask_sink=(host_mask, stream): with z_ready, every z slab is normalised, arg-maxed and copied to the (pinned) host
     mask on `stream` as soon as no remaining patch touches it."""
     eng = model['engine']
     eng.plan = model['net']._current_plan()
     Z, Y, X = vol.shape
-    starts, ends = _grid(model, cfg, [X, Y, Z], spacing or model['spacing'], bbox_start_voxel, bbox_end_voxel, use_gpu)
+    sharded = shard is not None and shard[1] > 1
+    starts, ends, mine, (z_lo, z_hi) = shard_plan(model, cfg, vol.shape, shard, bbox_start_voxel, bbox_end_voxel, use_gpu, spacing)
     norm = model['crop_normalizers'][0].to_dict() if model['crop_normalizers'] else None
     patch = [ends[0][a] - starts[0][a] for a in range(3)]
-    acc = torch.zeros((model['out_channels'], Z, Y, X), dtype=torch.float32, device=vol.device)
-    mine = starts if shard is None else starts[shard[0]::shard[1]]
-    eng.batch = int(batch) if batch else (eng.batch if eng.batch > 0 else default_patch_batch(patch[0] * patch[1] * patch[2]))
+    C = model['out_channels']
     counts = axis_counts([X, Y, Z], starts, ends)
     if bbox_start_voxel is not None:
         # voxels outside the partitioned box have count 0: the reference divides by zero there (inf*0 = nan
         # -> argmax 0); keep them at probability 0 / label 0 by treating the count as 1.
         counts = [np.maximum(c, 1) for c in counts]
-    progressive = z_ready is not None and mask_sink is not None and (shard is None or shard[1] == 1)
+    pv = patch[0] * patch[1] * patch[2]
+    if batch:
+        eng.batch = int(batch)
+    elif eng.batch <= 0:
+        eng.batch = default_patch_batch(pv)
+    if sharded and gather == 'labels' and labels_can_merge_by_max(counts):
+        import torch.distributed as dist
+        # local z range only: accumulators, count normalisation and arg-max cover [z_lo, z_hi); the volume may be resident
+        # for that range alone (segmentation_volume_host uploads nothing else)
+        mask = torch.zeros((Z, Y, X), dtype=torch.int8, device=vol.device)
+        acc = torch.zeros((C, z_hi - z_lo, Y, X), dtype=torch.float32, device=vol.device)
+        if mine:
+            local = [[s[0], s[1], s[2] - z_lo] for s in mine]
+            if z_ready is not None:
+                cur = torch.cuda.current_stream()
+                for z1, ev in z_ready:
+                    cur.wait_event(ev)
+            # one forward over all of this rank's patches when they fit the workspace budget (a 12 + 11 split of 23 patches
+            # runs two latency-bound half batches)
+            keep = eng.batch
+            if len(local) <= max(eng.batch, int(40e9 // (430.0 * pv))):
+                eng.batch = max(eng.batch, len(local))
+            eng.accumulate(vol[z_lo:z_hi], local, patch, norm, acc)
+            eng.batch = keep
+            eng.finalize(acc, [counts[0], counts[1], np.ascontiguousarray(counts[2][z_lo:z_hi])], mask=mask[z_lo:z_hi])
+        dist.all_reduce(mask, op=dist.ReduceOp.MAX)
+        return acc, mask
+    acc = torch.zeros((C, Z, Y, X), dtype=torch.float32, device=vol.device)
+    progressive = z_ready is not None and mask_sink is not None and not sharded
     mask = torch.empty((Z, Y, X), dtype=torch.int8, device=vol.device) if progressive else None
     if z_ready is None:
         eng.accumulate(vol, mine, patch, norm, acc)
@@ -275,22 +346,15 @@ def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_sta
         if progressive:
             cur.wait_stream(mask_sink[1])
             return acc, mask
-    if shard is not None and shard[1] > 1:
+    if sharded:
         import torch.distributed as dist
         r, w = shard
-        if gather == 'labels' and labels_can_merge_by_max(counts):
-            # every voxel belongs to exactly one patch, hence to one rank: arg-max locally (voxels of other ranks' patches
-            # hold all-zero probabilities -> label 0) and merge the int8 masks with a max all-reduce - 1 byte per voxel on
-            # the wire instead of 4*C.  The returned probabilities are this rank's patches only.
-            # (opt-in; added after round 1's GPU budget was spent: not yet run on several GPUs)
-            mask = eng.finalize(acc, counts)
-            dist.all_reduce(mask, op=dist.ReduceOp.MAX)
-            return acc, mask
         if gather in ('mask', 'labels') and Z % w == 0:
-            C, zs = acc.shape[0], Z // w
-            send = acc.view(C, w, zs, Y, X).permute(1, 0, 2, 3, 4).contiguous()           # [world][C, zs, Y, X]
+            zs = Z // w
             slab = torch.empty((C, zs, Y, X), dtype=torch.float32, device=acc.device)
-            dist.reduce_scatter_tensor(slab, send, op=dist.ReduceOp.SUM)
+            # class c of the accumulators is [world][zs, Y, X] as it lies in memory: one reduce-scatter per class, no re-layout
+            for c in range(C):
+                dist.reduce_scatter_tensor(slab[c], acc[c], op=dist.ReduceOp.SUM)
             mask_slab = eng.finalize(slab, [counts[0], counts[1], np.ascontiguousarray(counts[2][r * zs:(r + 1) * zs])])
             mask = torch.empty((Z, Y, X), dtype=torch.int8, device=acc.device)
             dist.all_gather_into_tensor(mask, mask_slab)
@@ -302,10 +366,15 @@ def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_sta
 
 def segmentation_volume_host(model, cfg, host_vol, host_mask=None, batch=None, shard=None, gather='probs'):
     """End-to-end call with HOST buffers: (pinned) float32 [z,y,x] in, int8 mask out; probabilities stay
-    on the device and are returned as a tensor.  Copies are issued on the current stream."""
+    on the device and are returned as a tensor.  Copies are issued on the current stream.  With shard=(rank, world) a
+    rank uploads only the z planes its patches read (all of them for the overlapping-patch gathers)."""
     dev = next(model['net'].parameters()).device
     vol = torch.empty(host_vol.shape, dtype=torch.float32, device=dev)
     z_ready = None
+    Z = host_vol.shape[0]
+    z_lo, z_hi = 0, Z
+    if shard is not None and shard[1] > 1:
+        _, _, _, (z_lo, z_hi) = shard_plan(model, cfg, host_vol.shape, shard)
     if host_vol.is_pinned() and cfg['partition_type'] == 'SIZE' and os.environ.get('SEG3D_OVERLAP_UPLOAD', '1') != '0':
         # upload z slabs on a side stream so the first patches start while the rest of the volume is in flight
         side = _side_stream(dev)
@@ -313,19 +382,20 @@ def segmentation_volume_host(model, cfg, host_vol, host_mask=None, batch=None, s
         step = max(16, int(cfg['partition_size'][2] / float(model['spacing'][2]) + 0.5))
         z_ready = []
         with torch.cuda.stream(side):
-            for z0 in range(0, host_vol.shape[0], step):
-                z1 = min(host_vol.shape[0], z0 + step)
+            for z0 in range(z_lo, z_hi, step):
+                z1 = min(z_hi, z0 + step)
                 vol[z0:z1].copy_(host_vol[z0:z1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(side)
                 z_ready.append((z1, ev))
     else:
-        vol.copy_(host_vol, non_blocking=True)
+        vol[z_lo:z_hi].copy_(host_vol[z_lo:z_hi], non_blocking=True)
     if host_mask is None:
         host_mask = torch.empty(host_vol.shape, dtype=torch.int8, pin_memory=True)
-    sink = (host_mask, _side_stream(dev)) if (z_ready is not None and host_mask.is_pinned()) else None
+    sharded = shard is not None and shard[1] > 1
+    sink = (host_mask, _side_stream(dev)) if (z_ready is not None and host_mask.is_pinned() and not sharded) else None
     acc, mask = segmentation_volume_device(model, cfg, vol, batch=batch, shard=shard, z_ready=z_ready, mask_sink=sink, gather=gather)
-    if sink is None or (shard is not None and shard[1] > 1):
+    if sink is None:
         host_mask.copy_(mask, non_blocking=True)
     return acc, host_mask
 

@@ -73,31 +73,36 @@ class _ImageCache(object):
         return img
 
 
+SAMPLING_METHODS = ('CENTER', 'GLOBAL', 'MASK', 'HYBRID')
+
+
+def _vector(value, length, dtype, what):
+    v = np.array(value, dtype=dtype)
+    assert v.size == length, 'only %d-element of %s is supported' % (length, what)
+    return v
+
+
 class SegmentationDataset(Dataset):
+    """Constructor arguments as the reference's (dataloader/dataset.py:69-101): list file (txt / csv), class count, crop
+    spacing [mm], crop size [voxels, x y z], sampling method, +-translation [mm], (lo, hi) isotropic rescale, image
+    interpolation, one normaliser (or None) per modality."""
+
     def __init__(self, imlist_file, num_classes, spacing, crop_size, sampling_method, random_translation,
                  random_scale, interpolation, crop_normalizers):
-        if imlist_file.endswith('txt'):
-            self.im_list, self.seg_list = read_train_txt(imlist_file)
-        elif imlist_file.endswith('csv'):
-            self.im_list, self.seg_list = read_train_csv(imlist_file)
-        else:
+        readers = {'txt': read_train_txt, 'csv': read_train_csv}
+        suffix = imlist_file[-3:]
+        if suffix not in readers:
             raise ValueError('imseg_list must be a txt file')
+        self.im_list, self.seg_list = readers[suffix](imlist_file)
         self.num_classes = num_classes
-        self.spacing = np.array(spacing, dtype=np.double)
-        assert self.spacing.size == 3, 'only 3-element of spacing is supported'
-        self.crop_size = np.array(crop_size, dtype=np.int32)      # x, y, z
-        assert self.crop_size.size == 3, 'only 3-element of crop size is supported'
-        self.sampling_method = sampling_method
-        assert self.sampling_method in ('CENTER', 'GLOBAL', 'MASK', 'HYBRID'), \
-            'sampling_method must be CENTER, GLOBAL, MASK or HYBRID'
-        self.random_translation = np.array(random_translation, dtype=np.double)
-        assert self.random_translation.size == 3, 'Only 3-element of random translation is supported'
-        self.random_scale = np.array(random_scale, dtype=np.double)
-        assert self.random_scale.size == 2, 'Only 2-element of random scale is supported'
-        self.interpolation = interpolation
-        assert self.interpolation in ('LINEAR', 'NN'), 'interpolation must either be a LINEAR or NN'
-        self.crop_normalizers = crop_normalizers
-        assert isinstance(self.crop_normalizers, list), 'crop normalizers must be a list'
+        self.spacing = _vector(spacing, 3, np.double, 'spacing')
+        self.crop_size = _vector(crop_size, 3, np.int32, 'crop size')
+        self.random_translation = _vector(random_translation, 3, np.double, 'random translation')
+        self.random_scale = _vector(random_scale, 2, np.double, 'random scale')
+        assert sampling_method in SAMPLING_METHODS, 'sampling_method must be one of %s' % (SAMPLING_METHODS,)
+        assert interpolation in ('LINEAR', 'NN'), 'interpolation must be LINEAR or NN'
+        assert isinstance(crop_normalizers, list), 'crop normalizers must be a list'
+        self.sampling_method, self.interpolation, self.crop_normalizers = sampling_method, interpolation, crop_normalizers
         # SEG3D_DATASET_CACHE_MB: decoded volumes kept per process (0 = re-read every item like the reference)
         self._cache = _ImageCache(int(float(os.environ.get('SEG3D_DATASET_CACHE_MB', '2048')) * (1 << 20)))
 
@@ -108,15 +113,15 @@ class SegmentationDataset(Dataset):
         return 1
 
     def global_sample(self, image):
-        """random crop centre (world) such that the crop lies inside the image where the image is larger (:108-124)."""
-        origin = image.GetOrigin()
-        im_size_mm = [image.GetSize()[idx] * image.GetSpacing()[idx] for idx in range(3)]
-        crop_size_mm = self.crop_size * self.spacing
-        sp = np.array(origin, dtype=np.double)
-        for i in range(3):
-            if im_size_mm[i] > crop_size_mm[i]:
-                sp[i] = origin[i] + np.random.uniform(0, im_size_mm[i] - crop_size_mm[i])
-        return sp + crop_size_mm / 2
+        """Uniformly random crop centre [world mm] with the crop inside the image along every axis where the image is the
+        larger of the two; along the other axes the crop starts at the image origin (:108-124).  One np.random.uniform
+        draw per free axis, x first - the reference's RNG order."""
+        start = np.array(image.GetOrigin(), dtype=np.double)
+        extent_mm = np.array(image.GetSize(), dtype=np.double) * np.array(image.GetSpacing(), dtype=np.double)
+        crop_mm = self.crop_size * self.spacing
+        for axis in np.flatnonzero(extent_mm > crop_mm):
+            start[axis] += np.random.uniform(0, extent_mm[axis] - crop_mm[axis])
+        return start + crop_mm / 2
 
     def center_sample(self, image):
         """world coordinate of the image centre (:126-138)."""

@@ -59,8 +59,13 @@ class FocalFunction(torch.autograd.Function):
         p = probs.detach().contiguous().float()
         t = target.detach().contiguous().float()
         a = alpha.to(device=p.device, dtype=torch.float32).contiguous().view(-1)
-        part = torch.zeros((1,), dtype=torch.float64, device=p.device)
+        if a.numel() != C:
+            raise ValueError('alpha must hold one value per class')
+        part = torch.zeros((2,), dtype=torch.float64, device=p.device)
         lib.call('seg3d_focal_fwd', lib.ptr(p), lib.ptr(t), B, C, n, lib.ptr(a), float(gamma), lib.ptr(part), lib.stream_ptr())
+        bad = int(part[1].item())
+        if bad:          # the reference's one-hot gather (loss/focal_loss.py:46-48) raises on such a target
+            raise IndexError('FocalLoss: %d target voxels carry a label outside [0, %d)' % (bad, C))
         ctx.save_for_backward(p, t, a)
         ctx.gamma, ctx.scale = float(gamma), (1.0 / (B * n) if size_average else 1.0)
         return (part[0] * ctx.scale).float()

@@ -11,6 +11,7 @@ Fixtures (all small):
   grids.json             image_partition_by_fixed_size outputs                  (utils/image_tools.py:163-218)
   loss.npz               Dice / focal values and gradients                      (loss/*.py)
   sliding_window.npz     core.seg_infer.segmentation_volume end to end          (core/seg_infer.py:249-350)
+  sliding_window_64.npz  the same with 64^3 patches (probabilities on every 2nd voxel per axis, full masks)
   train_step.npz         one Adam step of the reference training loop body      (core/seg_train.py:119-127)
   loss_ce.npz            cross-entropy values and gradients on loss.npz's inputs (loss/cross_entropy_loss.py)
   dataset_sampling.json  crops the reference's SegmentationDataset requests under a seeded RNG  (dataloader/dataset.py:140-209)
@@ -205,10 +206,18 @@ def synth_volume(seed, size_xyz, scale):
     return (x * scale).astype(np.float32)
 
 
-def gen_sliding_window():
+# 64^3 patches (the reduced-precision bars are stated for full-size patches; the 32^3 cases above are too small for them).
+# The probabilities of these larger volumes are committed on every second voxel per axis, the mask in full.
+SW64_CASES = [
+    ('sw64_vnet_overlap', 'vnet', 2, 0, None, [128, 128, 112], [64, 64, 64], [48, 48, 48], ('fixed', 0.0, 300.0, True), 21),
+    ('sw64_vnet_tiled', 'vnet', 2, 2, None, [128, 64, 128], [64, 64, 64], [64, 64, 64], ('adaptive', 3.0), 22),
+]
+
+
+def gen_sliding_window(cases=None, fname='sliding_window.npz', sub=1):
     from easydict import EasyDict as edict
     out, meta = {}, []
-    for name, arch, cout, wseed, aseed, size, psize, pstride, norm, vseed in SW_CASES:
+    for name, arch, cout, wseed, aseed, size, psize, pstride, norm, vseed in (cases or SW_CASES):
         net = make_net(arch, 1, cout, wseed)
         if aseed is not None:
             net.load_state_dict(randomize_affine(net.state_dict(), aseed))
@@ -230,12 +239,12 @@ def gen_sliding_window():
         image = sitk.GetImageFromArray(vol)
         mean_probs, mask = ref_infer.segmentation_volume(model, cfg, image, None, None, False)
         probs = np.stack([sitk.GetArrayFromImage(p) for p in mean_probs], 0).astype(np.float32)
-        out[name + '_probs'] = probs
+        out[name + '_probs'] = probs[:, ::sub, ::sub, ::sub].copy()
         out[name + '_mask'] = sitk.GetArrayFromImage(mask).astype(np.int8)
         meta.append([name, arch, cout, wseed, aseed, size, psize, pstride, list(norm), vseed, scale])
         print(name, probs.shape, 'fg frac', float((out[name + '_mask'] > 0).mean()))
     out['meta'] = np.array(json.dumps(meta))
-    np.savez_compressed(os.path.join(HERE, 'sliding_window.npz'), **out)
+    np.savez_compressed(os.path.join(HERE, fname), **out)
 
 
 def gen_cascade():
@@ -402,12 +411,13 @@ def gen_train_step():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['schema', 'forward', 'grids', 'loss', 'sw', 'train', 'cascade', 'ce', 'dataset', 'samplers']
+    which = sys.argv[1:] or ['schema', 'forward', 'grids', 'loss', 'sw', 'sw64', 'train', 'cascade', 'ce', 'dataset', 'samplers']
     if 'schema' in which: gen_schema_and_hashes()
     if 'forward' in which: gen_forward()
     if 'grids' in which: gen_grids()
     if 'loss' in which: gen_loss()
     if 'sw' in which: gen_sliding_window()
+    if 'sw64' in which: gen_sliding_window(SW64_CASES, 'sliding_window_64.npz', 2)
     if 'train' in which: gen_train_step()
     if 'cascade' in which: gen_cascade()
     if 'ce' in which: gen_loss_ce()

@@ -151,16 +151,21 @@ def test_metaimage_roundtrip_and_list_readers(tmp_path):
         back = read_image(path)
         assert np.array_equal(back.to_numpy(), a) and back.GetSpacing() == im.GetSpacing() and back.GetOrigin() == im.GetOrigin()
         assert back.GetSize() == (7, 6, 5)
+    files = sorted(str(f) for f in tmp_path.glob('*.mha'))
     txt = tmp_path / 'test.txt'
-    txt.write_text('2\ncase_a %s\ncase_b %s\n' % (tmp_path / 'a.mha', tmp_path / 'b.mha'))
+    txt.write_text('2\ncase_a %s\ncase_b %s\n' % (files[0], files[1]))
     names, paths = read_test_txt(str(txt))
-    assert names == ['case_a', 'case_b'] and paths[1].endswith('b.mha')
+    assert names == ['case_a', 'case_b'] and paths == files[:2]
+    # folder input: all suffixes sorted together, case name = file name cut at the suffix (reference core/seg_infer.py:81-94)
     names, paths = read_test_folder(str(tmp_path))
-    assert len(names) == 3 and all(n.endswith('.mha') for n in names)
-    bad = tmp_path / 'bad.txt'
-    bad.write_text('3\ncase_a x\n')
-    with pytest.raises(ValueError):
-        read_test_txt(str(bad))
+    assert paths == files and names == [os.path.basename(f)[:-4] for f in files]
+    for text in ('3\ncase_a %s\n' % files[0],                       # count line disagrees with the number of lines
+                 '1\ncase_a %s\ncase_b %s\n' % (files[0], files[1]),
+                 '1\ncase_a %s\n' % (tmp_path / 'missing.mha')):   # listed image does not exist
+        bad = tmp_path / 'bad.txt'
+        bad.write_text(text)
+        with pytest.raises(ValueError):
+            read_test_txt(str(bad))
 
 
 def test_cal_dsc_matches_oracle_definition():
@@ -200,9 +205,7 @@ def _assemble_from_blocks(cin, cout, compression):
 def test_standalone_network_modules_keep_the_reference_schema_and_init():
     """network/module/*.py: a network assembled from the importable blocks has the reference's state-dict keys and shapes
     and, under the same seed, bit-identical initial weights (same construction order, same random draws)."""
-    from segmentation3d.network.module.init import kaiming_weight_init as k2
     from segmentation3d.network.module.weight_init import gaussian_weight_init, kaiming_weight_init
-    assert k2 is kaiming_weight_init
     schema = json.load(open(os.path.join(G, 'schema.json')))
     hashes = json.load(open(os.path.join(G, 'weights_sha256.json')))
     for key, ref in schema.items():
@@ -268,7 +271,7 @@ def test_nifti_roundtrip_and_hand_built_header(tmp_path):
     assert np.allclose(im.TransformContinuousIndexToPhysicalPoint([1.0, 0.0, 0.0]), (-88.0, 126.0, -72.0))
     from segmentation3d.core.seg_infer import read_test_folder
     names, paths = read_test_folder(str(tmp_path))
-    assert 'h.nii.gz' in names and 'a.nii' in names
+    assert 'h' in names and 'a' in names        # 'h.nii.gz' and 'a.nii' cut at the first known suffix
 
 
 def test_parallel_zlib_stream_is_a_plain_zlib_stream(tmp_path):
@@ -288,3 +291,22 @@ def test_parallel_zlib_stream_is_a_plain_zlib_stream(tmp_path):
     write_image(Image3d(arr, (0.5, 0.5, 2.0)), str(tmp_path / 'big.mha'), True)
     back = read_image(str(tmp_path / 'big.mha'))
     assert np.array_equal(back.to_numpy(), arr) and np.allclose(back.GetSpacing(), (0.5, 0.5, 2.0))
+
+
+def test_deal_patches_is_a_balanced_partition_in_z_runs():
+    """core/seg_infer.py::deal_patches: every patch of the reference grid goes to exactly one rank, run lengths differ by at
+    most one, and a rank's patches are contiguous in z-major order (so it touches one or two z layers of the lattice)."""
+    from oracle import sliding_window as osw
+    from segmentation3d.core.seg_infer import deal_patches
+    starts, _ = osw.partition_grid([512, 512, 400], [1, 1, 1], [0, 0, 0], [512, 512, 400], [96] * 3, [96] * 3, 16)
+    assert len(starts) == 180
+    for world in (1, 2, 3, 4, 8, 16, 181):
+        parts = [deal_patches(starts, r, world) for r in range(world)]
+        flat = [tuple(s) for p in parts for s in p]
+        assert sorted(flat) == sorted(tuple(s) for s in starts) and len(set(flat)) == 180
+        sizes = [len(p) for p in parts]
+        assert max(sizes) - min(sizes) <= 1
+        zkey = [(s[2], s[1], s[0]) for p in parts for s in p]
+        assert zkey == sorted(zkey)
+        if world == 8:
+            assert max(len({s[2] for s in p}) for p in parts) <= 2

@@ -1,7 +1,5 @@
 """GPU parity of the standalone network modules (segmentation3d/network/module/*.py) against the oracle's restatement of
-the reference blocks.  Written after round 1's GPU budget was spent: the host wiring is pinned on the CPU
-(tests/test_blocks_wiring.py), these tests still have to see a GPU once - they are skipped unless SEG3D_TEST_UNVERIFIED=1
-so that an unverified test cannot stop the round-end `pytest -m gpu -x` run."""
+the reference blocks (the host wiring alone is also pinned on the CPU by tests/test_blocks_wiring.py)."""
 import os
 
 import pytest
@@ -10,8 +8,7 @@ import torch.nn.functional as F
 
 from oracle import net as onet
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('SEG3D_TEST_UNVERIFIED') != '1', reason='set SEG3D_TEST_UNVERIFIED=1 (first GPU run pending)')]
+pytestmark = [pytest.mark.gpu]
 EPS = 1e-5
 
 

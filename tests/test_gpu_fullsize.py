@@ -73,12 +73,20 @@ def test_config2_full_volume_properties():
     m3 = eng.finalize(tot, axis_counts([512, 512, 400], starts, ends))
     assert float((tot - acc).abs().max()) <= 1e-5
     assert float((m3 == mask).float().mean()) >= 0.99999
-    # one interior, non-overlapped patch against the oracle forward of the same crop
+    # eight patches drawn from the 180 (seeded; corners, faces and interior all occur) against the oracle forward of the same
+    # crops: BASELINE.json reduced-precision bars per patch - max|dp| <= 1e-2, label agreement >= 99.9 %, per-class Dice >= 0.999
     sd = oinit.init_state_dict('vnet', 1, 2, 0)
-    s0 = [96, 192, 96]
-    crop = vol[s0[2]:s0[2] + 96, s0[1]:s0[1] + 96, s0[0]:s0[0] + 96].cpu().numpy()
-    ref = onet.forward(sd, torch.from_numpy(osw.normalize_fixed(crop, 0.0, 1000.0, True))[None, None])[0].numpy()
-    got = acc[:, s0[2]:s0[2] + 96, s0[1]:s0[1] + 96, s0[0]:s0[0] + 96].cpu().numpy()
-    rep = parity_report(ref, got)
-    print('config-2 interior patch vs oracle', rep)
-    assert rep['max_abs'] <= 1e-2 and rep['agree'] >= 0.999, rep
+    rng = np.random.default_rng(5)
+    picked = sorted(rng.choice(len(starts), size=8, replace=False).tolist())
+    worst = {'max_abs': 0.0, 'agree': 1.0, 'dice': 1.0}
+    for i in picked:
+        s0, e0 = starts[i], ends[i]
+        crop = vol[s0[2]:e0[2], s0[1]:e0[1], s0[0]:e0[0]].cpu().numpy()
+        ref = onet.forward(sd, torch.from_numpy(osw.normalize_fixed(crop, 0.0, 1000.0, True))[None, None])[0].numpy()
+        got = acc[:, s0[2]:e0[2], s0[1]:e0[1], s0[0]:e0[0]].cpu().numpy()
+        rep = parity_report(ref, got)
+        print('config-2 patch %3d at %s vs oracle' % (i, s0), rep)
+        worst = {'max_abs': max(worst['max_abs'], rep['max_abs']), 'agree': min(worst['agree'], rep['agree']),
+                 'dice': min(worst['dice'], min(rep['dice']))}
+        assert rep['max_abs'] <= 1e-2 and rep['agree'] >= 0.999 and min(rep['dice']) >= 0.999, (i, rep)
+    print('config-2 worst over 8 patches', worst)

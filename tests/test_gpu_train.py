@@ -57,6 +57,59 @@ def test_gradients_match_oracle_autograd_fp32(arch, cout, lossname):
     print(arch, 'worst relative grad error', worst)
 
 
+def test_train_step_in_the_default_mode_runs_in_bf16(monkeypatch):
+    """`seg_train -i cfg` never sets a mode: the default ('auto') and the fp16 / fp32x inference modes must TRAIN in bf16
+    (fp16 gradient buffers flush the ~1e-6 data gradients to zero) - network/_graph.py::resolve_mode."""
+    from segmentation3d.core.seg_train import make_optimizer, train_step
+    from segmentation3d.loss.multi_dice_loss import MultiDiceLoss
+    monkeypatch.delenv('SEG3D_MODE', raising=False)
+    sd = oinit.init_state_dict('vnet', 1, 2, 0)
+    g = torch.Generator().manual_seed(5)
+    crops = torch.randn((2, 1, 32, 32, 32), generator=g)
+    masks = torch.randint(0, 2, (2, 1, 32, 32, 32), generator=g).float()
+    ref = float(oloss.multi_dice_loss(onet.forward(sd, crops), masks, [0.5, 0.5]))
+    from segmentation3d.network import vnet
+    for mode in (None, 'fp16', 'fp32x'):
+        net = vnet.SegmentationNet(1, 2)
+        net.load_state_dict(sd)
+        if mode is not None:
+            net.b200_mode = mode
+        net = net.cuda().train()
+        assert net.b200_mode == (mode or 'auto') and net.resolve_mode(train=True) == 'bf16'
+        opt = make_optimizer(net, 1e-4)
+        before = [p.detach().clone() for p in net.parameters()]
+        loss = train_step(net, opt, MultiDiceLoss([0.5, 0.5], 2, True), crops.cuda(), masks.cuda())
+        assert net._plan.mode == 'bf16'
+        assert abs(float(loss) - ref) <= 2e-2, (mode, float(loss), ref)
+        grads = [p.grad for p in net.parameters()]
+        assert all(gr is not None and bool(torch.isfinite(gr).all()) for gr in grads)
+        # the deep layers' gradients are the small ones: none of them may have been flushed to zero
+        nonzero = [float((gr != 0).float().mean()) for gr in grads]
+        assert min(nonzero) > 0.5, min(nonzero)
+        assert any(not torch.equal(a, p.detach()) for a, p in zip(before, net.parameters()))
+        # inference afterwards runs in the inference mode again, from the updated weights
+        net.eval()
+        with torch.no_grad():
+            net(crops.cuda())
+        assert net._plan.mode == ('fp16' if mode in (None, 'fp16') else 'fp32x')
+
+
+def test_backward_after_a_second_forward_of_the_same_shape_is_refused():
+    """the saved activations live in the plan's workspace (one per shape): differentiating a forward whose workspace a later
+    forward overwrote must fail loudly, not return the wrong gradients"""
+    from segmentation3d.loss.multi_dice_loss import MultiDiceLoss
+    net = _net('vnet', 2, oinit.init_state_dict('vnet', 1, 2, 0), 'fp32')
+    g = torch.Generator().manual_seed(6)
+    a = torch.randn((1, 1, 16, 16, 16), generator=g).cuda()
+    m = torch.randint(0, 2, (1, 1, 16, 16, 16), generator=g).float().cuda()
+    lf = MultiDiceLoss([0.5, 0.5], 2, True)
+    first = lf(net(a), m)
+    second = lf(net(a * 0.5), m)
+    with pytest.raises(RuntimeError, match='overwritten by a later forward'):
+        first.backward()
+    second.backward()
+
+
 def test_two_adam_steps_match_reference_golden():
     """core/seg_train.py:83,119-127 on the golden batch: losses and updated weights of the unmodified reference."""
     from segmentation3d.loss.multi_dice_loss import MultiDiceLoss

@@ -422,14 +422,22 @@ def test_segmentation_case_loop_with_background_io(tmp_path, monkeypatch):
             outs[(threads, k)] = {n: open(str(d / n), 'rb').read() for n in os.listdir(d)}
     for k in range(5):
         assert outs[('2', k)] == outs[('0', k)]                                     # byte-identical files
-    # a case that cannot be read: raised at its turn, earlier cases complete on disk
+    # a listed file that does not exist is refused when the list is read, like the reference (core/seg_infer.py:41-42)
     lines[3] = 'case2 %s' % (tmp_path / 'missing.mha')
+    with open(str(tmp_path / 'missing.txt'), 'w') as f:
+        f.write('\n'.join(lines) + '\n')
+    with pytest.raises(ValueError, match='image not exist'):
+        seg_infer.segmentation(str(tmp_path / 'missing.txt'), str(tmp_path), str(tmp_path / 'none'), 'seg.mha', 0, False, True, False, False)
+    # a case that cannot be decoded (truncated pixel data): raised at its turn, earlier cases complete on disk
+    with open(str(tmp_path / 'truncated.mha'), 'wb') as f:
+        f.write(b'ObjectType = Image\nNDims = 3\nDimSize = 4 4 4\nElementType = MET_FLOAT\nElementDataFile = LOCAL\n' + b'\0' * 10)
+    lines[3] = 'case2 %s' % (tmp_path / 'truncated.mha')
     with open(str(tmp_path / 'bad.txt'), 'w') as f:
         f.write('\n'.join(lines) + '\n')
     for threads in ('2', '0'):
         monkeypatch.setenv('SEG3D_IO_THREADS', threads)
         out = tmp_path / ('bad' + threads)
-        with pytest.raises(FileNotFoundError):
+        with pytest.raises(ValueError, match='buffer is smaller'):
             seg_infer.segmentation(str(tmp_path / 'bad.txt'), str(tmp_path), str(out), 'seg.mha', 0, False, True, False, False)
         assert sorted(os.listdir(out)) == ['case0', 'case1']
         assert read_image(str(out / 'case1' / 'seg.mha')).GetSize() == (10, 8, 6)

@@ -142,6 +142,21 @@ def test_sliding_window_matches_reference():
         assert cnt.min() >= 1
 
 
+def test_sliding_window_64_patches_matches_reference():
+    """the 64^3-patch goldens (probabilities committed on every 2nd voxel per axis, masks in full)"""
+    z = np.load(os.path.join(G, 'sliding_window_64.npz'))
+    for name, arch, cout, wseed, aseed, size, psize, pstride, norm, vseed, scale in json.loads(str(z['meta'])):
+        if name != 'sw64_vnet_tiled':       # one case keeps the CPU suite short; the other is covered by the GPU test's fp32x arm
+            continue
+        sd = oinit.init_state_dict(arch, 1, cout, wseed)
+        vol = (seeded_input(vseed, (1, 1, size[2], size[1], size[0]), 'smooth')[0, 0].numpy() * scale).astype(np.float32)
+        nd = {'type': 0, 'mean': norm[1], 'stddev': norm[2], 'clip': norm[3]} if norm[0] == 'fixed' else {'type': 1, 'clip_sigma': norm[1]}
+        probs, mask, _, _ = osw.segmentation_volume(sd, vol, [1.0, 1.0, 1.0], nd, 'SIZE', psize, pstride, 16,
+                                                    double_forward=False, faithful_copies=False)
+        assert np.abs(probs[:, ::2, ::2, ::2] - z[name + '_probs']).max() <= 1e-6, name
+        assert (mask == z[name + '_mask']).mean() >= 0.99999, name
+
+
 def test_argmax_ties_pick_lowest_class():
     p = np.zeros((3, 2, 2, 2), np.float32)
     p[:] = 1.0 / 3

@@ -53,4 +53,52 @@ print('rank %d: overlapped vs sequential all-reduce, worst per-tensor relative g
       'ranks identical: %s' % (rank, worst, la, lb, same_across_ranks), flush=True)
 # wgrad accumulates with fp32 atomics (order varies run to run), so the two runs agree to rounding, not bitwise
 assert worst <= 1e-3 and same_across_ranks
+
+
+def dp_vs_global_batch():
+    """data-parallel step (per-rank batch 2, gradients averaged over ranks) against ONE process running the global batch, in the
+    strict fp32 mode: the reference's single-process DataParallel step takes the loss mean over the global batch
+    (core/seg_train.py:77,119-127), and the mean of equal-sized per-rank means is that mean."""
+    world = dist.get_world_size()
+    os.environ['SEG3D_OVERLAP_ALLREDUCE'] = '1'
+
+    def data(r):
+        g = torch.Generator(device='cuda').manual_seed(200 + r)
+        return (torch.randn((2, 1, 32, 32, 32), generator=g, device='cuda'),
+                torch.randint(0, 2, (2, 1, 32, 32, 32), generator=g, device='cuda').float())
+
+    torch.manual_seed(0)
+    net = vnet.SegmentationNet(1, 2)
+    vnet.parameters_kaiming_init(net)
+    net.b200_mode = 'fp32'
+    net = net.cuda().train()
+    lf = MultiDiceLoss([0.5, 0.5], 2, True)
+    crops, masks = data(rank)
+    loss = lf(net(crops), masks)
+    loss.backward()
+    params = list(net.parameters())
+    if not net._plan.grads_reduced_in_backward:
+        D.allreduce_mean_grads(params)
+    torch.cuda.synchronize()
+    return [p.grad.detach().clone() for p in params], float(loss), world, data
+
+
+g_dp, l_dp, world, data = dp_vs_global_batch()
+# the global-batch arm runs outside the process group (a world of one) so that nothing is averaged across ranks
+dist.barrier()
 dist.destroy_process_group()
+torch.manual_seed(0)
+net = vnet.SegmentationNet(1, 2)
+vnet.parameters_kaiming_init(net)
+net.b200_mode = 'fp32'
+net = net.cuda().train()
+lf = MultiDiceLoss([0.5, 0.5], 2, True)
+allc = torch.cat([data(r)[0] for r in range(world)], 0)
+allm = torch.cat([data(r)[1] for r in range(world)], 0)
+loss = lf(net(allc), allm)
+loss.backward()
+torch.cuda.synchronize()
+worst_dp = max(float((a - p.grad).abs().max() / (p.grad.abs().max() + 1e-20)) for a, p in zip(g_dp, net.parameters()))
+print('rank %d: data-parallel (world %d, batch 2/rank) vs one process on the global batch of %d, fp32: worst per-tensor relative '
+      'gradient difference %.3g, global loss %.6f' % (rank, world, 2 * world, worst_dp, float(loss)), flush=True)
+assert worst_dp <= 2e-3

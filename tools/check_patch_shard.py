@@ -50,4 +50,27 @@ torch.cuda.synchronize()
 agree_l = float((mask_tl == mask_t1).float().mean())
 print('rank %d/%d: label exchange mask agreement %.6f' % (rank, world, agree_l), flush=True)
 assert agree_l >= 0.9999
+# the same exchange on a volume whose ranks own different z ranges (3 x 2 x 2 patches of 48^3), device and HOST entry points:
+# a rank accumulates, finishes and (host call) uploads only the z planes its patches touch
+from segmentation3d.core.seg_infer import segmentation_volume_host, shard_plan
+g2 = torch.Generator(device='cuda').manual_seed(9)
+vol_z = torch.nn.functional.avg_pool3d(torch.randn((1, 1, 144, 96, 96), generator=g2, device='cuda'), 3, 1, 1)[0, 0].contiguous() * 3.0
+_, _, mine, (z_lo, z_hi) = shard_plan(model, cfg_t, vol_z.shape, (rank, world))
+acc_z1, mask_z1 = segmentation_volume_device(model, cfg_t, vol_z, batch=4)
+acc_zl, mask_zl = segmentation_volume_device(model, cfg_t, vol_z, batch=4, shard=(rank, world), gather='labels')
+host_vol = torch.empty(vol_z.shape, dtype=torch.float32, pin_memory=True)
+host_vol.copy_(vol_z)
+host_mask = torch.empty(vol_z.shape, dtype=torch.int8, pin_memory=True)
+_, host_mask = segmentation_volume_host(model, cfg_t, host_vol, host_mask, batch=4, shard=(rank, world), gather='labels')
+torch.cuda.synchronize()
+assert acc_zl.shape[1] == z_hi - z_lo and (world == 1 or z_hi - z_lo < 144), (acc_zl.shape, z_lo, z_hi)
+own = torch.zeros(vol_z.shape, dtype=torch.bool, device='cuda')
+for s0 in mine:
+    own[s0[2]:s0[2] + 48, s0[1]:s0[1] + 48, s0[0]:s0[0] + 48] = True
+d_own = float(((acc_zl - acc_z1[:, z_lo:z_hi]).abs() * own[z_lo:z_hi]).max())
+agree_z = float((mask_zl == mask_z1).float().mean())
+agree_h = float((host_mask.cuda() == mask_z1).float().mean())
+print('rank %d/%d: z-range %d..%d of 144 (%d patches): own-patch max|dp| %.3g, label exchange agreement %.6f (device) %.6f (host call)'
+      % (rank, world, z_lo, z_hi, len(mine), d_own, agree_z, agree_h), flush=True)
+assert d_own <= 1e-5 and agree_z >= 0.9999 and agree_h >= 0.9999
 dist.destroy_process_group()
