@@ -201,12 +201,6 @@ def _grid(model, cfg, size_xyz, spacing, bbox_start_voxel, bbox_end_voxel, use_g
     return image_partition_by_fixed_size(frame, bs, be, psize, pstride, model['max_stride'])
 
 
-def labels_can_merge_by_max(counts):
-    """patch-sharded inference may exchange labels instead of probability maps when no two patches overlap: every
-    per-axis overlap count is at most 1 (partition_stride >= partition_size, or a single patch)."""
-    return all(int(np.asarray(c).max()) <= 1 for c in counts)
-
-
 def segmentation_voi(model, iso_image, start_voxel, end_voxel, use_gpu):
     """Probability maps of one volume of interest [start_voxel, end_voxel) of an image already at the model spacing
     (reference :208-246): crop -> crop normaliser -> network -> one image per class carrying the VOI's frame.  The
@@ -233,28 +227,67 @@ def segmentation_voi(model, iso_image, start_voxel, end_voxel, use_gpu):
     return maps
 
 
-def deal_patches(starts, rank, world):
-    """Patches of ONE volume for rank `rank` of `world`: the reference list (x outer, z inner; utils/image_tools.py:202-204)
-    re-ordered by first z plane and cut into `world` contiguous runs whose lengths differ by at most one.  A rank's patches
-    then span one or two z layers of the lattice, so it reads, accumulates and finishes only that z range of the volume."""
-    order = sorted(range(len(starts)), key=lambda i: (starts[i][2], starts[i][1], starts[i][0]))
-    n = len(order)
+def overlap_components(starts, ends):
+    """Groups of patches that overlap, directly or through a chain.  The reference grid (utils/image_tools.py:200-216) is the
+    Cartesian product of per-axis box lists, so two patches overlap iff their boxes overlap on every axis: merging the
+    overlapping intervals of each axis and taking the product of the merged groups gives the connected components.  With
+    partition_stride >= partition_size only the LAST box of an axis, clamped back into the volume (:209-213), overlaps its
+    neighbour, so the components hold 1, 2, 4 or 8 patches.  Returned in z-major order as lists of patch indices."""
+    group_of = []
+    for a in range(3):
+        boxes = sorted(set((int(s[a]), int(e[a])) for s, e in zip(starts, ends)))
+        gid, reach, ids = -1, None, {}
+        for lo, hi in boxes:
+            if reach is None or lo >= reach:
+                gid, reach = gid + 1, hi
+            else:
+                reach = max(reach, hi)
+            ids[lo] = gid
+        group_of.append(ids)
+    comps = {}
+    for i, s in enumerate(starts):
+        key = (group_of[2][int(s[2])], group_of[1][int(s[1])], group_of[0][int(s[0])])
+        comps.setdefault(key, []).append(i)
+    return [comps[k] for k in sorted(comps)]
+
+
+def deal_patches(starts, ends, rank, world, max_imbalance=1.15):
+    """Patches of ONE volume for rank `rank` of `world`.  Returns (patches, disjoint).
+    disjoint = True: whole overlap components (see above) are dealt, in z-major order, to the rank whose share of the patch
+    count their midpoint falls in.  No voxel is then touched by two ranks: a rank's accumulators are final where its patches
+    lie and exactly zero elsewhere, so it can count-normalise and arg-max locally and the ranks exchange LABELS.  A rank's
+    patches span one or two z layers of the lattice: it reads, accumulates and finishes only that z range of the volume.
+    disjoint = False (a component is too large to balance, e.g. partition_stride < partition_size chains every patch to its
+    neighbour): single patches in z-major order, cut into `world` runs whose lengths differ by at most one; the ranks must
+    then exchange probability sums."""
+    n = len(starts)
+    comps = overlap_components(starts, ends)
+    loads, mine, done = [0] * world, [], 0
+    for comp in comps:
+        r = min(world - 1, int((done + len(comp) / 2.0) * world / n))
+        loads[r] += len(comp)
+        done += len(comp)
+        if r == rank:
+            mine += comp
+    if max(loads) <= max_imbalance * -(-n // world):
+        return [starts[i] for i in mine], True
+    order = sorted(range(n), key=lambda i: (starts[i][2], starts[i][1], starts[i][0]))
     lo, hi = (n * rank) // world, (n * (rank + 1)) // world
-    return [starts[i] for i in order[lo:hi]]
+    return [starts[i] for i in order[lo:hi]], False
 
 
 def shard_plan(model, cfg, shape_zyx, shard, bbox_start_voxel=None, bbox_end_voxel=None, use_gpu=True, spacing=None):
-    """Grid of a volume [Z,Y,X] and this rank's part of it: (starts, ends, mine, (z_lo, z_hi)).  z range = the planes this
-    rank's patches read and write ((0, Z) without sharding)."""
+    """Grid of a volume [Z,Y,X] and this rank's part of it: (starts, ends, mine, (z_lo, z_hi), disjoint).  z range = the planes
+    this rank's patches read and write ((0, Z) without sharding)."""
     Z, Y, X = [int(v) for v in shape_zyx]
     starts, ends = _grid(model, cfg, [X, Y, Z], spacing or model['spacing'], bbox_start_voxel, bbox_end_voxel, use_gpu)
     if shard is None or shard[1] <= 1:
-        return starts, ends, starts, (0, Z)
-    mine = deal_patches(starts, shard[0], shard[1])
+        return starts, ends, starts, (0, Z), True
+    mine, disjoint = deal_patches(starts, ends, shard[0], shard[1])
     pz = ends[0][2] - starts[0][2]
     if not mine:
-        return starts, ends, mine, (0, 0)
-    return starts, ends, mine, (min(s[2] for s in mine), max(s[2] for s in mine) + pz)
+        return starts, ends, mine, (0, 0), disjoint
+    return starts, ends, mine, (min(s[2] for s in mine), max(s[2] for s in mine) + pz), disjoint
 
 
 def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_start_voxel=None, bbox_end_voxel=None,
@@ -263,10 +296,10 @@ def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_sta
     the model spacing.  Returns (mean_probs [C,z,y,x] fp32, mask [z,y,x] int8) on the device.
     shard=(rank, world): the patches of this ONE volume are dealt over the ranks of the default process group (NCCL) in
     contiguous z runs (`deal_patches`); every rank touches only the z range of its patches.  The exchange step:
-      gather='labels' (taken when no two patches overlap, i.e. partition_stride >= partition_size - the BASELINE configs):
-          every voxel belongs to exactly one patch, hence to one rank: count-normalise + arg-max the local z range and merge
-          the int8 masks with ONE max all-reduce (1 byte per voxel on the wire).  Returned probabilities: this rank's z range.
-      gather='mask' (needs Z % world == 0; also what 'labels' falls back to when patches overlap): per-class reduce-scatter
+      gather='labels' (taken when the patches can be dealt so that no voxel is touched by two ranks - `deal_patches`; true for
+          partition_stride >= partition_size, the BASELINE configs): count-normalise + arg-max the local z range and merge the
+          int8 masks with ONE max all-reduce (1 byte per voxel on the wire).  Returned probabilities: this rank's z range.
+      gather='mask' (needs Z % world == 0; also what 'labels' falls back to otherwise): per-class reduce-scatter
           of z slabs of the fp32 accumulators, count normalisation + arg-max on the local slab, all-gather of the int8 mask;
           the returned probabilities are this rank's slab [C, Z/world, Y, X].
       gather='probs': all-reduce of the full maps; every rank returns the full probability maps.
@@ -276,7 +309,7 @@ def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_sta
     eng.plan = model['net']._current_plan()
     Z, Y, X = vol.shape
     sharded = shard is not None and shard[1] > 1
-    starts, ends, mine, (z_lo, z_hi) = shard_plan(model, cfg, vol.shape, shard, bbox_start_voxel, bbox_end_voxel, use_gpu, spacing)
+    starts, ends, mine, (z_lo, z_hi), disjoint = shard_plan(model, cfg, vol.shape, shard, bbox_start_voxel, bbox_end_voxel, use_gpu, spacing)
     norm = model['crop_normalizers'][0].to_dict() if model['crop_normalizers'] else None
     patch = [ends[0][a] - starts[0][a] for a in range(3)]
     C = model['out_channels']
@@ -290,7 +323,7 @@ def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_sta
         eng.batch = int(batch)
     elif eng.batch <= 0:
         eng.batch = default_patch_batch(pv)
-    if sharded and gather == 'labels' and labels_can_merge_by_max(counts):
+    if sharded and gather == 'labels' and disjoint:
         import torch.distributed as dist
         # local z range only: accumulators, count normalisation and arg-max cover [z_lo, z_hi); the volume may be resident
         # for that range alone (segmentation_volume_host uploads nothing else)
@@ -374,7 +407,7 @@ def segmentation_volume_host(model, cfg, host_vol, host_mask=None, batch=None, s
     Z = host_vol.shape[0]
     z_lo, z_hi = 0, Z
     if shard is not None and shard[1] > 1:
-        _, _, _, (z_lo, z_hi) = shard_plan(model, cfg, host_vol.shape, shard)
+        _, _, _, (z_lo, z_hi), _ = shard_plan(model, cfg, host_vol.shape, shard)
     if host_vol.is_pinned() and cfg['partition_type'] == 'SIZE' and os.environ.get('SEG3D_OVERLAP_UPLOAD', '1') != '0':
         # upload z slabs on a side stream so the first patches start while the rest of the volume is in flight
         side = _side_stream(dev)

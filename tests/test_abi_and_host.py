@@ -293,20 +293,37 @@ def test_parallel_zlib_stream_is_a_plain_zlib_stream(tmp_path):
     assert np.array_equal(back.to_numpy(), arr) and np.allclose(back.GetSpacing(), (0.5, 0.5, 2.0))
 
 
-def test_deal_patches_is_a_balanced_partition_in_z_runs():
-    """core/seg_infer.py::deal_patches: every patch of the reference grid goes to exactly one rank, run lengths differ by at
-    most one, and a rank's patches are contiguous in z-major order (so it touches one or two z layers of the lattice)."""
+def test_deal_patches_keeps_overlap_components_on_one_rank():
+    """core/seg_infer.py::deal_patches: every patch of the reference grid goes to exactly one rank; for BASELINE configs[1]
+    (512 = 5 x 96 + 32: the clamped last box of each axis overlaps its neighbour) whole overlap components are dealt, so no
+    voxel is touched by two ranks, the loads stay within 15 % of ceil(n / world), and a rank spans at most the z layers of
+    one or two lattice rows; with partition_stride < partition_size everything chains into one component and the fallback
+    deals single patches in balanced z runs."""
     from oracle import sliding_window as osw
-    from segmentation3d.core.seg_infer import deal_patches
-    starts, _ = osw.partition_grid([512, 512, 400], [1, 1, 1], [0, 0, 0], [512, 512, 400], [96] * 3, [96] * 3, 16)
+    from segmentation3d.core.seg_infer import deal_patches, overlap_components
+    starts, ends = osw.partition_grid([512, 512, 400], [1, 1, 1], [0, 0, 0], [512, 512, 400], [96] * 3, [96] * 3, 16)
     assert len(starts) == 180
-    for world in (1, 2, 3, 4, 8, 16, 181):
-        parts = [deal_patches(starts, r, world) for r in range(world)]
-        flat = [tuple(s) for p in parts for s in p]
+    comps = overlap_components(starts, ends)
+    assert sorted(len(c) for c in comps) == [1] * 48 + [2] * 40 + [4] * 11 + [8]
+    for world in (1, 2, 4, 8):
+        parts = [deal_patches(starts, ends, r, world) for r in range(world)]
+        assert all(d for _, d in parts)
+        flat = [tuple(s) for p, _ in parts for s in p]
         assert sorted(flat) == sorted(tuple(s) for s in starts) and len(set(flat)) == 180
-        sizes = [len(p) for p in parts]
-        assert max(sizes) - min(sizes) <= 1
-        zkey = [(s[2], s[1], s[0]) for p in parts for s in p]
-        assert zkey == sorted(zkey)
-        if world == 8:
-            assert max(len({s[2] for s in p}) for p in parts) <= 2
+        assert max(len(p) for p, _ in parts) <= 1.15 * -(-180 // world)
+        owner = np.full((400, 512, 512), -1, np.int8)
+        for r, (p, _) in enumerate(parts):
+            for s in p:
+                box = owner[s[2]:s[2] + 96, s[1]:s[1] + 96, s[0]:s[0] + 96]
+                assert ((box == -1) | (box == r)).all()            # no voxel of another rank
+                box[...] = r
+        assert (owner >= 0).all()
+    # overlapping stride: one component -> balanced runs of single patches, probability sums must be exchanged
+    starts, ends = osw.partition_grid([256, 256, 256], [1, 1, 1], [0, 0, 0], [256, 256, 256], [96] * 3, [48] * 3, 16)
+    assert len(overlap_components(starts, ends)) == 1
+    parts = [deal_patches(starts, ends, r, 8) for r in range(8)]
+    assert not any(d for _, d in parts)
+    sizes = [len(p) for p, _ in parts]
+    assert sum(sizes) == len(starts) and max(sizes) - min(sizes) <= 1
+    zkey = [(s[2], s[1], s[0]) for p, _ in parts for s in p]
+    assert zkey == sorted(zkey)

@@ -107,12 +107,11 @@ def test_patch_sharded_labels_merge_by_max():
     """gather='labels' (core/seg_infer.py::segmentation_volume_device): with non-overlapping patches every voxel is
     labelled by exactly one rank, the others hold 0 there, so a max all-reduce of the int8 masks is the full mask."""
     import multiprocessing as mp
-    from segmentation3d._b200.sliding import axis_counts
-    from segmentation3d.core.seg_infer import labels_can_merge_by_max
+    from segmentation3d.core.seg_infer import deal_patches
     starts = [[x, y, z] for x in (0, 4) for y in (0, 4) for z in (0, 4)]
-    assert labels_can_merge_by_max(axis_counts([8, 8, 8], starts, [[s[0] + 4, s[1] + 4, s[2] + 4] for s in starts]))
+    assert deal_patches(starts, [[s[0] + 4, s[1] + 4, s[2] + 4] for s in starts], 0, 2)[1]          # tiled: ranks touch disjoint voxels
     starts = [[x, 0, 0] for x in (0, 2, 4)]
-    assert not labels_can_merge_by_max(axis_counts([8, 4, 4], starts, [[s[0] + 4, 4, 4] for s in starts]))   # stride 2 < size 4
+    assert not deal_patches(starts, [[s[0] + 4, 4, 4] for s in starts], 0, 2)[1]    # stride 2 < size 4: one chain, cannot be dealt whole
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()

@@ -73,11 +73,15 @@ def test_config2_full_volume_properties():
     m3 = eng.finalize(tot, axis_counts([512, 512, 400], starts, ends))
     assert float((tot - acc).abs().max()) <= 1e-5
     assert float((m3 == mask).float().mean()) >= 0.99999
-    # eight patches drawn from the 180 (seeded; corners, faces and interior all occur) against the oracle forward of the same
+    # eight patches drawn from the 180 (seeded; corner, face and interior patches occur) against the oracle forward of the same
     # crops: BASELINE.json reduced-precision bars per patch - max|dp| <= 1e-2, label agreement >= 99.9 %, per-class Dice >= 0.999
     sd = oinit.init_state_dict('vnet', 1, 2, 0)
+    # only patches no other patch overlaps: 512 = 5 x 96 + 32 and 400 = 4 x 96 + 16, so the clamped last box of every axis
+    # overlaps its neighbour and those two average their probabilities (checked against the reference blend elsewhere)
+    alone = [i for i, s0 in enumerate(starts) if s0[0] <= 288 and s0[1] <= 288 and s0[2] <= 192]
+    assert len(alone) == 4 * 4 * 3
     rng = np.random.default_rng(5)
-    picked = sorted(rng.choice(len(starts), size=8, replace=False).tolist())
+    picked = sorted(rng.choice(alone, size=8, replace=False).tolist())
     worst = {'max_abs': 0.0, 'agree': 1.0, 'dice': 1.0}
     for i in picked:
         s0, e0 = starts[i], ends[i]

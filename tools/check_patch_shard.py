@@ -38,12 +38,11 @@ print('rank %d/%d: all-reduce max|dp| %.3g, reduce-scatter slab max|dp| %.3g, ma
 assert d_probs <= 1e-5 and d_slab <= 1e-5 and agree_p >= 0.9999 and agree_m >= 0.9999
 assert accm.shape == (2, zs) + tuple(vol.shape[1:]) and maskm.shape == vol.shape
 # label exchange (gather='labels'): non-overlapping patches, local arg-max + max all-reduce of the int8 mask
-from segmentation3d.core.seg_infer import _grid, labels_can_merge_by_max
-from segmentation3d._b200.sliding import axis_counts
+from segmentation3d.core.seg_infer import _grid, deal_patches
 cfg_t = {'partition_type': 'SIZE', 'partition_size': [48, 48, 48], 'partition_stride': [48, 48, 48]}
 vol_t = vol[:96, :96, :96].contiguous()
 st, en = _grid(model, cfg_t, [96, 96, 96], [1.0, 1.0, 1.0], None, None)
-assert labels_can_merge_by_max(axis_counts([96, 96, 96], st, en)) and len(st) == 8
+assert deal_patches(st, en, rank, world)[1] and len(st) == 8
 _, mask_t1 = segmentation_volume_device(model, cfg_t, vol_t, batch=4)
 _, mask_tl = segmentation_volume_device(model, cfg_t, vol_t, batch=4, shard=(rank, world), gather='labels')
 torch.cuda.synchronize()
@@ -55,7 +54,8 @@ assert agree_l >= 0.9999
 from segmentation3d.core.seg_infer import segmentation_volume_host, shard_plan
 g2 = torch.Generator(device='cuda').manual_seed(9)
 vol_z = torch.nn.functional.avg_pool3d(torch.randn((1, 1, 144, 96, 96), generator=g2, device='cuda'), 3, 1, 1)[0, 0].contiguous() * 3.0
-_, _, mine, (z_lo, z_hi) = shard_plan(model, cfg_t, vol_z.shape, (rank, world))
+_, _, mine, (z_lo, z_hi), disjoint = shard_plan(model, cfg_t, vol_z.shape, (rank, world))
+assert disjoint
 acc_z1, mask_z1 = segmentation_volume_device(model, cfg_t, vol_z, batch=4)
 acc_zl, mask_zl = segmentation_volume_device(model, cfg_t, vol_z, batch=4, shard=(rank, world), gather='labels')
 host_vol = torch.empty(vol_z.shape, dtype=torch.float32, pin_memory=True)
@@ -73,4 +73,16 @@ agree_h = float((host_mask.cuda() == mask_z1).float().mean())
 print('rank %d/%d: z-range %d..%d of 144 (%d patches): own-patch max|dp| %.3g, label exchange agreement %.6f (device) %.6f (host call)'
       % (rank, world, z_lo, z_hi, len(mine), d_own, agree_z, agree_h), flush=True)
 assert d_own <= 1e-5 and agree_z >= 0.9999 and agree_h >= 0.9999
+# ragged volume: the last box of every axis is clamped back into the volume and overlaps its neighbour (as in BASELINE
+# configs[1]: 512 = 5 x 96 + 32); whole overlap components go to one rank, so the label exchange is still exact
+vol_r = torch.nn.functional.avg_pool3d(torch.randn((1, 1, 160, 112, 128), generator=g2, device='cuda'), 3, 1, 1)[0, 0].contiguous() * 3.0
+st_r, en_r, mine_r, zr, disjoint_r = shard_plan(model, cfg_t, vol_r.shape, (rank, world))
+assert disjoint_r and len(st_r) == 4 * 3 * 3
+_, mask_r1 = segmentation_volume_device(model, cfg_t, vol_r, batch=6)
+_, mask_rl = segmentation_volume_device(model, cfg_t, vol_r, batch=6, shard=(rank, world), gather='labels')
+torch.cuda.synchronize()
+agree_r = float((mask_rl == mask_r1).float().mean())
+print('rank %d/%d: ragged volume (36 patches, clamped last boxes overlap): %d patches here, z-range %s, label exchange agreement %.6f'
+      % (rank, world, len(mine_r), zr, agree_r), flush=True)
+assert agree_r >= 0.9999
 dist.destroy_process_group()
