@@ -215,14 +215,17 @@ int seg3d_ce_bwd(const float* logits, const float* target, int B, int C, int64_t
  * swapped channels; k2s2 <-> transposed conv).
  * seg3d_gn_bwd, two passes over the same arguments:
  *   g0..g2 : up to three gradient contributions wrt `out` (g1/g2 may be NULL), each with its own pitch;
- *   out    : the unit's saved post-ReLU output (mask = out > 0);  y : saved raw conv output;  stats : forward sums.
+ *   out    : the unit's saved post-ReLU output (mask = out > 0), or NULL for a unit WITHOUT a residual: the mask is then
+ *            recomputed from y as fma(y, rstd*gamma, beta - mean*rstd*gamma) > 0, the expression seg3d_gn_apply evaluated on
+ *            the same stored y (beta must be given; `out` is not read, a third of pass 0's traffic);
+ *   y      : saved raw conv output;  stats : forward sums.
  *   pass 0 : sums[n] += {sum gamma*dz, sum gamma*dz*xhat} (double), dgamma[c] += sum dz*xhat, dbeta[c] += sum dz.
  *   pass 1 : dy = rstd*(gamma*dz - mean(gamma dz) - xhat*mean(gamma dz xhat)) stored with pitch dy_ld;
  *            dres (optional) = dz (the residual branch's gradient); dbias[c] (optional) += sum dy.
  * C % 8 == 0, 256 % (C/8) == 0. */
 int seg3d_gn_bwd(int dtype, int pass, const void* g0, int ld0, const void* g1, int ld1, const void* g2, int ld2,
                  const void* out, int out_ld, const void* y, int y_ld, int C, const double* stats,
-                 const float* gamma, float eps, double* sums, float* dgamma, float* dbeta,
+                 const float* gamma, const float* beta, float eps, double* sums, float* dgamma, float* dbeta,
                  void* dy, int dy_ld, void* dres, int dres_ld, float* dbias, int N, int64_t nvox, void* stream);
 /* dw (fp32, SIMT weight layout of seg3d_conv3d_fwd: [taps][Cin][Cout], T2S2 [Cin][8*Cout]) += x (*) dy; the caller
  * zeroes dw.  D,H,W are the spatial dims of x (the convolution's input). */
@@ -239,6 +242,34 @@ int seg3d_outblock_tail_bwd(int dtype, int pass, const void* y1, int ld, int C,
                             float* dgamma2, float* dbeta2, float* dw2, float* db2,
                             float* dgamma1, float* dbeta1, float* db1,
                             void* dy1, int dy_ld, int N, int64_t nvox, void* stream);
+
+/* ---- training: the parameter side of the step (reference core/seg_train.py:83 `optim.Adam(net.parameters(), lr, betas)`,
+ * :127 `opt.step()`; the per-step weight re-layout replaces what nn.Conv3d does implicitly by reading its own parameter) ----
+ * seg3d_gather_pack: table-driven strided gather with a cast.  Entry e fills the logical 5-D index space size[0..4]
+ * (row-major, unused dims = 1):
+ *     dst[dst_base + sum_d i_d*dst_stride[d]]  =  (all i_d < limit[d]) ? src[src_base + sum_d i_d*src_stride[d]] : 0
+ * stored as `dtype` (SEG3D_F32 / F16 / BF16).  kind SEG3D_PACK_SPLIT_HI / _LO store f16(w) / f16(w - f16(w)) (the split-operand
+ * strict mode).  Strides are in elements and may be negative (flipped taps of the data-gradient convolution).  `table` is a
+ * DEVICE array of n_entries entries; one launch serves them all (grid.y = entry); max_elems = the largest entry's element count.
+ * Used for: every convolution's kernel-layout weights (forward and data-gradient) from the fp32 OIDHW / IODHW parameters, and
+ * the kernel-layout weight gradients back to parameter layout. */
+#define SEG3D_PACK_PLAIN 0
+#define SEG3D_PACK_SPLIT_HI 1
+#define SEG3D_PACK_SPLIT_LO 2
+typedef struct seg3d_pack_entry {
+  const float* src;
+  void* dst;
+  int64_t src_base, dst_base;
+  int64_t src_stride[5], dst_stride[5];
+  int32_t size[5], limit[5];
+  int32_t dtype, kind;
+} seg3d_pack_entry;
+int seg3d_gather_pack(const seg3d_pack_entry* table, int n_entries, int64_t max_elems, void* stream);
+/* torch.optim.Adam's update (no amsgrad, no maximize) over one flat fp32 range of n elements, `step` = 1, 2, ...:
+ *   g += weight_decay*p;  m += (1-beta1)*(g-m);  v = beta2*v + (1-beta2)*g*g;
+ *   p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps).       All pointers 16-byte aligned. */
+int seg3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,8 @@
 //     z = gamma*(y-mean)*rstd + beta    xhat = (y-mean)*rstd
 //     out = relu(z [+ res])             saved (its sign is the ReLU mask)
 // Given g = dL/d out (sum of up to three contributions), dz = g*[out>0] and
+// (units without a residual: the mask is recomputed as fma(y, rstd*gamma, beta - mean*rstd*gamma) > 0, the very expression
+// the forward apply evaluated on the same stored y, so `out` is not read at all - a third of pass 0's traffic)
 //     dy = rstd*(gamma*dz - mean_all(gamma*dz) - xhat*mean_all(gamma*dz*xhat)),
 //     dgamma_c = sum dz*xhat, dbeta_c = sum dz, dres = dz, dbias_c = sum dy.
 #include "common.cuh"
@@ -21,11 +23,11 @@ constexpr int GN_BWD_U = 4;
 
 // PASS 0: per-sample sums S1 = sum gamma*dz, S2 = sum gamma*dz*xhat; per-channel dgamma, dbeta.
 // PASS 1: dy (+ optional dres), per-channel dbias.
-template <typename T, int PASS>
+template <typename T, int PASS, bool REMASK>
 __global__ void __launch_bounds__(256, 2)
 gn_bwd_kernel(const T* __restrict__ g0, int ld0, const T* __restrict__ g1, int ld1, const T* __restrict__ g2, int ld2,
               const T* __restrict__ out, int out_ld, const T* __restrict__ y, int y_ld, int C,
-              const double* __restrict__ stats, const float* __restrict__ gamma, float eps,
+              const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
               double* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
               T* __restrict__ dy, int dy_ld, T* __restrict__ dres, int dres_ld, float* __restrict__ dbias, long long nvox) {
   __shared__ float sacc[2 * GN_BWD_MAXC];
@@ -44,9 +46,13 @@ gn_bwd_kernel(const T* __restrict__ g0, int ld0, const T* __restrict__ g1, int l
   // blockDim (256) is a multiple of cv and so is the grid stride: a thread keeps one channel group
   const int grp = threadIdx.x % cv, c0 = grp << 3;
   const long long vstep = (long long)gridDim.x * (blockDim.x / cv);
-  float gam[8];
+  float gam[8], za[8], zb[8];          // REMASK: z = fma(y, za, zb) exactly as gn_apply_kernel forms it
 #pragma unroll
-  for (int j = 0; j < 8; ++j) gam[j] = gamma[c0 + j];
+  for (int j = 0; j < 8; ++j) {
+    gam[j] = gamma[c0 + j];
+    za[j] = rstd * gam[j];
+    zb[j] = REMASK ? beta[c0 + j] - mean * za[j] : 0.f;
+  }
   float a0[8], a1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
@@ -63,7 +69,7 @@ gn_bwd_kernel(const T* __restrict__ g0, int ld0, const T* __restrict__ g1, int l
       rg0[u].load(g0 + vv * ld0 + c0);
       if (g1) rg1[u].load(g1 + vv * ld1 + c0); else rg1[u].zero();
       if (g2) rg2[u].load(g2 + vv * ld2 + c0); else rg2[u].zero();
-      ro[u].load(out + vv * out_ld + c0);
+      if (!REMASK) ro[u].load(out + vv * out_ld + c0);
       ry[u].load(y + vv * y_ld + c0);
     }
 #pragma unroll
@@ -72,11 +78,13 @@ gn_bwd_kernel(const T* __restrict__ g0, int ld0, const T* __restrict__ g1, int l
       if (vu >= nvox) break;
       const size_t vv = nb + vu;
       float ga[8], gb[8], gc[8], o[8], yy[8];
-      rg0[u].get(ga); rg1[u].get(gb); rg2[u].get(gc); ro[u].get(o); ry[u].get(yy);
+      rg0[u].get(ga); rg1[u].get(gb); rg2[u].get(gc); ry[u].get(yy);
+      if (!REMASK) ro[u].get(o);
       float dyv[8], dzv[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float dz = o[j] > 0.f ? (ga[j] + gb[j] + gc[j]) : 0.f;
+        const bool on = REMASK ? (fmaf(yy[j], za[j], zb[j]) > 0.f) : (o[j] > 0.f);
+        const float dz = on ? (ga[j] + gb[j] + gc[j]) : 0.f;
         const float xh = (yy[j] - mean) * rstd;
         if (PASS == 0) {
           a0[j] = fmaf(dz, xh, a0[j]); a1[j] += dz;        // the per-sample sums follow from these at the end (a block = one sample)
@@ -450,26 +458,27 @@ wgrad_cin1_kernel(const T* __restrict__ x, const T* __restrict__ dy, int dy_ld, 
 
 extern "C" int seg3d_gn_bwd(int dtype, int pass, const void* g0, int ld0, const void* g1, int ld1, const void* g2, int ld2,
                             const void* out, int out_ld, const void* y, int y_ld, int C, const double* stats,
-                            const float* gamma, float eps, double* sums, float* dgamma, float* dbeta,
+                            const float* gamma, const float* beta, float eps, double* sums, float* dgamma, float* dbeta,
                             void* dy, int dy_ld, void* dres, int dres_ld, float* dbias, int N, int64_t nvox, void* stream) {
   SEG3D_REQUIRE(C > 0 && C % 8 == 0 && C <= GN_BWD_MAXC && 256 % (C / 8) == 0, "gn_bwd: unsupported C=%d", C);
-  SEG3D_REQUIRE(g0 && out && y && stats && gamma && sums && N > 0 && nvox > 0, "gn_bwd: bad arguments");
+  SEG3D_REQUIRE(g0 && y && stats && gamma && sums && N > 0 && nvox > 0, "gn_bwd: bad arguments");
+  SEG3D_REQUIRE(out || beta, "gn_bwd: pass the saved output, or beta to recompute the ReLU mask from y (units without a residual)");
+  SEG3D_REQUIRE(out || !dres, "gn_bwd: a unit with a residual needs its saved output for the ReLU mask");
   SEG3D_REQUIRE(pass == 0 ? (dgamma && dbeta) : (dy != nullptr), "gn_bwd: missing outputs for pass %d", pass);
-  SEG3D_REQUIRE(ld0 % 8 == 0 && out_ld % 8 == 0 && y_ld % 8 == 0, "gn_bwd: pitches must be multiples of 8");
+  SEG3D_REQUIRE(ld0 % 8 == 0 && (!out || out_ld % 8 == 0) && y_ld % 8 == 0, "gn_bwd: pitches must be multiples of 8");
   const int cv = C / 8, vpb = 256 / cv;
   long long want = (nvox + vpb * 4 - 1) / (vpb * 4);
   const int sms = seg3d_num_sms();
   int gx = (int)(want < 1 ? 1 : (want > 4LL * sms ? 4LL * sms : want));
   dim3 grid(gx, N);
   cudaStream_t st = (cudaStream_t)stream;
+#define SEG3D_GNB(PS, RM) gn_bwd_kernel<T, PS, RM><<<grid, 256, 0, st>>>((const T*)g0, ld0, (const T*)g1, ld1, (const T*)g2, ld2, (const T*)out, out_ld, \
+        (const T*)y, y_ld, C, stats, gamma, beta, eps, sums, dgamma, dbeta, (T*)dy, dy_ld, (T*)dres, dres_ld, dbias, nvox)
   SEG3D_DISPATCH_DTYPE(dtype, T, {
-    if (pass == 0)
-      gn_bwd_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)g0, ld0, (const T*)g1, ld1, (const T*)g2, ld2, (const T*)out, out_ld, (const T*)y, y_ld,
-                                                C, stats, gamma, eps, sums, dgamma, dbeta, (T*)dy, dy_ld, (T*)dres, dres_ld, dbias, nvox);
-    else
-      gn_bwd_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)g0, ld0, (const T*)g1, ld1, (const T*)g2, ld2, (const T*)out, out_ld, (const T*)y, y_ld,
-                                                C, stats, gamma, eps, sums, dgamma, dbeta, (T*)dy, dy_ld, (T*)dres, dres_ld, dbias, nvox);
+    if (pass == 0) { if (out) SEG3D_GNB(0, false); else SEG3D_GNB(0, true); }
+    else           { if (out) SEG3D_GNB(1, false); else SEG3D_GNB(1, true); }
   });
+#undef SEG3D_GNB
   SEG3D_CHECK_LAUNCH("gn_bwd_kernel");
   return SEG3D_OK;
 }

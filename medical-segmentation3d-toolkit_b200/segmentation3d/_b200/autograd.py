@@ -25,6 +25,14 @@ def _k3_dgrad_weight(w):        # [Co,Ci,3,3,3] -> conv weight of the data-gradi
     return w.flip(2, 3, 4).permute(1, 0, 2, 3, 4).contiguous()
 
 
+def _same_weight(w):            # k2s2 dgrad = transposed conv (and vice versa) on the very same tensor
+    return w
+
+
+_k3_dgrad_weight.seg3d_kind = 'k3_dgrad'       # index-map forms of these transforms: packing.py::add_conv_pack
+_same_weight.seg3d_kind = 'identity'
+
+
 class _Backward(object):
     """Per (plan, shape) backward state: gradient buffers, dgrad convolutions, parameter-gradient slots."""
 
@@ -75,6 +83,7 @@ class _Backward(object):
         self.gd_tail = _View(torch.empty((B, vox[0], tx.C), dtype=td, device=dev), 0, tx.C, tx.C)
         self.sums = torch.zeros((len(self.units) + 2, B, 2), dtype=torch.float64, device=dev)
         self._make_dgrad_convs()
+        self._make_tables()
 
     def _has_producer(self, x):
         return any(id(x.buf) == k[0] and x.off <= k[1] < x.off + x.C for k in self.produced)
@@ -90,14 +99,62 @@ class _Backward(object):
                 self.dconv[name] = _Conv(sd, name, lib.CONV_K3, plan.dt, plan.device, plan.tc_modes,
                                          transform=_k3_dgrad_weight, pad_dim0=pad)
             elif c.mode == lib.CONV_K2S2:    # dgrad of the stride-2 conv = transposed conv with the same tensor
-                self.dconv[name] = _Conv(sd, name, lib.CONV_T2S2, plan.dt, plan.device, plan.tc_modes, transform=lambda w: w)
+                self.dconv[name] = _Conv(sd, name, lib.CONV_T2S2, plan.dt, plan.device, plan.tc_modes, transform=_same_weight)
             else:                            # dgrad of the transposed conv = stride-2 conv with the same tensor
-                self.dconv[name] = _Conv(sd, name, lib.CONV_K2S2, plan.dt, plan.device, plan.tc_modes, transform=lambda w: w)
+                self.dconv[name] = _Conv(sd, name, lib.CONV_K2S2, plan.dt, plan.device, plan.tc_modes, transform=_same_weight)
 
     def _weights(self):
         return self.plan._last_sd
 
+    def _make_tables(self):
+        """one-launch re-pack of the data-gradient weights and one-launch un-pack of the weight gradients (packing.py), when the
+        plan is bound to the live parameter tensors"""
+        from . import packing
+        plan = self.plan
+        self.pack_table, self.unpack_table, self.gflat = None, None, None
+        if not plan._bound_valid():
+            return
+        named = plan.bound
+        t = packing.PackTable(plan.device)
+        for name, c in self.dconv.items():
+            packing.add_conv_pack(t, c, named[name + '.weight'].data, None)
+        self.pack_table = t
+        # kernel-layout gradient slots -> one flat buffer in parameter layout and order
+        offsets, total = packing.flat_layout(list(named.items()))
+        self.gflat = torch.zeros((total,), dtype=torch.float32, device=plan.device)
+        self.g_offsets, self.g_shapes = offsets, {k: tuple(v.shape) for k, v in named.items()}
+        u = packing.PackTable(plan.device)
+        for name, c in plan.convs.items():
+            slot = self.pgrad[name + '.weight']
+            co_slot = self.conv1_co if name == 'out_block.conv1' else c.cout
+            P0, P1, k = self.g_shapes[name + '.weight'][:3]
+            base = offsets[name + '.weight']
+            if c.mode == lib.CONV_T2S2:          # slot [Cin][tap][Cout] -> parameter [Cin][Cout][a][b][c]
+                sstride = [8 * co_slot, 1, 4 * co_slot, 2 * co_slot, co_slot]
+            else:                                # slot [tap][Cin][Cout] -> parameter [Cout][Cin][a][b][c]
+                sstride = [1, co_slot, k * k * P1 * co_slot, k * P1 * co_slot, P1 * co_slot]
+            u.add(self.pgrad_flat, self.gflat, [P0, P1, k, k, k], sstride, [P1 * k ** 3, k ** 3, k * k, k, 1],
+                  src_base=self.pg_off[name + '.weight'], dst_base=base)
+            nb = self.g_shapes[name + '.bias'][0]
+            u.add(self.pgrad_flat, self.gflat, [1, 1, 1, 1, nb], [0, 0, 0, 0, 1], [0, 0, 0, 0, 1],
+                  src_base=self.pg_off[name + '.bias'], dst_base=offsets[name + '.bias'])
+        for key in ('out_block.conv2.weight', 'out_block.conv2.bias'):
+            n = 1
+            for d in self.g_shapes[key]:
+                n *= d
+            u.add(self.pgrad_flat, self.gflat, [1, 1, 1, 1, n], [0, 0, 0, 0, 1], [0, 0, 0, 0, 1],
+                  src_base=self.pg_off[key], dst_base=offsets[key])
+        for name in plan.gns:
+            for leaf in ('.weight', '.bias'):
+                n = self.g_shapes[name + leaf][0]
+                u.add(self.pgrad_flat, self.gflat, [1, 1, 1, 1, n], [0, 0, 0, 0, 1], [0, 0, 0, 0, 1],
+                      src_base=self.pg_off[name + leaf], dst_base=offsets[name + leaf])
+        self.unpack_table = u
+
     def refresh(self):
+        if self.pack_table is not None and self.plan._bound_valid():
+            self.pack_table.run()
+            return
         sd = self._weights()
         for c in self.dconv.values():
             c.load(sd)
@@ -170,10 +227,13 @@ class _Backward(object):
             gy = self.gy[u['conv']]
             dres = self.dres.get(u['conv'])
             nv = vox[u['lout']]
+            # without a residual the ReLU mask is recomputed from the raw tensor the kernel reads anyway (out = NULL)
+            remask = dres is None and os.environ.get('SEG3D_GN_BWD_REMASK', '1') != '0'
             for p in range(2):
                 lib.call('seg3d_gn_bwd', dt, p, gv[0].p, gv[0].ld, gv[1].p if gv[1] else None, gv[1].ld if gv[1] else 0,
                          gv[2].p if gv[2] else None, gv[2].ld if gv[2] else 0,
-                         u['out'].p, u['out'].ld, u['raw'].p, u['raw'].ld, c.cout, sf, lib.ptr(gnp.gamma), GN_EPS,
+                         None if remask else u['out'].p, u['out'].ld, u['raw'].p, u['raw'].ld, c.cout, sf, lib.ptr(gnp.gamma),
+                         lib.ptr(gnp.beta), GN_EPS,
                          lib.ptr(self.sums[ui]), lib.ptr(pg[u['gn'] + '.weight']), lib.ptr(pg[u['gn'] + '.bias']),
                          gy.p, gy.ld, dres.p if dres else None, dres.ld if dres else 0,
                          lib.ptr(pg[u['conv'] + '.bias']), B, nv, st())
@@ -198,7 +258,19 @@ class _Backward(object):
         return self._param_grads()
 
     def _param_grads(self):
-        """kernel-layout fp32 gradients -> the reference's parameter layouts (plumbing)."""
+        """kernel-layout fp32 gradients -> the reference's parameter layouts: one seg3d_gather_pack launch into a flat buffer
+        in parameter order, handed to autograd as views of ONE fresh copy (the slots are rewritten next step; the optimiser of
+        _b200/optim.py recognises the flat buffer and updates every parameter with one launch)."""
+        if self.unpack_table is not None and self.plan._bound_valid():
+            self.unpack_table.run()
+            flat = self.gflat.clone()
+            out = {}
+            for name, shape in self.g_shapes.items():
+                n = 1
+                for d in shape:
+                    n *= d
+                out[name] = flat[self.g_offsets[name]:self.g_offsets[name] + n].view(shape)
+            return out
         plan, out = self.plan, {}
         for name, c in plan.convs.items():
             g = self.pgrad[name + '.weight']
@@ -246,6 +318,8 @@ class _NetFunction(torch.autograd.Function):
         grads = bw.run(dprobs)
         plan.grads_reduced_in_backward = bw.grads_reduced       # train_step then skips its own all-reduce
         # the slots are reused next step: hand autograd its own copy (one copy, in the reference's parameter layout)
+        if bw.unpack_table is not None:
+            return (None, None, None) + tuple(grads[n] for n in ctx.names)          # already views of a private flat copy
         return (None, None, None) + tuple(g.clone() if g.is_contiguous() else g.contiguous()
                                           for g in (grads[n] for n in ctx.names))
 

@@ -51,13 +51,25 @@ _SIGNATURES = {
     'seg3d_focal_bwd': (_i, [_vp, _vp, _i, _i, _i64, _vp, _f, _f, _vp, _vp]),
     'seg3d_ce_fwd': (_i, [_vp, _vp, _i, _i, _i64, _vp, _i, _vp, _vp, _vp]),
     'seg3d_ce_bwd': (_i, [_vp, _vp, _i, _i, _i64, _vp, _i, _f, _vp, _vp, _vp]),
-    'seg3d_gn_bwd': (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _f, _vp, _vp, _vp,
+    'seg3d_gn_bwd': (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp,
                           _vp, _i, _vp, _i, _vp, _i, _i64, _vp]),
     'seg3d_conv3d_wgrad': (_i, [_i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     'seg3d_outblock_tail_bwd': (_i, [_i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp,
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp]),
+    'seg3d_gather_pack': (_i, [_vp, _i, _i64, _vp]),
+    'seg3d_adam_step': (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class PackEntry(ctypes.Structure):
+    """seg3d_pack_entry of include/seg3d_b200.h"""
+    _fields_ = [('src', ctypes.c_void_p), ('dst', ctypes.c_void_p), ('src_base', ctypes.c_int64), ('dst_base', ctypes.c_int64),
+                ('src_stride', ctypes.c_int64 * 5), ('dst_stride', ctypes.c_int64 * 5),
+                ('size', ctypes.c_int32 * 5), ('limit', ctypes.c_int32 * 5), ('dtype', ctypes.c_int32), ('kind', ctypes.c_int32)]
+
+
+PACK_PLAIN, PACK_SPLIT_HI, PACK_SPLIT_LO = 0, 1, 2
 
 _lib = None
 

@@ -143,15 +143,24 @@ class _GN(object):
 
 
 class _View(object):
-    """Channel window [off, off+C) of an NDHWC buffer with pitch ld."""
-    __slots__ = ('buf', 'off', 'ld', 'C')
+    """Channel window [off, off+C) of an NDHWC buffer with pitch ld.  `sample` = elements per sample (0: unknown, whole-batch
+    use only); `scratch`: a per-launch scratch (the raw pre-GroupNorm tensor) that every sub-batch of a schedule places at the
+    start of the buffer, so consecutive sub-batches reuse the same, L2-resident addresses."""
+    __slots__ = ('buf', 'off', 'ld', 'C', 'sample', 'scratch')
 
-    def __init__(self, buf, off, ld, C):
-        self.buf, self.off, self.ld, self.C = buf, off, ld, C
+    def __init__(self, buf, off, ld, C, sample=0, scratch=False):
+        self.buf, self.off, self.ld, self.C, self.sample, self.scratch = buf, off, ld, C, sample, scratch
 
     @property
     def p(self):
         return lib.ptr(self.buf, self.off)
+
+    def at(self, b0):
+        """pointer of sample b0"""
+        if b0 == 0 or self.scratch:
+            return lib.ptr(self.buf, self.off)
+        assert self.sample > 0
+        return lib.ptr(self.buf, self.off + b0 * self.sample)
 
 
 class NetPlan(object):
@@ -204,13 +213,41 @@ class NetPlan(object):
         self.gn_names = sorted(self.gns)
         self.gn_index = {n: i for i, n in enumerate(self.gn_names)}
         self._plans = {}
+        self.bound, self.pack_table = None, None
         self.launches_per_forward = 0
         self.use_graph = os.environ.get('SEG3D_GRAPH', '0') == '1'
+
+    def bind_parameters(self, named_params):
+        """Tie the plan to the live parameter tensors (fp32, contiguous, on the plan's device): `refresh` then re-packs every
+        weight with ONE seg3d_gather_pack launch reading the parameters in place, instead of ~130 framework launches."""
+        from . import packing
+        named = {(k[7:] if k.startswith('module.') else k): v for k, v in named_params}
+        ok = all(v.dtype == torch.float32 and v.is_contiguous() and v.device == self.device for v in named.values())
+        if not ok or os.environ.get('SEG3D_PACK_KERNEL', '1') == '0':
+            self.bound, self.pack_table = None, None
+            return
+        t = packing.PackTable(self.device)
+        for name, c in self.convs.items():
+            packing.add_conv_pack(t, c, named[name + '.weight'].data, named[name + '.bias'].data if (name + '.bias') in named else None)
+        for name, g in self.gns.items():
+            t.add_copy(named[name + '.weight'].data, g.gamma)
+            t.add_copy(named[name + '.bias'].data, g.beta)
+        t.add_copy(named['out_block.conv2.weight'].data, self.w2)
+        t.add_copy(named['out_block.conv2.bias'].data, self.b2)
+        self.bound = named
+        self.bound_ptrs = {k: v.data_ptr() for k, v in named.items()}
+        self.pack_table = t
+
+    def _bound_valid(self):
+        return getattr(self, 'bound', None) is not None and all(v.data_ptr() == self.bound_ptrs[k] for k, v in self.bound.items())
 
     def refresh(self, state_dict):
         """Re-pack changed weights in place (pointers captured by cached plans stay valid)."""
         sd = strip_prefix(state_dict)
         self._last_sd = sd
+        if self._bound_valid():
+            self.pack_table.run()
+            return
         for c in self.convs.values():
             c.load(sd)
         for g in self.gns.values():
@@ -239,7 +276,7 @@ class NetPlan(object):
             return torch.empty((B, vox[l], C * cm), dtype=td, device=dev)
 
         def V(b, off, ld, C):           # channel window of an activation buffer (ld = logical channel count of the buffer)
-            return _View(b, off, ld * cm, C)
+            return _View(b, off, ld * cm, C, sample=b.shape[1] * b.shape[2])
 
         ws = {}
         ws['x_in'] = torch.empty((B, vox[0], self.in_channels), dtype=torch.float32 if split else td, device=dev)
@@ -255,29 +292,37 @@ class NetPlan(object):
             ws['T%da' % l], ws['T%db' % l] = buf(l, C), buf(l, C)
             ws['U%d' % l] = buf(l, C)                            # rblock result (up path; level 4: down_256 output)
             ws['M%da' % l], ws['M%db' % l] = buf(l, C // 4), buf(l, C // 4)   # bottleneck mids (VBNet)
-        ops, meta, units = [], [], []
-        ws['meta'], ws['units'], ws['dims'], ws['vox'], ws['B'] = meta, units, dims, vox, B
+        # ops: callables op(b0, nb) that launch one kernel on samples [b0, b0 + nb) of the batch; levels[i] = pyramid level
+        # of op i's OUTPUT (the schedule runs the shallow levels in L2-sized sub-batches, see _schedule)
+        ops, meta, units, levels = [], [], [], []
+        ws['meta'], ws['units'], ws['dims'], ws['vox'], ws['B'], ws['levels'] = meta, units, dims, vox, B, levels
         ws['train'] = train
         st = lib.stream_ptr
         raw = ws['raw']
 
-        def conv(name, x, xdims, y, stats_name):
+        def stats_ptr(name, b0):
+            return lib.ptr(ws['stats'][self.gn_index[name]], 2 * b0)
+
+        def add(fn, level):
+            ops.append(fn)
+            levels.append(level)
+
+        def conv(name, x, xdims, y, stats_name, lout):
             c = self.convs[name]
             assert c.cin == x.C and c.cout == y.C, (name, c.cin, x.C, c.cout, y.C)
-            sp = lib.ptr(ws['stats'][self.gn_index[stats_name]]) if stats_name else None
             if split and c.impl == lib.IMPL_TCGEN05:       # x: [hi | lo] f16 rows, y: fp32 raw
-                args = (c.mode, x.p, x.ld, x.ld // 2, c.cin, lib.ptr(c.w), lib.ptr(c.bias), y.p, y.ld, c.cout,
-                        B, xdims[0], xdims[1], xdims[2], sp)
-                ops.append(lambda a=args: lib.call('seg3d_conv3d_split_fwd', *a, st()))
+                add(lambda b0, nb: lib.call('seg3d_conv3d_split_fwd', c.mode, x.at(b0), x.ld, x.ld // 2, c.cin, lib.ptr(c.w),
+                                            lib.ptr(c.bias), y.at(b0), y.ld, c.cout, nb, xdims[0], xdims[1], xdims[2],
+                                            stats_ptr(stats_name, b0) if stats_name else None, st()), lout)
             elif split:                                    # input block: fp32 in, fp32 weights, fp32 out on the CUDA cores
                 assert x.buf.dtype == torch.float32 and y.buf.dtype == torch.float32
-                args = (c.mode, lib.F32, lib.IMPL_SIMT, x.p, x.ld, c.cin, lib.ptr(c.w), lib.ptr(c.bias), y.p, y.ld, c.cout,
-                        B, xdims[0], xdims[1], xdims[2], sp)
-                ops.append(lambda a=args: lib.call('seg3d_conv3d_fwd', *a, st()))
+                add(lambda b0, nb: lib.call('seg3d_conv3d_fwd', c.mode, lib.F32, lib.IMPL_SIMT, x.at(b0), x.ld, c.cin, lib.ptr(c.w),
+                                            lib.ptr(c.bias), y.at(b0), y.ld, c.cout, nb, xdims[0], xdims[1], xdims[2],
+                                            stats_ptr(stats_name, b0) if stats_name else None, st()), lout)
             else:
-                args = (c.mode, dt, c.call_impl, x.p, x.ld, c.cin, lib.ptr(c.w), lib.ptr(c.bias), y.p, y.ld, c.cout,
-                        B, xdims[0], xdims[1], xdims[2], sp)
-                ops.append(lambda a=args: lib.call('seg3d_conv3d_fwd', *a, st()))
+                add(lambda b0, nb: lib.call('seg3d_conv3d_fwd', c.mode, dt, c.call_impl, x.at(b0), x.ld, c.cin, lib.ptr(c.w),
+                                            lib.ptr(c.bias), y.at(b0), y.ld, c.cout, nb, xdims[0], xdims[1], xdims[2],
+                                            stats_ptr(stats_name, b0) if stats_name else None, st()), lout)
             nv_in = B * xdims[0] * xdims[1] * xdims[2]
             taps = {lib.CONV_K3: 27, lib.CONV_K2S2: 1, lib.CONV_T2S2: 8, lib.CONV_K1: 1}[c.mode]   # MACs per INPUT voxel / (cin*cout)
             nv_out = nv_in // 8 if c.mode == lib.CONV_K2S2 else (nv_in * 8 if c.mode == lib.CONV_T2S2 else nv_in)
@@ -290,46 +335,44 @@ class NetPlan(object):
                          'flops': 2.0 * nv_in * taps * c.cin * c.cout,
                          'bytes': esz * (nv_in * c.cin + nv_out * c.cout) + c.w.numel() * c.w.element_size()})
 
-        def gn(name, y, out, nvox, relu, res=None):
+        def gn(name, y, out, nvox, relu, res, lout):
             g = self.gns[name]
-            sp = lib.ptr(ws['stats'][self.gn_index[name]])
             if split:
-                args = (y.p, y.ld, y.C, sp, lib.ptr(g.gamma), lib.ptr(g.beta), GN_EPS,
-                        res.p if res is not None else None, res.ld if res is not None else 0, res.ld // 2 if res is not None else 0,
-                        out.p, out.ld, out.ld // 2, 1 if relu else 0, B, nvox)
-                ops.append(lambda a=args: lib.call('seg3d_gn_apply_split', *a, st()))
+                add(lambda b0, nb: lib.call('seg3d_gn_apply_split', y.at(b0), y.ld, y.C, stats_ptr(name, b0), lib.ptr(g.gamma),
+                                            lib.ptr(g.beta), GN_EPS, res.at(b0) if res is not None else None,
+                                            res.ld if res is not None else 0, res.ld // 2 if res is not None else 0,
+                                            out.at(b0), out.ld, out.ld // 2, 1 if relu else 0, nb, nvox, st()), lout)
             else:
-                args = (dt, y.p, y.ld, y.C, sp, lib.ptr(g.gamma), lib.ptr(g.beta), GN_EPS,
-                        res.p if res is not None else None, res.ld if res is not None else 0,
-                        out.p, out.ld, 1 if relu else 0, B, nvox)
-                ops.append(lambda a=args: lib.call('seg3d_gn_apply', *a, st()))
+                add(lambda b0, nb: lib.call('seg3d_gn_apply', dt, y.at(b0), y.ld, y.C, stats_ptr(name, b0), lib.ptr(g.gamma),
+                                            lib.ptr(g.beta), GN_EPS, res.at(b0) if res is not None else None,
+                                            res.ld if res is not None else 0, out.at(b0), out.ld, 1 if relu else 0, nb, nvox, st()),
+                    lout)
             esz = 4 if dt == lib.F32 else 2
             meta.append({'name': name, 'kind': 'gn_apply', 'flops': 0.0,
                          'bytes': esz * B * nvox * y.C * (3 if res is not None else 2)})
 
         def rawview(C, l=0):
             if train:       # training keeps every pre-GroupNorm tensor for the backward pass
-                return _View(torch.empty((B, vox[l], C), dtype=td, device=dev), 0, C, C)
-            return _View(raw, 0, C, C)          # split mode: the raw scratch is fp32, one value per channel
+                return _View(torch.empty((B, vox[l], C), dtype=td, device=dev), 0, C, C, sample=vox[l] * C)
+            return _View(raw, 0, C, C, sample=vox[l] * C, scratch=True)   # split mode: the raw scratch is fp32, one value per channel
 
         def tmpbuf(l, C, key):
             if train:
-                return _View(torch.empty((B, vox[l], C), dtype=td, device=dev), 0, C, C)
+                return _View(torch.empty((B, vox[l], C), dtype=td, device=dev), 0, C, C, sample=vox[l] * C)
             return V(ws[key], 0, C, C)
 
-        def conv_gn_twice(cname, gname, x, xdims, out, nvox_out):
+        def conv_gn_twice(cname, gname, x, xdims, out, nvox_out, lout):
             """HBM-bound stride-2 / transposed conv: run it twice (statistics, then GroupNorm + ReLU in the epilogue)
             instead of storing the raw result and streaming it through seg3d_gn_apply"""
             c, g = self.convs[cname], self.gns[gname]
-            sp = lib.ptr(ws['stats'][self.gn_index[gname]])
             esz = 2
             nv_in = B * xdims[0] * xdims[1] * xdims[2]
             taps = 1 if c.mode == lib.CONV_K2S2 else 8
             kind = 'conv_tc_' + ('k2s2' if c.mode == lib.CONV_K2S2 else 't2s2')
             for ps in (0, 1):
-                args = (c.mode, dt, ps, x.p, x.ld, c.cin, lib.ptr(c.w), lib.ptr(c.bias), out.p, out.ld, c.cout,
-                        B, xdims[0], xdims[1], xdims[2], sp, lib.ptr(g.gamma), lib.ptr(g.beta), GN_EPS)
-                ops.append(lambda a=args: lib.call('seg3d_conv3d_gn_relu_fwd', *a, st()))
+                add(lambda b0, nb, ps=ps: lib.call('seg3d_conv3d_gn_relu_fwd', c.mode, dt, ps, x.at(b0), x.ld, c.cin, lib.ptr(c.w),
+                                                   lib.ptr(c.bias), out.at(b0), out.ld, c.cout, nb, xdims[0], xdims[1], xdims[2],
+                                                   stats_ptr(gname, b0), lib.ptr(g.gamma), lib.ptr(g.beta), GN_EPS, st()), lout)
                 meta.append({'name': cname + ('.stats' if ps == 0 else '.gn_relu'), 'kind': kind,
                              'flops': 2.0 * nv_in * taps * c.cin * c.cout if ps == 1 else 0.0,
                              'bytes': esz * (nv_in * c.cin + (B * nvox_out * c.cout if ps == 1 else 0)) + c.w.numel() * 2})
@@ -344,18 +387,18 @@ class NetPlan(object):
             C = c.cout
             if defer_gn:        # the consumer applies GroupNorm + residual + ReLU itself (seg3d_conv3d_k3_narrow_gn_fwd)
                 rv = rawview(C, lout)
-                conv(cname, x, dims[lin], rv, gname)
+                conv(cname, x, dims[lin], rv, gname, lout)
                 ws['deferred'] = {'raw': rv, 'res': res, 'gn': gname}
                 units.append({'conv': cname, 'gn': gname, 'x': x, 'lin': lin, 'lout': lout, 'raw': rv, 'out': out, 'res': res})
                 return
             if (fuse_s2 and res is None and c.impl == lib.IMPL_TCGEN05 and c.mode in (lib.CONV_K2S2, lib.CONV_T2S2)
                     and out.ld % 8 == 0):
-                conv_gn_twice(cname, gname, x, dims[lin], out, vox[lout])
+                conv_gn_twice(cname, gname, x, dims[lin], out, vox[lout], lout)
                 units.append({'conv': cname, 'gn': gname, 'x': x, 'lin': lin, 'lout': lout, 'raw': None, 'out': out, 'res': res})
                 return
             rv = rawview(C, lout)
-            conv(cname, x, dims[lin], rv, gname)
-            gn(gname, rv, out, vox[lout], True, res)
+            conv(cname, x, dims[lin], rv, gname, lout)
+            gn(gname, rv, out, vox[lout], True, res, lout)
             units.append({'conv': cname, 'gn': gname, 'x': x, 'lin': lin, 'lout': lout, 'raw': rv, 'out': out, 'res': res})
 
         def conv_gn(cname, gname, x, l, out, relu, res=None, defer_gn=False):
@@ -391,7 +434,7 @@ class NetPlan(object):
                      and os.environ.get('SEG3D_TAIL_F32', '1') != '0' and os.environ.get('SEG3D_FUSE_TAIL', '1') != '0')
 
         # in_block -> second half of cat0
-        x_in = _View(ws['x_in'], 0, self.in_channels, self.in_channels)
+        x_in = _View(ws['x_in'], 0, self.in_channels, self.in_channels, sample=vox[0] * self.in_channels)
         skip = [V(ws['cat%d' % l], widths[l] // 2, widths[l], widths[l] // 2) for l in range(4)]
         conv_gn('in_block.conv', 'in_block.gn', x_in, 0, skip[0], relu=True)
         # down path
@@ -424,51 +467,82 @@ class NetPlan(object):
         if tail_f32 and c1.fold:
             # nine in-plane taps folded into the GEMM N dimension (csrc/conv_tc_narrow.cu), fp32 result
             ncp = nc
-            rv1 = _View(torch.empty((B, vox[0], nc), dtype=torch.float32, device=dev), 0, nc, nc)
-            sp1 = lib.ptr(ws['stats'][self.gn_index['out_block.gn1']])
+            rv1 = _View(torch.empty((B, vox[0], nc), dtype=torch.float32, device=dev), 0, nc, nc, sample=vox[0] * nc)
             dfr = ws.get('deferred')
             if dfr is not None:
                 g0 = self.gns[dfr['gn']]
-                args = (dt, dfr['raw'].p, dfr['raw'].ld, dfr['res'].p, dfr['res'].ld, c1.cin,
-                        lib.ptr(ws['stats'][self.gn_index[dfr['gn']]]), lib.ptr(g0.gamma), lib.ptr(g0.beta), GN_EPS,
-                        lib.ptr(c1.w_fold), lib.ptr(c1.bias), rv1.p, nc, B, dims[0][0], dims[0][1], dims[0][2], sp1)
-                ops.append(lambda a=args: lib.call('seg3d_conv3d_k3_narrow_gn_fwd', *a, st()))
+                draw, dres, dgn = dfr['raw'], dfr['res'], dfr['gn']
+                add(lambda b0, nb: lib.call('seg3d_conv3d_k3_narrow_gn_fwd', dt, draw.at(b0), draw.ld, dres.at(b0), dres.ld, c1.cin,
+                                            stats_ptr(dgn, b0), lib.ptr(g0.gamma), lib.ptr(g0.beta), GN_EPS,
+                                            lib.ptr(c1.w_fold), lib.ptr(c1.bias), rv1.at(b0), nc, nb, dims[0][0], dims[0][1], dims[0][2],
+                                            stats_ptr('out_block.gn1', b0), st()), 0)
                 rd = 2 * (2 * B * vox[0] * c1.cin)
             else:
-                args = (dt, src.p, src.ld, c1.cin, lib.ptr(c1.w_fold), lib.ptr(c1.bias), rv1.p, nc,
-                        B, dims[0][0], dims[0][1], dims[0][2], sp1)
-                ops.append(lambda a=args: lib.call('seg3d_conv3d_k3_narrow_fwd', *a, st()))
+                add(lambda b0, nb: lib.call('seg3d_conv3d_k3_narrow_fwd', dt, src.at(b0), src.ld, c1.cin, lib.ptr(c1.w_fold),
+                                            lib.ptr(c1.bias), rv1.at(b0), nc, nb, dims[0][0], dims[0][1], dims[0][2],
+                                            stats_ptr('out_block.gn1', b0), st()), 0)
                 rd = 2 * B * vox[0] * c1.cin
             meta.append({'name': 'out_block.conv1', 'kind': 'conv_tc_narrow', 'flops': 2.0 * B * vox[0] * 27 * c1.cin * nc,
                          'bytes': rd + 4 * B * vox[0] * nc + c1.w_fold.numel() * 2})
         elif tail_f32:
             ncp = nc                                       # the fp32 store keeps only the real channels
-            rv1 = _View(torch.empty((B, vox[0], nc), dtype=torch.float32, device=dev), 0, nc, nc)
-            sp1 = lib.ptr(ws['stats'][self.gn_index['out_block.gn1']])
-            args = (c1.mode, dt | lib.OUT_F32, c1.impl, src.p, src.ld, c1.cin, lib.ptr(c1.w), lib.ptr(c1.bias), rv1.p, rv1.ld,
-                    c1.cout, B, dims[0][0], dims[0][1], dims[0][2], sp1)
-            ops.append(lambda a=args: lib.call('seg3d_conv3d_fwd', *a, st()))
+            rv1 = _View(torch.empty((B, vox[0], nc), dtype=torch.float32, device=dev), 0, nc, nc, sample=vox[0] * nc)
+            add(lambda b0, nb: lib.call('seg3d_conv3d_fwd', c1.mode, dt | lib.OUT_F32, c1.impl, src.at(b0), src.ld, c1.cin, lib.ptr(c1.w),
+                                        lib.ptr(c1.bias), rv1.at(b0), rv1.ld, c1.cout, nb, dims[0][0], dims[0][1], dims[0][2],
+                                        stats_ptr('out_block.gn1', b0), st()), 0)
             meta.append({'name': 'out_block.conv1', 'kind': 'conv_tc_k3', 'flops': 2.0 * B * vox[0] * 27 * c1.cin * c1.cout,
                          'bytes': 2 * B * vox[0] * c1.cin + 4 * B * vox[0] * nc + c1.w.numel() * 2})
         else:
-            rv1 = rawview(ncp, 0)
-            conv('out_block.conv1', src, dims[0], rv1, 'out_block.gn1')
+            rv1 = rawview(ncp, 0)           # the two tail launches of a sub-batch read it before the next sub-batch rewrites it
+            conv('out_block.conv1', src, dims[0], rv1, 'out_block.gn1', 0)
         ws['tail'] = {'x': src, 'raw': rv1, 'ncp': ncp}
-        raw = rv1.buf
         g1, g2 = self.gns['out_block.gn1'], self.gns['out_block.gn2']
-        s1 = lib.ptr(ws['stats'][self.gn_index['out_block.gn1']])
-        s2 = lib.ptr(ws['stats2'])
-        a1 = (tail_dt, lib.ptr(raw), ncp, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),
-              GN_EPS, s2, B, vox[0])
-        ops.append(lambda a=a1: lib.call('seg3d_outblock_tail_stats', *a, st()))
+        probs = ws['probs']
+        psample = self.out_channels * vox[0]
+
+        def tail_stats(b0, nb):
+            lib.call('seg3d_outblock_tail_stats', tail_dt, rv1.at(b0), ncp, nc, stats_ptr('out_block.gn1', b0), lib.ptr(g1.gamma),
+                     lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2), GN_EPS, lib.ptr(ws['stats2'], 2 * b0), nb, vox[0], st())
+
+        def tail_probs(b0, nb):
+            lib.call('seg3d_outblock_tail_probs', tail_dt, rv1.at(b0), ncp, nc, stats_ptr('out_block.gn1', b0), lib.ptr(g1.gamma),
+                     lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2), lib.ptr(ws['stats2'], 2 * b0), lib.ptr(g2.gamma),
+                     lib.ptr(g2.beta), GN_EPS, lib.ptr(probs, b0 * psample), nb, vox[0], st())
+
+        add(tail_stats, 0)
+        add(tail_probs, 0)
         esz = 4 if dt == lib.F32 else 2
         esz = 4 if (tail_f32 or split) else esz
         meta.append({'name': 'out_block.tail_stats', 'kind': 'tail', 'flops': 0.0, 'bytes': esz * B * vox[0] * ncp})
         meta.append({'name': 'out_block.tail_probs', 'kind': 'tail', 'flops': 0.0, 'bytes': esz * B * vox[0] * ncp + 4 * B * vox[0] * nc})
-        a2 = (tail_dt, lib.ptr(raw), ncp, nc, s1, lib.ptr(g1.gamma), lib.ptr(g1.beta), lib.ptr(self.w2), lib.ptr(self.b2),
-              s2, lib.ptr(g2.gamma), lib.ptr(g2.beta), GN_EPS, lib.ptr(ws['probs']), B, vox[0])
-        ops.append(lambda a=a2: lib.call('seg3d_outblock_tail_probs', *a, st()))
+        ws['schedule'] = self._schedule(B, levels, vox, train)
         return ws, ops
+
+    def _schedule(self, B, levels, vox, train):
+        """[(first op, last op + 1, sub-batch)]: the order in which run() issues the launches.
+        The levels 0 and 1 of the pyramid are HBM-bound (GroupNorm applies, stride-2 / transposed convs, the input block and the
+        narrow out-block conv move whole 16-32-channel tensors and do little math); their tensors are 28-57 MB per 96^3
+        patch, so a batch of 20 streams every one of them through HBM between producer and consumer.  GroupNorm is per
+        sample and every op is a batched launch, so each maximal run of consecutive level <= 1 ops is issued in sub-batches
+        of a few patches: the raw conv output a GroupNorm apply reads, and the activation the next conv reads, are then
+        still in the 126 MB L2, and the raw scratch is re-written in place by the next sub-batch before it is ever evicted.
+        The deep levels (small tensors, tensor-bound, better at a large batch) run once over the whole batch.
+        SEG3D_SUBBATCH_MB = L2 budget for one sub-batch's level-0 working set (0 = no sub-batching)."""
+        budget = float(os.environ.get('SEG3D_SUBBATCH_MB', '0')) * 1e6
+        n = len(levels)
+        if train or budget <= 0 or B <= 1:
+            return [(0, n, B)]
+        per_sample = vox[0] * 32 * (4 if self.dt == lib.F32 else 2) * (2 if self.split else 1)    # one 32-channel level-0 tensor
+        sb = int(max(1, min(B, budget // per_sample)))
+        sched, i = [], 0
+        while i < n:
+            j = i
+            shallow = levels[i] <= 1
+            while j < n and (levels[j] <= 1) == shallow:
+                j += 1
+            sched.append((i, j, sb if shallow else B))
+            i = j
+        return sched
 
     def plan(self, B, D, H, W, train=False):
         """(workspaces, launch list) for one input shape.  The cache is a small LRU (SEG3D_PLAN_CACHE shapes, default 4):
@@ -495,13 +569,22 @@ class NetPlan(object):
     def _run_eager(self, ws, ops):
         ws['stats'].zero_()
         ws['stats2'].zero_()
-        for op in ops:
-            op()
+        B = ws['B']
+        for i0, i1, sb in ws['schedule']:
+            for b0 in range(0, B, sb):
+                nb = min(sb, B - b0)
+                for op in ops[i0:i1]:
+                    op(b0, nb)
+
+    def launches(self, ws):
+        """kernel launches of one forward under the plan's schedule"""
+        B = ws['B']
+        return sum((i1 - i0) * ((B + sb - 1) // sb) for i0, i1, sb in ws['schedule'])
 
     def run(self, ws, ops):
         """One forward over the plan's workspaces.  With SEG3D_GRAPH=1 an inference plan is captured into a CUDA graph after
-        one eager run (all buffers, packed weights and tensor maps are fixed per plan) and replayed afterwards: ~60 launches
-        become one, which matters for small patch batches where the forward is launch-bound."""
+        one eager run (all buffers, packed weights and tensor maps are fixed per plan) and replayed afterwards: the launches of
+        a forward become one, which matters for small patch batches and for sub-batched schedules."""
         if self.use_graph and not ws.get('train', False):
             g = ws.get('graph')
             if g is None:
@@ -514,23 +597,28 @@ class NetPlan(object):
             g.replay()
         else:
             self._run_eager(ws, ops)
-        self.launches_per_forward = len(ops)
+        self.launches_per_forward = self.launches(ws)
         return ws['probs']
 
     def run_profiled(self, ws, ops):
         """Same as run() with a CUDA-event pair around every launch (current stream).  Returns
-        [(meta dict, milliseconds)] - used by bench.py for the per-kernel roofline table."""
+        [(meta dict, milliseconds)], the launches of one op (sub-batches) summed - used by bench.py for the per-kernel
+        roofline table."""
         ws['stats'].zero_()
         ws['stats2'].zero_()
-        evs = []
-        for op in ops:
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            op()
-            b.record()
-            evs.append((a, b))
+        B = ws['B']
+        evs = [[] for _ in ops]
+        for i0, i1, sb in ws['schedule']:
+            for b0 in range(0, B, sb):
+                nb = min(sb, B - b0)
+                for i in range(i0, i1):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    ops[i](b0, nb)
+                    b.record()
+                    evs[i].append((a, b))
         torch.cuda.synchronize()
-        return [(m, a.elapsed_time(b)) for m, (a, b) in zip(ws['meta'], evs)]
+        return [(m, sum(a.elapsed_time(b) for a, b in e)) for m, e in zip(ws['meta'], evs)]
 
     def forward(self, x):
         """probabilities [B,C,D,H,W] float32 (a view of the plan's output buffer; clone to keep)."""

@@ -84,7 +84,7 @@ class SlidingWindow(object):
                      lib.ptr(pstats), plan.in_dt, lib.ptr(ws['x_in']), st())
             probs = plan.run(ws, ops)
             lib.call('seg3d_blend_accumulate', lib.ptr(probs), nb, C, pz, py, px, sp, lib.ptr(acc), Z, Y, X, st())
-            self.kernel_launches += 2 + len(ops)
+            self.kernel_launches += 2 + plan.launches(ws)
 
     def finalize(self, acc, counts, want_mask=True, z_range=None, mask=None):
         """acc *= 1/count in place; returns the int8 first-argmax mask [Z,Y,X].  z_range=(z0, z1) finishes only those

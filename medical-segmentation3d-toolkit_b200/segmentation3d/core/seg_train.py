@@ -50,10 +50,11 @@ def make_loss(train_cfg, use_gpu=True):
 
 
 def make_optimizer(net, lr, betas=(0.9, 0.999)):
-    """The reference's optim.Adam(net.parameters(), lr, betas) (core/seg_train.py:83).  `fused` keeps the update rule and
-    the state-dict layout and only changes how torch launches it (one kernel instead of ~30 multi-tensor launches)."""
-    params = list(net.parameters())
-    return optim.Adam(params, lr=lr, betas=betas, fused=all(p.is_cuda for p in params))
+    """The reference's optim.Adam(net.parameters(), lr, betas) (core/seg_train.py:83): a torch.optim.Adam subclass - same
+    state-dict layout, same update rule - whose step() is one C-ABI launch over all parameters (_b200/optim.py)."""
+    from segmentation3d._b200.optim import FlatAdam
+    root = getattr(net, 'module', net)
+    return FlatAdam(net.parameters(), lr=lr, betas=betas, on_step=getattr(root, 'mark_weights_changed', None))
 
 
 def train_step(net, opt, loss_func, crops, masks, params=None, return_outputs=False):

@@ -118,6 +118,7 @@ class VShapedNet(nn.Module):
         # strict parity) | 'fp32' (CUDA cores) | 'auto' (see resolve_mode).  SEG3D_MODE overrides the default.
         self.b200_mode = os.environ.get('SEG3D_MODE', 'auto')
         self._plans = {}            # resolved mode -> [NetPlan, weight key]
+        self._weights_epoch = 0
         self._plan = None           # the plan of the most recent forward
 
     def max_stride(self):
@@ -138,16 +139,23 @@ class VShapedNet(nn.Module):
             return 'fp16' if self.out_channels <= 2 else 'fp32x'
         return mode
 
+    def mark_weights_changed(self):
+        """for code that writes the parameters behind torch's back (the C-ABI Adam kernel)"""
+        self._weights_epoch += 1
+
     # -- kernel plan management -----------------------------------------------------------
     def _current_plan(self, train=False):
         params = list(self.parameters())
         dev = params[0].device
         _plan._require_cuda(dev, 'segmentation3d (B200 build) has no CPU path: move the network to a CUDA device')
         mode = self.resolve_mode(train)
-        key = (str(dev), tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        # weights changed <=> a parameter's version counter moved (torch in-place ops) or an optimiser that updates the
+        # parameters through the C-ABI kernel (segmentation3d/_b200/optim.py) said so
+        key = (str(dev), (self._weights_epoch,) + tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
         entry = self._plans.get(mode)
         if entry is None or entry[1][0] != key[0] or entry[1][2] != key[2]:
             entry = self._plans[mode] = [NetPlan(self.state_dict(), mode=mode, device=dev, arch=self.arch), key]
+            entry[0].bind_parameters(list(self.named_parameters()))
         elif entry[1] != key:
             entry[0].refresh(self.state_dict())            # same device and storage: re-pack the weights in place
             entry[1] = key

@@ -25,17 +25,24 @@ def _install(monkeypatch, calls):
     table = {}
     fwd_call = lib.call
 
-    def gn_bwd(dtype, ps, g0, ld0, g1, ld1, g2, ld2, out, out_ld, y, y_ld, C, stats, gamma, eps, sums, dgamma, dbeta,
+    def gn_bwd(dtype, ps, g0, ld0, g1, ld1, g2, ld2, out, out_ld, y, y_ld, C, stats, gamma, beta, eps, sums, dgamma, dbeta,
                dy, dy_ld, dres, dres_ld, dbias, N, nvox, stream):
         g = _rows(g0, N * nvox, ld0, C).double()
         if g1 is not None:
             g = g + _rows(g1, N * nvox, ld1, C).double()
         if g2 is not None:
             g = g + _rows(g2, N * nvox, ld2, C).double()
-        dz = (g * (_rows(out, N * nvox, out_ld, C).double() > 0)).view(N, nvox, C)
         mean, rstd = _mean_rstd(stats, float(nvox * C), eps, N)
-        xh = (_rows(y, N * nvox, y_ld, C).double().view(N, nvox, C) - mean) * rstd
+        yv = _rows(y, N * nvox, y_ld, C).double().view(N, nvox, C)
+        xh = (yv - mean) * rstd
         gd = gamma.t.double().view(1, 1, C)
+        if out is None:         # ReLU mask recomputed from the raw tensor: fma(y, rstd*gamma, beta - mean*rstd*gamma) > 0
+            assert beta is not None and dres is None
+            a = (rstd.float() * gamma.t.float().view(1, 1, C))
+            z = yv.float() * a + (beta.t.float().view(1, 1, C) - mean.float() * a)
+            dz = g.view(N, nvox, C) * (z > 0)
+        else:
+            dz = (g * (_rows(out, N * nvox, out_ld, C).double() > 0)).view(N, nvox, C)
         if ps == 0:
             st = sums.t.reshape(-1, 2)
             st[:N, 0] += (dz * gd).flatten(1).sum(1)
@@ -141,6 +148,18 @@ def _install(monkeypatch, calls):
         grad.t.copy_(out.reshape(grad.t.shape))
         return 0
 
+    def adam_step(param, grad, m, v, n, lr, b1, b2, eps, wd, step, stream):
+        """torch/optim/adam.py::_single_tensor_adam on flat ranges"""
+        p_, g_, m_, v_ = (t.flat()[:n] for t in (param, grad, m, v))
+        g = g_ + wd * p_ if wd else g_.clone()
+        m_.lerp_(g, 1 - b1)
+        v_.mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = (v_.sqrt() / (1 - b2 ** step) ** 0.5).add_(eps)
+        p_.addcdiv_(m_, denom, value=-lr / (1 - b1 ** step))
+        calls.append('adam_step')
+        return 0
+
+    table.update({'seg3d_adam_step': adam_step})
     table.update({'seg3d_gn_bwd': gn_bwd, 'seg3d_conv3d_wgrad': wgrad, 'seg3d_outblock_tail_bwd': tail_bwd,
                   'seg3d_dice_terms': dice_terms, 'seg3d_dice_bwd': dice_bwd, 'seg3d_focal_fwd': focal_fwd, 'seg3d_focal_bwd': focal_bwd})
     monkeypatch.setattr(lib, 'call', lambda name, *a: table[name](*a) if name in table else fwd_call(name, *a))
@@ -197,3 +216,44 @@ def test_backward_walk_reproduces_oracle_autograd(monkeypatch, arch, cout, lossn
     n_units = sum(1 for k, v in sd.items() if k.endswith('.weight') and v.dim() == 5) - 2      # conv1 / conv2 of the out block
     assert calls.count('gn_bwd0') == calls.count('gn_bwd1') == 2 * n_units
     assert calls.count('tail_bwd2') == 2
+
+
+def test_one_launch_repack_unpack_and_flat_adam_match_the_torch_path(monkeypatch):
+    """_b200/packing.py + _b200/optim.py: with the parameters bound to the plan, a training step re-packs every forward and
+    data-gradient weight with one seg3d_gather_pack launch, un-packs the weight gradients with another, and updates all
+    parameters with one seg3d_adam_step - the same numbers as the per-tensor torch path (SEG3D_PACK_KERNEL=0 + torch Adam)."""
+    from segmentation3d.core.seg_train import make_optimizer, train_step
+    from segmentation3d.loss.multi_dice_loss import MultiDiceLoss
+    import contextlib
+    import importlib
+    from segmentation3d._b200.optim import FlatAdam
+    monkeypatch.setattr(FlatAdam, '_on_device', staticmethod(lambda p: True))
+    monkeypatch.setattr(torch.cuda, 'device', lambda d: contextlib.nullcontext())
+    results = {}
+    for arch, cout, mode in (('vnet', 2, 'bf16'), ('vbnet', 3, 'fp32')):
+        for fast in (True, False):
+            calls = []
+            _install(monkeypatch, calls)
+            monkeypatch.setenv('SEG3D_PACK_KERNEL', '1' if fast else '0')
+            mod = importlib.import_module('segmentation3d.network.' + arch)
+            torch.manual_seed(0)
+            net = mod.SegmentationNet(1, cout)
+            net.load_state_dict(oinit.randomize_affine(oinit.init_state_dict(arch, 1, cout, 0), 3))
+            net.b200_mode = mode
+            net.train()
+            opt = make_optimizer(net, 1e-3) if fast else torch.optim.Adam(net.parameters(), lr=1e-3)
+            g = torch.Generator().manual_seed(9)
+            crops = torch.randn((2, 1, 16, 16, 16), generator=g)
+            masks = torch.randint(0, cout, (2, 1, 16, 16, 16), generator=g).float()
+            lf = MultiDiceLoss([1.0] * cout, cout, False)
+            losses = [float(train_step(net, opt, lf, crops, masks)) for _ in range(3)]
+            if fast:
+                assert calls.count('adam_step') == 3 and opt.used_flat_grads
+                st = opt.state_dict()['state']
+                assert len(st) == len(list(net.parameters())) and float(st[0]['step']) == 3.0
+                assert st[0]['exp_avg'].shape == net.in_block.conv.weight.shape
+            results[(arch, fast)] = (losses, [p.detach().clone() for p in net.parameters()])
+        (la, pa), (lb, pb) = results[(arch, True)], results[(arch, False)]
+        assert max(abs(a - b) for a, b in zip(la, lb)) <= 1e-5, (arch, la, lb)
+        worst = max(float((a - b).abs().max()) for a, b in zip(pa, pb))
+        assert worst <= 2e-5, (arch, worst)        # three Adam steps of size 1e-3: identical update rule, fp32 rounding apart

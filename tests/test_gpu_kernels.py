@@ -593,11 +593,14 @@ def test_forward_cuda_graph_replay_equals_eager(lib):
 
 
 @pytest.mark.parametrize('dt_name', ['F32', 'BF16', 'F16'])
-@pytest.mark.parametrize('C,nvox,two_grads,use_res', [(32, 1000, True, True), (16, 517, False, False), (64, 96, True, False), (256, 40, False, True)],
-                         ids=['c32', 'c16', 'c64', 'c256'])
-def test_gn_bwd_matches_closed_form(lib, dt_name, C, nvox, two_grads, use_res):
+@pytest.mark.parametrize('C,nvox,two_grads,use_res,remask', [(32, 1000, True, True, False), (16, 517, False, False, False), (64, 96, True, False, False),
+                                                             (256, 40, False, True, False), (16, 517, False, False, True), (64, 96, True, False, True),
+                                                             (32, 4001, False, False, True)],
+                         ids=['c32', 'c16', 'c64', 'c256', 'c16-remask', 'c64-remask', 'c32-remask'])
+def test_gn_bwd_matches_closed_form(lib, dt_name, C, nvox, two_grads, use_res, remask):
     """seg3d_gn_bwd (both passes) against the closed-form GroupNorm(1,C)+ReLU(+residual) backward in float64, on the
-    same stored (rounded) tensors: dy, dres, dgamma, dbeta, dbias and the per-sample sums."""
+    same stored (rounded) tensors: dy, dres, dgamma, dbeta, dbias and the per-sample sums.  remask: out = NULL, the ReLU mask
+    is recomputed from the stored raw tensor (units without a residual)."""
     L = lib
     dt = getattr(L, dt_name)
     tdt = L.TORCH_DTYPE[dt]
@@ -619,6 +622,11 @@ def test_gn_bwd_matches_closed_form(lib, dt_name, C, nvox, two_grads, use_res):
     z = xhat * gamma.double() + beta.double() + (res.double() if use_res else 0.0)
     out = q(torch.relu(z).float().cpu())                            # the saved post-ReLU activation, as stored
     mask = (out.double() > 0)
+    if remask:      # the forward apply's own expression on the stored y: fma(y, a, b) > 0, a = rstd*gamma, b = beta - mean*a (fp32)
+        a32 = rstd.float() * gamma.view(1, 1, C)
+        b32 = beta.view(1, 1, C) - mean.float() * a32
+        mask = (yd * a32.double() + b32.double()) > 0
+        assert float((mask != (out.double() > 0)).double().mean()) <= (2e-3 if dt_name != 'F32' else 1e-5)   # the two masks differ only by storage underflow
     gsum = g0w[..., C:].double() + (g1.double() if two_grads else 0.0)
     dz = gsum * mask
     gd = gamma.double()
@@ -633,7 +641,7 @@ def test_gn_bwd_matches_closed_form(lib, dt_name, C, nvox, two_grads, use_res):
     dres = torch.zeros((N, nvox, C), dtype=tdt, device='cuda')
     for p in range(2):
         L.call('seg3d_gn_bwd', dt, p, L.ptr(g0w, C), 2 * C, L.ptr(g1) if two_grads else None, C if two_grads else 0, None, 0,
-               L.ptr(out), C, L.ptr(y), C, C, L.ptr(stats), L.ptr(gamma), eps, L.ptr(sums), L.ptr(dgamma), L.ptr(dbeta),
+               None if remask else L.ptr(out), C, L.ptr(y), C, C, L.ptr(stats), L.ptr(gamma), L.ptr(beta), eps, L.ptr(sums), L.ptr(dgamma), L.ptr(dbeta),
                L.ptr(dy), 2 * C, L.ptr(dres) if use_res else None, C if use_res else 0, L.ptr(dbias), N, nvox, L.stream_ptr())
     torch.cuda.synchronize()
     store = {'F32': 2e-6, 'BF16': 4.5e-3, 'F16': 6e-4}[dt_name]      # half an ulp of the stored type (2^-8, 2^-11) + fp32 arithmetic

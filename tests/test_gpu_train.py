@@ -196,3 +196,89 @@ def test_bf16_training_gradients():
             assert cos >= 0.95 and rel <= 0.35, (tag, name, cos, rel)
             if name.startswith(SHALLOW):
                 assert cos >= 0.99 and rel <= 0.15, (tag, name, cos, rel)
+
+
+def test_adam_step_kernel_matches_torch_adam():
+    """seg3d_adam_step against torch.optim.Adam (the reference's optimiser, core/seg_train.py:83) over 4 steps, with and
+    without weight decay, on a range whose length is not a multiple of 4"""
+    from segmentation3d._b200 import lib as L
+    L.load()
+    for wd in (0.0, 0.01):
+        g = torch.Generator().manual_seed(3)
+        n = 100003
+        p0 = torch.randn(n, generator=g)
+        ref = p0.clone().cuda().requires_grad_(True)
+        opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.999), weight_decay=wd)
+        p = torch.zeros(n + 1, device='cuda')[:n]
+        p.copy_(p0)
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        for step in range(1, 5):
+            grad = (torch.randn(n, generator=g) * 10 ** float(torch.randint(-6, 1, (1,), generator=g))).cuda()
+            ref.grad = grad.clone()
+            opt.step()
+            L.call('seg3d_adam_step', L.ptr(p), L.ptr(grad), L.ptr(m), L.ptr(v), n, 1e-3, 0.9, 0.999, 1e-8, wd, step, L.stream_ptr())
+            torch.cuda.synchronize()
+            assert float((p - ref.detach()).abs().max()) <= 2e-6, (wd, step)
+        st = opt.state[ref]
+        assert float((m - st['exp_avg']).abs().max()) <= 1e-6 * float(st['exp_avg'].abs().max()) + 1e-12
+        assert float((v - st['exp_avg_sq']).abs().max()) <= 1e-5 * float(st['exp_avg_sq'].abs().max()) + 1e-20
+
+
+@pytest.mark.parametrize('arch,cout,mode', [('vnet', 2, 'fp16'), ('vbnet', 5, 'fp32x'), ('vnet', 2, 'fp32'), ('vbnet', 3, 'bf16')])
+def test_gather_pack_kernel_reproduces_every_weight_layout(arch, cout, mode):
+    """seg3d_gather_pack (one launch, table of index maps) against the per-tensor torch re-layout (plan.py::_Conv.load) for every
+    convolution of the network, bit for bit: tensor-core [tap][Cout][Cin], the folded narrow-output layout, split hi / lo
+    halves, SIMT [tap][Cin][Cout], transposed convs, zero-padded output channels, biases and GroupNorm affines; and for a
+    training plan the flipped / transposed data-gradient weights."""
+    import importlib
+    mod = importlib.import_module('segmentation3d.network.' + arch)
+    net = mod.SegmentationNet(1, cout)
+    net.load_state_dict(oinit.randomize_affine(oinit.init_state_dict(arch, 1, cout, 0), 5))
+    net.b200_mode = mode
+    net = net.cuda().eval()
+    train = mode in ('bf16', 'fp32')
+    plan = net._current_plan(train=train)
+    assert plan.pack_table is not None and plan._bound_valid()
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(1)
+        for p in net.parameters():
+            p.mul_((1.0 + 0.05 * torch.randn(p.shape, generator=g)).cuda())
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+
+    def snapshot(convs):
+        out = {}
+        for name, c in convs.items():
+            out[name] = [t.clone() for t in (c.w, c.w_fold, c.bias) if t is not None]
+        return out
+    plan.pack_table.run()
+    torch.cuda.synchronize()
+    fast = snapshot(plan.convs)
+    fast_gn = {n: (g_.gamma.clone(), g_.beta.clone()) for n, g_ in plan.gns.items()}
+    for c in plan.convs.values():
+        c.load(sd)
+    slow = snapshot(plan.convs)
+    for name in fast:
+        for a, b in zip(fast[name], slow[name]):
+            assert a.dtype == b.dtype and torch.equal(a, b), (name, mode)
+    for n, (ga, be) in fast_gn.items():
+        assert torch.equal(ga, sd[n + '.weight']) and torch.equal(be, sd[n + '.bias'])
+    if train:
+        from segmentation3d._b200.autograd import _Backward
+        ws, _ = plan.plan(1, 16, 16, 16, train=True)
+        plan._last_sd = sd
+        bw = _Backward(plan, ws)
+        assert bw.pack_table is not None
+        with torch.no_grad():
+            for p in net.parameters():
+                p.mul_(1.01)
+        sd = {k: v.detach() for k, v in net.state_dict().items()}
+        plan._last_sd = sd
+        bw.pack_table.run()
+        torch.cuda.synchronize()
+        fast = snapshot(bw.dconv)
+        for c in bw.dconv.values():
+            c.load(sd)
+        slow = snapshot(bw.dconv)
+        for name in fast:
+            for a, b in zip(fast[name], slow[name]):
+                assert torch.equal(a, b), ('dgrad', name, mode)

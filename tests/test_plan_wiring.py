@@ -7,6 +7,7 @@ hi/lo format of the strict mode), "device" tensors are CPU tensors and the plan'
 for real is the plan: buffer allocation, views and offsets, weight packing, the order of ~60 calls per forward, for VNet and
 VBNet in every execution mode.  A host-side regression in the plan then fails the CPU gate; the kernels themselves are
 pinned by the `-m gpu` tests."""
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -18,6 +19,9 @@ from oracle import net as onet
 class _P(object):
     def __init__(self, t, off):
         self.t, self.off = t, off
+
+    def flat(self):
+        return self.t.reshape(-1)[self.off:]
 
 
 def _rows(p, n_rows, ld, C):
@@ -31,10 +35,47 @@ def _stats(y):
     return y.double().flatten(1).sum(1), (y.double() ** 2).flatten(1).sum(1)
 
 
+def _stat_rows(stats, N):
+    """[N, 2] view of the double sums behind pointer `stats` (element offset honoured: a sub-batch starts at sample b0)"""
+    return stats.t.reshape(-1)[stats.off:stats.off + 2 * N].view(N, 2)
+
+
 def _mean_rstd(stats, cnt, eps, N):
-    mean = (stats.t.reshape(-1, 2)[:N, 0] / cnt).view(N, 1, 1)
-    var = (stats.t.reshape(-1, 2)[:N, 1] / cnt).view(N, 1, 1) - mean * mean
+    rows = _stat_rows(stats, N)
+    mean = (rows[:, 0] / cnt).view(N, 1, 1)
+    var = (rows[:, 1] / cnt).view(N, 1, 1) - mean * mean
     return mean, 1.0 / torch.sqrt(var + eps)
+
+
+def emulate_gather_pack(table, n_entries, max_elems, stream):
+    """seg3d_gather_pack per include/seg3d_b200.h on HOST memory: the table holds raw addresses (CPU tensors here)"""
+    import ctypes
+    from segmentation3d._b200 import lib
+    raw = bytes(table.t.reshape(-1)[table.off:].numpy().tobytes())
+    entries = (lib.PackEntry * n_entries).from_buffer_copy(raw[:n_entries * ctypes.sizeof(lib.PackEntry)])
+    for e in entries:
+        size, limit = list(e.size), list(e.limit)
+        idx = np.indices(size).reshape(5, -1)
+        n = idx.shape[1]
+        assert n <= max_elems
+        so = e.src_base + sum(idx[d] * e.src_stride[d] for d in range(5))
+        do = e.dst_base + sum(idx[d] * e.dst_stride[d] for d in range(5))
+        inside = np.ones(n, bool)
+        for d in range(5):
+            inside &= idx[d] < limit[d]
+        assert so[inside].min() >= 0 and do.min() >= 0 and len(np.unique(do)) == n
+        src = np.ctypeslib.as_array((ctypes.c_float * int(so[inside].max() + 1)).from_address(e.src))
+        vals = np.where(inside, src[np.where(inside, so, 0)], np.float32(0)).astype(np.float32)
+        if e.kind != lib.PACK_PLAIN:
+            hi = vals.astype(np.float16).astype(np.float32)
+            vals = hi if e.kind == lib.PACK_SPLIT_HI else vals - hi
+        nd = int(do.max() + 1)
+        if e.dtype == lib.F32:
+            np.ctypeslib.as_array((ctypes.c_float * nd).from_address(e.dst))[do] = vals
+        else:
+            bits = torch.from_numpy(vals).to(lib.TORCH_DTYPE[e.dtype]).view(torch.int16).numpy()
+            np.ctypeslib.as_array((ctypes.c_int16 * nd).from_address(e.dst))[do] = bits
+    return 0
 
 
 def _install(monkeypatch, calls):
@@ -57,7 +98,7 @@ def _install(monkeypatch, calls):
     def _store(r, y, y_ld, C, stats, N):
         if stats is not None:
             s0, s1 = _stats(r)
-            st = stats.t.reshape(-1, 2)
+            st = _stat_rows(stats, N)
             st[:N, 0] += s0
             st[:N, 1] += s1
         rn = r.permute(0, 2, 3, 4, 1).reshape(-1, r.shape[1])
@@ -146,8 +187,9 @@ def _install(monkeypatch, calls):
 
     def tail_stats(dtype, y1, ld, C, stats1, g1, b1, w2, bias2, eps, stats2, N, nvox, stream):
         z = _tail(y1, ld, C, stats1, g1, b1, w2, bias2, eps, N, nvox)
-        stats2.t[:, 0] += z.double().flatten(1).sum(1)
-        stats2.t[:, 1] += (z.double() ** 2).flatten(1).sum(1)
+        rows = _stat_rows(stats2, N)
+        rows[:, 0] += z.double().flatten(1).sum(1)
+        rows[:, 1] += (z.double() ** 2).flatten(1).sum(1)
         calls.append('tail_stats')
         return 0
 
@@ -155,13 +197,15 @@ def _install(monkeypatch, calls):
         z = _tail(y1, ld, C, stats1, g1, b1, w2, bias2, eps, N, nvox)
         mean, rstd = _mean_rstd(stats2, float(nvox * C), eps, N)
         z = ((z.double() - mean) * rstd).float() * g2.t.view(1, 1, C) + b2.t.view(1, 1, C)
-        probs.t.copy_(F.softmax(z, 2).permute(0, 2, 1).reshape(probs.t.shape))
+        dst = probs.t.reshape(-1)[probs.off:probs.off + N * C * nvox]
+        dst.copy_(F.softmax(z, 2).permute(0, 2, 1).reshape(-1))
         calls.append('tail_probs')
         return 0
 
     table = {'seg3d_conv3d_fwd': conv3d_fwd, 'seg3d_conv3d_k3_narrow_fwd': narrow_fwd, 'seg3d_conv3d_k3_narrow_gn_fwd': narrow_gn_fwd,
              'seg3d_gn_apply': gn_apply, 'seg3d_conv3d_split_fwd': split_fwd, 'seg3d_gn_apply_split': gn_apply_split,
-             'seg3d_outblock_tail_stats': tail_stats, 'seg3d_outblock_tail_probs': tail_probs}
+             'seg3d_outblock_tail_stats': tail_stats, 'seg3d_outblock_tail_probs': tail_probs,
+             'seg3d_gather_pack': emulate_gather_pack}
     monkeypatch.setattr(lib, 'ptr', ptr)
     monkeypatch.setattr(lib, 'call', lambda name, *a: table[name](*a))
     monkeypatch.setattr(lib, 'stream_ptr', lambda: 0)
@@ -196,6 +240,33 @@ def test_plan_issues_the_reference_network(monkeypatch, arch, cout, mode, tol):
     assert err <= tol, (arch, mode, 'refresh', err)
 
 
+@pytest.mark.parametrize('arch,cout,mode', [('vnet', 2, 'fp16'), ('vbnet', 5, 'fp32x'), ('vnet', 3, 'fp32')])
+def test_sub_batched_schedule_is_the_same_network(monkeypatch, arch, cout, mode):
+    """plan.py::_schedule: the level 0 / 1 runs issued in sub-batches (pointer offsets per sample, the raw scratch re-used in
+    place) give the probabilities of the whole-batch schedule, also for a ragged last sub-batch"""
+    calls = []
+    plan = _install(monkeypatch, calls)
+    monkeypatch.delenv('SEG3D_MODE', raising=False)
+    sd = oinit.randomize_affine(oinit.init_state_dict(arch, 1, cout, 0), 9)
+    x = torch.randn((5, 1, 16, 16, 32), generator=torch.Generator().manual_seed(4))
+    monkeypatch.setenv('SEG3D_SUBBATCH_MB', '0')
+    p0 = plan.NetPlan(sd, mode=mode, device='cpu')
+    whole = p0.forward(x).clone()
+    n0 = len(calls)
+    assert p0.launches_per_forward == n0
+    per_sample_mb = 16 * 16 * 32 * 32 * (4 if mode == 'fp32' else (4 if mode == 'fp32x' else 2)) / 1e6
+    monkeypatch.setenv('SEG3D_SUBBATCH_MB', str(2.5 * per_sample_mb))        # sub-batches of 2, 2, 1
+    del calls[:]
+    p1 = plan.NetPlan(sd, mode=mode, device='cpu')
+    ws, ops = p1.plan(5, 16, 16, 32)
+    assert [sb for _, _, sb in ws['schedule']] == [2, 5, 2] and sum(i1 - i0 for i0, i1, _ in ws['schedule']) == len(ops)
+    sub = p1.forward(x).clone()
+    # (the CPU emulation's convolutions sum in a batch-size dependent order, and a half-precision store can flip on that)
+    assert float((whole - sub).abs().max()) <= (2e-3 if mode == 'fp16' else 1e-5)
+    assert len(calls) == p1.launches_per_forward > n0
+    assert float((sub - onet.forward(sd, x)).abs().max()) <= (2e-5 if mode == 'fp32' else (1e-4 if mode == 'fp32x' else 2e-2))
+
+
 def test_plan_without_the_fused_tail_and_with_batches(monkeypatch):
     calls = []
     plan = _install(monkeypatch, calls)
@@ -217,3 +288,30 @@ def test_plan_without_the_fused_tail_and_with_batches(monkeypatch):
     whole = p.forward(x).clone()
     for i in range(3):
         assert float((p.forward(x[i:i + 1]) - whole[i:i + 1]).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize('arch,cout,mode,tol', [('vnet', 2, 'fp16', 2e-2), ('vbnet', 5, 'fp32x', 1e-4), ('vnet', 3, 'fp32', 2e-5)])
+def test_bound_plan_repacks_changed_weights_with_one_launch(monkeypatch, arch, cout, mode, tol):
+    """network/_graph.py binds the plan to the live parameters: after an in-place weight change the next forward re-packs
+    every layout (tensor-core, folded narrow-output, split hi/lo, SIMT, biases, GroupNorm affines) through the gather table"""
+    import importlib
+    calls = []
+    plan = _install(monkeypatch, calls)
+    real = plan.lib.call
+    seen = []
+    monkeypatch.setattr(plan.lib, 'call', lambda name, *a: (seen.append(name), real(name, *a))[1])
+    mod = importlib.import_module('segmentation3d.network.' + arch)
+    net = mod.SegmentationNet(1, cout)
+    net.load_state_dict(oinit.randomize_affine(oinit.init_state_dict(arch, 1, cout, 0), 5))
+    net.b200_mode = mode
+    net.eval()
+    x = torch.randn((1, 1, 16, 16, 32), generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        assert float((net(x) - onet.forward(net.state_dict(), x)).abs().max()) <= tol
+        assert 'seg3d_gather_pack' not in seen
+        g = torch.Generator().manual_seed(1)
+        for p in net.parameters():
+            p.mul_(1.0 + 0.05 * torch.randn(p.shape, generator=g)).add_(0.01 * torch.randn(p.shape, generator=g))
+        err = float((net(x) - onet.forward(net.state_dict(), x)).abs().max())
+    assert seen.count('seg3d_gather_pack') == 1
+    assert err <= tol, (arch, mode, err)

@@ -102,6 +102,9 @@ class _OraclePlan(object):
     def plan(self, nb, pz, py, px):
         return {'x_in': torch.empty((nb, pz * py * px, 1), dtype=torch.float32)}, (nb, pz, py, px)
 
+    def launches(self, ws):
+        return 1
+
     def run(self, ws, ops):
         nb, pz, py, px = ops
         self.forwards.append(nb)
