@@ -250,12 +250,14 @@ int seg3d_outblock_tail_bwd(int dtype, int pass, const void* y1, int ld, int C,
  *     dst[dst_base + sum_d i_d*dst_stride[d]]  =  (all i_d < limit[d]) ? src[src_base + sum_d i_d*src_stride[d]] : 0
  * stored as `dtype` (SEG3D_F32 / F16 / BF16).  kind SEG3D_PACK_SPLIT_HI / _LO store f16(w) / f16(w - f16(w)) (the split-operand
  * strict mode).  Strides are in elements and may be negative (flipped taps of the data-gradient convolution).  `table` is a
- * DEVICE array of n_entries entries; one launch serves them all (grid.y = entry); max_elems = the largest entry's element count.
+ * DEVICE array of entries (each < 2^31 elements); one launch serves them all: block b handles elements
+ * [block_map[2b+1]*SEG3D_PACK_CHUNK, +SEG3D_PACK_CHUNK) of entry block_map[2b] (block_map: device int32 pairs, n_blocks of them).
  * Used for: every convolution's kernel-layout weights (forward and data-gradient) from the fp32 OIDHW / IODHW parameters, and
  * the kernel-layout weight gradients back to parameter layout. */
 #define SEG3D_PACK_PLAIN 0
 #define SEG3D_PACK_SPLIT_HI 1
 #define SEG3D_PACK_SPLIT_LO 2
+#define SEG3D_PACK_CHUNK 4096
 typedef struct seg3d_pack_entry {
   const float* src;
   void* dst;
@@ -264,7 +266,7 @@ typedef struct seg3d_pack_entry {
   int32_t size[5], limit[5];
   int32_t dtype, kind;
 } seg3d_pack_entry;
-int seg3d_gather_pack(const seg3d_pack_entry* table, int n_entries, int64_t max_elems, void* stream);
+int seg3d_gather_pack(const seg3d_pack_entry* table, const int32_t* block_map, int n_blocks, void* stream);
 /* torch.optim.Adam's update (no amsgrad, no maximize) over one flat fp32 range of n elements, `step` = 1, 2, ...:
  *   g += weight_decay*p;  m += (1-beta1)*(g-m);  v = beta2*v + (1-beta2)*g*g;
  *   p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps).       All pointers 16-byte aligned. */

@@ -17,26 +17,37 @@ __device__ __forceinline__ void store_as(void* dst, long long i, int dtype, floa
   else reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(v);
 }
 
+// Block b serves chunk block_map[2b+1] (SEG3D_PACK_CHUNK elements) of entry block_map[2b]: the entries range from 2 to 1.8 M
+// elements, and a (chunks x entries) grid would launch ~100 000 empty blocks.  Index arithmetic is 32-bit (an entry has
+// < 2^31 elements); consecutive threads take consecutive DESTINATION elements, so stores coalesce and the gathers hit L2 (all
+// parameters together are 58 MB).
 __global__ void __launch_bounds__(256)
-gather_pack_kernel(const seg3d_pack_entry* __restrict__ table, int n_entries) {
-  const seg3d_pack_entry e = table[blockIdx.y];
-  const long long n = (long long)e.size[0] * e.size[1] * e.size[2] * e.size[3] * e.size[4];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    long long r = i, so = e.src_base, d_o = e.dst_base;
-    bool inside = true;
-#pragma unroll
-    for (int d = 4; d >= 0; --d) {
-      const int idx = (int)(r % e.size[d]); r /= e.size[d];
-      inside = inside && idx < e.limit[d];
-      so += (long long)idx * e.src_stride[d];
-      d_o += (long long)idx * e.dst_stride[d];
-    }
-    float v = inside ? e.src[so] : 0.f;
-    if (e.kind != SEG3D_PACK_PLAIN) {              // split operands: hi = f16(w), lo = f16(w - hi)
+gather_pack_kernel(const seg3d_pack_entry* __restrict__ table, const int32_t* __restrict__ block_map) {
+  __shared__ seg3d_pack_entry se;
+  if (threadIdx.x == 0) se = table[block_map[2 * blockIdx.x]];
+  __syncthreads();
+  const uint32_t first = (uint32_t)block_map[2 * blockIdx.x + 1] * (uint32_t)SEG3D_PACK_CHUNK;
+  const uint32_t s1 = (uint32_t)se.size[1], s2 = (uint32_t)se.size[2], s3 = (uint32_t)se.size[3], s4 = (uint32_t)se.size[4];
+  const uint32_t total = (uint32_t)se.size[0] * s1 * s2 * s3 * s4;
+  const uint32_t n = total - first < (uint32_t)SEG3D_PACK_CHUNK ? total : first + (uint32_t)SEG3D_PACK_CHUNK;
+  const float* __restrict__ src = se.src;
+  for (uint32_t i = first + threadIdx.x; i < n; i += blockDim.x) {
+    uint32_t r = i;
+    const uint32_t i4 = r % s4; r /= s4;
+    const uint32_t i3 = r % s3; r /= s3;
+    const uint32_t i2 = r % s2; r /= s2;
+    const uint32_t i1 = r % s1; const uint32_t i0 = r / s1;
+    const bool inside = (int)i0 < se.limit[0] && (int)i1 < se.limit[1] && (int)i2 < se.limit[2] && (int)i3 < se.limit[3] && (int)i4 < se.limit[4];
+    const long long so = se.src_base + (long long)i0 * se.src_stride[0] + (long long)i1 * se.src_stride[1] + (long long)i2 * se.src_stride[2] +
+                         (long long)i3 * se.src_stride[3] + (long long)i4 * se.src_stride[4];
+    const long long d_o = se.dst_base + (long long)i0 * se.dst_stride[0] + (long long)i1 * se.dst_stride[1] + (long long)i2 * se.dst_stride[2] +
+                          (long long)i3 * se.dst_stride[3] + (long long)i4 * se.dst_stride[4];
+    float v = inside ? src[so] : 0.f;
+    if (se.kind != SEG3D_PACK_PLAIN) {             // split operands: hi = f16(w), lo = f16(w - hi)
       const float hi = __half2float(__float2half_rn(v));
-      v = e.kind == SEG3D_PACK_SPLIT_HI ? hi : v - hi;
+      v = se.kind == SEG3D_PACK_SPLIT_HI ? hi : v - hi;
     }
-    store_as(e.dst, d_o, e.dtype, v);
+    store_as(se.dst, d_o, se.dtype, v);
   }
 }
 
@@ -70,12 +81,9 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 
 }  // namespace
 
-extern "C" int seg3d_gather_pack(const seg3d_pack_entry* table, int n_entries, int64_t max_elems, void* stream) {
-  SEG3D_REQUIRE(table && n_entries > 0 && max_elems > 0, "gather_pack: bad arguments");
-  long long want = (max_elems + 256 * 4 - 1) / (256 * 4);
-  const int cap = 2 * seg3d_num_sms();
-  const int gx = (int)(want < 1 ? 1 : (want > cap ? cap : want));
-  gather_pack_kernel<<<dim3(gx, n_entries), 256, 0, (cudaStream_t)stream>>>(table, n_entries);
+extern "C" int seg3d_gather_pack(const seg3d_pack_entry* table, const int32_t* block_map, int n_blocks, void* stream) {
+  SEG3D_REQUIRE(table && block_map && n_blocks > 0, "gather_pack: bad arguments");
+  gather_pack_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(table, block_map);
   SEG3D_CHECK_LAUNCH("gather_pack_kernel");
   return SEG3D_OK;
 }

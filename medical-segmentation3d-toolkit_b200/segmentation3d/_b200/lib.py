@@ -56,7 +56,7 @@ _SIGNATURES = {
     'seg3d_conv3d_wgrad': (_i, [_i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     'seg3d_outblock_tail_bwd': (_i, [_i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp,
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp]),
-    'seg3d_gather_pack': (_i, [_vp, _i, _i64, _vp]),
+    'seg3d_gather_pack': (_i, [_vp, _vp, _i, _vp]),
     'seg3d_adam_step': (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -70,6 +70,7 @@ class PackEntry(ctypes.Structure):
 
 
 PACK_PLAIN, PACK_SPLIT_HI, PACK_SPLIT_LO = 0, 1, 2
+PACK_CHUNK = 4096
 
 _lib = None
 

@@ -58,7 +58,7 @@ class _WView(object):
 
 class PackTable(object):
     def __init__(self, device):
-        self.device, self.entries, self.max_elems, self.table = device, [], 1, None
+        self.device, self.entries, self.counts, self.table, self.block_map = device, [], [], None, None
         self._keep = []
 
     def add(self, src, dst, size, src_stride, dst_stride, limit=None, src_base=0, dst_base=0, kind=lib.PACK_PLAIN):
@@ -76,7 +76,8 @@ class PackTable(object):
         n = 1
         for v in size:
             n *= v
-        self.max_elems = max(self.max_elems, n)
+        assert 0 < n < (1 << 31)
+        self.counts.append(n)
         self.entries.append(e)
         self._keep += [src, dst]
         self.table = None
@@ -105,7 +106,9 @@ class PackTable(object):
             arr = (lib.PackEntry * len(self.entries))(*self.entries)
             raw = bytes(ctypes.string_at(ctypes.addressof(arr), ctypes.sizeof(arr)))
             self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
-        lib.call('seg3d_gather_pack', lib.ptr(self.table), len(self.entries), self.max_elems, lib.stream_ptr())
+            pairs = [(i, c) for i, n in enumerate(self.counts) for c in range((n + lib.PACK_CHUNK - 1) // lib.PACK_CHUNK)]
+            self.block_map = torch.tensor(pairs, dtype=torch.int32).reshape(-1).to(self.device)
+        lib.call('seg3d_gather_pack', lib.ptr(self.table), lib.ptr(self.block_map), self.block_map.numel() // 2, lib.stream_ptr())
 
 
 def add_conv_pack(table, conv, weight, bias):

@@ -47,17 +47,21 @@ def _mean_rstd(stats, cnt, eps, N):
     return mean, 1.0 / torch.sqrt(var + eps)
 
 
-def emulate_gather_pack(table, n_entries, max_elems, stream):
+def emulate_gather_pack(table, block_map, n_blocks, stream):
     """seg3d_gather_pack per include/seg3d_b200.h on HOST memory: the table holds raw addresses (CPU tensors here)"""
     import ctypes
     from segmentation3d._b200 import lib
     raw = bytes(table.t.reshape(-1)[table.off:].numpy().tobytes())
+    bm = block_map.flat()[:2 * n_blocks].view(-1, 2)
+    n_entries = int(bm[:, 0].max()) + 1
     entries = (lib.PackEntry * n_entries).from_buffer_copy(raw[:n_entries * ctypes.sizeof(lib.PackEntry)])
-    for e in entries:
+    for k, e in enumerate(entries):
+        chunks = bm[bm[:, 0] == k][:, 1].tolist()
+        n_e = int(np.prod(list(e.size)))
+        assert chunks == list(range((n_e + lib.PACK_CHUNK - 1) // lib.PACK_CHUNK)), 'every chunk of every entry exactly once'
         size, limit = list(e.size), list(e.limit)
         idx = np.indices(size).reshape(5, -1)
         n = idx.shape[1]
-        assert n <= max_elems
         so = e.src_base + sum(idx[d] * e.src_stride[d] for d in range(5))
         do = e.dst_base + sum(idx[d] * e.dst_stride[d] for d in range(5))
         inside = np.ones(n, bool)
