@@ -73,6 +73,19 @@ int seg3d_conv3d_fwd(int mode, int dtype, int impl,
                      int N, int D, int H, int W,
                      double* stats, void* stream);
 
+/* Input block on the tensor cores as a banded-Toeplitz GEMM fed by TMA (vnet_inblock.py:9-15; csrc/conv_tc_cin1t.cu).
+ * xpad: the single-channel input in a row-padded layout [N][D][H][W + SEG3D_CIN1_PAD] (dtype f16/bf16, W % 8 == 0): x index i
+ * of a row sits at column i + SEG3D_CIN1_LEFT, every other column is zero (seg3d_patch_gather_rows writes this layout).
+ * w: fp32 [27][16] (tap-major, as the SIMT layout); y: [N,D,H,W,16] pitch y_ld.
+ * epi_mode 0: y = conv + bias, stats[n] += {sum, sum of squares};  1: the sums only, y is not touched;
+ * 2: y = relu(GroupNorm(conv + bias)) with `stats` holding the FINISHED sums (written by a mode-1 call), gamma / beta
+ * the GroupNorm affine.  1 then 2 is the inference schedule: the raw tensor and the GroupNorm-apply pass never reach HBM. */
+#define SEG3D_CIN1_PAD 16
+#define SEG3D_CIN1_LEFT 9
+int seg3d_conv3d_cin1_fwd(int dtype, int epi_mode, const void* xpad, int x_pitch, const float* w, const float* bias,
+                          void* y, int y_ld, int N, int D, int H, int W, double* stats,
+                          const float* gamma, const float* beta, float eps, void* stream);
+
 /* k3 s1 p1 convolution with a narrow output (Cout = classes <= 7; vnet_outblock.py:13) on the tensor cores: the nine
  * in-plane taps are folded into the GEMM N dimension and summed in the epilogue (csrc/conv_tc_narrow.cu).
  * x: [N,D,H,W,Cin] f16/bf16, Cin in {16,32,64}, W % 8 == 0.  w (dtype): [3 kd][NP][Cin] with row (kh*3+kw)*Cout + co,
@@ -146,6 +159,12 @@ int seg3d_patch_gather(const float* vol, int Z, int Y, int X, const int32_t* sta
                        int pz, int py, int px, int norm, float mean, float stddev, int clip,
                        float clip_lo, float clip_hi, const double* stats,
                        int dtype, void* out, void* stream);
+/* the same crop written with a row pitch: out[((n*pz + z)*py + y)*row_pitch + x_off + x]; elements outside [x_off, x_off+px)
+ * are not touched (the row-padded input layout of seg3d_conv3d_cin1_fwd: row_pitch = px + SEG3D_CIN1_PAD, x_off = SEG3D_CIN1_LEFT) */
+int seg3d_patch_gather_rows(const float* vol, int Z, int Y, int X, const int32_t* starts, int N,
+                            int pz, int py, int px, int norm, float mean, float stddev, int clip,
+                            float clip_lo, float clip_hi, const double* stats,
+                            int dtype, void* out, int row_pitch, int x_off, void* stream);
 /* acc[c][z0+z][y0+y][x0+x] += probs[n][c][z][y][x]  (add_image_region) */
 int seg3d_blend_accumulate(const float* probs, int N, int C, int pz, int py, int px,
                            const int32_t* starts, float* acc, int Z, int Y, int X, void* stream);

@@ -43,7 +43,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 patch_gather_kernel(const float* __restrict__ vol, int Z, int Y, int X, const int32_t* __restrict__ starts,
                     int pz, int py, int px, int norm, float mean, float stddev, int clip, float lo, float hi,
-                    const double* __restrict__ stats, T* __restrict__ out) {
+                    const double* __restrict__ stats, T* __restrict__ out, int row_pitch, int x_off) {
   const int n = blockIdx.y;
   const int x0 = starts[3 * n], y0 = starts[3 * n + 1], z0 = starts[3 * n + 2];
   const long long nv = (long long)pz * py * px;
@@ -53,7 +53,7 @@ patch_gather_kernel(const float* __restrict__ vol, int Z, int Y, int X, const in
     double var = stats[2 * n + 1] / (double)nv - m * m; if (var < 0) var = 0;
     mean = (float)m; stddev = fmaxf((float)sqrt(var), 1e-6f);
   }
-  T* on = out + (size_t)n * nv;
+  T* on = out + (size_t)n * pz * py * row_pitch + x_off;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % px); const long long t = i / px; const int yy = (int)(t % py), z = (int)(t / py);
     float v = vol[((size_t)(z0 + z) * Y + (y0 + yy)) * X + (x0 + x)];
@@ -61,24 +61,33 @@ patch_gather_kernel(const float* __restrict__ vol, int Z, int Y, int X, const in
       v = __fdiv_rn(__fsub_rn(v, mean), stddev);           // numpy float32: (a - mean) / std
       if (clip) { v = v < lo ? lo : v; v = v > hi ? hi : v; }
     }
-    on[i] = from_f32<T>(v);
+    on[(size_t)(z * py + yy) * row_pitch + x] = from_f32<T>(v);
   }
+}
+
+extern "C" int seg3d_patch_gather_rows(const float* vol, int Z, int Y, int X, const int32_t* starts, int N,
+                                       int pz, int py, int px, int norm, float mean, float stddev, int clip,
+                                       float clip_lo, float clip_hi, const double* stats, int dtype, void* out,
+                                       int row_pitch, int x_off, void* stream) {
+  SEG3D_REQUIRE(vol && starts && out && N > 0 && pz > 0 && py > 0 && px > 0, "patch_gather: bad arguments");
+  SEG3D_REQUIRE(pz <= Z && py <= Y && px <= X, "patch_gather: patch larger than volume");
+  SEG3D_REQUIRE(norm != SEG3D_NORM_ADAPTIVE || stats, "patch_gather: adaptive normaliser needs stats");
+  SEG3D_REQUIRE(norm != SEG3D_NORM_FIXED || stddev > 0.f, "patch_gather: stddev must be positive");
+  SEG3D_REQUIRE(x_off >= 0 && row_pitch >= x_off + px, "patch_gather: row pitch smaller than offset + width");
+  const long long nv = (long long)pz * py * px;
+  int gx = (int)((nv + 256 * 4 - 1) / (256 * 4)); if (gx < 1) gx = 1; if (gx > 2048) gx = 2048;
+  dim3 grid(gx, N);
+  SEG3D_DISPATCH_DTYPE(dtype, T, (patch_gather_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      vol, Z, Y, X, starts, pz, py, px, norm, mean, stddev, clip, clip_lo, clip_hi, stats, (T*)out, row_pitch, x_off)));
+  SEG3D_CHECK_LAUNCH("patch_gather_kernel");
+  return SEG3D_OK;
 }
 
 extern "C" int seg3d_patch_gather(const float* vol, int Z, int Y, int X, const int32_t* starts, int N,
                                   int pz, int py, int px, int norm, float mean, float stddev, int clip,
                                   float clip_lo, float clip_hi, const double* stats, int dtype, void* out, void* stream) {
-  SEG3D_REQUIRE(vol && starts && out && N > 0 && pz > 0 && py > 0 && px > 0, "patch_gather: bad arguments");
-  SEG3D_REQUIRE(pz <= Z && py <= Y && px <= X, "patch_gather: patch larger than volume");
-  SEG3D_REQUIRE(norm != SEG3D_NORM_ADAPTIVE || stats, "patch_gather: adaptive normaliser needs stats");
-  SEG3D_REQUIRE(norm != SEG3D_NORM_FIXED || stddev > 0.f, "patch_gather: stddev must be positive");
-  const long long nv = (long long)pz * py * px;
-  int gx = (int)((nv + 256 * 4 - 1) / (256 * 4)); if (gx < 1) gx = 1; if (gx > 2048) gx = 2048;
-  dim3 grid(gx, N);
-  SEG3D_DISPATCH_DTYPE(dtype, T, (patch_gather_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
-      vol, Z, Y, X, starts, pz, py, px, norm, mean, stddev, clip, clip_lo, clip_hi, stats, (T*)out)));
-  SEG3D_CHECK_LAUNCH("patch_gather_kernel");
-  return SEG3D_OK;
+  return seg3d_patch_gather_rows(vol, Z, Y, X, starts, N, pz, py, px, norm, mean, stddev, clip, clip_lo, clip_hi, stats, dtype, out,
+                                 px, 0, stream);
 }
 
 // ---- acc[c][region] += probs (add_image_region, image_tools.py:435-452) ----------------------

@@ -279,7 +279,16 @@ class NetPlan(object):
             return _View(b, off, ld * cm, C, sample=b.shape[1] * b.shape[2])
 
         ws = {}
-        ws['x_in'] = torch.empty((B, vox[0], self.in_channels), dtype=torch.float32 if split else td, device=dev)
+        # input block as a TMA-fed Toeplitz GEMM (csrc/conv_tc_cin1t.cu): the single-channel input lives in a row-padded
+        # layout [B][D][H][W + CIN1_PAD] whose padding columns stay zero (written once here, never by the gather)
+        c_in = self.convs['in_block.conv']
+        cin1_t = (c_in.cin1_tc and not train and W % 8 == 0 and dt in (lib.F16, lib.BF16)
+                  and os.environ.get('SEG3D_CIN1_TOEPLITZ', '1') != '0')
+        ws['x_pad'] = cin1_t
+        if cin1_t:
+            ws['x_in'] = torch.zeros((B, D * H, W + lib.CIN1_PAD), dtype=td, device=dev)
+        else:
+            ws['x_in'] = torch.empty((B, vox[0], self.in_channels), dtype=torch.float32 if split else td, device=dev)
         ws['raw'] = torch.empty((B * vox[0] * 32,), dtype=torch.float32 if split else td, device=dev)
         ws['stats'] = torch.zeros((len(self.gn_names), B, 2), dtype=torch.float64, device=dev)
         ws['stats2'] = torch.zeros((B, 2), dtype=torch.float64, device=dev)
@@ -379,7 +388,8 @@ class NetPlan(object):
 
         # measured on B200: the stride-2 convs are epilogue-bound, not HBM-bound, so running them twice costs more than the
         # GroupNorm pass it saves (1535 vs 1640 Mvox/s); kept behind SEG3D_FUSE_S2=1
-        fuse_s2 = (not train) and dt != lib.F32 and not split and os.environ.get('SEG3D_FUSE_S2', '0') == '1'
+        fuse_s2_env = os.environ.get('SEG3D_FUSE_S2', '0')         # '1': every stride-2 conv; 'up': the transposed convs only
+        fuse_s2 = (not train) and dt != lib.F32 and not split and fuse_s2_env in ('1', 'up')
 
         def unit(cname, gname, x, lin, lout, out, res=None, defer_gn=False):
             """conv -> GroupNorm -> (+res) -> ReLU with the conv reading level `lin` and writing level `lout`"""
@@ -391,8 +401,8 @@ class NetPlan(object):
                 ws['deferred'] = {'raw': rv, 'res': res, 'gn': gname}
                 units.append({'conv': cname, 'gn': gname, 'x': x, 'lin': lin, 'lout': lout, 'raw': rv, 'out': out, 'res': res})
                 return
-            if (fuse_s2 and res is None and c.impl == lib.IMPL_TCGEN05 and c.mode in (lib.CONV_K2S2, lib.CONV_T2S2)
-                    and out.ld % 8 == 0):
+            if (fuse_s2 and res is None and c.impl == lib.IMPL_TCGEN05 and out.ld % 8 == 0
+                    and c.mode in ((lib.CONV_T2S2,) if fuse_s2_env == 'up' else (lib.CONV_K2S2, lib.CONV_T2S2))):
                 conv_gn_twice(cname, gname, x, dims[lin], out, vox[lout], lout)
                 units.append({'conv': cname, 'gn': gname, 'x': x, 'lin': lin, 'lout': lout, 'raw': None, 'out': out, 'res': res})
                 return
@@ -436,7 +446,36 @@ class NetPlan(object):
         # in_block -> second half of cat0
         x_in = _View(ws['x_in'], 0, self.in_channels, self.in_channels, sample=vox[0] * self.in_channels)
         skip = [V(ws['cat%d' % l], widths[l] // 2, widths[l], widths[l] // 2) for l in range(4)]
-        conv_gn('in_block.conv', 'in_block.gn', x_in, 0, skip[0], relu=True)
+        if cin1_t:
+            # run the layer twice (its input is 1/16 of its output): GroupNorm sums only, then conv + GroupNorm + ReLU in the
+            # epilogue - the raw tensor and the GroupNorm-apply pass of vnet_inblock.py:13-14 never touch HBM.
+            # SEG3D_FUSE_IN=0: one raw pass + seg3d_gn_apply
+            g_in = self.gns['in_block.gn']
+            xp_sample = D * H * (W + lib.CIN1_PAD)
+            xpad = _View(ws['x_in'], 0, 1, 1, sample=xp_sample)
+
+            def cin1(epi, out):
+                return lambda b0, nb: lib.call('seg3d_conv3d_cin1_fwd', dt, epi, xpad.at(b0), W + lib.CIN1_PAD, lib.ptr(c_in.w),
+                                               lib.ptr(c_in.bias), out.at(b0) if out is not None else None,
+                                               out.ld if out is not None else 0, nb, D, H, W, stats_ptr('in_block.gn', b0),
+                                               lib.ptr(g_in.gamma), lib.ptr(g_in.beta), GN_EPS, st())
+            flops = 2.0 * B * vox[0] * 27 * 16
+            if os.environ.get('SEG3D_FUSE_IN', '1') != '0':
+                add(cin1(1, None), 0)
+                meta.append({'name': 'in_block.conv.stats', 'kind': 'conv_tc_cin1', 'flops': flops, 'bytes': 2 * B * vox[0]})
+                add(cin1(2, skip[0]), 0)
+                meta.append({'name': 'in_block.conv.gn_relu', 'kind': 'conv_tc_cin1', 'flops': flops, 'bytes': 2 * B * vox[0] * 17})
+                units.append({'conv': 'in_block.conv', 'gn': 'in_block.gn', 'x': x_in, 'lin': 0, 'lout': 0, 'raw': None,
+                              'out': skip[0], 'res': None})
+            else:
+                rv = rawview(16, 0)
+                add(cin1(0, rv), 0)
+                meta.append({'name': 'in_block.conv', 'kind': 'conv_tc_cin1', 'flops': flops, 'bytes': 2 * B * vox[0] * 17})
+                gn('in_block.gn', rv, skip[0], vox[0], True, None, 0)
+                units.append({'conv': 'in_block.conv', 'gn': 'in_block.gn', 'x': x_in, 'lin': 0, 'lout': 0, 'raw': rv,
+                              'out': skip[0], 'res': None})
+        else:
+            conv_gn('in_block.conv', 'in_block.gn', x_in, 0, skip[0], relu=True)
         # down path
         src = skip[0]
         for l, name in ((1, 'down_32'), (2, 'down_64'), (3, 'down_128'), (4, 'down_256')):
@@ -561,7 +600,10 @@ class NetPlan(object):
     def load_input(self, ws, x):
         """x: [B,Cin,D,H,W] float32 CUDA tensor -> NDHWC storage dtype."""
         B = x.shape[0]
-        if self.in_channels == 1:
+        if ws.get('x_pad'):
+            D, H, W = x.shape[2:]
+            ws['x_in'].view(B, D, H, W + lib.CIN1_PAD)[..., lib.CIN1_LEFT:lib.CIN1_LEFT + W].copy_(x[:, 0])
+        elif self.in_channels == 1:
             ws['x_in'].view(-1).copy_(x.reshape(-1))
         else:
             ws['x_in'].copy_(x.reshape(B, self.in_channels, -1).permute(0, 2, 1))

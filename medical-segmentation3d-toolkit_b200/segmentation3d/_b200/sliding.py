@@ -80,8 +80,12 @@ class SlidingWindow(object):
                 pstats.zero_()
                 lib.call('seg3d_patch_stats', lib.ptr(vol), Z, Y, X, sp, nb, pz, py, px, lib.ptr(pstats), st())
                 self.kernel_launches += 1
-            lib.call('seg3d_patch_gather', lib.ptr(vol), Z, Y, X, sp, nb, pz, py, px, norm, mean, std, clip, lo, hi,
-                     lib.ptr(pstats), plan.in_dt, lib.ptr(ws['x_in']), st())
+            if ws.get('x_pad'):          # row-padded input layout of the Toeplitz input block (plan.py)
+                lib.call('seg3d_patch_gather_rows', lib.ptr(vol), Z, Y, X, sp, nb, pz, py, px, norm, mean, std, clip, lo, hi,
+                         lib.ptr(pstats), plan.in_dt, lib.ptr(ws['x_in']), px + lib.CIN1_PAD, lib.CIN1_LEFT, st())
+            else:
+                lib.call('seg3d_patch_gather', lib.ptr(vol), Z, Y, X, sp, nb, pz, py, px, norm, mean, std, clip, lo, hi,
+                         lib.ptr(pstats), plan.in_dt, lib.ptr(ws['x_in']), st())
             probs = plan.run(ws, ops)
             lib.call('seg3d_blend_accumulate', lib.ptr(probs), nb, C, pz, py, px, sp, lib.ptr(acc), Z, Y, X, st())
             self.kernel_launches += 2 + plan.launches(ws)

@@ -481,6 +481,61 @@ def test_conv_cin1_tensor_core_matches_torch(lib, shape, dt_name):
     assert torch.allclose(stats.cpu(), s_ref, rtol=rt, atol=rt * float(s_ref[:, 1].max()))
 
 
+@pytest.mark.parametrize('shape', [(2, 8, 12, 16), (1, 20, 40, 24), (3, 5, 16, 8), (2, 33, 70, 72), (1, 96, 96, 96)], ids=str)
+@pytest.mark.parametrize('dt_name', ['F16', 'BF16'])
+def test_conv_cin1_toeplitz_matches_torch(lib, shape, dt_name):
+    """Input block as a TMA-fed banded-Toeplitz GEMM (seg3d_conv3d_cin1_fwd, row-padded input): the three epilogue modes vs
+    F.conv3d / F.group_norm on the input rounded to the storage type with fp32 weights.  Shapes cover partial 32 x 32 tiles,
+    several z segments and W / 8 not a multiple of the 4-segment box."""
+    L = lib
+    dt = getattr(L, dt_name)
+    tdt = L.TORCH_DTYPE[dt]
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(D * 7 + W)
+    x = torch.randn((N, 1, D, H, W), generator=g).to(tdt).float()
+    w = torch.randn((16, 1, 3, 3, 3), generator=g) * 0.3
+    b = torch.randn((16,), generator=g) * 0.1
+    gamma = torch.rand((16,), generator=g) + 0.5
+    beta = torch.randn((16,), generator=g) * 0.2
+    ref = F.conv3d(x, w, b, padding=1)
+    ref_gn = F.relu(F.group_norm(ref, 1, gamma, beta, 1e-5))
+    pitch = W + L.CIN1_PAD
+    xp = torch.zeros((N, D, H, pitch), dtype=tdt, device='cuda')
+    xp[..., L.CIN1_LEFT:L.CIN1_LEFT + W] = x[:, 0].to(tdt).cuda()
+    wp = pack_simt(w, L.CONV_K3, L)
+    bd, gd, btd = b.cuda(), gamma.cuda(), beta.cuda()
+    ld = 32                                            # written into the upper half of a 32-channel concat buffer
+    s_ref = torch.stack([ref.double().flatten(1).sum(1), (ref.double() ** 2).flatten(1).sum(1)], 1)
+    rt = 1e-5 if dt == L.F16 else 2e-4                 # the sums come from the fp32 accumulators (hi+lo weights)
+    tol_store = 2.0 ** (-11 if dt == L.F16 else -8)    # output rounding to the storage type
+
+    def run(epi, stats):
+        y = torch.full((N, D, H, W, ld), float('nan'), dtype=tdt, device='cuda')
+        L.call('seg3d_conv3d_cin1_fwd', dt, epi, L.ptr(xp), pitch, L.ptr(wp), L.ptr(bd), None if epi == 1 else L.ptr(y, 16), ld,
+               N, D, H, W, L.ptr(stats), L.ptr(gd), L.ptr(btd), 1e-5, L.stream_ptr())
+        torch.cuda.synchronize()
+        return y
+
+    # mode 0: raw conv + sums
+    st0 = torch.zeros((N, 2), dtype=torch.float64, device='cuda')
+    y0 = run(0, st0)
+    assert torch.isnan(y0[..., :16].float()).all()     # the other half of the concat buffer is untouched
+    yc = from_ndhwc(y0[..., 16:])
+    assert not torch.isnan(yc).any()
+    assert (yc - ref).abs().max() <= tol_store * float(ref.abs().max()) * 1.01 + 1e-5
+    assert torch.allclose(st0.cpu(), s_ref, rtol=rt, atol=rt * float(s_ref[:, 1].max()))
+    # mode 1: the same sums, bit for bit, nothing stored
+    st1 = torch.zeros((N, 2), dtype=torch.float64, device='cuda')
+    run(1, st1)
+    assert torch.allclose(st1.cpu(), s_ref, rtol=rt, atol=rt * float(s_ref[:, 1].max()))
+    # mode 2: relu(GroupNorm(conv)) from the finished sums
+    y2 = run(2, st1)
+    assert torch.isnan(y2[..., :16].float()).all()
+    yg = from_ndhwc(y2[..., 16:])
+    assert not torch.isnan(yg).any()
+    assert (yg - ref_gn).abs().max() <= tol_store * float(ref_gn.abs().max()) * 1.01 + 2e-5
+
+
 @pytest.mark.parametrize('case', [('K2S2', 16, 32, 2, 8, 12, 16), ('K2S2', 64, 128, 1, 8, 8, 8), ('T2S2', 64, 16, 2, 4, 6, 8),
                                   ('T2S2', 256, 128, 1, 2, 4, 4)], ids=lambda c: '-'.join(map(str, c)))
 def test_conv_gn_relu_two_pass_matches_torch(lib, case):

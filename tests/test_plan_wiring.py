@@ -120,6 +120,31 @@ def _install(monkeypatch, calls):
         calls.append('conv')
         return 0
 
+    def cin1_fwd(dtype, epi, xpad, x_pitch, w, bias, y, y_ld, N, D, H, W, stats, gamma, beta, eps, stream):
+        # row-padded single-channel input: x index i at column i + CIN1_LEFT, every other column zero
+        assert x_pitch == W + lib.CIN1_PAD and W % 8 == 0
+        rows = _rows(xpad, N * D * H, x_pitch, x_pitch).float()
+        assert float(rows[:, :lib.CIN1_LEFT].abs().max()) == 0 and float(rows[:, lib.CIN1_LEFT + W:].abs().max()) == 0
+        xs = rows[:, lib.CIN1_LEFT:lib.CIN1_LEFT + W].reshape(N, 1, D, H, W)
+        r = _conv(lib.CONV_K3, True, xs, w, bias, 1, 16)
+        if epi in (0, 1):
+            s0, s1 = _stats(r)
+            st = _stat_rows(stats, N)
+            st[:N, 0] += s0
+            st[:N, 1] += s1
+        if epi == 1:
+            assert y is None
+            calls.append('conv_stats')
+            return 0
+        rn = r.permute(0, 2, 3, 4, 1).reshape(N, D * H * W, 16)
+        if epi == 2:
+            mean, rstd = _mean_rstd(stats, float(D * H * W * 16), eps, N)
+            rn = F.relu(((rn.double() - mean) * rstd).float() * gamma.t.view(1, 1, 16) + beta.t.view(1, 1, 16))
+        dst = _rows(y, N * D * H * W, y_ld, 16)
+        dst.copy_(rn.reshape(-1, 16).to(dst.dtype))
+        calls.append('conv')
+        return 0
+
     def narrow_np(Cout):
         return (9 * Cout + 15) // 16 * 16
 
@@ -206,7 +231,7 @@ def _install(monkeypatch, calls):
         calls.append('tail_probs')
         return 0
 
-    table = {'seg3d_conv3d_fwd': conv3d_fwd, 'seg3d_conv3d_k3_narrow_fwd': narrow_fwd, 'seg3d_conv3d_k3_narrow_gn_fwd': narrow_gn_fwd,
+    table = {'seg3d_conv3d_fwd': conv3d_fwd, 'seg3d_conv3d_cin1_fwd': cin1_fwd, 'seg3d_conv3d_k3_narrow_fwd': narrow_fwd, 'seg3d_conv3d_k3_narrow_gn_fwd': narrow_gn_fwd,
              'seg3d_gn_apply': gn_apply, 'seg3d_conv3d_split_fwd': split_fwd, 'seg3d_gn_apply_split': gn_apply_split,
              'seg3d_outblock_tail_stats': tail_stats, 'seg3d_outblock_tail_probs': tail_probs,
              'seg3d_gather_pack': emulate_gather_pack}
@@ -235,6 +260,7 @@ def test_plan_issues_the_reference_network(monkeypatch, arch, cout, mode, tol):
     assert sum(c in ('conv', 'narrow', 'narrow_gn', 'split_conv') for c in calls) == n_convs
     if mode in ('fp16', 'bf16'):
         assert 'narrow_gn' in calls                                                   # fused last GroupNorm + narrow-output conv is the default
+        assert 'conv_stats' in calls                                                  # input block: statistics pass + fused GroupNorm/ReLU pass
     if mode == 'fp32x':
         assert 'split_conv' in calls and 'gn_split' in calls
     # a second forward through the cached plan, and after an in-place weight refresh, stays correct
