@@ -350,7 +350,7 @@ def main():
     ap.add_argument('--mode', default='fp16', choices=['auto', 'fp16', 'bf16', 'fp32', 'fp32x'],
                     help="fp32x = strict parity on the tensor cores (f16 hi/lo split operands, fp32 accumulate)")
     ap.add_argument('--train-mode', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--batch', type=int, default=20, help='patches per network forward')
+    ap.add_argument('--batch', type=int, default=36, help='patches per network forward (36 = one z layer of the 6x6x5 patch grid)')
     ap.add_argument('--volume', default='512,512,400')
     ap.add_argument('--patch', type=int, default=96)
     ap.add_argument('--stride', type=int, default=96)

@@ -103,6 +103,12 @@ int seg3d_conv3d_k3_narrow_gn_fwd(int dtype, const void* raw, int raw_ld, const 
                                   const void* w, const float* bias, float* y, int Cout, int N, int D, int H, int W,
                                   double* stats, void* stream);
 
+/* the narrow-output convolution in the strict-parity mode (split operands, see seg3d_conv3d_split_fwd below): x rows are
+ * [hi(32) | lo(32)] f16 halves of the activation (Cin must be 32, the lo half directly behind the hi half, pitch x_ld >= 64),
+ * w is [3 kd][NP][whi(32) | wlo(32)] f16 (rows as in seg3d_conv3d_k3_narrow_fwd); accumulates hi*whi + lo*whi + hi*wlo in fp32. */
+int seg3d_conv3d_k3_narrow_split_fwd(const void* x, int x_ld, int Cin, const void* w, const float* bias,
+                                     float* y, int Cout, int N, int D, int H, int W, double* stats, void* stream);
+
 /* conv -> GroupNorm(1,C) -> ReLU without the raw intermediate, as two launches of the same tensor-core convolution
  * (vnet_downblock.py:19, vnet_upblock.py:19: the stride-2 / transposed convolutions are HBM-bound and cheap to run twice).
  * pass 0: stats[n] += {sum, sum of squares} of conv + bias, nothing is stored;  pass 1: recompute and store
@@ -165,9 +171,11 @@ int seg3d_patch_gather_rows(const float* vol, int Z, int Y, int X, const int32_t
                             int pz, int py, int px, int norm, float mean, float stddev, int clip,
                             float clip_lo, float clip_hi, const double* stats,
                             int dtype, void* out, int row_pitch, int x_off, void* stream);
-/* acc[c][z0+z][y0+y][x0+x] += probs[n][c][z][y][x]  (add_image_region) */
+/* acc[c][z0+z][y0+y][x0+x] += probs[n][c][z][y][x]  (add_image_region).  starts_x_mult4 != 0: the caller guarantees every
+ * start x is a multiple of 4 (the list lives on the device; the host that built it knows), which lets the kernel add four
+ * voxels per red.global.add.v4.f32 when px and X are multiples of 4 too */
 int seg3d_blend_accumulate(const float* probs, int N, int C, int pz, int py, int px,
-                           const int32_t* starts, float* acc, int Z, int Y, int X, void* stream);
+                           const int32_t* starts, float* acc, int Z, int Y, int X, int starts_x_mult4, void* stream);
 /* acc[c] *= float(1.0/count) with count = cx[x]*cy[y]*cz[z] (add_image_value, seg_infer.py:325-327),
  * then mask = first argmax over c (seg_infer.py:337), int8.  mask may be NULL. */
 int seg3d_blend_finalize_argmax(float* acc, int C, int Z, int Y, int X,

@@ -312,7 +312,10 @@ struct ZmParams {
 };
 constexpr int ZM_MAXNB = 8;
 
-template <typename T, int KC>
+// SPLIT (strict-parity mode, seg3d_conv3d_split_fwd): the KC channels of a voxel row are [hi(KC/2) | lo(KC/2)] f16 halves of the
+// activation, a weight row is [whi(KC/2) | wlo(KC/2)], and the k loop runs the three products hi*whi, lo*whi, hi*wlo
+// (A k-step, B k-step) instead of the diagonal - the plane, the slabs and the N-fold over three output planes are unchanged.
+template <typename T, int KC, bool SPLIT>
 __global__ void __launch_bounds__(TCE_THREADS)
 conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                         const ZmParams p, const float* __restrict__ bias, T* __restrict__ y, double* __restrict__ stats) {
@@ -408,9 +411,12 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                const uint32_t da = lo_a + (((kh * 10 + kw) * ROWB + k * 32) >> 4);
-                const uint32_t db = w16 + (uint32_t)((kh * 3 + kw) * 3) * slab16 + ((k * 32) >> 4);
+              for (int k = 0; k < (SPLIT ? KSTEPS / 2 * 3 : KSTEPS); ++k) {
+                constexpr int KH = KSTEPS / 2;
+                const int ka = SPLIT ? (k < 2 * KH ? k : k - 2 * KH) : k;          // hi, lo, hi
+                const int kb = SPLIT ? (k < KH ? k : k - KH) : k;                  // whi, whi, wlo
+                const uint32_t da = lo_a + (((kh * 10 + kw) * ROWB + ka * 32) >> 4);
+                const uint32_t db = w16 + (uint32_t)((kh * 3 + kw) * 3) * slab16 + ((kb * 32) >> 4);
                 if (kh == 0 && kw == 0 && k == 0 && fresh) {
                   tc_mma_f16_e(dF, desc_pack(hi_a, da), desc_pack(hi_b, db + 2 * slab16), id1, 0);
                   for (int kd = kd_hi; kd >= 1; --kd)
@@ -472,7 +478,11 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             if (valid) { s += f[jj]; ss += f[jj] * f[jj]; }
           }
           if (valid) {
-            if (p.out_f32) {           // only the first y_ld (= real) channels are kept, densely packed
+            if (p.out_f32 == 2) {      // fp32 rows of pitch y_ld >= Cout (16-byte aligned): split mode
+              float4* d4 = reinterpret_cast<float4*>(yrow32 + c0);
+#pragma unroll
+              for (int jj = 0; jj < 16; jj += 4) d4[jj >> 2] = make_float4(f[jj], f[jj + 1], f[jj + 2], f[jj + 3]);
+            } else if (p.out_f32) {    // only the first y_ld (= real) channels are kept, densely packed
 #pragma unroll
               for (int jj = 0; jj < 16; ++jj) if (c0 + jj < p.y_ld) yrow32[c0 + jj] = f[jj];
             } else {
@@ -832,11 +842,17 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
   // ---- z-marching kernel for narrow k3 layers --------------------------------------------------------
   const int out_f32 = (dtype & SEG3D_OUT_F32) ? 1 : 0;
   dtype &= ~SEG3D_OUT_F32;
-  if (epi_mode == 0 && split_lo_off == 0 && !out_f32_generic && mode == SEG3D_CONV_K3 && (Cin == 16 || Cin == 32 || Cin == 64) && W % 8 == 0 && D >= 4 && env_int("SEG3D_TC_ZMARCH", 1) != 0) {
+  // split operands take the z-march kernel when the lo half follows the hi half directly (rows [hi(Cin) | lo(Cin)]): the row is
+  // then one K block of 2*Cin channels
+  const bool zm_split = split_lo_off > 0 && split_lo_off == Cin && out_f32_generic && (Cin == 16 || Cin == 32) && y_ld % 4 == 0 &&
+                        dtype == SEG3D_F16 && env_int("SEG3D_ZM_SPLIT", 1) != 0;
+  if (epi_mode == 0 && ((split_lo_off == 0 && !out_f32_generic && (Cin == 16 || Cin == 32 || Cin == 64)) || zm_split) && mode == SEG3D_CONV_K3 && W % 8 == 0 && D >= 4 && env_int("SEG3D_TC_ZMARCH", 1) != 0) {
     ZmParams z;
     memset(&z, 0, sizeof(z));
+    const int Cin_real = Cin;
+    if (zm_split) Cin = 2 * Cin;                       // the K block: [hi | lo] channels of a row, [whi | wlo] of a weight row
     z.Cout = Cout; z.KC = Cin; z.row_bytes = Cin * 2;
-    z.D = D; z.H = H; z.W = W; z.N = N; z.y_ld = y_ld; z.out_f32 = out_f32;
+    z.D = D; z.H = H; z.W = W; z.N = N; z.y_ld = y_ld; z.out_f32 = zm_split ? 2 : out_f32;
     z.wide = (!out_f32 && wide_ok(y, y_ld, 2) && env_int("SEG3D_WIDE_ST", 1)) ? 1 : 0;
     z.w_slab = (Cout * z.row_bytes + 1023) & ~1023;
     z.plane_tx = 180 * z.row_bytes;
@@ -898,18 +914,25 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
         dim3 grid((unsigned)(nitems < max_grid ? nitems : max_grid));
         cudaError_t e = cudaSuccess;
 #define SEG3D_LAUNCH_Z(TT, KCV)                                                                                             \
-        { e = cudaFuncSetAttribute(conv3d_k3_zmarch_kernel<TT, KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-          if (e == cudaSuccess) { conv3d_k3_zmarch_kernel<TT, KCV><<<grid, TCE_THREADS, smem, st>>>(map_x, map_w, z, bias, (TT*)y, stats); e = cudaGetLastError(); } }
-        if (dtype == SEG3D_BF16) {
+        { e = cudaFuncSetAttribute(conv3d_k3_zmarch_kernel<TT, KCV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+          if (e == cudaSuccess) { conv3d_k3_zmarch_kernel<TT, KCV, false><<<grid, TCE_THREADS, smem, st>>>(map_x, map_w, z, bias, (TT*)y, stats); e = cudaGetLastError(); } }
+#define SEG3D_LAUNCH_ZS(KCV)                                                                                                \
+        { e = cudaFuncSetAttribute(conv3d_k3_zmarch_kernel<__half, KCV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+          if (e == cudaSuccess) { conv3d_k3_zmarch_kernel<__half, KCV, true><<<grid, TCE_THREADS, smem, st>>>(map_x, map_w, z, bias, (__half*)y, stats); e = cudaGetLastError(); } }
+        if (zm_split) {
+          if (Cin == 64) SEG3D_LAUNCH_ZS(64) else SEG3D_LAUNCH_ZS(32)
+        } else if (dtype == SEG3D_BF16) {
           if (Cin == 64) SEG3D_LAUNCH_Z(__nv_bfloat16, 64) else if (Cin == 32) SEG3D_LAUNCH_Z(__nv_bfloat16, 32) else SEG3D_LAUNCH_Z(__nv_bfloat16, 16)
         } else {
           if (Cin == 64) SEG3D_LAUNCH_Z(__half, 64) else if (Cin == 32) SEG3D_LAUNCH_Z(__half, 32) else SEG3D_LAUNCH_Z(__half, 16)
         }
 #undef SEG3D_LAUNCH_Z
+#undef SEG3D_LAUNCH_ZS
         if (e != cudaSuccess) { seg3d_set_error("conv3d_k3_zmarch_kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
         return SEG3D_OK;
       }
     }
+    Cin = Cin_real;            // the shape did not fit the z-march kernel: generic path below
   }
 
   SEG3D_REQUIRE(!out_f32, "conv_tc: SEG3D_OUT_F32 (dense real channels) is only available on the z-march k3 path");

@@ -38,7 +38,8 @@ constexpr int FD_NB = 4;            // rotating TMEM accumulators
 constexpr int FD_TX = 8, FD_TY = 10, FD_HX = 10, FD_HY = 12;
 constexpr int FDG_THREADS = 320;     // fused variant: + 4 transform warps
 
-template <typename T, int KC, bool FUSE_GN>
+// SPLIT (strict-parity mode): a voxel row is [hi(KC/2) | lo(KC/2)], a weight row [whi | wlo]; the k loop runs hi*whi, lo*whi, hi*wlo.
+template <typename T, int KC, bool FUSE_GN, bool SPLIT = false>
 __global__ void __launch_bounds__(FUSE_GN ? FDG_THREADS : TC_THREADS, FUSE_GN ? 3 : 1)
 conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                       const __grid_constant__ CUtensorMap map_r,
@@ -125,8 +126,12 @@ conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             const uint32_t dcol = tmem_base + (uint32_t)(buf * p.acc_cols);
             const uint32_t lo_w = w16 + (uint32_t)kd * slab16;
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k)
-              tc_mma_f16_e(dcol, desc_pack(hi, lo_a + ((k * 32) >> 4)), desc_pack(hi, lo_w + ((k * 32) >> 4)), p.idesc, (kd | k) != 0);
+            for (int k = 0; k < (SPLIT ? KSTEPS / 2 * 3 : KSTEPS); ++k) {
+              constexpr int KH = KSTEPS / 2;
+              const int ka = SPLIT ? (k < 2 * KH ? k : k - 2 * KH) : k;            // hi, lo, hi
+              const int kb = SPLIT ? (k < KH ? k : k - KH) : k;                    // whi, whi, wlo
+              tc_mma_f16_e(dcol, desc_pack(hi, lo_a + ((ka * 32) >> 4)), desc_pack(hi, lo_w + ((kb * 32) >> 4)), p.idesc, (kd | k) != 0);
+            }
           }
           tc_commit_e(empty_bar + 8 * stage_i);
           if (ip >= 2) tc_commit_e(tfull_bar + 8 * ((oc + ip - 2) % FD_NB));
@@ -296,9 +301,14 @@ extern "C" int seg3d_conv3d_k3_narrow_np(int C) { return C >= 1 && 9 * C <= 64 ?
 
 static int launch_fold(int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
                        float* y, int C, int N, int D, int H, int W, double* stats, void* stream,
-                       const void* res, int res_ld, const double* gn_stats, const float* gn_gamma, const float* gn_beta, float gn_eps) {
+                       const void* res, int res_ld, const double* gn_stats, const float* gn_gamma, const float* gn_beta, float gn_eps,
+                       bool split = false) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool fuse = res != nullptr;
+  if (split) {       // rows [hi(Cin) | lo(Cin)]: one K block of 2*Cin channels
+    SEG3D_REQUIRE(!fuse && dtype == SEG3D_F16 && Cin == 32 && x_ld >= 64, "conv3d_k3_narrow_split_fwd: Cin must be 32 with rows [hi | lo] of 64 f16 values");
+    Cin = 64;
+  }
   if (fuse) {
     SEG3D_REQUIRE(Cin == 32, "conv3d_k3_narrow_gn_fwd: Cin must be 32 (64-byte rows), got %d", Cin);
     SEG3D_REQUIRE(gn_stats && gn_gamma && gn_beta && res_ld % 8 == 0 && ((uintptr_t)res) % 16 == 0, "conv3d_k3_narrow_gn_fwd: bad GroupNorm / residual arguments");
@@ -393,7 +403,10 @@ static int launch_fold(int dtype, const void* x, int x_ld, int Cin, const void* 
 #define SEG3D_LAUNCH_FG(TT)                                                                                                     \
   { e = cudaFuncSetAttribute(conv3d_k3_fold_kernel<TT, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e == cudaSuccess) { conv3d_k3_fold_kernel<TT, 32, true><<<grid, FDG_THREADS, smem, st>>>(map_x, map_w, map_r, p, bias, y, stats); e = cudaGetLastError(); } }
-  if (fuse) {
+  if (split) {
+    e = cudaFuncSetAttribute(conv3d_k3_fold_kernel<__half, 64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) { conv3d_k3_fold_kernel<__half, 64, false, true><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, map_r, p, bias, y, stats); e = cudaGetLastError(); }
+  } else if (fuse) {
     if (dtype == SEG3D_BF16) SEG3D_LAUNCH_FG(__nv_bfloat16) else SEG3D_LAUNCH_FG(__half)
   } else if (dtype == SEG3D_BF16) {
     if (Cin == 64) SEG3D_LAUNCH_F(__nv_bfloat16, 64) else if (Cin == 32) SEG3D_LAUNCH_F(__nv_bfloat16, 32) else SEG3D_LAUNCH_F(__nv_bfloat16, 16)
@@ -420,4 +433,11 @@ extern "C" int seg3d_conv3d_k3_narrow_gn_fwd(int dtype, const void* raw, int raw
                                              double* stats, void* stream) {
   SEG3D_REQUIRE(res != nullptr, "conv3d_k3_narrow_gn_fwd: null residual");
   return launch_fold(dtype, raw, raw_ld, Cin, w, bias, y, C, N, D, H, W, stats, stream, res, res_ld, gn_stats, gamma, beta, eps);
+}
+
+// Strict-parity variant (split operands, see seg3d_conv3d_split_fwd): x rows are [hi(32) | lo(32)] f16 (pitch x_ld >= 64, the lo
+// half directly behind the hi half), w is [3 kd][NP][whi(32) | wlo(32)] f16; the MMAs accumulate hi*whi + lo*whi + hi*wlo.
+extern "C" int seg3d_conv3d_k3_narrow_split_fwd(const void* x, int x_ld, int Cin, const void* w, const float* bias,
+                                                float* y, int C, int N, int D, int H, int W, double* stats, void* stream) {
+  return launch_fold(SEG3D_F16, x, x_ld, Cin, w, bias, y, C, N, D, H, W, stats, stream, nullptr, 0, nullptr, nullptr, nullptr, 0.f, true);
 }

@@ -109,12 +109,38 @@ blend_accumulate_kernel(const float* __restrict__ probs, int C, int pz, int py, 
   }
 }
 
+// four x-consecutive voxels per thread: one 16-byte load and one red.global.add.v4.f32 (px, X and every x0 multiples of 4,
+// 16-byte aligned pointers), 32-bit index arithmetic
+__global__ void __launch_bounds__(256)
+blend_accumulate_v4_kernel(const float4* __restrict__ probs, int C, int pz, int py, int px4,
+                           const int32_t* __restrict__ starts, float* __restrict__ acc, int Z, int Y, int X) {
+  const int n = blockIdx.y;
+  const int x0 = starts[3 * n], y0 = starts[3 * n + 1], z0 = starts[3 * n + 2];
+  const unsigned tot4 = (unsigned)C * pz * py * px4;
+  const float4* pn = probs + (size_t)n * tot4;
+  const size_t vsz = (size_t)Z * Y * X;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < tot4; i += gridDim.x * blockDim.x) {
+    const unsigned x4 = i % px4; unsigned t = i / px4;
+    const unsigned yy = t % py; t /= py;
+    const unsigned z = t % pz; const unsigned c = t / pz;
+    const float4 v = pn[i];
+    float* dst = acc + c * vsz + ((size_t)(z0 + z) * Y + (y0 + yy)) * X + (x0 + 4 * x4);
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
+}
+
 extern "C" int seg3d_blend_accumulate(const float* probs, int N, int C, int pz, int py, int px,
-                                      const int32_t* starts, float* acc, int Z, int Y, int X, void* stream) {
+                                      const int32_t* starts, float* acc, int Z, int Y, int X, int starts_x_mult4, void* stream) {
   SEG3D_REQUIRE(probs && starts && acc && N > 0 && C > 0, "blend_accumulate: bad arguments");
   const long long tot = (long long)pz * py * px * C;
-  int gx = (int)((tot + 256 * 4 - 1) / (256 * 4)); if (gx < 1) gx = 1; if (gx > 4096) gx = 4096;
-  blend_accumulate_kernel<<<dim3(gx, N), 256, 0, (cudaStream_t)stream>>>(probs, C, pz, py, px, starts, acc, Z, Y, X);
+  const bool v4 = starts_x_mult4 && px % 4 == 0 && X % 4 == 0 && ((uintptr_t)probs) % 16 == 0 && ((uintptr_t)acc) % 16 == 0 && tot / 4 < (1ll << 31);
+  if (v4) {
+    int gx = (int)((tot / 4 + 256 * 4 - 1) / (256 * 4)); if (gx < 1) gx = 1; if (gx > 4096) gx = 4096;
+    blend_accumulate_v4_kernel<<<dim3(gx, N), 256, 0, (cudaStream_t)stream>>>((const float4*)probs, C, pz, py, px / 4, starts, acc, Z, Y, X);
+  } else {
+    int gx = (int)((tot + 256 * 4 - 1) / (256 * 4)); if (gx < 1) gx = 1; if (gx > 4096) gx = 4096;
+    blend_accumulate_kernel<<<dim3(gx, N), 256, 0, (cudaStream_t)stream>>>(probs, C, pz, py, px, starts, acc, Z, Y, X);
+  }
   SEG3D_CHECK_LAUNCH("blend_accumulate_kernel");
   return SEG3D_OK;
 }

@@ -145,8 +145,13 @@ def add_conv_pack(table, conv, weight, bias):
     if conv.fold:
         C = conv.real_cout
         f = _WView(weight.shape).crop0(C)
-        NP, cin = conv.w_fold.shape[1], conv.w_fold.shape[2]
-        # wf[kd][(kh, kw, co)][ci]; rows 9C..NP stay zero
-        table.add_view(weight, f, (2, 3, 4, 0, 1), conv.w_fold, dst_stride=[NP * cin, 3 * C * cin, C * cin, cin, 1])
+        NP, row = conv.w_fold.shape[1], conv.w_fold.shape[2]
+        # wf[kd][(kh, kw, co)][ci]; rows 9C..NP stay zero.  Split mode: rows are [whi(Cin) | wlo(Cin)]
+        ds = [NP * row, 3 * C * row, C * row, row, 1]
+        if conv.split:
+            table.add_view(weight, f, (2, 3, 4, 0, 1), conv.w_fold, dst_stride=ds, dst_base=0, kind=lib.PACK_SPLIT_HI)
+            table.add_view(weight, f, (2, 3, 4, 0, 1), conv.w_fold, dst_stride=ds, dst_base=row // 2, kind=lib.PACK_SPLIT_LO)
+        else:
+            table.add_view(weight, f, (2, 3, 4, 0, 1), conv.w_fold, dst_stride=ds)
     if conv.bias is not None and bias is not None:
         table.add_copy(bias, conv.bias, conv.bias.numel(), limit=bias.numel())

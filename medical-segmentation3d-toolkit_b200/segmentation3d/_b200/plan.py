@@ -117,7 +117,11 @@ class _Conv(object):
             NP = lib.load().seg3d_conv3d_k3_narrow_np(C)
             wf = torch.zeros((3, NP, self.cin), dtype=torch.float32, device=self.device)
             wf[:, :9 * C] = w[:C].permute(2, 3, 4, 0, 1).reshape(3, 9 * C, self.cin)
-            wf = wf.to(lib.TORCH_DTYPE[self.dt]).contiguous()
+            if self.split:              # rows [whi(Cin) | wlo(Cin)] (seg3d_conv3d_k3_narrow_split_fwd)
+                fhi = wf.to(torch.float16)
+                wf = torch.cat([fhi, (wf - fhi.float()).to(torch.float16)], dim=-1).contiguous()
+            else:
+                wf = wf.to(lib.TORCH_DTYPE[self.dt]).contiguous()
             if self.w_fold is None:
                 self.w_fold = wf
             else:
@@ -198,8 +202,8 @@ class NetPlan(object):
                     continue
                 else:
                     m = lib.CONV_K3
-                narrow = (name == 'out_block.conv1' and self.dt != lib.F32 and not self.split and lib.CONV_K3 in self.tc_modes
-                          and sd[k].shape[0] <= 7 and sd[k].shape[1] in (16, 32, 64)
+                narrow = (name == 'out_block.conv1' and self.dt != lib.F32 and lib.CONV_K3 in self.tc_modes
+                          and sd[k].shape[0] <= 7 and sd[k].shape[1] in ((32,) if self.split else (16, 32, 64))
                           and os.environ.get('SEG3D_NARROW', '1') != '0')
                 self.convs[name] = _Conv(sd, name, m, self.dt, self.device, self.tc_modes,
                                          pad_cout=16 if name == 'out_block.conv1' else 0, fold=narrow, split=self.split)
@@ -523,6 +527,15 @@ class NetPlan(object):
                 rd = 2 * B * vox[0] * c1.cin
             meta.append({'name': 'out_block.conv1', 'kind': 'conv_tc_narrow', 'flops': 2.0 * B * vox[0] * 27 * c1.cin * nc,
                          'bytes': rd + 4 * B * vox[0] * nc + c1.w_fold.numel() * 2})
+        elif split and c1.fold and c1.impl == lib.IMPL_TCGEN05 and src.C == 32 and src.off == 0 and src.ld == 64 and W % 8 == 0:
+            # strict mode: the same folded kernel on split operands (rows [hi(32) | lo(32)]), fp32 result
+            ncp = nc
+            rv1 = _View(torch.empty((B, vox[0], nc), dtype=torch.float32, device=dev), 0, nc, nc, sample=vox[0] * nc)
+            add(lambda b0, nb: lib.call('seg3d_conv3d_k3_narrow_split_fwd', src.at(b0), src.ld, c1.cin, lib.ptr(c1.w_fold),
+                                        lib.ptr(c1.bias), rv1.at(b0), nc, nb, dims[0][0], dims[0][1], dims[0][2],
+                                        stats_ptr('out_block.gn1', b0), st()), 0)
+            meta.append({'name': 'out_block.conv1', 'kind': 'conv_tc_narrow', 'flops': 2.0 * B * vox[0] * 27 * c1.cin * nc,
+                         'bytes': 2 * 2 * B * vox[0] * c1.cin + 4 * B * vox[0] * nc + c1.w_fold.numel() * 2})
         elif tail_f32:
             ncp = nc                                       # the fp32 store keeps only the real channels
             rv1 = _View(torch.empty((B, vox[0], nc), dtype=torch.float32, device=dev), 0, nc, nc, sample=vox[0] * nc)

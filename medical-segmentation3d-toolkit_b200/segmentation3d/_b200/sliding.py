@@ -56,6 +56,7 @@ class SlidingWindow(object):
         n = len(starts)
         if n == 0:
             return
+        x_mult4 = 1 if all(int(s[0]) % 4 == 0 for s in starts) else 0
         starts_dev = torch.tensor(np.asarray(starts, dtype=np.int32).reshape(-1, 3), dtype=torch.int32, device=vol.device)
         norm, mean, std, clip, lo, hi = lib.NORM_NONE, 0.0, 1.0, 0, -1.0, 1.0
         if normalizer is not None:
@@ -87,7 +88,7 @@ class SlidingWindow(object):
                 lib.call('seg3d_patch_gather', lib.ptr(vol), Z, Y, X, sp, nb, pz, py, px, norm, mean, std, clip, lo, hi,
                          lib.ptr(pstats), plan.in_dt, lib.ptr(ws['x_in']), st())
             probs = plan.run(ws, ops)
-            lib.call('seg3d_blend_accumulate', lib.ptr(probs), nb, C, pz, py, px, sp, lib.ptr(acc), Z, Y, X, st())
+            lib.call('seg3d_blend_accumulate', lib.ptr(probs), nb, C, pz, py, px, sp, lib.ptr(acc), Z, Y, X, x_mult4, st())
             self.kernel_launches += 2 + plan.launches(ws)
 
     def finalize(self, acc, counts, want_mask=True, z_range=None, mask=None):

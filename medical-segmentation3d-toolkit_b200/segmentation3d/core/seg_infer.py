@@ -36,11 +36,12 @@ DEFAULT_PATCH_BATCH = int(os.environ.get('SEG3D_PATCH_BATCH', '0'))      # 0: ch
 
 
 def default_patch_batch(patch_voxels):
-    """patches per network forward: as many as fit ~40 GB of fp16 workspace (~430 B/voxel), at most 20.
+    """patches per network forward: as many as fit ~40 GB of fp16 workspace (~430 B/voxel), at most 36 (measured on B200,
+    profiles/r02_batch_graph_sweep.txt: 20 -> 36..45 patches per forward is +2-4 %; 36 is one z layer of BASELINE configs[1]).
     GroupNorm is per sample, so the batch size changes throughput, not results."""
     if DEFAULT_PATCH_BATCH > 0:
         return DEFAULT_PATCH_BATCH
-    return int(min(20, max(1, 40e9 // (430.0 * max(1, patch_voxels)))))
+    return int(min(36, max(1, 40e9 // (430.0 * max(1, patch_voxels)))))
 
 
 # ---- test-list readers -----------------------------------------------------------------------------

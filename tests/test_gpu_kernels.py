@@ -613,6 +613,76 @@ def test_conv_k3_narrow_fused_gn_residual_equals_unfused(lib, shape, dt_name):
     assert torch.allclose(s0, s1, rtol=1e-9, atol=1e-6)
 
 
+def _split_rows(x5):
+    """[N,C,D,H,W] fp32 -> NDHWC rows [hi(C) | lo(C)] f16 on the GPU, and the value the kernels see (hi + lo)"""
+    rows = x5.permute(0, 2, 3, 4, 1).contiguous()
+    hi = rows.half()
+    lo = (rows - hi.float()).half()
+    seen = (hi.float() + lo.float()).permute(0, 4, 1, 2, 3).contiguous()
+    return torch.cat([hi, lo], dim=-1).contiguous().cuda(), seen
+
+
+@pytest.mark.parametrize('case', [(32, 32, 2, 8, 18, 16), (16, 16, 1, 12, 40, 24), (32, 32, 1, 5, 16, 8), (16, 64, 2, 6, 20, 8)],
+                         ids=lambda c: '-'.join(map(str, c)))
+def test_conv_k3_split_zmarch_matches_torch(lib, case):
+    """seg3d_conv3d_split_fwd on rows [hi(Cin) | lo(Cin)] (the z-march kernel with the three-product k loop for Cin = 16 / 32):
+    fp32 result within 2e-5 of F.conv3d in fp32 on the values the kernel sees; sums from the fp32 accumulators."""
+    L = lib
+    Cin, Cout, N, D, H, W = case
+    g = torch.Generator().manual_seed(Cin * 3 + Cout + D)
+    x = torch.randn((N, Cin, D, H, W), generator=g)
+    w = torch.randn((Cout, Cin, 3, 3, 3), generator=g) * 0.1
+    b = torch.randn((Cout,), generator=g) * 0.1
+    xd, xs = _split_rows(x)
+    q = w.permute(2, 3, 4, 0, 1).reshape(27, Cout, Cin)
+    whi = q.half()
+    wlo = (q - whi.float()).half()
+    wp = torch.cat([whi, wlo], dim=-1).contiguous().cuda()
+    wseen = (whi.float() + wlo.float()).view(3, 3, 3, Cout, Cin).permute(3, 4, 0, 1, 2).contiguous()
+    ref = F.conv3d(xs.double(), wseen.double(), b.double(), padding=1).float()
+    y = torch.full((N, D, H, W, Cout), float('nan'), dtype=torch.float32, device='cuda')
+    stats = torch.zeros((N, 2), dtype=torch.float64, device='cuda')
+    L.call('seg3d_conv3d_split_fwd', L.CONV_K3, L.ptr(xd), 2 * Cin, Cin, Cin, L.ptr(wp), L.ptr(b.cuda()), L.ptr(y), Cout, Cout,
+           N, D, H, W, L.ptr(stats), L.stream_ptr())
+    torch.cuda.synchronize()
+    yc = y.cpu().permute(0, 4, 1, 2, 3)
+    assert not torch.isnan(yc).any()
+    assert float((yc - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    s_ref = torch.stack([ref.double().flatten(1).sum(1), (ref.double() ** 2).flatten(1).sum(1)], 1)
+    assert torch.allclose(stats.cpu(), s_ref, rtol=1e-5, atol=1e-5 * float(s_ref[:, 1].max()))
+
+
+@pytest.mark.parametrize('case', [(2, 2, 8, 20, 16), (5, 1, 12, 18, 24), (3, 1, 5, 10, 8)], ids=lambda c: '-'.join(map(str, c)))
+def test_conv_narrow_split_matches_torch(lib, case):
+    """seg3d_conv3d_k3_narrow_split_fwd (out_block.conv1 in the strict mode: folded in-plane taps on split operands)."""
+    L = lib
+    C, N, D, H, W = case
+    Cin = 32
+    g = torch.Generator().manual_seed(C * 5 + D)
+    x = torch.randn((N, Cin, D, H, W), generator=g)
+    w = torch.randn((C, Cin, 3, 3, 3), generator=g) * 0.1
+    b = torch.randn((C,), generator=g) * 0.1
+    xd, xs = _split_rows(x)
+    NP = L.load().seg3d_conv3d_k3_narrow_np(C)
+    wf = torch.zeros((3, NP, Cin))
+    wf[:, :9 * C] = w.permute(2, 3, 4, 0, 1).reshape(3, 9 * C, Cin)
+    fhi = wf.half()
+    flo = (wf - fhi.float()).half()
+    wp = torch.cat([fhi, flo], dim=-1).contiguous().cuda()
+    wseen = (fhi.float() + flo.float())[:, :9 * C].view(3, 3, 3, C, Cin).permute(3, 4, 0, 1, 2).contiguous()
+    ref = F.conv3d(xs.double(), wseen.double(), b.double(), padding=1).float()
+    y = torch.full((N, D, H, W, C), float('nan'), dtype=torch.float32, device='cuda')
+    stats = torch.zeros((N, 2), dtype=torch.float64, device='cuda')
+    L.call('seg3d_conv3d_k3_narrow_split_fwd', L.ptr(xd), 2 * Cin, Cin, L.ptr(wp), L.ptr(b.cuda()), L.ptr(y), C, N, D, H, W,
+           L.ptr(stats), L.stream_ptr())
+    torch.cuda.synchronize()
+    yc = y.cpu().permute(0, 4, 1, 2, 3)
+    assert not torch.isnan(yc).any()
+    assert float((yc - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    s_ref = torch.stack([ref.double().flatten(1).sum(1), (ref.double() ** 2).flatten(1).sum(1)], 1)
+    assert torch.allclose(stats.cpu(), s_ref, rtol=1e-5, atol=1e-5 * float(s_ref[:, 1].max()))
+
+
 @pytest.mark.parametrize('arch,cout,seed', [('vnet', 2, 0), ('vbnet', 5, 1)])
 def test_forward_split_operand_strict_mode_on_tensor_cores(lib, arch, cout, seed):
     """mode 'fp32x': f16 hi/lo split operands, three MMAs per product, fp32 raw tensors.  Must meet the STRICT bar

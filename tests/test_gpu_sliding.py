@@ -109,7 +109,13 @@ def test_patch_grid_count_and_blend_kernels():
     acc = torch.zeros((C, size[2], size[1], size[0]), device='cuda')
     sd = torch.tensor(np.asarray(starts, np.int32), device='cuda')
     pd = probs.cuda()
-    L.call('seg3d_blend_accumulate', L.ptr(pd), n, C, 32, 32, 32, L.ptr(sd), L.ptr(acc), size[2], size[1], size[0], L.stream_ptr())
+    # both code paths: four voxels per vector atomic (every start x is a multiple of 4 here) and the scalar one
+    acc1 = torch.zeros_like(acc)
+    L.call('seg3d_blend_accumulate', L.ptr(pd), n, C, 32, 32, 32, L.ptr(sd), L.ptr(acc1), size[2], size[1], size[0], 0, L.stream_ptr())
+    assert all(s[0] % 4 == 0 for s in starts)
+    L.call('seg3d_blend_accumulate', L.ptr(pd), n, C, 32, 32, 32, L.ptr(sd), L.ptr(acc), size[2], size[1], size[0], 1, L.stream_ptr())
+    torch.cuda.synchronize()
+    assert float((acc - acc1).abs().max()) <= 1e-5
     mask = torch.empty((size[2], size[1], size[0]), dtype=torch.int8, device='cuda')
     cxd, cyd, czd = [torch.tensor(c, device='cuda') for c in (cx, cy, cz)]
     L.call('seg3d_blend_finalize_argmax', L.ptr(acc), C, size[2], size[1], size[0], L.ptr(cxd), L.ptr(cyd), L.ptr(czd), L.ptr(mask), L.stream_ptr())

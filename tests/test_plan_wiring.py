@@ -159,6 +159,17 @@ def _install(monkeypatch, calls):
         calls.append('narrow')
         return 0
 
+    def narrow_split_fwd(x, x_ld, Cin, w, bias, y, Cout, N, D, H, W, stats, stream):
+        rows = N * D * H * W
+        assert Cin == 32 and x_ld >= 64
+        xs = (_rows(x, rows, x_ld, Cin).float() + _rows(_P(x.t, x.off + Cin), rows, x_ld, Cin).float())
+        xs = xs.view(N, D, H, W, Cin).permute(0, 4, 1, 2, 3)
+        wq = w.t.float().view(3, narrow_np(Cout), 2 * Cin)                                # rows [whi(Cin) | wlo(Cin)]
+        wsum = _P((wq[..., :Cin] + wq[..., Cin:]).contiguous(), 0)
+        _store(_narrow(xs, wsum, bias, Cin, Cout), y, Cout, Cout, stats, N)
+        calls.append('narrow')
+        return 0
+
     def narrow_gn_fwd(dtype, raw, raw_ld, res, res_ld, Cin, gn_stats, gamma, beta, eps, w, bias, y, Cout, N, D, H, W, stats, stream):
         nvox = D * H * W
         r = _rows(raw, N * nvox, raw_ld, Cin).float().view(N, nvox, Cin)
@@ -231,7 +242,8 @@ def _install(monkeypatch, calls):
         calls.append('tail_probs')
         return 0
 
-    table = {'seg3d_conv3d_fwd': conv3d_fwd, 'seg3d_conv3d_cin1_fwd': cin1_fwd, 'seg3d_conv3d_k3_narrow_fwd': narrow_fwd, 'seg3d_conv3d_k3_narrow_gn_fwd': narrow_gn_fwd,
+    table = {'seg3d_conv3d_fwd': conv3d_fwd, 'seg3d_conv3d_cin1_fwd': cin1_fwd, 'seg3d_conv3d_k3_narrow_split_fwd': narrow_split_fwd,
+             'seg3d_conv3d_k3_narrow_fwd': narrow_fwd, 'seg3d_conv3d_k3_narrow_gn_fwd': narrow_gn_fwd,
              'seg3d_gn_apply': gn_apply, 'seg3d_conv3d_split_fwd': split_fwd, 'seg3d_gn_apply_split': gn_apply_split,
              'seg3d_outblock_tail_stats': tail_stats, 'seg3d_outblock_tail_probs': tail_probs,
              'seg3d_gather_pack': emulate_gather_pack}

@@ -65,7 +65,8 @@ def _install(monkeypatch, calls):
         calls.append(('gather', N))
         return 0
 
-    def blend_accumulate(probs, N, C, pz, py, px, starts, acc, Z, Y, X, stream):
+    def blend_accumulate(probs, N, C, pz, py, px, starts, acc, Z, Y, X, x_mult4, stream):
+        assert (x_mult4 == 0) or all(s[0] % 4 == 0 for s in _starts(starts, N))
         a = acc.t.numpy().reshape(C, Z, Y, X)
         p = probs.t.numpy().reshape(-1, C, pz, py, px)
         for n, s in enumerate(_starts(starts, N)):
