@@ -263,13 +263,48 @@ def deal_patches(starts, ends, rank, world, max_imbalance=1.15):
     then exchange probability sums."""
     n = len(starts)
     comps = overlap_components(starts, ends)
-    loads, mine, done = [0] * world, [], 0
+    # Every rank owns the window [rank*n/world, (rank+1)*n/world) of the z-major patch order, so a z group of components
+    # (one z layer of the lattice; the last two layers when the last box was clamped back) is shared by the few ranks whose
+    # windows reach into it, each with the capacity of that overlap.  Inside a group the components go, largest first, to the
+    # rank with the most capacity left: loads end within a patch or two of n/world (180 patches over 8 ranks: 22 or 23 each),
+    # and a rank still touches only the z layers of its window.
+    groups = {}
     for comp in comps:
-        r = min(world - 1, int((done + len(comp) / 2.0) * world / n))
-        loads[r] += len(comp)
-        done += len(comp)
-        if r == rank:
-            mine += comp
+        groups.setdefault(min(int(starts[i][2]) for i in comp), []).append(comp)
+    loads, a, owner, sharers = [0] * world, 0, [], []
+    for z in sorted(groups):
+        gcomps = sorted(groups[z], key=lambda c: -len(c))
+        b = a + sum(len(c) for c in gcomps)
+        cap = {}
+        for r in range(world):
+            lo, hi = n * r / float(world), n * (r + 1) / float(world)
+            ov = min(b, hi) - max(a, lo)
+            if ov > 1e-9:
+                cap[r] = ov
+        for comp in gcomps:
+            r = max(cap, key=lambda k: (cap[k], -k))
+            cap[r] -= len(comp)
+            loads[r] += len(comp)
+            owner.append([comp, r])
+            sharers.append(tuple(cap))
+        a = b
+    # refinement: while the fullest rank can hand one of its components to a rank of the same z group that stays below it
+    for _ in range(4 * world):
+        rmax = max(range(world), key=lambda k: loads[k])
+        best = None
+        for j, (comp, r) in enumerate(owner):
+            if r != rmax:
+                continue
+            for r2 in sharers[j]:
+                if r2 != rmax and loads[r2] + len(comp) < loads[rmax] and (best is None or len(comp) < len(owner[best[0]][0])):
+                    best = (j, r2)
+        if best is None:
+            break
+        j, r2 = best
+        loads[rmax] -= len(owner[j][0])
+        loads[r2] += len(owner[j][0])
+        owner[j][1] = r2
+    mine = [i for comp, r in owner if r == rank for i in comp]
     if max(loads) <= max_imbalance * -(-n // world):
         return [starts[i] for i in mine], True
     order = sorted(range(n), key=lambda i: (starts[i][2], starts[i][1], starts[i][0]))
