@@ -86,6 +86,11 @@ int seg3d_conv3d_cin1_fwd(int dtype, int epi_mode, const void* xpad, int x_pitch
                           void* y, int y_ld, int N, int D, int H, int W, double* stats,
                           const float* gamma, const float* beta, float eps, void* stream);
 
+/* weight gradient of the input block with the operands of seg3d_conv3d_cin1_fwd: dw (fp32 [27][16], tap-major, accumulated -
+ * the caller zeroes it) += sum over voxels of x[v + tap] * dy[v][co].  dy: [N,D,H,W,16] f16/bf16, DENSE (dy_ld must be 16). */
+int seg3d_conv3d_cin1_wgrad(int dtype, const void* xpad, int x_pitch, const void* dy, int dy_ld, float* dw,
+                            int N, int D, int H, int W, void* stream);
+
 /* k3 s1 p1 convolution with a narrow output (Cout = classes <= 7; vnet_outblock.py:13) on the tensor cores: the nine
  * in-plane taps are folded into the GEMM N dimension and summed in the epilogue (csrc/conv_tc_narrow.cu).
  * x: [N,D,H,W,Cin] f16/bf16, Cin in {16,32,64}, W % 8 == 0.  w (dtype): [3 kd][NP][Cin] with row (kh*3+kw)*Cout + co,

@@ -259,6 +259,163 @@ conv3d_k3_cin1_toeplitz_kernel(const __grid_constant__ CUtensorMap map_x, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient of the input block with the same Toeplitz operands:
+//     G[(xo, co)][(kd, kh, xi)]  =  sum over segments  dY[segment][(xo, co)] * A_(kd,kh)[segment][xi]
+//     dW[kd][kh][kw][co]         =  sum over xo        G[(xo, co)][(kd, kh, xi = xo + kw)]
+// K = segments, and both operands are MN-major exactly as TMA delivers them: a segment of dy is 8 voxels x 16 channels =
+// 256 contiguous bytes (two 128-byte rows of a 128B-swizzled tile: M-atoms 0 and 1), a segment of the padded input is the
+// 32-byte window row of the forward pass.  The three kh taps are three N-atoms one y-row (4 window rows = 128 bytes) apart, so
+// ONE MMA 128 x 48 x 16 per kd and K step covers (kh, xi); the three kd taps are three accumulators fed from the three resident
+// halo planes.  A CTA accumulates over all its tiles in TMEM and folds the band of G into the 27 x 16 gradient once.
+struct CwParams {
+  int D, H, W, N;
+  int ntx, nty, nseg, lseg, nitems, ring, dstages;
+  uint32_t idesc;
+};
+constexpr int CW_THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: final fold
+constexpr int CW_DY_BYTES = 32768;       // one dy plane tile: 2 M-atoms x [128 segments x 128 B]
+
+template <typename T>
+__global__ void __launch_bounds__(CW_THREADS, 1)
+conv3d_k3_cin1_wgrad_toeplitz_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                                     const CwParams p, float* __restrict__ dw) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ float red_s[27 * 16];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t d_base = smem_base;                                     // [dstages][2][128 rows][128 B], 128B-swizzled
+  const uint32_t a_base = smem_base + p.dstages * CW_DY_BYTES;           // [ring][136 rows][32 B], 32B-swizzled
+  float* stage = reinterpret_cast<float*>(smem_al + p.dstages * CW_DY_BYTES + p.ring * CT_PLANE_BYTES);   // [128][17]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 128 * 17);
+  const uint32_t full_bar = smem_u32(bars);                              // [ring]
+  const uint32_t empty_bar = full_bar + 8 * CT_MAXRING;                  // [ring]
+  const uint32_t dfull_bar = empty_bar + 8 * CT_MAXRING;                 // [dstages <= 4]
+  const uint32_t dempty_bar = dfull_bar + 32;                            // [dstages]
+  const uint32_t done_bar = dempty_bar + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CT_MAXRING + 9);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 27 * 16; i += CW_THREADS) red_s[i] = 0.f;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+    for (int s = 0; s < p.ring; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < p.dstages; ++s) { mbar_init(dfull_bar + 8 * s, 1); mbar_init(dempty_bar + 8 * s, 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 0) {
+    // ===== TMA producer: per item the halo planes zs-1, zs, then for every output plane the next halo plane + the dy tile =====
+    int slot = 0; uint32_t phase = 0; int ds = 0; uint32_t dphase = 0;
+    auto load_plane = [&](int tx, int ty, int z, int n) {
+      mbar_wait(empty_bar + 8 * slot, phase ^ 1);
+      mbar_expect_tx_e(full_bar + 8 * slot, (uint32_t)(CT_PLANE_ROWS * 32));
+      tma_load_5d_e(a_base + slot * CT_PLANE_BYTES, &map_x, full_bar + 8 * slot, 0, 4 * tx, 32 * ty - 1, z, n);
+      if (++slot == p.ring) { slot = 0; phase ^= 1; }
+    };
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      int t = item;
+      const int seg = t % p.nseg; t /= p.nseg;
+      const int tx = t % p.ntx; t /= p.ntx;
+      const int ty = t % p.nty; const int n = t / p.nty;
+      const int zs = seg * p.lseg;
+      const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
+      load_plane(tx, ty, zs - 1, n);
+      load_plane(tx, ty, zs, n);
+      for (int zl = 0; zl < L; ++zl) {
+        load_plane(tx, ty, zs + zl + 1, n);
+        mbar_wait(dempty_bar + 8 * ds, dphase ^ 1);
+        mbar_expect_tx_e(dfull_bar + 8 * ds, (uint32_t)CW_DY_BYTES);
+        tma_load_5d_e(d_base + ds * CW_DY_BYTES, &map_dy, dfull_bar + 8 * ds, 0, 4 * tx, 32 * ty, zs + zl, n);
+        tma_load_5d_e(d_base + ds * CW_DY_BYTES + 16384, &map_dy, dfull_bar + 8 * ds, 64, 4 * tx, 32 * ty, zs + zl, n);
+        if (++ds == p.dstages) { ds = 0; dphase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t hi_a = desc_hi(1024, 2);           // dy: K-atoms (8 segments x 128 B) 1 KB apart, 128B swizzle
+    const uint32_t hi_b = desc_hi(256, 6);            // x windows: K-atoms (8 segments x 32 B) 256 B apart, 32B swizzle
+    const uint32_t lbo_a = ((16384u >> 4) & 0x3FFFu) << 16;       // M-atom 1 = the second half of every segment
+    const uint32_t lbo_b = ((128u >> 4) & 0x3FFFu) << 16;         // N-atoms = the kh taps, one y row (4 segments) apart
+    int s0 = 0; uint32_t ph0 = 0; int ds = 0; uint32_t dphase = 0;
+    uint32_t accumulate = 0;
+    const int ring = p.ring;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      const int seg = item % p.nseg;
+      const int zs = seg * p.lseg;
+      const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
+      for (int zl = 0; zl < L; ++zl) {
+        int s1 = s0 + 1; uint32_t ph1 = ph0; if (s1 == ring) { s1 = 0; ph1 ^= 1; }
+        int s2 = s1 + 1; uint32_t ph2 = ph1; if (s2 == ring) { s2 = 0; ph2 ^= 1; }
+        if (zl == 0) { mbar_wait(full_bar + 8 * s0, ph0); mbar_wait(full_bar + 8 * s1, ph1); }
+        mbar_wait(full_bar + 8 * s2, ph2);
+        mbar_wait(dfull_bar + 8 * ds, dphase);
+        tc_fence_after();
+        const uint32_t da = ((d_base + (uint32_t)ds * CW_DY_BYTES) >> 4) | lbo_a;
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd) {
+          const int sk = kd == 0 ? s0 : (kd == 1 ? s1 : s2);
+          const uint32_t db = ((a_base + (uint32_t)sk * CT_PLANE_BYTES) >> 4) | lbo_b;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            tc_mma_f16_e(tmem_base + (uint32_t)(kd * 48), desc_pack(hi_a, da + (uint32_t)(ks * (2048 >> 4))),
+                         desc_pack(hi_b, db + (uint32_t)(ks * (512 >> 4))), p.idesc, ks == 0 ? accumulate : 1u);
+        }
+        accumulate = 1;
+        tc_commit_e(dempty_bar + 8 * ds);
+        tc_commit_e(empty_bar + 8 * s0);
+        if (++ds == p.dstages) { ds = 0; dphase ^= 1; }
+        if (zl == L - 1) {
+          tc_commit_e(empty_bar + 8 * s1);
+          tc_commit_e(empty_bar + 8 * s2);
+          s0 = s2 + 1; ph0 = ph2; if (s0 == ring) { s0 = 0; ph0 ^= 1; }
+        } else {
+          s0 = s1; ph0 = ph1;
+        }
+      }
+    }
+    tc_commit_e(done_bar);
+  } else {
+    // ===== fold (once): TMEM lane = (xo, co), column = kd*48 + kh*16 + xi; keep xi = xo + kw =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int xo = r >> 4, co = r & 15;
+    float* my = stage + r * 17;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    for (int g = 0; g < 9; ++g) {                     // g = kd*3 + kh
+      uint32_t v[16];
+      tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 16), v);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) my[j] = __uint_as_float(v[j]);
+      __syncwarp();
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) atomicAdd(&red_s[(g * 3 + kw) * 16 + co], my[xo + kw]);
+      __syncwarp();
+    }
+    named_bar_sync(1, 128);
+    for (int i = threadIdx.x - 64; i < 27 * 16; i += 128) atomicAdd(dw + i, red_s[i]);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
 }  // namespace
 
 // xpad: [N][D][H][W + 16] dtype, x index i of a row at column i + 9, columns 0..8 and W+9..W+15 zero.
@@ -330,5 +487,69 @@ extern "C" int seg3d_conv3d_cin1_fwd(int dtype, int epi_mode, const void* xpad, 
 #undef SEG3D_LAUNCH_CT
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { seg3d_set_error("conv3d_k3_cin1_toeplitz_kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
+  return SEG3D_OK;
+}
+
+// dw (fp32 [27][16], accumulated; the caller zeroes it) += xpad (*) dy.  xpad as in seg3d_conv3d_cin1_fwd; dy: [N,D,H,W,16]
+// DENSE (pitch 16: a segment of 8 voxels is 256 contiguous bytes).
+extern "C" int seg3d_conv3d_cin1_wgrad(int dtype, const void* xpad, int x_pitch, const void* dy, int dy_ld, float* dw,
+                                       int N, int D, int H, int W, void* stream) {
+  SEG3D_REQUIRE(dtype == SEG3D_F16 || dtype == SEG3D_BF16, "conv3d_cin1_wgrad: dtype must be f16 or bf16");
+  SEG3D_REQUIRE(xpad && dy && dw && N > 0 && D > 0 && H > 0 && W > 0 && W % 8 == 0, "conv3d_cin1_wgrad: bad dims (W must be a multiple of 8)");
+  SEG3D_REQUIRE(x_pitch == W + SEG3D_CIN1_PAD && dy_ld == 16, "conv3d_cin1_wgrad: x_pitch must be W + SEG3D_CIN1_PAD and dy dense (pitch 16)");
+  SEG3D_REQUIRE(((uintptr_t)xpad) % 16 == 0 && ((uintptr_t)dy) % 16 == 0, "conv3d_cin1_wgrad: misaligned pointer");
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { seg3d_set_error("conv3d_cin1_wgrad: cuTensorMapEncodeTiled entry point not available"); return SEG3D_ECUDA; }
+  cudaStream_t st = (cudaStream_t)stream;
+  CwParams p;
+  memset(&p, 0, sizeof(p));
+  p.D = D; p.H = H; p.W = W; p.N = N;
+  p.ntx = (W + 31) / 32; p.nty = (H + 31) / 32;
+  p.ring = 8; p.dstages = 4;
+  const long long cols = (long long)N * p.ntx * p.nty;
+  const long long want = 6ll * seg3d_num_sms();
+  int nseg = (int)((want + cols - 1) / cols);
+  if (nseg < 1) nseg = 1;
+  int lseg = (D + nseg - 1) / nseg;
+  if (lseg < 8) lseg = D < 8 ? D : 8;
+  p.lseg = lseg; p.nseg = (D + lseg - 1) / lseg;
+  const long long nitems = cols * p.nseg;
+  SEG3D_REQUIRE(nitems > 0 && nitems < (1ll << 31), "conv3d_cin1_wgrad: work-item count out of range");
+  p.nitems = (int)nitems;
+  const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(48 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const CUtensorMapDataType tdt = dtype == SEG3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap map_x, map_dy;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  {
+    cuuint64_t dims[5] = {16, (cuuint64_t)W / 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {16, (cuuint64_t)x_pitch * 2, (cuuint64_t)H * x_pitch * 2, (cuuint64_t)D * H * x_pitch * 2};
+    cuuint32_t box[5] = {16, 4, 34, 1, 1};
+    void* base = const_cast<void*>(static_cast<const void*>(static_cast<const uint8_t*>(xpad) + 16));
+    CUresult r = encode(&map_x, tdt, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { seg3d_set_error("conv3d_cin1_wgrad: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SEG3D_ECUDA; }
+  }
+  {
+    cuuint64_t dims[5] = {128, (cuuint64_t)W / 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {256, (cuuint64_t)W * 32, (cuuint64_t)H * W * 32, (cuuint64_t)D * H * W * 32};
+    cuuint32_t box[5] = {64, 4, 32, 1, 1};
+    CUresult r = encode(&map_dy, tdt, 5, const_cast<void*>(dy), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { seg3d_set_error("conv3d_cin1_wgrad: cuTensorMapEncodeTiled(dy) failed with %d", (int)r); return SEG3D_ECUDA; }
+  }
+  const size_t smem = 1024 + (size_t)p.dstages * CW_DY_BYTES + (size_t)p.ring * CT_PLANE_BYTES + 128 * 17 * 4 + (2 * CT_MAXRING + 9) * 8 + 64;
+  const long long max_grid = seg3d_num_sms();
+  dim3 grid((unsigned)(nitems < max_grid ? nitems : max_grid));
+  cudaError_t e;
+  if (dtype == SEG3D_BF16) {
+    e = cudaFuncSetAttribute(conv3d_k3_cin1_wgrad_toeplitz_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) conv3d_k3_cin1_wgrad_toeplitz_kernel<__nv_bfloat16><<<grid, CW_THREADS, smem, st>>>(map_x, map_dy, p, dw);
+  } else {
+    e = cudaFuncSetAttribute(conv3d_k3_cin1_wgrad_toeplitz_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) conv3d_k3_cin1_wgrad_toeplitz_kernel<__half><<<grid, CW_THREADS, smem, st>>>(map_x, map_dy, p, dw);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { seg3d_set_error("conv3d_k3_cin1_wgrad_toeplitz_kernel launch failed: %s", cudaGetErrorString(e)); return SEG3D_ECUDA; }
   return SEG3D_OK;
 }

@@ -240,8 +240,12 @@ class _Backward(object):
             if dres is not None:
                 add_contrib(u['res'], dres)
             xd = dims[u['lin']]
-            lib.call('seg3d_conv3d_wgrad', c.mode, dt, u['x'].p, u['x'].ld, c.cin, gy.p, gy.ld, c.cout,
-                     lib.ptr(pg[u['conv'] + '.weight']), B, xd[0], xd[1], xd[2], st())
+            if u.get('xpad') is not None and gy.ld == 16:       # input block on the row-padded input (Toeplitz operands)
+                lib.call('seg3d_conv3d_cin1_wgrad', dt, u['xpad'].p, xd[2] + lib.CIN1_PAD, gy.p, gy.ld,
+                         lib.ptr(pg[u['conv'] + '.weight']), B, xd[0], xd[1], xd[2], st())
+            else:
+                lib.call('seg3d_conv3d_wgrad', c.mode, dt, u['x'].p, u['x'].ld, c.cin, gy.p, gy.ld, c.cout,
+                         lib.ptr(pg[u['conv'] + '.weight']), B, xd[0], xd[1], xd[2], st())
             if u['conv'] in self.gd:
                 dcv, gd = self.dconv[u['conv']], self.gd[u['conv']]
                 od = dims[u['lout']]          # the dgrad convolution's input is dy, living at the unit's output level

@@ -29,6 +29,7 @@ _SIGNATURES = {
     'seg3d_device_check': (_i, [_i]),
     'seg3d_conv3d_fwd': (_i, [_i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     'seg3d_conv3d_cin1_fwd': (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
+    'seg3d_conv3d_cin1_wgrad': (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     'seg3d_conv3d_k3_narrow_np': (_i, [_i]),
     'seg3d_conv3d_k3_narrow_fwd': (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     'seg3d_conv3d_k3_narrow_split_fwd': (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -286,7 +286,7 @@ class NetPlan(object):
         # input block as a TMA-fed Toeplitz GEMM (csrc/conv_tc_cin1t.cu): the single-channel input lives in a row-padded
         # layout [B][D][H][W + CIN1_PAD] whose padding columns stay zero (written once here, never by the gather)
         c_in = self.convs['in_block.conv']
-        cin1_t = (c_in.cin1_tc and not train and W % 8 == 0 and dt in (lib.F16, lib.BF16)
+        cin1_t = (c_in.cin1_tc and W % 8 == 0 and dt in (lib.F16, lib.BF16)
                   and os.environ.get('SEG3D_CIN1_TOEPLITZ', '1') != '0')
         ws['x_pad'] = cin1_t
         if cin1_t:
@@ -464,7 +464,7 @@ class NetPlan(object):
                                                out.ld if out is not None else 0, nb, D, H, W, stats_ptr('in_block.gn', b0),
                                                lib.ptr(g_in.gamma), lib.ptr(g_in.beta), GN_EPS, st())
             flops = 2.0 * B * vox[0] * 27 * 16
-            if os.environ.get('SEG3D_FUSE_IN', '1') != '0':
+            if not train and os.environ.get('SEG3D_FUSE_IN', '1') != '0':
                 add(cin1(1, None), 0)
                 meta.append({'name': 'in_block.conv.stats', 'kind': 'conv_tc_cin1', 'flops': flops, 'bytes': 2 * B * vox[0]})
                 add(cin1(2, skip[0]), 0)
@@ -476,8 +476,9 @@ class NetPlan(object):
                 add(cin1(0, rv), 0)
                 meta.append({'name': 'in_block.conv', 'kind': 'conv_tc_cin1', 'flops': flops, 'bytes': 2 * B * vox[0] * 17})
                 gn('in_block.gn', rv, skip[0], vox[0], True, None, 0)
+                # training keeps the raw tensor; 'xpad': the weight gradient reads the same padded input (seg3d_conv3d_cin1_wgrad)
                 units.append({'conv': 'in_block.conv', 'gn': 'in_block.gn', 'x': x_in, 'lin': 0, 'lout': 0, 'raw': rv,
-                              'out': skip[0], 'res': None})
+                              'out': skip[0], 'res': None, 'xpad': xpad})
         else:
             conv_gn('in_block.conv', 'in_block.gn', x_in, 0, skip[0], relu=True)
         # down path

@@ -85,6 +85,13 @@ def _install(monkeypatch, calls):
         calls.append('wgrad%d' % mode)
         return 0
 
+    def cin1_wgrad(dtype, xpad, x_pitch, dy, dy_ld, dw, N, D, H, W, stream):
+        # the row-padded input of seg3d_conv3d_cin1_fwd; dy must be dense
+        assert x_pitch == W + lib.CIN1_PAD and dy_ld == 16
+        rows = _rows(xpad, N * D * H, x_pitch, x_pitch)
+        xs = rows[:, lib.CIN1_LEFT:lib.CIN1_LEFT + W].contiguous().reshape(-1)
+        return wgrad(lib.CONV_K3, dtype, type(xpad)(xs, 0), 1, 1, dy, dy_ld, 16, dw, N, D, H, W, stream)
+
     def tail_bwd(dtype, ps, y1, ld, C, stats1, g1, b1, w2, bias2, stats2, g2, b2, eps, dprobs, sums2, sums1,
                  dgamma2, dbeta2, dw2, db2, dgamma1, dbeta1, db1, dy1, dy_ld, N, nvox, stream):
         if ps != 2:                 # every output is produced in the last pass here; the sums are internal to the kernel
@@ -160,7 +167,7 @@ def _install(monkeypatch, calls):
         return 0
 
     table.update({'seg3d_adam_step': adam_step})
-    table.update({'seg3d_gn_bwd': gn_bwd, 'seg3d_conv3d_wgrad': wgrad, 'seg3d_outblock_tail_bwd': tail_bwd,
+    table.update({'seg3d_gn_bwd': gn_bwd, 'seg3d_conv3d_wgrad': wgrad, 'seg3d_conv3d_cin1_wgrad': cin1_wgrad, 'seg3d_outblock_tail_bwd': tail_bwd,
                   'seg3d_dice_terms': dice_terms, 'seg3d_dice_bwd': dice_bwd, 'seg3d_focal_fwd': focal_fwd, 'seg3d_focal_bwd': focal_bwd})
     monkeypatch.setattr(lib, 'call', lambda name, *a: table[name](*a) if name in table else fwd_call(name, *a))
 

@@ -536,6 +536,34 @@ def test_conv_cin1_toeplitz_matches_torch(lib, shape, dt_name):
     assert (yg - ref_gn).abs().max() <= tol_store * float(ref_gn.abs().max()) * 1.01 + 2e-5
 
 
+@pytest.mark.parametrize('shape', [(2, 8, 12, 16), (1, 20, 40, 24), (2, 33, 70, 72), (2, 96, 96, 96)], ids=str)
+@pytest.mark.parametrize('dt_name', ['BF16', 'F16'])
+def test_wgrad_cin1_toeplitz_matches_torch(lib, shape, dt_name):
+    """Weight gradient of the input block with the Toeplitz operands (seg3d_conv3d_cin1_wgrad: MN-major dy segments and padded
+    input windows, K = segments) vs the float64 gradient of F.conv3d on the same stored (rounded) tensors."""
+    L = lib
+    dt = getattr(L, dt_name)
+    tdt = L.TORCH_DTYPE[dt]
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(D * 11 + W)
+    x = torch.randn((N, 1, D, H, W), generator=g).to(tdt)
+    dy = (torch.randn((N, 16, D, H, W), generator=g) * 0.05).to(tdt)
+    w = torch.zeros((16, 1, 3, 3, 3), dtype=torch.float64, requires_grad=True)
+    F.conv3d(x.double(), w, None, padding=1).backward(dy.double())
+    ref = w.grad.permute(2, 3, 4, 1, 0).reshape(27, 16)                  # [tap][co]
+    pitch = W + L.CIN1_PAD
+    xp = torch.zeros((N, D, H, pitch), dtype=tdt, device='cuda')
+    xp[..., L.CIN1_LEFT:L.CIN1_LEFT + W] = x[:, 0].cuda()
+    dyd = dy.permute(0, 2, 3, 4, 1).contiguous().cuda()
+    dw = torch.zeros((27, 16), dtype=torch.float32, device='cuda')
+    L.call('seg3d_conv3d_cin1_wgrad', dt, L.ptr(xp), pitch, L.ptr(dyd), 16, L.ptr(dw), N, D, H, W, L.stream_ptr())
+    L.call('seg3d_conv3d_cin1_wgrad', dt, L.ptr(xp), pitch, L.ptr(dyd), 16, L.ptr(dw), N, D, H, W, L.stream_ptr())   # accumulates
+    torch.cuda.synchronize()
+    got = dw.cpu().double() / 2
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= 2e-4 * scale + 1e-6, (float((got - ref).abs().max()), scale)
+
+
 @pytest.mark.parametrize('case', [('K2S2', 16, 32, 2, 8, 12, 16), ('K2S2', 64, 128, 1, 8, 8, 8), ('T2S2', 64, 16, 2, 4, 6, 8),
                                   ('T2S2', 256, 128, 1, 2, 4, 4)], ids=lambda c: '-'.join(map(str, c)))
 def test_conv_gn_relu_two_pass_matches_torch(lib, case):
