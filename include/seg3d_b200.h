@@ -108,6 +108,22 @@ int seg3d_conv3d_k3_narrow_gn_fwd(int dtype, const void* raw, int raw_ld, const 
                                   const void* w, const float* bias, float* y, int Cout, int N, int D, int H, int W,
                                   double* stats, void* stream);
 
+/* GroupNorm-apply folded into the CONSUMERS of the last up-block (vnet_upblock.py:19-22 -> residual_block3.py:21-26 ->
+ * vnet_outblock.py:13).  The transposed convolution writes its RAW result into the lower half of the concat buffer; then
+ *  - seg3d_conv3d_k3_gnin_fwd: k3 convolution (z-march kernel, Cin == 32) whose first gn_ch input channels become
+ *    relu(GroupNorm(1, gn_ch)(x[:, :gn_ch])) in shared memory between the TMA loads and the MMAs (finished sums gn_stats);
+ *  - seg3d_conv3d_k3_narrow_gn2_fwd: seg3d_conv3d_k3_narrow_gn_fwd whose residual gets the same treatment for its first
+ *    res_gn_ch channels.
+ * Both are bit-identical to seg3d_gn_apply(relu = 1) followed by the plain call; the apply pass never touches HBM. */
+int seg3d_conv3d_k3_gnin_fwd(int dtype, const void* x, int x_ld, int Cin, int gn_ch, const double* gn_stats,
+                             const float* gamma, const float* beta, float eps, const void* w, const float* bias,
+                             void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, void* stream);
+int seg3d_conv3d_k3_narrow_gn2_fwd(int dtype, const void* raw, int raw_ld, const void* res, int res_ld, int Cin,
+                                   const double* gn_stats, const float* gamma, const float* beta, float eps,
+                                   int res_gn_ch, const double* res_gn_stats, const float* res_gamma, const float* res_beta,
+                                   const void* w, const float* bias, float* y, int Cout, int N, int D, int H, int W,
+                                   double* stats, void* stream);
+
 /* the narrow-output convolution in the strict-parity mode (split operands, see seg3d_conv3d_split_fwd below): x rows are
  * [hi(32) | lo(32)] f16 halves of the activation (Cin must be 32, the lo half directly behind the hi half, pitch x_ld >= 64),
  * w is [3 kd][NP][whi(32) | wlo(32)] f16 (rows as in seg3d_conv3d_k3_narrow_fwd); accumulates hi*whi + lo*whi + hi*wlo in fp32. */

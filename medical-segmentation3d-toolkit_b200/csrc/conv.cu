@@ -6,7 +6,9 @@ int seg3d_conv_simt(int mode, int dtype, const void* x, int x_ld, int Cin, const
 int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
                   void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st,
                   int epi_mode, const double* gn_stats, const float* gn_gamma, const float* gn_beta, float gn_eps,
-                  int split_lo_off, int out_f32_generic);
+                  int split_lo_off, int out_f32_generic,
+                  int xf_nch = 0, const double* xf_stats = nullptr, const float* xf_gamma = nullptr, const float* xf_beta = nullptr,
+                  float xf_eps = 0.f);
 int seg3d_conv_cin1_tc_supported(int dtype, int Cin, int Cout, int x_ld, int y_ld, int W);
 int seg3d_conv_cin1_tc(int dtype, const void* x, const void* w, const float* bias, void* y, int y_ld,
                        int N, int D, int H, int W, double* stats, cudaStream_t st);
@@ -73,4 +75,21 @@ extern "C" int seg3d_conv3d_split_fwd(int mode, const void* x, int x_ld, int lo_
   }
   return seg3d_conv_tc(mode, SEG3D_F16, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, stats, (cudaStream_t)stream,
                        0, nullptr, nullptr, nullptr, 0.f, lo_off, 1);
+}
+
+// k3 convolution whose first gn_ch INPUT channels are still the raw result of the producing convolution: relu(GroupNorm(1, gn_ch))
+// of those channels (finished sums gn_stats, as seg3d_gn_apply with relu = 1 would write them) is formed in shared memory between
+// the TMA loads and the MMAs of the z-march kernel, so the apply pass of vnet_upblock.py:19 never touches HBM.  The remaining
+// channels (the skip half of the concat buffer, vnet_upblock.py:21) are used as stored.  Cin must be 32, gn_ch 8, 16 or 32.
+extern "C" int seg3d_conv3d_k3_gnin_fwd(int dtype, const void* x, int x_ld, int Cin, int gn_ch, const double* gn_stats,
+                                        const float* gamma, const float* beta, float eps, const void* w, const float* bias,
+                                        void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, void* stream) {
+  SEG3D_REQUIRE(x && w && y && gn_stats && gamma && beta, "conv3d_k3_gnin_fwd: null pointer");
+  SEG3D_REQUIRE(Cin == 32 && Cout > 0 && N > 0 && D >= 4 && H > 0 && W > 0 && W % 8 == 0 && x_ld >= Cin && y_ld >= Cout, "conv3d_k3_gnin_fwd: bad dims");
+  if (!seg3d_conv_tc_supported(SEG3D_CONV_K3, dtype, Cin, Cout, x_ld, y_ld, D, H, W)) {
+    seg3d_set_error("conv3d_k3_gnin_fwd: tcgen05 path does not take dtype=%d Cin=%d Cout=%d", dtype, Cin, Cout);
+    return SEG3D_EUNSUPPORTED;
+  }
+  return seg3d_conv_tc(SEG3D_CONV_K3, dtype, x, x_ld, Cin, w, bias, y, y_ld, Cout, N, D, H, W, stats, (cudaStream_t)stream,
+                       0, nullptr, nullptr, nullptr, 0.f, 0, 0, gn_ch, gn_stats, gamma, beta, eps);
 }

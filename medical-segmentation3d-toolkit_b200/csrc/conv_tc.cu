@@ -309,14 +309,23 @@ struct ZmParams {
   int wide;                         // epilogue may use 256-bit stores
   int out_f32;                      // store the raw conv result as fp32 (out_block.conv1: its rounding would dominate the probability error)
   uint32_t idesc0, n8, sbo, a_sbo, layout_type;   // instruction descriptor without N; N/8 of one block (Cout >> 3)
+  // XF: the first xf_nch input channels are a RAW convolution result whose GroupNorm(1, xf_nch) + ReLU has not been applied:
+  // four transform warps form relu(gn(raw)) in place in every loaded halo plane (finished sums xf_stats, per sample)
+  int xf_nch;
+  float xf_eps;
+  double xf_count;
+  const double* xf_stats;
+  const float* xf_gamma;
+  const float* xf_beta;
 };
 constexpr int ZM_MAXNB = 8;
+constexpr int ZMX_THREADS = TCE_THREADS + 128;
 
 // SPLIT (strict-parity mode, seg3d_conv3d_split_fwd): the KC channels of a voxel row are [hi(KC/2) | lo(KC/2)] f16 halves of the
 // activation, a weight row is [whi(KC/2) | wlo(KC/2)], and the k loop runs the three products hi*whi, lo*whi, hi*wlo
 // (A k-step, B k-step) instead of the diagonal - the plane, the slabs and the N-fold over three output planes are unchanged.
-template <typename T, int KC, bool SPLIT>
-__global__ void __launch_bounds__(TCE_THREADS)
+template <typename T, int KC, bool SPLIT, bool XF = false>
+__global__ void __launch_bounds__(XF ? ZMX_THREADS : TCE_THREADS)
 conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                         const ZmParams p, const float* __restrict__ bias, T* __restrict__ y, double* __restrict__ stats) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -330,13 +339,14 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   const uint32_t tfull_bar = empty_bar + 8 * p.ring;          // [ZM_MAXNB]
   const uint32_t tempty_bar = tfull_bar + 8 * ZM_MAXNB;       // [ZM_MAXNB]
   const uint32_t wfull_bar = tempty_bar + 8 * ZM_MAXNB;       // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.ring + 2 * ZM_MAXNB + 1);
+  const uint32_t xf_bar = wfull_bar + 8;                      // [ring] plane transformed (XF)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.ring + 2 * ZM_MAXNB + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    for (int s = 0; s < p.ring; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < p.ring; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); mbar_init(xf_bar + 8 * s, 4); }
     for (int b = 0; b < ZM_MAXNB; ++b) { mbar_init(tfull_bar + 8 * b, 1); mbar_init(tempty_bar + 8 * b, 8); }
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -385,7 +395,7 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         const int zs = seg * p.lseg;
         const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
         for (int ip = 0; ip < L + 2; ++ip) {
-          mbar_wait(full_bar + 8 * stage, phase);
+          mbar_wait((XF ? xf_bar : full_bar) + 8 * stage, phase);
           tc_fence_after();
           const uint32_t lo_a = (a_base + stage * p.plane_bytes) >> 4;
           const int kd_hi = ip < 2 ? ip : 2;                      // kd with 0 <= ip - kd < L
@@ -433,6 +443,55 @@ conv3d_k3_zmarch_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           if (++stage == p.ring) { stage = 0; phase ^= 1; }
         }
         oc += L;
+      }
+    }
+  } else if (XF && warp >= 10) {
+    // ===== transform: channels [0, xf_nch) of every in-volume voxel of the plane become relu(fma(raw, a, b)), the very
+    // expression seg3d_gn_apply evaluates; in place, same swizzled addresses (64-byte rows: 16-byte chunk c of row r sits at
+    // chunk c ^ ((r >> 1) & 3)); zero padding stays zero.  A thread owns ONE logical chunk, so its 8 scales / shifts are fixed.
+    if constexpr (XF) {
+      static_assert(!XF || KC == 32, "the transform stage is written for 64-byte rows");
+      const int t = (warp - 10) * 32 + lane;
+      const int gch = p.xf_nch >> 3;                  // chunks per row that need the transform (1..4)
+      const int c = t % gch, r0 = t / gch, rstep = 128 / gch;
+      float sa[8], sb[8];
+      int stage = 0; uint32_t phase = 0; int cur_n = -1;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        int tt = item;
+        const int seg = tt % p.nseg; tt /= p.nseg;
+        const int x0 = (tt % p.ntx) * 8; tt /= p.ntx;
+        const int y0 = (tt % p.nty) * 16; const int n = tt / p.nty;
+        const int zs = seg * p.lseg;
+        const int L = (p.D - zs) < p.lseg ? (p.D - zs) : p.lseg;
+        if (n != cur_n) {
+          float mean, rstd;
+          gn_mean_rstd(p.xf_stats + 2 * n, p.xf_count, p.xf_eps, mean, rstd);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { sa[j] = rstd * p.xf_gamma[8 * c + j]; sb[j] = p.xf_beta[8 * c + j] - mean * sa[j]; }
+          cur_n = n;
+        }
+        for (int ip = 0; ip < L + 2; ++ip) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          const int gz = zs - 1 + ip;
+          if (gz >= 0 && gz < p.D && r0 < rstep) {
+            uint8_t* plane = smem_al + 27 * p.w_slab + stage * p.plane_bytes;
+            for (int r = r0; r < 180; r += rstep) {
+              const int hy = r / 10, hx = r - hy * 10;
+              const int gx = x0 - 1 + hx, gy = y0 - 1 + hy;
+              if (gx < 0 || gx >= p.W || gy < 0 || gy >= p.H) continue;
+              T* slot = reinterpret_cast<T*>(plane + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+              Vec8<T> v; v.load(slot);
+              float f[8]; v.get(f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sa[j], sb[j]), 0.f);
+              v.set(f); v.store(slot);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(xf_bar + 8 * stage);
+          if (++stage == p.ring) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else {
@@ -834,7 +893,8 @@ int seg3d_conv_tc_supported(int mode, int dtype, int Cin, int Cout, int x_ld, in
 int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
                   void* y, int y_ld, int Cout, int N, int D, int H, int W, double* stats, cudaStream_t st,
                   int epi_mode, const double* gn_stats, const float* gn_gamma, const float* gn_beta, float gn_eps,
-                  int split_lo_off, int out_f32_generic) {
+                  int split_lo_off, int out_f32_generic,
+                  int xf_nch, const double* xf_stats, const float* xf_gamma, const float* xf_beta, float xf_eps) {
   EncodeTiledFn encode = get_encode();
   if (!encode) { seg3d_set_error("conv_tc: cuTensorMapEncodeTiled entry point not available"); return SEG3D_ECUDA; }
   SEG3D_REQUIRE(((uintptr_t)x) % 16 == 0 && ((uintptr_t)w) % 16 == 0 && ((uintptr_t)y) % 16 == 0, "conv_tc: pointers must be 16-byte aligned");
@@ -853,6 +913,8 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
     if (zm_split) Cin = 2 * Cin;                       // the K block: [hi | lo] channels of a row, [whi | wlo] of a weight row
     z.Cout = Cout; z.KC = Cin; z.row_bytes = Cin * 2;
     z.D = D; z.H = H; z.W = W; z.N = N; z.y_ld = y_ld; z.out_f32 = zm_split ? 2 : out_f32;
+    z.xf_nch = xf_nch; z.xf_stats = xf_stats; z.xf_gamma = xf_gamma; z.xf_beta = xf_beta; z.xf_eps = xf_eps;
+    z.xf_count = (double)xf_nch * D * H * W;
     z.wide = (!out_f32 && wide_ok(y, y_ld, 2) && env_int("SEG3D_WIDE_ST", 1)) ? 1 : 0;
     z.w_slab = (Cout * z.row_bytes + 1023) & ~1023;
     z.plane_tx = 180 * z.row_bytes;
@@ -909,7 +971,7 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
         r = encode(&map_w, tdt, 2, const_cast<void*>(w), wdims, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { seg3d_set_error("conv_tc(zmarch): cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SEG3D_ECUDA; }
-        const size_t smem = 1024 + (size_t)27 * z.w_slab + (size_t)ring * z.plane_bytes + (2 * ring + 2 * ZM_MAXNB + 1) * 8 + 64;
+        const size_t smem = 1024 + (size_t)27 * z.w_slab + (size_t)ring * z.plane_bytes + (3 * ring + 2 * ZM_MAXNB + 1) * 8 + 64;
         const long long max_grid = (long long)ctas_per_sm * seg3d_num_sms();
         dim3 grid((unsigned)(nitems < max_grid ? nitems : max_grid));
         cudaError_t e = cudaSuccess;
@@ -919,7 +981,19 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
 #define SEG3D_LAUNCH_ZS(KCV)                                                                                                \
         { e = cudaFuncSetAttribute(conv3d_k3_zmarch_kernel<__half, KCV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
           if (e == cudaSuccess) { conv3d_k3_zmarch_kernel<__half, KCV, true><<<grid, TCE_THREADS, smem, st>>>(map_x, map_w, z, bias, (__half*)y, stats); e = cudaGetLastError(); } }
-        if (zm_split) {
+        if (xf_nch > 0) {          // GroupNorm + ReLU of the first xf_nch input channels formed in shared memory (64-byte rows only)
+          if (zm_split || Cin != 32 || (xf_nch != 8 && xf_nch != 16 && xf_nch != 32) || !xf_stats || !xf_gamma || !xf_beta) {
+            seg3d_set_error("conv_tc(zmarch): the input transform needs Cin == 32 and 8, 16 or 32 transformed channels");
+            return SEG3D_EUNSUPPORTED;
+          }
+          if (dtype == SEG3D_BF16) {
+            e = cudaFuncSetAttribute(conv3d_k3_zmarch_kernel<__nv_bfloat16, 32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) { conv3d_k3_zmarch_kernel<__nv_bfloat16, 32, false, true><<<grid, ZMX_THREADS, smem, st>>>(map_x, map_w, z, bias, (__nv_bfloat16*)y, stats); e = cudaGetLastError(); }
+          } else {
+            e = cudaFuncSetAttribute(conv3d_k3_zmarch_kernel<__half, 32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) { conv3d_k3_zmarch_kernel<__half, 32, false, true><<<grid, ZMX_THREADS, smem, st>>>(map_x, map_w, z, bias, (__half*)y, stats); e = cudaGetLastError(); }
+          }
+        } else if (zm_split) {
           if (Cin == 64) SEG3D_LAUNCH_ZS(64) else SEG3D_LAUNCH_ZS(32)
         } else if (dtype == SEG3D_BF16) {
           if (Cin == 64) SEG3D_LAUNCH_Z(__nv_bfloat16, 64) else if (Cin == 32) SEG3D_LAUNCH_Z(__nv_bfloat16, 32) else SEG3D_LAUNCH_Z(__nv_bfloat16, 16)
@@ -934,6 +1008,7 @@ int seg3d_conv_tc(int mode, int dtype, const void* x, int x_ld, int Cin, const v
     }
     Cin = Cin_real;            // the shape did not fit the z-march kernel: generic path below
   }
+  if (xf_nch > 0) { seg3d_set_error("conv_tc: the input transform is only available on the z-march k3 path (Cin 32, W %% 8 == 0, D >= 4)"); return SEG3D_EUNSUPPORTED; }
 
   SEG3D_REQUIRE(!out_f32, "conv_tc: SEG3D_OUT_F32 (dense real channels) is only available on the z-march k3 path");
   TcParams p;

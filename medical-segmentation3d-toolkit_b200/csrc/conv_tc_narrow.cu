@@ -33,14 +33,31 @@ struct FoldParams {
   const double* gn_stats;           // [N][2] finished sums of the producing convolution
   const float* gn_gamma;
   const float* gn_beta;
+  // the first rg_nch channels of the RESIDUAL are themselves a raw convolution result: res = relu(gn(res_raw)) for those
+  // (the up-conv half of the concat buffer whose GroupNorm-apply pass was skipped, see seg3d_conv3d_k3_gnin_fwd)
+  int rg_nch;
+  float rg_eps;
+  double rg_count;
+  const double* rg_stats;
+  const float* rg_gamma;
+  const float* rg_beta;
 };
 constexpr int FD_NB = 4;            // rotating TMEM accumulators
 constexpr int FD_TX = 8, FD_TY = 10, FD_HX = 10, FD_HY = 12;
-constexpr int FDG_THREADS = 320;     // fused variant: + 4 transform warps
+#ifndef SEG3D_FDG_MINB
+#define SEG3D_FDG_MINB 2
+#endif
+#ifndef SEG3D_FDG_XW
+#define SEG3D_FDG_XW 4
+#endif
+constexpr int FDG_XW = SEG3D_FDG_XW;                 // transform warps of the fused variant (4 or 8)
+constexpr int FDG_THREADS = 192 + 32 * FDG_XW;       // fused variant: TMA, MMA, 4 epilogue warps + the transform warps
+constexpr int FDG_NSLOT = 512 / (32 * FDG_XW);       // 16-byte slots of a plane per transform thread
+constexpr int FDG_MINB = SEG3D_FDG_MINB;   // co-resident CTAs the fused variant is compiled for (register cap 65536 / (320 * MINB))
 
 // SPLIT (strict-parity mode): a voxel row is [hi(KC/2) | lo(KC/2)], a weight row [whi | wlo]; the k loop runs hi*whi, lo*whi, hi*wlo.
 template <typename T, int KC, bool FUSE_GN, bool SPLIT = false>
-__global__ void __launch_bounds__(FUSE_GN ? FDG_THREADS : TC_THREADS, FUSE_GN ? 3 : 1)
+__global__ void __launch_bounds__(FUSE_GN ? FDG_THREADS : TC_THREADS, FUSE_GN ? FDG_MINB : 1)
 conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                       const __grid_constant__ CUtensorMap map_r,
                       const FoldParams p, const float* __restrict__ bias, float* __restrict__ y, double* __restrict__ stats) {
@@ -66,7 +83,7 @@ conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     if (FUSE_GN) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
-    for (int s = 0; s < p.ring; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); mbar_init(xf_bar + 8 * s, 4); }
+    for (int s = 0; s < p.ring; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); mbar_init(xf_bar + 8 * s, FUSE_GN ? FDG_XW : 4); }
     for (int b = 0; b < FD_NB; ++b) { mbar_init(tfull_bar + 8 * b, 1); mbar_init(tempty_bar + 8 * b, 4); }
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -147,14 +164,15 @@ conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       // swizzle phase of their rows are the same, so the 8 channels (and their scale / shift) are fixed per thread
       const int t = (warp - 6) * 32 + lane;
       const int c8 = ((t & 3) ^ ((t >> 3) & 3)) << 3;
-      int hxk[4], hyk[4];
+      int hxk[FDG_NSLOT], hyk[FDG_NSLOT];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int row = (t >> 2) + 32 * k;
+      for (int k = 0; k < FDG_NSLOT; ++k) {
+        const int row = (t >> 2) + 8 * FDG_XW * k;
         hyk[k] = row < FD_HX * FD_HY ? row / FD_HX : -1000;
         hxk[k] = row - (row / FD_HX) * FD_HX;
       }
-      float sa[8], sb[8];
+      float sa[8], sb[8], ra[8], rb[8];
+      const bool rg = c8 < p.rg_nch;
       int stage_i = 0; uint32_t phase = 0; int cur_n = -1;
       for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
         int tt = item;
@@ -168,35 +186,44 @@ conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           gn_mean_rstd(p.gn_stats + 2 * n, p.gn_count, p.gn_eps, mean, rstd);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { sa[j] = rstd * p.gn_gamma[c8 + j]; sb[j] = p.gn_beta[c8 + j] - mean * sa[j]; }
+          if (rg) {
+            gn_mean_rstd(p.rg_stats + 2 * n, p.rg_count, p.rg_eps, mean, rstd);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ra[j] = rstd * p.rg_gamma[c8 + j]; rb[j] = p.rg_beta[c8 + j] - mean * ra[j]; }
+          }
           cur_n = n;
         }
-        bool inb[4];
+        bool inb[FDG_NSLOT];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < FDG_NSLOT; ++k) {
           const int gx = x0 - 1 + hxk[k], gy = y0 - 1 + hyk[k];
           inb[k] = gx >= 0 && gx < p.W && gy >= 0 && gy < p.H;      // zero padding stays zero (TMA zero fill); rows >= 120 never
         }
         for (int ip = 0; ip < L + 2; ++ip) {
-          mbar_wait(full_bar + 8 * stage_i, phase);
+          mbar_wait_relaxed(full_bar + 8 * stage_i, phase);
           const int gz = zs - 1 + ip;
           if (gz >= 0 && gz < p.D) {
             uint8_t* raw = smem_al + 3 * p.w_slab + stage_i * slot_bytes + t * 16;
             const uint8_t* res = raw + p.plane_bytes;
 #pragma unroll
-            for (int k0 = 0; k0 < 4; k0 += 2) {               // two slots in flight (register budget: 3 CTAs of 320 threads per SM)
+            for (int k0 = 0; k0 < FDG_NSLOT; k0 += 2) {       // two slots in flight
               Vec8<T> a[2], r[2];
 #pragma unroll
               for (int k = 0; k < 2; ++k)
-                if (inb[k0 + k]) { a[k].load(reinterpret_cast<const T*>(raw + (k0 + k) * 2048)); r[k].load(reinterpret_cast<const T*>(res + (k0 + k) * 2048)); }
+                if (inb[k0 + k]) { a[k].load(reinterpret_cast<const T*>(raw + (k0 + k) * (512 * FDG_XW))); r[k].load(reinterpret_cast<const T*>(res + (k0 + k) * (512 * FDG_XW))); }
 #pragma unroll
               for (int k = 0; k < 2; ++k)
                 if (inb[k0 + k]) {
                   float fa[8], fr[8];
                   a[k].get(fa); r[k].get(fr);
+                  if (rg) {            // the value seg3d_gn_apply would have stored: relu(fma(raw, a, b)) rounded to T
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) fr[j] = to_f32<T>(from_f32<T>(fmaxf(fmaf(fr[j], ra[j], rb[j]), 0.f)));
+                  }
 #pragma unroll
                   for (int j = 0; j < 8; ++j) fa[j] = fmaxf(fmaf(fa[j], sa[j], sb[j]) + fr[j], 0.f);
                   a[k].set(fa);
-                  a[k].store(reinterpret_cast<T*>(raw + (k0 + k) * 2048));
+                  a[k].store(reinterpret_cast<T*>(raw + (k0 + k) * (512 * FDG_XW)));
                 }
             }
           }
@@ -235,7 +262,7 @@ conv3d_k3_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       const bool valid = is_out && (gx < p.W) && (gy < p.H);
       for (int zl = 0; zl < L; ++zl) {
         const int ocz = oc + zl, buf = ocz % FD_NB;
-        mbar_wait(tfull_bar + 8 * buf, (ocz / FD_NB) & 1);
+        mbar_wait_relaxed(tfull_bar + 8 * buf, (ocz / FD_NB) & 1);
         tc_fence_after();
         const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.acc_cols);
         for (int c0 = 0; c0 < p.NP; c0 += 16) {
@@ -302,7 +329,8 @@ extern "C" int seg3d_conv3d_k3_narrow_np(int C) { return C >= 1 && 9 * C <= 64 ?
 static int launch_fold(int dtype, const void* x, int x_ld, int Cin, const void* w, const float* bias,
                        float* y, int C, int N, int D, int H, int W, double* stats, void* stream,
                        const void* res, int res_ld, const double* gn_stats, const float* gn_gamma, const float* gn_beta, float gn_eps,
-                       bool split = false) {
+                       bool split = false, int rg_nch = 0, const double* rg_stats = nullptr, const float* rg_gamma = nullptr,
+                       const float* rg_beta = nullptr, float rg_eps = 0.f) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool fuse = res != nullptr;
   if (split) {       // rows [hi(Cin) | lo(Cin)]: one K block of 2*Cin channels
@@ -335,7 +363,8 @@ static int launch_fold(int dtype, const void* x, int x_ld, int Cin, const void* 
   p.ntx = W / FD_TX; p.nty = (H + FD_TY - 1) / FD_TY;
   p.acc_cols = NP <= 32 ? 32 : 64;
   p.tmem_cols = FD_NB * p.acc_cols;
-  int ctas_per_sm = env_int("SEG3D_FD_CTAS_PER_SM", fuse ? 3 : 4);
+  int ctas_per_sm = env_int("SEG3D_FD_CTAS_PER_SM", fuse ? FDG_MINB : 4);
+  if (fuse && ctas_per_sm > FDG_MINB) ctas_per_sm = FDG_MINB;       // the fused variant is compiled for FDG_MINB co-resident CTAs
   if (ctas_per_sm * p.tmem_cols > 512) ctas_per_sm = 512 / p.tmem_cols;
   const int fixed = 3 * p.w_slab + 128 * p.pitch * 4 + 1024;
   int ring = 0;
@@ -360,6 +389,8 @@ static int launch_fold(int dtype, const void* x, int x_ld, int Cin, const void* 
   SEG3D_REQUIRE(nitems > 0 && nitems < (1ll << 31), "conv3d_k3_narrow_fwd: work-item count out of range");
   p.nitems = (int)nitems;
   p.gn_eps = gn_eps; p.gn_count = (double)Cin * D * H * W; p.gn_stats = gn_stats; p.gn_gamma = gn_gamma; p.gn_beta = gn_beta;
+  SEG3D_REQUIRE(rg_nch == 0 || (fuse && rg_nch % 8 == 0 && rg_nch <= Cin && rg_stats && rg_gamma && rg_beta), "conv3d_k3_narrow_gn2_fwd: bad residual GroupNorm arguments");
+  p.rg_nch = rg_nch; p.rg_eps = rg_eps; p.rg_count = (double)rg_nch * D * H * W; p.rg_stats = rg_stats; p.rg_gamma = rg_gamma; p.rg_beta = rg_beta;
   p.sbo = 8 * p.row_bytes;
   p.layout_type = p.row_bytes == 128 ? 2u : (p.row_bytes == 64 ? 4u : 6u);
   const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
@@ -440,4 +471,17 @@ extern "C" int seg3d_conv3d_k3_narrow_gn_fwd(int dtype, const void* raw, int raw
 extern "C" int seg3d_conv3d_k3_narrow_split_fwd(const void* x, int x_ld, int Cin, const void* w, const float* bias,
                                                 float* y, int C, int N, int D, int H, int W, double* stats, void* stream) {
   return launch_fold(SEG3D_F16, x, x_ld, Cin, w, bias, y, C, N, D, H, W, stats, stream, nullptr, 0, nullptr, nullptr, nullptr, 0.f, true);
+}
+
+// seg3d_conv3d_k3_narrow_gn_fwd whose residual's first res_gn_ch channels are still a raw convolution result: the kernel uses
+// relu(GroupNorm(1, res_gn_ch)(res[:, :res_gn_ch])) for them (finished sums res_gn_stats), rounded to the storage type exactly as
+// seg3d_gn_apply would have stored it, so the result is bit-identical to the unfused sequence.
+extern "C" int seg3d_conv3d_k3_narrow_gn2_fwd(int dtype, const void* raw, int raw_ld, const void* res, int res_ld, int Cin,
+                                              const double* gn_stats, const float* gamma, const float* beta, float eps,
+                                              int res_gn_ch, const double* res_gn_stats, const float* res_gamma, const float* res_beta,
+                                              const void* w, const float* bias, float* y, int C, int N, int D, int H, int W,
+                                              double* stats, void* stream) {
+  SEG3D_REQUIRE(res != nullptr, "conv3d_k3_narrow_gn2_fwd: null residual");
+  return launch_fold(dtype, raw, raw_ld, Cin, w, bias, y, C, N, D, H, W, stats, stream, res, res_ld, gn_stats, gamma, beta, eps,
+                     false, res_gn_ch, res_gn_stats, res_gamma, res_beta, eps);
 }

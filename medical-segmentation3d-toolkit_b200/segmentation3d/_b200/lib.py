@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.abspath(os.path.join(_HERE, '..', '..', 'lib', 'libseg3d_b200.so'))
+LIB_PATH = os.environ.get('SEG3D_LIB') or os.path.abspath(os.path.join(_HERE, '..', '..', 'lib', 'libseg3d_b200.so'))   # SEG3D_LIB: a variant build (kernel experiments)
 
 F32, F16, BF16 = 0, 1, 2
 OUT_F32 = 0x100
@@ -32,6 +32,8 @@ _SIGNATURES = {
     'seg3d_conv3d_cin1_wgrad': (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     'seg3d_conv3d_k3_narrow_np': (_i, [_i]),
     'seg3d_conv3d_k3_narrow_fwd': (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    'seg3d_conv3d_k3_gnin_fwd': (_i, [_i, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    'seg3d_conv3d_k3_narrow_gn2_fwd': (_i, [_i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     'seg3d_conv3d_k3_narrow_split_fwd': (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     'seg3d_conv3d_k3_narrow_gn_fwd': (_i, [_i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     'seg3d_conv3d_gn_relu_fwd': (_i, [_i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),

@@ -320,10 +320,16 @@ class NetPlan(object):
             ops.append(fn)
             levels.append(level)
 
-        def conv(name, x, xdims, y, stats_name, lout):
+        def conv(name, x, xdims, y, stats_name, lout, gnin=None):
             c = self.convs[name]
             assert c.cin == x.C and c.cout == y.C, (name, c.cin, x.C, c.cout, y.C)
-            if split and c.impl == lib.IMPL_TCGEN05:       # x: [hi | lo] f16 rows, y: fp32 raw
+            if gnin is not None:       # the first gnin['nch'] input channels are a raw conv result: GroupNorm + ReLU formed on load
+                gg = self.gns[gnin['gn']]
+                add(lambda b0, nb: lib.call('seg3d_conv3d_k3_gnin_fwd', dt, x.at(b0), x.ld, c.cin, gnin['nch'], stats_ptr(gnin['gn'], b0),
+                                            lib.ptr(gg.gamma), lib.ptr(gg.beta), GN_EPS, lib.ptr(c.w), lib.ptr(c.bias), y.at(b0), y.ld,
+                                            c.cout, nb, xdims[0], xdims[1], xdims[2], stats_ptr(stats_name, b0) if stats_name else None,
+                                            st()), lout)
+            elif split and c.impl == lib.IMPL_TCGEN05:       # x: [hi | lo] f16 rows, y: fp32 raw
                 add(lambda b0, nb: lib.call('seg3d_conv3d_split_fwd', c.mode, x.at(b0), x.ld, x.ld // 2, c.cin, lib.ptr(c.w),
                                             lib.ptr(c.bias), y.at(b0), y.ld, c.cout, nb, xdims[0], xdims[1], xdims[2],
                                             stats_ptr(stats_name, b0) if stats_name else None, st()), lout)
@@ -395,14 +401,14 @@ class NetPlan(object):
         fuse_s2_env = os.environ.get('SEG3D_FUSE_S2', '0')         # '1': every stride-2 conv; 'up': the transposed convs only
         fuse_s2 = (not train) and dt != lib.F32 and not split and fuse_s2_env in ('1', 'up')
 
-        def unit(cname, gname, x, lin, lout, out, res=None, defer_gn=False):
+        def unit(cname, gname, x, lin, lout, out, res=None, defer_gn=False, gnin=None):
             """conv -> GroupNorm -> (+res) -> ReLU with the conv reading level `lin` and writing level `lout`"""
             c = self.convs[cname]
             C = c.cout
             if defer_gn:        # the consumer applies GroupNorm + residual + ReLU itself (seg3d_conv3d_k3_narrow_gn_fwd)
                 rv = rawview(C, lout)
-                conv(cname, x, dims[lin], rv, gname, lout)
-                ws['deferred'] = {'raw': rv, 'res': res, 'gn': gname}
+                conv(cname, x, dims[lin], rv, gname, lout, gnin=gnin)
+                ws['deferred'] = {'raw': rv, 'res': res, 'gn': gname, 'res_gnin': gnin}
                 units.append({'conv': cname, 'gn': gname, 'x': x, 'lin': lin, 'lout': lout, 'raw': rv, 'out': out, 'res': res})
                 return
             if (fuse_s2 and res is None and c.impl == lib.IMPL_TCGEN05 and out.ld % 8 == 0
@@ -415,11 +421,12 @@ class NetPlan(object):
             gn(gname, rv, out, vox[lout], True, res, lout)
             units.append({'conv': cname, 'gn': gname, 'x': x, 'lin': lin, 'lout': lout, 'raw': rv, 'out': out, 'res': res})
 
-        def conv_gn(cname, gname, x, l, out, relu, res=None, defer_gn=False):
+        def conv_gn(cname, gname, x, l, out, relu, res=None, defer_gn=False, gnin=None):
             assert relu
-            unit(cname, gname, x, l, l, out, res, defer_gn)
+            assert gnin is None or defer_gn
+            unit(cname, gname, x, l, l, out, res, defer_gn, gnin)
 
-        def rblock(prefix, X, l, dest, defer_last=False):
+        def rblock(prefix, X, l, dest, defer_last=False, gnin=None):
             n = self._rblock_len(prefix)
             C = X.C
             cur = X
@@ -429,7 +436,7 @@ class NetPlan(object):
                 op = '%s.ops.%d' % (prefix, i)
                 if (op + '.conv') in self.convs:
                     conv_gn(op + '.conv', op + '.gn', cur, l, out, relu=True, res=X if last else None,
-                            defer_gn=defer_last and last)
+                            defer_gn=defer_last and last, gnin=gnin if (n == 1 and defer_last) else None)
                 else:
                     m1 = tmpbuf(l, C // 4, 'M%da' % l)
                     m2 = tmpbuf(l, C // 4, 'M%db' % l)
@@ -446,6 +453,11 @@ class NetPlan(object):
         fuse_tail = (not train and not split and c1_.fold and c1_.impl == lib.IMPL_TCGEN05 and c1_.cin == 32 and W % 8 == 0
                      and ('up_32.rblock.ops.%d.conv' % (self._rblock_len('up_32.rblock') - 1)) in self.convs
                      and os.environ.get('SEG3D_TAIL_F32', '1') != '0' and os.environ.get('SEG3D_FUSE_TAIL', '1') != '0')
+
+        cu_ = self.convs.get('up_32.rblock.ops.0.conv')
+        fuse_up = (fuse_tail and self._rblock_len('up_32.rblock') == 1 and cu_ is not None and cu_.impl == lib.IMPL_TCGEN05
+                   and cu_.cin == 32 and cu_.cout == 32 and self.convs['up_32.up_conv'].impl == lib.IMPL_TCGEN05
+                   and os.environ.get('SEG3D_TC_ZMARCH', '1') != '0' and os.environ.get('SEG3D_FUSE_UP', '1') != '0')
 
         # in_block -> second half of cat0
         x_in = _View(ws['x_in'], 0, self.in_channels, self.in_channels, sample=vox[0] * self.in_channels)
@@ -494,10 +506,20 @@ class NetPlan(object):
         for l, name in ((3, 'up_256'), (2, 'up_128'), (1, 'up_64'), (0, 'up_32')):
             C = widths[l]
             up = V(ws['cat%d' % l], 0, C, C // 2)
-            unit(name + '.up_conv', name + '.up_gn', src, l + 1, l, up)
+            gnin = None
+            if l == 0 and fuse_up:
+                # the transposed convolution leaves its RAW result in the lower half of the concat buffer; both readers of that
+                # half (the residual block's convolution and the residual input of the fused out-block convolution) apply
+                # GroupNorm + ReLU on load, so up_32.up_gn's apply pass (vnet_upblock.py:19) never touches HBM
+                conv(name + '.up_conv', src, dims[l + 1], up, name + '.up_gn', l)
+                gnin = {'gn': name + '.up_gn', 'nch': C // 2}
+                units.append({'conv': name + '.up_conv', 'gn': name + '.up_gn', 'x': src, 'lin': l + 1, 'lout': l, 'raw': up,
+                              'out': up, 'res': None})
+            else:
+                unit(name + '.up_conv', name + '.up_gn', src, l + 1, l, up)
             cat = V(ws['cat%d' % l], 0, C, C)
             dest = V(ws['U%d' % l], 0, C, C)
-            rblock(name + '.rblock', cat, l, dest, defer_last=(l == 0 and fuse_tail))
+            rblock(name + '.rblock', cat, l, dest, defer_last=(l == 0 and fuse_tail), gnin=gnin)
             src = dest
         # out block: conv1 -> raw, then the fused tail
         nc = self.out_channels
@@ -515,11 +537,19 @@ class NetPlan(object):
             dfr = ws.get('deferred')
             if dfr is not None:
                 g0 = self.gns[dfr['gn']]
-                draw, dres, dgn = dfr['raw'], dfr['res'], dfr['gn']
-                add(lambda b0, nb: lib.call('seg3d_conv3d_k3_narrow_gn_fwd', dt, draw.at(b0), draw.ld, dres.at(b0), dres.ld, c1.cin,
-                                            stats_ptr(dgn, b0), lib.ptr(g0.gamma), lib.ptr(g0.beta), GN_EPS,
-                                            lib.ptr(c1.w_fold), lib.ptr(c1.bias), rv1.at(b0), nc, nb, dims[0][0], dims[0][1], dims[0][2],
-                                            stats_ptr('out_block.gn1', b0), st()), 0)
+                draw, dres, dgn, rgn = dfr['raw'], dfr['res'], dfr['gn'], dfr.get('res_gnin')
+                if rgn is not None:       # the residual's lower half is still raw (fuse_up above)
+                    gr = self.gns[rgn['gn']]
+                    add(lambda b0, nb: lib.call('seg3d_conv3d_k3_narrow_gn2_fwd', dt, draw.at(b0), draw.ld, dres.at(b0), dres.ld, c1.cin,
+                                                stats_ptr(dgn, b0), lib.ptr(g0.gamma), lib.ptr(g0.beta), GN_EPS,
+                                                rgn['nch'], stats_ptr(rgn['gn'], b0), lib.ptr(gr.gamma), lib.ptr(gr.beta),
+                                                lib.ptr(c1.w_fold), lib.ptr(c1.bias), rv1.at(b0), nc, nb, dims[0][0], dims[0][1],
+                                                dims[0][2], stats_ptr('out_block.gn1', b0), st()), 0)
+                else:
+                    add(lambda b0, nb: lib.call('seg3d_conv3d_k3_narrow_gn_fwd', dt, draw.at(b0), draw.ld, dres.at(b0), dres.ld, c1.cin,
+                                                stats_ptr(dgn, b0), lib.ptr(g0.gamma), lib.ptr(g0.beta), GN_EPS,
+                                                lib.ptr(c1.w_fold), lib.ptr(c1.bias), rv1.at(b0), nc, nb, dims[0][0], dims[0][1], dims[0][2],
+                                                stats_ptr('out_block.gn1', b0), st()), 0)
                 rd = 2 * (2 * B * vox[0] * c1.cin)
             else:
                 add(lambda b0, nb: lib.call('seg3d_conv3d_k3_narrow_fwd', dt, src.at(b0), src.ld, c1.cin, lib.ptr(c1.w_fold),

@@ -641,6 +641,68 @@ def test_conv_k3_narrow_fused_gn_residual_equals_unfused(lib, shape, dt_name):
     assert torch.allclose(s0, s1, rtol=1e-9, atol=1e-6)
 
 
+@pytest.mark.parametrize('shape', [(2, 16, 16, 16), (1, 8, 24, 8), (2, 20, 40, 24), (3, 32, 48, 48)], ids=str)
+@pytest.mark.parametrize('dt_name', ['F16', 'BF16'])
+def test_up_block_gn_folded_into_both_consumers_equals_unfused(lib, shape, dt_name):
+    """The last up-block with up_gn's apply pass folded into its two readers: seg3d_conv3d_k3_gnin_fwd (z-march kernel with the
+    transform stage) and seg3d_conv3d_k3_narrow_gn2_fwd (fused out-block convolution whose residual's lower half is still raw)
+    must reproduce seg3d_gn_apply -> seg3d_conv3d_fwd -> seg3d_conv3d_k3_narrow_gn_fwd bit for bit."""
+    L = lib
+    dt = getattr(L, dt_name)
+    tdt = L.TORCH_DTYPE[dt]
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(N * 7 + W)
+    nvox = D * H * W
+    raw_up = to_ndhwc(torch.randn((N, 16, D, H, W), generator=g) * 1.5 + 0.2, tdt)            # raw result of the transposed conv
+    skip = to_ndhwc(torch.relu(torch.randn((N, 16, D, H, W), generator=g)), tdt)
+    gam_u = (torch.rand((16,), generator=g) + 0.5).cuda()
+    bet_u = (torch.randn((16,), generator=g) * 0.2).cuda()
+    st_u = torch.stack([raw_up.double().flatten(1).sum(1), (raw_up.double() ** 2).flatten(1).sum(1)], 1).contiguous()
+    w = (torch.randn((32, 32, 3, 3, 3), generator=g) * 0.06).to(tdt).float()
+    b = (torch.randn((32,), generator=g) * 0.1).cuda()
+    wp = pack_tc(w, L.CONV_K3, L, tdt)
+    gam_r = (torch.rand((32,), generator=g) + 0.5).cuda()
+    bet_r = (torch.randn((32,), generator=g) * 0.2).cuda()
+    C = 2
+    w1 = torch.randn((C, 32, 3, 3, 3), generator=g) * 0.1
+    b1 = (torch.randn((C,), generator=g) * 0.1).cuda()
+    NP = L.load().seg3d_conv3d_k3_narrow_np(C)
+    wf = torch.zeros((3, NP, 32))
+    wf[:, :9 * C] = w1.permute(2, 3, 4, 0, 1).reshape(3, 9 * C, 32)
+    wf = wf.to(tdt).cuda()
+
+    def run(fused):
+        cat = torch.empty((N, D, H, W, 32), dtype=tdt, device='cuda')
+        cat[..., 16:] = skip
+        raw2 = torch.full((N, D, H, W, 32), float('nan'), dtype=tdt, device='cuda')
+        st2 = torch.zeros((N, 2), dtype=torch.float64, device='cuda')
+        y = torch.full((N, D, H, W, C), float('nan'), dtype=torch.float32, device='cuda')
+        st3 = torch.zeros((N, 2), dtype=torch.float64, device='cuda')
+        if fused:
+            cat[..., :16] = raw_up                   # the lower half stays raw
+            L.call('seg3d_conv3d_k3_gnin_fwd', dt, L.ptr(cat), 32, 32, 16, L.ptr(st_u), L.ptr(gam_u), L.ptr(bet_u), 1e-5, L.ptr(wp),
+                   L.ptr(b), L.ptr(raw2), 32, 32, N, D, H, W, L.ptr(st2), L.stream_ptr())
+            L.call('seg3d_conv3d_k3_narrow_gn2_fwd', dt, L.ptr(raw2), 32, L.ptr(cat), 32, 32, L.ptr(st2), L.ptr(gam_r), L.ptr(bet_r), 1e-5,
+                   16, L.ptr(st_u), L.ptr(gam_u), L.ptr(bet_u), L.ptr(wf), L.ptr(b1), L.ptr(y), C, N, D, H, W, L.ptr(st3), L.stream_ptr())
+        else:
+            L.call('seg3d_gn_apply', dt, L.ptr(raw_up), 16, 16, L.ptr(st_u), L.ptr(gam_u), L.ptr(bet_u), 1e-5, None, 0,
+                   L.ptr(cat), 32, 1, N, nvox, L.stream_ptr())
+            L.call('seg3d_conv3d_fwd', L.CONV_K3, dt, L.IMPL_TCGEN05, L.ptr(cat), 32, 32, L.ptr(wp), L.ptr(b), L.ptr(raw2), 32, 32,
+                   N, D, H, W, L.ptr(st2), L.stream_ptr())
+            L.call('seg3d_conv3d_k3_narrow_gn_fwd', dt, L.ptr(raw2), 32, L.ptr(cat), 32, 32, L.ptr(st2), L.ptr(gam_r), L.ptr(bet_r), 1e-5,
+                   L.ptr(wf), L.ptr(b1), L.ptr(y), C, N, D, H, W, L.ptr(st3), L.stream_ptr())
+        torch.cuda.synchronize()
+        return raw2, st2, y, st3
+
+    r0, s0, y0, t0 = run(False)
+    r1, s1, y1, t1 = run(True)
+    assert not torch.isnan(r1.float()).any() and not torch.isnan(y1).any()
+    assert torch.equal(r0, r1)
+    assert torch.allclose(s0, s1, rtol=1e-9, atol=1e-6)
+    assert torch.equal(y0, y1)
+    assert torch.allclose(t0, t1, rtol=1e-9, atol=1e-6)
+
+
 def _split_rows(x5):
     """[N,C,D,H,W] fp32 -> NDHWC rows [hi(C) | lo(C)] f16 on the GPU, and the value the kernels see (hi + lo)"""
     rows = x5.permute(0, 2, 3, 4, 1).contiguous()

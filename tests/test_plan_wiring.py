@@ -159,6 +159,30 @@ def _install(monkeypatch, calls):
         calls.append('narrow')
         return 0
 
+    def gnin_fwd(dtype, x, x_ld, Cin, gn_ch, gn_stats, gamma, beta, eps, w, bias, y, y_ld, Cout, N, D, H, W, stats, stream):
+        # the first gn_ch input channels are raw: relu(GroupNorm(1, gn_ch)) of them, rounded to the storage type, on load
+        nvox = D * H * W
+        xr = _rows(x, N * nvox, x_ld, Cin).float().view(N, nvox, Cin).clone()
+        mean, rstd = _mean_rstd(gn_stats, float(nvox * gn_ch), eps, N)
+        z = ((xr[..., :gn_ch].double() - mean) * rstd).float() * gamma.t[:gn_ch].view(1, 1, gn_ch) + beta.t[:gn_ch].view(1, 1, gn_ch)
+        xr[..., :gn_ch] = F.relu(z).to(x.t.dtype).float()
+        xs = xr.view(N, D, H, W, Cin).permute(0, 4, 1, 2, 3)
+        _store(_conv(lib.CONV_K3, False, xs, w, bias, Cin, Cout), y, y_ld, Cout, stats, N)
+        calls.append('conv_gnin')
+        return 0
+
+    def narrow_gn2_fwd(dtype, raw, raw_ld, res, res_ld, Cin, gn_stats, gamma, beta, eps, rg_ch, rg_stats, rg_gamma, rg_beta,
+                       w, bias, y, Cout, N, D, H, W, stats, stream):
+        nvox = D * H * W
+        rr = _rows(res, N * nvox, res_ld, Cin).float().view(N, nvox, Cin).clone()
+        mean, rstd = _mean_rstd(rg_stats, float(nvox * rg_ch), eps, N)
+        z = ((rr[..., :rg_ch].double() - mean) * rstd).float() * rg_gamma.t[:rg_ch].view(1, 1, rg_ch) + rg_beta.t[:rg_ch].view(1, 1, rg_ch)
+        rr[..., :rg_ch] = F.relu(z).to(res.t.dtype).float()
+        resolved = _P(rr.reshape(-1).to(res.t.dtype), 0)
+        rc = narrow_gn_fwd(dtype, raw, raw_ld, resolved, Cin, Cin, gn_stats, gamma, beta, eps, w, bias, y, Cout, N, D, H, W, stats, stream)
+        calls[-1] = 'narrow_gn2'
+        return rc
+
     def narrow_split_fwd(x, x_ld, Cin, w, bias, y, Cout, N, D, H, W, stats, stream):
         rows = N * D * H * W
         assert Cin == 32 and x_ld >= 64
@@ -243,6 +267,7 @@ def _install(monkeypatch, calls):
         return 0
 
     table = {'seg3d_conv3d_fwd': conv3d_fwd, 'seg3d_conv3d_cin1_fwd': cin1_fwd, 'seg3d_conv3d_k3_narrow_split_fwd': narrow_split_fwd,
+             'seg3d_conv3d_k3_gnin_fwd': gnin_fwd, 'seg3d_conv3d_k3_narrow_gn2_fwd': narrow_gn2_fwd,
              'seg3d_conv3d_k3_narrow_fwd': narrow_fwd, 'seg3d_conv3d_k3_narrow_gn_fwd': narrow_gn_fwd,
              'seg3d_gn_apply': gn_apply, 'seg3d_conv3d_split_fwd': split_fwd, 'seg3d_gn_apply_split': gn_apply_split,
              'seg3d_outblock_tail_stats': tail_stats, 'seg3d_outblock_tail_probs': tail_probs,
@@ -269,10 +294,11 @@ def test_plan_issues_the_reference_network(monkeypatch, arch, cout, mode, tol):
     assert err <= tol, (arch, mode, err)
     assert float((got.sum(1) - 1).abs().max()) <= 1e-5
     n_convs = sum(1 for k, v in sd.items() if k.endswith('.weight') and v.dim() == 5) - 1          # out_block.conv2 lives in the tail
-    assert sum(c in ('conv', 'narrow', 'narrow_gn', 'split_conv') for c in calls) == n_convs
+    assert sum(c in ('conv', 'conv_gnin', 'narrow', 'narrow_gn', 'narrow_gn2', 'split_conv') for c in calls) == n_convs
     if mode in ('fp16', 'bf16'):
-        assert 'narrow_gn' in calls                                                   # fused last GroupNorm + narrow-output conv is the default
         assert 'conv_stats' in calls                                                  # input block: statistics pass + fused GroupNorm/ReLU pass
+        # fused last GroupNorm + narrow-output conv is the default; up_32.up_gn is applied on load by both of its readers
+        assert 'conv_gnin' in calls and 'narrow_gn2' in calls
     if mode == 'fp32x':
         assert 'split_conv' in calls and 'gn_split' in calls
     # a second forward through the cached plan, and after an in-place weight refresh, stays correct
