@@ -437,7 +437,9 @@ def main():
         shard = (rank, world) if (shard_mode == 'patches' and world > 1) else None
         ms_dev, launches = timed(lambda: segmentation_volume_device(model, cfg, vol, batch=args.batch, shard=shard, gather=args.gather),
                                  args.steps, max(args.warmup, 3))
-        ms_e2e, _ = timed(lambda: segmentation_volume_host(model, cfg, host_vol, host_mask, batch=args.batch, shard=shard, gather=args.gather),
+        # sharded: the merged mask is reduced to rank 0, the one process that copies it out (and would write the result file)
+        ms_e2e, _ = timed(lambda: segmentation_volume_host(model, cfg, host_vol, host_mask, batch=args.batch, shard=shard, gather=args.gather,
+                                                           mask_root=0 if shard is not None else None),
                           max(2, args.steps // 2), 3)
         units = nvox * (world if shard is None else 1)
         return {'value': units / (ms_dev * 1e-3) / 1e6, 'ms_per_step': ms_dev, 'launches': launches,
@@ -558,7 +560,7 @@ def main():
             from segmentation3d.core.seg_infer import shard_plan
             _, _, mine, (z_lo, z_hi), disjoint = shard_plan(model, cfg, (size[2], size[1], size[0]), (0, world))
             line['e2e']['h2d_bytes_per_step'] = int((z_hi - z_lo) * size[1] * size[0] * 4)
-            line['e2e']['note'] = 'per rank: only the z planes its patches read are uploaded; every rank copies the merged mask out'
+            line['e2e']['note'] = 'per rank: only the z planes its patches read are uploaded (h2d_bytes_per_step = rank 0); the merged mask is reduced to rank 0, which copies it out'
             line['collective'] = ('max all-reduce of the int8 label mask (%d MB) after a local count-normalise + arg-max of each '
                                   'rank\'s z range (whole overlap components are dealt to one rank)' % int(nvox / 1e6)) if (args.gather == 'labels' and disjoint) else \
                 ('per-class reduce-scatter of fp32 probability slabs (%d MB) + all-gather of the int8 mask' % int(nvox * 4 * args.classes / 1e6)

@@ -327,7 +327,7 @@ def shard_plan(model, cfg, shape_zyx, shard, bbox_start_voxel=None, bbox_end_vox
 
 
 def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_start_voxel=None, bbox_end_voxel=None,
-                               use_gpu=True, spacing=None, z_ready=None, mask_sink=None, gather='probs'):
+                               use_gpu=True, spacing=None, z_ready=None, mask_sink=None, gather='probs', mask_root=None):
     """Device-resident core of segmentation_volume: `vol` is a CUDA float32 [z,y,x] tensor already at
     the model spacing.  Returns (mean_probs [C,z,y,x] fp32, mask [z,y,x] int8) on the device.
     shard=(rank, world): the patches of this ONE volume are dealt over the ranks of the default process group (NCCL) in
@@ -379,7 +379,10 @@ def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_sta
             eng.accumulate(vol[z_lo:z_hi], local, patch, norm, acc)
             eng.batch = keep
             eng.finalize(acc, [counts[0], counts[1], np.ascontiguousarray(counts[2][z_lo:z_hi])], mask=mask[z_lo:z_hi])
-        dist.all_reduce(mask, op=dist.ReduceOp.MAX)
+        if mask_root is None:
+            dist.all_reduce(mask, op=dist.ReduceOp.MAX)
+        else:                 # only one process consumes the merged mask (it writes the result): reduce instead of all-reduce
+            dist.reduce(mask, dst=int(mask_root), op=dist.ReduceOp.MAX)
         return acc, mask
     acc = torch.zeros((C, Z, Y, X), dtype=torch.float32, device=vol.device)
     progressive = z_ready is not None and mask_sink is not None and not sharded
@@ -433,10 +436,12 @@ def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_sta
     return acc, mask
 
 
-def segmentation_volume_host(model, cfg, host_vol, host_mask=None, batch=None, shard=None, gather='probs'):
+def segmentation_volume_host(model, cfg, host_vol, host_mask=None, batch=None, shard=None, gather='probs', mask_root=None):
     """End-to-end call with HOST buffers: (pinned) float32 [z,y,x] in, int8 mask out; probabilities stay
     on the device and are returned as a tensor.  Copies are issued on the current stream.  With shard=(rank, world) a
-    rank uploads only the z planes its patches read (all of them for the overlapping-patch gathers)."""
+    rank uploads only the z planes its patches read (all of them for the overlapping-patch gathers).  mask_root = r (sharded
+    'labels' exchange only): the merged mask is reduced to rank r alone and only that process copies it to its host buffer
+    (the others return their partial device mask) - one 105 MB device-to-host copy per volume instead of one per rank."""
     dev = next(model['net'].parameters()).device
     vol = torch.empty(host_vol.shape, dtype=torch.float32, device=dev)
     z_ready = None
@@ -463,7 +468,10 @@ def segmentation_volume_host(model, cfg, host_vol, host_mask=None, batch=None, s
         host_mask = torch.empty(host_vol.shape, dtype=torch.int8, pin_memory=True)
     sharded = shard is not None and shard[1] > 1
     sink = (host_mask, _side_stream(dev)) if (z_ready is not None and host_mask.is_pinned() and not sharded) else None
-    acc, mask = segmentation_volume_device(model, cfg, vol, batch=batch, shard=shard, z_ready=z_ready, mask_sink=sink, gather=gather)
+    acc, mask = segmentation_volume_device(model, cfg, vol, batch=batch, shard=shard, z_ready=z_ready, mask_sink=sink, gather=gather,
+                                           mask_root=mask_root if sharded else None)
+    if sharded and mask_root is not None and gather == 'labels' and shard[0] != int(mask_root):
+        return acc, mask
     if sink is None:
         host_mask.copy_(mask, non_blocking=True)
     return acc, host_mask

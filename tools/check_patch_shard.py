@@ -73,6 +73,16 @@ agree_h = float((host_mask.cuda() == mask_z1).float().mean())
 print('rank %d/%d: z-range %d..%d of 144 (%d patches): own-patch max|dp| %.3g, label exchange agreement %.6f (device) %.6f (host call)'
       % (rank, world, z_lo, z_hi, len(mine), d_own, agree_z, agree_h), flush=True)
 assert d_own <= 1e-5 and agree_z >= 0.9999 and agree_h >= 0.9999
+# mask_root = 0: the merged mask is reduced to rank 0 alone, and only rank 0's host buffer receives it
+host_mask0 = torch.full(vol_z.shape, -1, dtype=torch.int8).pin_memory()
+_, out0 = segmentation_volume_host(model, cfg_t, host_vol, host_mask0, batch=4, shard=(rank, world), gather='labels', mask_root=0)
+torch.cuda.synchronize()
+if rank == 0:
+    agree_0 = float((host_mask0.cuda() == mask_z1).float().mean())
+    print('rank 0/%d: mask reduced to rank 0 only, agreement of its host mask %.6f' % (world, agree_0), flush=True)
+    assert out0 is host_mask0 and agree_0 >= 0.9999
+else:
+    assert out0.is_cuda and int(host_mask0.max()) == -1          # the other ranks keep their partial device mask, no host copy
 # ragged volume: the last box of every axis is clamped back into the volume and overlaps its neighbour (as in BASELINE
 # configs[1]: 512 = 5 x 96 + 32); whole overlap components go to one rank, so the label exchange is still exact
 vol_r = torch.nn.functional.avg_pool3d(torch.randn((1, 1, 160, 112, 128), generator=g2, device='cuda'), 3, 1, 1)[0, 0].contiguous() * 3.0

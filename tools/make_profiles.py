@@ -20,11 +20,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PROF = os.path.join(ROOT, 'profiles')
 
 # tensor-core launches of one VNet forward in plan order (segmentation3d/_b200/plan.py)
-VNET_ORDER = (['conv_tc_cin1', 'conv_tc_k2s2', 'conv_tc_k3', 'conv_tc_k2s2', 'conv_tc_k3', 'conv_tc_k3', 'conv_tc_k2s2'] +
+VNET_ORDER = (['conv_tc_cin1', 'conv_tc_cin1', 'conv_tc_k2s2', 'conv_tc_k3', 'conv_tc_k2s2', 'conv_tc_k3', 'conv_tc_k3', 'conv_tc_k2s2'] +
               ['conv_tc_k3'] * 3 + ['conv_tc_k2s2'] + ['conv_tc_k3'] * 3 + ['conv_tc_t2s2'] + ['conv_tc_k3'] * 3 +
               ['conv_tc_t2s2'] + ['conv_tc_k3'] * 3 + ['conv_tc_t2s2'] + ['conv_tc_k3'] * 2 + ['conv_tc_t2s2', 'conv_tc_k3',
                                                                                                'conv_tc_narrow'])
-VNET_NAMES = (['in_block.conv', 'down_32.down_conv', 'down_32.rblock.0', 'down_64.down_conv', 'down_64.rblock.0', 'down_64.rblock.1',
+VNET_NAMES = (['in_block.conv.stats', 'in_block.conv.gn_relu', 'down_32.down_conv', 'down_32.rblock.0', 'down_64.down_conv', 'down_64.rblock.0', 'down_64.rblock.1',
                'down_128.down_conv'] + ['down_128.rblock.%d' % i for i in range(3)] + ['down_256.down_conv'] +
               ['down_256.rblock.%d' % i for i in range(3)] + ['up_256.up_conv'] + ['up_256.rblock.%d' % i for i in range(3)] +
               ['up_128.up_conv'] + ['up_128.rblock.%d' % i for i in range(3)] + ['up_64.up_conv', 'up_64.rblock.0', 'up_64.rblock.1',
@@ -36,8 +36,14 @@ def short(name):
     return re.sub(r'void |<unnamed>::|at::native::', '', name)[:60]
 
 
+BATCH = int(os.environ.get('PROFILE_BATCH', '36'))
+
+
 def full_summary(tag, rep):
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    if rep.endswith('.csv'):      # `ncu -i <rep> --page raw --csv` already run on the GPU box (a 29-launch --set full report exceeds the transfer limit)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
@@ -60,9 +66,9 @@ def full_summary(tag, rep):
         return v
 
     data = rows[2:]
-    lines = ['# %s: `ncu --set full` of the tensor-core launches of one VNet forward (B = 20 patches of 96^3, fp16)' % tag, '',
-             'Command: `ncu --set full --clock-control none --import-source on -k regex:"zmarch|persistent|fold|cin1" -s 28 -c 28 '
-             'python tools/profile_forward.py 20 fp16` (per-launch times are cold-cache and serialised).', '',
+    lines = ['# %s: `ncu --set full` of the tensor-core launches of one VNet forward (B = %d patches of 96^3, fp16)' % (tag, BATCH), '',
+             'Command: `ncu --set full --clock-control none --import-source on -k regex:"zmarch|persistent|fold|cin1" -s %d -c %d '
+             'python tools/profile_forward.py %d fp16` (per-launch times are cold-cache and serialised).' % (len(VNET_ORDER), len(VNET_ORDER), BATCH), '',
              '| # | layer | class | kernel | ' + ' | '.join(c[1] for c in cols) + ' |', '|' + '---|' * (4 + len(cols))]
     traffic = collections.defaultdict(lambda: {'launches': 0, 'dram_bytes': 0.0, 'us': 0.0})
     for i, r in enumerate(data):
@@ -78,9 +84,10 @@ def full_summary(tag, rep):
     for k, t in traffic.items():
         out[k] = {'launches_per_forward': t['launches'], 'dram_bytes_per_launch': t['dram_bytes'] / t['launches'],
                   'avg_launch_us_under_ncu': t['us'] / t['launches']}
-    out['_source'] = ('dram__bytes_read.sum + dram__bytes_write.sum from ncu --set full of one VNet forward, batch 20 x 96^3 fp16 '
-                      '(profiles/%s_fwd_full_summary.md)' % tag)
-    out['_batch'] = 20
+    out['_source'] = ('dram__bytes_read.sum + dram__bytes_write.sum from ncu --set full of one VNet forward, batch %d x 96^3 fp16 '
+                      '(profiles/%s_fwd_full_summary.md)' % (BATCH, tag))
+    out['_batch'] = BATCH
+    out['_dram_bytes_per_patch_conv_launches'] = sum(t['dram_bytes'] for t in traffic.values()) / BATCH
     lines += ['', 'DRAM bytes per launch by class (written to `%s_traffic.json`):' % tag, '']
     for k, v in out.items():
         if not k.startswith('_'):
@@ -127,7 +134,7 @@ if __name__ == '__main__':
     os.makedirs(PROF, exist_ok=True)
     full_summary(tag, rep)
     launch_summary(tag, 'infer', infer_csv, 1, 'Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 1900 -c 660 --csv python bench.py '
-                   '--steps 1 --warmup 3 --no-cpu-baseline` (one 512x512x400 volume = 9 forwards of 20 patches + gather / blend / finalize).')
+                   '--steps 1 --warmup 3 --no-cpu-baseline` (one 512x512x400 volume = 5 forwards of 36 patches + gather / blend / finalize).')
     launch_summary(tag, 'train', train_csv, 3, 'Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/train_one_step.py '
-                   'bf16 8 3`; the launches between the last two dice_terms_kernel launches = one steady-state training step '
-                   '(backward + Adam of step 2, forward of step 3; B = 8 x 96^3, bf16, Dice, Adam).', marker='dice_terms_kernel')
+                   'bf16 8 4`; the launches between the last two dice_terms_kernel launches = one steady-state training step '
+                   '(backward + Adam of step 3, forward of step 4; B = 8 x 96^3, bf16, Dice, Adam).', marker='dice_terms_kernel')
