@@ -23,7 +23,7 @@ def main(path):
             continue
         rows.append((f[0], f[1], float(f[2]), float(f[4]), float(f[6])))
     total = sum(r[2] for r in rows)
-    print('# r01: every launch of one VNet forward against its roofline (batch 20 x 96^3, fp16)\n')
+    print('# every launch of one VNet forward against its roofline (batch of 96^3 patches as in the source listing, fp16)\n')
     print('Source: `%s` (`python bench.py --layers`, CUDA events per launch).  Peaks (MEASURED_PEAKS.json): HBM %.0f GB/s, bf16 tensor %.1f '
           'TFLOP/s sustained; ridge %.0f flop/B.  A launch is tensor-bound when its algorithmic flop/byte exceeds the ridge.  Launches under '
           '~20 us are dominated by the event pair around them (their GB/s is a lower bound).\n' % (os.path.relpath(path, ROOT), hbm, tf, ridge))
