@@ -65,6 +65,14 @@ def _install(monkeypatch, calls):
         calls.append(('gather', N))
         return 0
 
+    def patch_gather_rows(vol, Z, Y, X, starts, N, pz, py, px, norm, mean, std, clip, lo, hi, stats, dtype, out, row_pitch, x_off, stream):
+        # the same crop into rows of pitch row_pitch at column x_off; every other column is left as it is
+        tmp = torch.empty((N * pz * py * px,), dtype=torch.float32)
+        patch_gather(vol, Z, Y, X, starts, N, pz, py, px, norm, mean, std, clip, lo, hi, stats, dtype, type(out)(tmp, 0), stream)
+        rows = torch.as_strided(out.t.reshape(-1), (N * pz * py, px), (row_pitch, 1), out.off + x_off)
+        rows.copy_(tmp.view(N * pz * py, px).to(rows.dtype))
+        return 0
+
     def blend_accumulate(probs, N, C, pz, py, px, starts, acc, Z, Y, X, x_mult4, stream):
         assert (x_mult4 == 0) or all(s[0] % 4 == 0 for s in _starts(starts, N))
         a = acc.t.numpy().reshape(C, Z, Y, X)
@@ -85,7 +93,8 @@ def _install(monkeypatch, calls):
         calls.append(('finalize', z0, z1))
         return 0
 
-    table = {'seg3d_patch_stats': patch_stats, 'seg3d_patch_gather': patch_gather, 'seg3d_blend_accumulate': blend_accumulate,
+    table = {'seg3d_patch_stats': patch_stats, 'seg3d_patch_gather': patch_gather, 'seg3d_patch_gather_rows': patch_gather_rows,
+             'seg3d_blend_accumulate': blend_accumulate,
              'seg3d_blend_finalize_argmax_z': finalize_z}
     monkeypatch.setattr(lib, 'ptr', ptr)
     monkeypatch.setattr(lib, 'call', lambda name, *a: table[name](*a))
