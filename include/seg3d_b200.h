@@ -186,8 +186,10 @@ int seg3d_patch_gather(const float* vol, int Z, int Y, int X, const int32_t* sta
                        int pz, int py, int px, int norm, float mean, float stddev, int clip,
                        float clip_lo, float clip_hi, const double* stats,
                        int dtype, void* out, void* stream);
-/* the same crop written with a row pitch: out[((n*pz + z)*py + y)*row_pitch + x_off + x]; elements outside [x_off, x_off+px)
- * are not touched (the row-padded input layout of seg3d_conv3d_cin1_fwd: row_pitch = px + SEG3D_CIN1_PAD, x_off = SEG3D_CIN1_LEFT) */
+/* the same crop written with a row pitch: out[((n*pz + z)*py + y)*row_pitch + x_off + x].  Elements of a row outside
+ * [x_off, x_off+px) are either left untouched or written as ZERO (2-byte types with row_pitch % 8 == 0 write whole 16-byte
+ * words) - the row-padded input layout of seg3d_conv3d_cin1_fwd (row_pitch = px + SEG3D_CIN1_PAD, x_off = SEG3D_CIN1_LEFT)
+ * wants zeros there either way. */
 int seg3d_patch_gather_rows(const float* vol, int Z, int Y, int X, const int32_t* starts, int N,
                             int pz, int py, int px, int norm, float mean, float stddev, int clip,
                             float clip_lo, float clip_hi, const double* stats,

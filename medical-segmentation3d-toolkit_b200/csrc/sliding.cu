@@ -65,6 +65,48 @@ patch_gather_kernel(const float* __restrict__ vol, int Z, int Y, int X, const in
   }
 }
 
+// Row-padded output with 16-byte words: a thread owns ONE aligned word of 8 stored values of a padded row (columns 8j .. 8j+7 =
+// x indices 8j - x_off ..), reads its up to 8 voxels and writes the word once - columns outside [x_off, x_off + px) are written as
+// zeros, which is exactly what the padded layout wants there.  32-bit index arithmetic.  (2-byte storage types, row_pitch % 8 == 0.)
+template <typename T>
+__global__ void __launch_bounds__(256)
+patch_gather_rows_w8_kernel(const float* __restrict__ vol, int Z, int Y, int X, const int32_t* __restrict__ starts,
+                            int pz, int py, int px, int norm, float mean, float stddev, int clip, float lo, float hi,
+                            const double* __restrict__ stats, T* __restrict__ out, int row_pitch, int x_off) {
+  const int n = blockIdx.y;
+  const int x0 = starts[3 * n], y0 = starts[3 * n + 1], z0 = starts[3 * n + 2];
+  if (norm == SEG3D_NORM_ADAPTIVE) {
+    const double nv = (double)pz * py * px;
+    const double m = stats[2 * n] / nv;
+    double var = stats[2 * n + 1] / nv - m * m; if (var < 0) var = 0;
+    mean = (float)m; stddev = fmaxf((float)sqrt(var), 1e-6f);
+  }
+  const unsigned wpr = (unsigned)row_pitch >> 3;                    // words per row
+  const unsigned nwords = (unsigned)pz * py * wpr;
+  T* on = out + (size_t)n * pz * py * row_pitch;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) {
+    const unsigned j = i % wpr, row = i / wpr;
+    const unsigned yy = row % py, z = row / py;
+    const float* src = vol + ((size_t)(z0 + z) * Y + (y0 + yy)) * X + x0;
+    const int xb = (int)(8 * j) - x_off;
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int x = xb + k;
+      float v = 0.f;
+      if (x >= 0 && x < px) {
+        v = src[x];
+        if (norm != SEG3D_NORM_NONE) {
+          v = __fdiv_rn(__fsub_rn(v, mean), stddev);           // numpy float32: (a - mean) / std
+          if (clip) { v = v < lo ? lo : v; v = v > hi ? hi : v; }
+        }
+      }
+      f[k] = v;
+    }
+    Vec8<T> w; w.set(f); w.store(on + (size_t)row * row_pitch + 8 * j);
+  }
+}
+
 extern "C" int seg3d_patch_gather_rows(const float* vol, int Z, int Y, int X, const int32_t* starts, int N,
                                        int pz, int py, int px, int norm, float mean, float stddev, int clip,
                                        float clip_lo, float clip_hi, const double* stats, int dtype, void* out,
@@ -75,6 +117,20 @@ extern "C" int seg3d_patch_gather_rows(const float* vol, int Z, int Y, int X, co
   SEG3D_REQUIRE(norm != SEG3D_NORM_FIXED || stddev > 0.f, "patch_gather: stddev must be positive");
   SEG3D_REQUIRE(x_off >= 0 && row_pitch >= x_off + px, "patch_gather: row pitch smaller than offset + width");
   const long long nv = (long long)pz * py * px;
+  if ((dtype == SEG3D_F16 || dtype == SEG3D_BF16) && x_off > 0 && row_pitch % 8 == 0 && row_pitch >= x_off + px && ((uintptr_t)out) % 16 == 0 &&
+      (long long)pz * py * (row_pitch / 8) < (1ll << 31)) {
+    const long long nwords = (long long)pz * py * (row_pitch / 8);
+    int gxw = (int)((nwords + 255) / 256); if (gxw < 1) gxw = 1; if (gxw > 4096) gxw = 4096;
+    dim3 gridw(gxw, N);
+    if (dtype == SEG3D_F16)
+      patch_gather_rows_w8_kernel<__half><<<gridw, 256, 0, (cudaStream_t)stream>>>(vol, Z, Y, X, starts, pz, py, px, norm, mean, stddev, clip,
+                                                                                   clip_lo, clip_hi, stats, (__half*)out, row_pitch, x_off);
+    else
+      patch_gather_rows_w8_kernel<__nv_bfloat16><<<gridw, 256, 0, (cudaStream_t)stream>>>(vol, Z, Y, X, starts, pz, py, px, norm, mean, stddev, clip,
+                                                                                          clip_lo, clip_hi, stats, (__nv_bfloat16*)out, row_pitch, x_off);
+    SEG3D_CHECK_LAUNCH("patch_gather_rows_w8_kernel");
+    return SEG3D_OK;
+  }
   int gx = (int)((nv + 256 * 4 - 1) / (256 * 4)); if (gx < 1) gx = 1; if (gx > 2048) gx = 2048;
   dim3 grid(gx, N);
   SEG3D_DISPATCH_DTYPE(dtype, T, (patch_gather_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(

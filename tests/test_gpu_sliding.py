@@ -151,6 +151,34 @@ def test_patch_gather_normalisers_bit_exact_fixed():
         assert np.abs(out[i].cpu().numpy() - ref).max() <= 1e-5
 
 
+@pytest.mark.parametrize('dt_name', ['F16', 'BF16', 'F32'])
+def test_patch_gather_rows_writes_the_padded_layout(dt_name):
+    """seg3d_patch_gather_rows (the row-padded input of the Toeplitz input block): every voxel lands at column x_off + x with the
+    value seg3d_patch_gather stores, and the padding columns are zero (2-byte types: written as zeros by the word-wise kernel;
+    fp32: left as the caller initialised them)."""
+    from segmentation3d._b200 import lib as L
+    L.load()
+    dt = getattr(L, dt_name)
+    tdt = L.TORCH_DTYPE[dt]
+    g = torch.Generator().manual_seed(4)
+    vol = (torch.randn((40, 48, 56), generator=g) * 300).float()
+    starts = [[3, 5, 7], [24, 16, 8], [0, 0, 0]]
+    sd = torch.tensor(np.asarray(starts, np.int32), device='cuda')
+    vd = vol.cuda()
+    pz, py, px = 24, 32, 32
+    pitch, off = px + L.CIN1_PAD, L.CIN1_LEFT
+    dense = torch.empty((3, pz, py, px), dtype=tdt, device='cuda')
+    L.call('seg3d_patch_gather', L.ptr(vd), 40, 48, 56, L.ptr(sd), 3, pz, py, px, L.NORM_FIXED, 50.0, 200.0, 1, -1.0, 1.0,
+           None, dt, L.ptr(dense), L.stream_ptr())
+    fill = 0.0 if dt == L.F32 else 7.0            # the word-wise kernel must overwrite the padding of the 2-byte layouts with zeros
+    rows = torch.full((3, pz, py, pitch), fill, dtype=tdt, device='cuda')
+    L.call('seg3d_patch_gather_rows', L.ptr(vd), 40, 48, 56, L.ptr(sd), 3, pz, py, px, L.NORM_FIXED, 50.0, 200.0, 1, -1.0, 1.0,
+           None, dt, L.ptr(rows), pitch, off, L.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(rows[..., off:off + px], dense)
+    assert float(rows[..., :off].float().abs().max()) == 0 and float(rows[..., off + px:].float().abs().max()) == 0
+
+
 @pytest.mark.parametrize('size,psize,pstride', [((64, 48, 80), 32, 16), ((48, 48, 96), 32, 32)], ids=['overlap', 'tiled'])
 def test_host_path_progressive_finalize_equals_device_path(size, psize, pstride):
     """segmentation_volume_host (slab-wise upload, z-ordered patches, slab-wise finalize + mask copy-out) must give the
