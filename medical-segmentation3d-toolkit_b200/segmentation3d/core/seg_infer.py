@@ -366,17 +366,34 @@ def segmentation_volume_device(model, cfg, vol, batch=None, shard=None, bbox_sta
         mask = torch.zeros((Z, Y, X), dtype=torch.int8, device=vol.device)
         acc = torch.zeros((C, z_hi - z_lo, Y, X), dtype=torch.float32, device=vol.device)
         if mine:
-            local = [[s[0], s[1], s[2] - z_lo] for s in mine]
-            if z_ready is not None:
-                cur = torch.cuda.current_stream()
-                for z1, ev in z_ready:
-                    cur.wait_event(ev)
-            # one forward over all of this rank's patches when they fit the workspace budget (a 12 + 11 split of 23 patches
-            # runs two latency-bound half batches)
+            local = sorted([[s[0], s[1], s[2] - z_lo] for s in mine], key=lambda s: s[2])
             keep = eng.batch
-            if len(local) <= max(eng.batch, int(40e9 // (430.0 * pv))):
-                eng.batch = max(eng.batch, len(local))
-            eng.accumulate(vol[z_lo:z_hi], local, patch, norm, acc)
+            budget = max(eng.batch, int(40e9 // (430.0 * pv)))
+            if z_ready is None:
+                # one forward over all of this rank's patches when they fit the workspace budget (a 12 + 11 split of 23 patches
+                # runs two latency-bound half batches)
+                chunks = [local] if len(local) <= budget else [local[i:i + eng.batch] for i in range(0, len(local), eng.batch)]
+            else:
+                # the z range is still being uploaded slab by slab (segmentation_volume_host): one forward per z layer of the
+                # lattice (layers merged while they stay within a patch batch), each waiting only for the planes it reads, so
+                # the upload of the later layers hides behind the first forward
+                chunks = []
+                for s in local:
+                    if chunks and (s[2] == chunks[-1][-1][2] or len(chunks[-1]) + sum(1 for t in local if t[2] == s[2]) <= eng.batch) \
+                            and len(chunks[-1]) < budget:
+                        chunks[-1].append(s)
+                    else:
+                        chunks.append([s])
+            cur = torch.cuda.current_stream() if z_ready is not None else None
+            for chunk in chunks:
+                if z_ready is not None:
+                    zmax = z_lo + max(s[2] for s in chunk) + patch[2]
+                    for z1, ev in z_ready:
+                        cur.wait_event(ev)
+                        if z1 >= zmax:
+                            break
+                eng.batch = max(keep, len(chunk)) if len(chunk) <= budget else keep
+                eng.accumulate(vol[z_lo:z_hi], chunk, patch, norm, acc)
             eng.batch = keep
             eng.finalize(acc, [counts[0], counts[1], np.ascontiguousarray(counts[2][z_lo:z_hi])], mask=mask[z_lo:z_hi])
         if mask_root is None:

@@ -17,14 +17,14 @@ torch.cuda.set_device(local)
 dist.init_process_group('nccl', device_id=torch.device('cuda:%d' % local))
 
 
-def run(overlap):
+def run(overlap, mode='fp32'):
     """averaged gradients of one data-parallel step (compared before Adam, which would amplify rounding noise on
     near-zero gradients to +-lr)"""
     os.environ['SEG3D_OVERLAP_ALLREDUCE'] = '1' if overlap else '0'
     torch.manual_seed(0)
     net = vnet.SegmentationNet(1, 2)
     vnet.parameters_kaiming_init(net)
-    net.b200_mode = 'bf16'
+    net.b200_mode = mode
     net = net.cuda().train()
     D.broadcast_params(net)
     lf = MultiDiceLoss([0.5, 0.5], 2, True)
@@ -41,10 +41,26 @@ def run(overlap):
     return [p.grad.detach().clone() for p in params], float(loss), reduced
 
 
+# The exchange is checked in the strict fp32 mode, where a step is reproducible to fp32-atomic rounding (~1e-6).  In bf16 two
+# runs of the SAME schedule already differ by up to ~1e-2 in the deep layers in about half of the processes: the double-precision
+# atomics of the loss / tail reductions land in a different order, one stored bf16 gradient flips by an ulp, and the deep layers
+# of a random-init net amplify that (tools/diag_overlap.py shows the first differing tensor is the tail's
+# gradient, with the forward sums bit-identical) - so bf16 gets the band of that noise, not the 1e-3 of a race check.
 ga, la, fa = run(True)
 gb, lb, fb = run(False)
 assert fa and not fb, (fa, fb)
 worst = max(float((a - b).abs().max() / (b.abs().max() + 1e-20)) for a, b in zip(ga, gb))
+ha, _, _ = run(True, 'bf16')
+hb, _, _ = run(False, 'bf16')
+worst_bf16 = max(float((a - b).abs().max() / (b.abs().max() + 1e-20)) for a, b in zip(ha, hb))
+print('rank %d: bf16 step, overlapped vs sequential: worst per-tensor relative gradient difference %.3g (run-to-run band of bf16)'
+      % (rank, worst_bf16), flush=True)
+assert worst_bf16 <= 5e-2
+if worst > 1e-4:        # name the tensors: a race between an all-reduce and a kernel still writing its range shows up here
+    _net = vnet.SegmentationNet(1, 2)
+    names = [n for n, _ in _net.named_parameters()]
+    rows = sorted(((float((a - b).abs().max() / (b.abs().max() + 1e-20)), n) for n, a, b in zip(names, ga, gb)), reverse=True)
+    print('rank %d: largest differences: %s' % (rank, ', '.join('%s %.2g' % (n, r) for r, n in rows[:6])), flush=True)
 flat = torch.cat([g.reshape(-1) for g in ga])
 other = flat.clone()
 dist.broadcast(other, 0)
@@ -52,7 +68,7 @@ same_across_ranks = bool(torch.equal(other, flat))
 print('rank %d: overlapped vs sequential all-reduce, worst per-tensor relative gradient difference %.3g, losses %.6f / %.6f, '
       'ranks identical: %s' % (rank, worst, la, lb, same_across_ranks), flush=True)
 # wgrad accumulates with fp32 atomics (order varies run to run), so the two runs agree to rounding, not bitwise
-assert worst <= 1e-3 and same_across_ranks
+assert worst <= 1e-4 and same_across_ranks
 
 
 def dp_vs_global_batch():
