@@ -13,6 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def main(path):
+    import re
+    m = re.search(r'_b(\d+)', os.path.basename(path))
+    batch = int(m.group(1)) if m else 20
     pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     hbm, tf = pk['hbm_gbs'], pk['bf16_tflops_sustained']
     ridge = tf * 1e3 / hbm
@@ -40,7 +43,7 @@ def main(path):
         a[0] += ms
         a[1] += ms * frac
     print('\nTime-weighted: ' + '; '.join('%s-bound launches %.2f ms (%.0f %% of the forward) at %.2f of their roofline' % (
-        b, a[0], 100 * a[0] / total, a[1] / a[0]) for b, a in sorted(agg.items())) + '.  Whole forward %.2f ms per batch = %.3f ms per patch.' % (total, total / 20))
+        b, a[0], 100 * a[0] / total, a[1] / a[0]) for b, a in sorted(agg.items())) + '.  Whole forward %.2f ms per batch of %d = %.3f ms per patch.' % (total, batch, total / batch))
     big = [(n, ms) for n, k, ms, t, g in rows if ms >= 0.02]
     below = []
     for name, kind, ms, tfl, gbs in rows:
