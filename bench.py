@@ -44,8 +44,27 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+
 import numpy as np   # noqa: E402
 import torch         # noqa: E402
+
+def init_nccl(dev):
+    """init_process_group with NCCL's start-up banner ("NCCL version ..." is printf'ed to stdout by the first communicator) sent to
+    stderr: stdout carries exactly ONE JSON line."""
+    import torch.distributed as dist
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+        dist.barrier()                       # the communicator (and its banner) exists before stdout is restored
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    return dist
+
 
 METRIC = 'sliding-window infer Mvoxels/s (512x512x400 CT, VNet, 96^3 patches)'  # BASELINE.json headline (configs[1]); main() renames it for --arch vbnet
 TRAIN_METRIC = 'train patches/s (VNet, 96^3 patches, batch %d/GPU, Dice, Adam)'
@@ -330,8 +349,7 @@ def run_train(args):
     dev = 'cuda:%d' % local
     dist = None
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device(dev))
+        dist = init_nccl(dev)
     rec = measure_train(args, dist, rank, world, dev)
     if rank == 0:
         rec['vs_baseline'] = None
@@ -390,8 +408,7 @@ def main():
     dev = 'cuda:%d' % local
     dist = None
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device(dev))
+        dist = init_nccl(dev)
 
     from segmentation3d._b200 import lib
     from segmentation3d.core.seg_infer import segmentation_volume_device, segmentation_volume_host, make_model
