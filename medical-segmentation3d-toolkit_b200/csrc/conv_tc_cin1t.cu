@@ -15,11 +15,11 @@
 // lives in a row-padded buffer [N][D][H][W+16] with x index i at column i+9, which makes every window start 16-byte aligned
 // and supplies the left/right zero halo; the y/z halo is the TMA unit's out-of-bounds zero fill.  A CTA owns a 32(x) x 32(y)
 // column tile (rows = (y, segment-in-tile), so the kh tap is a row shift of 4 = 128 bytes of the descriptor start address),
-// marches along z with a ring of halo planes (each loaded once: 4.3 KB for 1024 voxels), and issues 2 x 9 MMAs
-// 128 x 128 x 16 per output plane: the weights are split into two half-precision terms hi(T) + lo(T) so they stay
-// fp32-accurate, and both terms accumulate into the same 128 TMEM columns.  Eight epilogue warps drain four rotating
+// marches along z with a ring of halo planes (each loaded once: 4.3 KB for 1024 voxels), and issues 9 MMAs
+// 128 x 128 x 16 per output plane (weights rounded to the storage type, as in every other layer; SEG3D_CIN1_LO=1 splits them into
+// two half-precision terms hi(T) + lo(T) accumulated into the same 128 TMEM columns: fp32-accurate weights at twice the MMAs).  Eight epilogue warps drain four rotating
 // accumulators: every thread owns half a segment and writes its 4 voxels x 16 channels as full 32-byte sectors.  The banded
-// matrix wastes tensor flops (163 GFLOP issued for 15 real ones at batch 20) to buy a layer without a single per-voxel
+// matrix wastes tensor flops (82 GFLOP issued for 15 real ones at batch 20) to buy a layer without a single per-voxel
 // instruction outside the epilogue: algorithmic bytes = 2 B read + 32 B written per voxel.
 //
 // Epilogue modes: 0 = store conv + bias and accumulate the GroupNorm sums; 1 = sums only (nothing stored);
@@ -455,7 +455,10 @@ extern "C" int seg3d_conv3d_cin1_fwd(int dtype, int epi_mode, const void* xpad, 
   SEG3D_REQUIRE(nitems > 0 && nitems < (1ll << 31), "conv3d_cin1_fwd: work-item count out of range");
   p.nitems = (int)nitems;
   const uint32_t fmt = dtype == SEG3D_BF16 ? 1u : 0u;
-  p.lo = env_int("SEG3D_CIN1_LO", 1) ? 1 : 0;
+  // weights: 0 (default) = rounded to the storage type like every other layer's tensor-core weights (9 MMAs per plane);
+  // 1 = split hi + lo, fp32-accurate (18 MMAs).  The layer is tensor-bound on the band's wasted flops and the step is power-limited:
+  // the second half of the MMAs cost 2.5 % of the whole sliding-window step for no measurable parity change.
+  p.lo = env_int("SEG3D_CIN1_LO", 0) ? 1 : 0;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   // overlapping-window tensor map: element (i, s, y, z, n) = xpad[n][z][y][8 + 8 s + i], i.e. x index 8 s - 1 + i
   CUtensorMap map_x;

@@ -482,8 +482,8 @@ def test_conv_cin1_tensor_core_matches_torch(lib, shape, dt_name):
 
 
 @pytest.mark.parametrize('shape', [(2, 8, 12, 16), (1, 20, 40, 24), (3, 5, 16, 8), (2, 33, 70, 72), (1, 96, 96, 96)], ids=str)
-@pytest.mark.parametrize('dt_name', ['F16', 'BF16'])
-def test_conv_cin1_toeplitz_matches_torch(lib, shape, dt_name):
+@pytest.mark.parametrize('dt_name,lo', [('F16', 0), ('BF16', 0), ('F16', 1)])
+def test_conv_cin1_toeplitz_matches_torch(lib, monkeypatch, shape, dt_name, lo):
     """Input block as a TMA-fed banded-Toeplitz GEMM (seg3d_conv3d_cin1_fwd, row-padded input): the three epilogue modes vs
     F.conv3d / F.group_norm on the input rounded to the storage type with fp32 weights.  Shapes cover partial 32 x 32 tiles,
     several z segments and W / 8 not a multiple of the 4-segment box."""
@@ -491,13 +491,15 @@ def test_conv_cin1_toeplitz_matches_torch(lib, shape, dt_name):
     dt = getattr(L, dt_name)
     tdt = L.TORCH_DTYPE[dt]
     N, D, H, W = shape
+    monkeypatch.setenv('SEG3D_CIN1_LO', str(lo))       # 0 (default): weights rounded to the storage type; 1: hi + lo split, fp32-accurate
     g = torch.Generator().manual_seed(D * 7 + W)
     x = torch.randn((N, 1, D, H, W), generator=g).to(tdt).float()
     w = torch.randn((16, 1, 3, 3, 3), generator=g) * 0.3
     b = torch.randn((16,), generator=g) * 0.1
     gamma = torch.rand((16,), generator=g) + 0.5
     beta = torch.randn((16,), generator=g) * 0.2
-    ref = F.conv3d(x, w, b, padding=1)
+    w_seen = w if lo else w.to(tdt).float()
+    ref = F.conv3d(x, w_seen, b, padding=1)
     ref_gn = F.relu(F.group_norm(ref, 1, gamma, beta, 1e-5))
     pitch = W + L.CIN1_PAD
     xp = torch.zeros((N, D, H, pitch), dtype=tdt, device='cuda')
