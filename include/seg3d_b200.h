@@ -76,7 +76,8 @@ int seg3d_conv3d_fwd(int mode, int dtype, int impl,
 /* Input block on the tensor cores as a banded-Toeplitz GEMM fed by TMA (vnet_inblock.py:9-15; csrc/conv_tc_cin1t.cu).
  * xpad: the single-channel input in a row-padded layout [N][D][H][W + SEG3D_CIN1_PAD] (dtype f16/bf16, W % 8 == 0): x index i
  * of a row sits at column i + SEG3D_CIN1_LEFT, every other column is zero (seg3d_patch_gather_rows writes this layout).
- * w: fp32 [27][16] (tap-major, as the SIMT layout); y: [N,D,H,W,16] pitch y_ld.
+ * w: fp32 [27][16] (tap-major, as the SIMT layout), rounded to `dtype` inside the kernel like every other tensor-core layer's
+ * weights (environment SEG3D_CIN1_LO=1: split into two `dtype` terms, fp32-accurate, twice the MMAs); y: [N,D,H,W,16] pitch y_ld.
  * epi_mode 0: y = conv + bias, stats[n] += {sum, sum of squares};  1: the sums only, y is not touched;
  * 2: y = relu(GroupNorm(conv + bias)) with `stats` holding the FINISHED sums (written by a mode-1 call), gamma / beta
  * the GroupNorm affine.  1 then 2 is the inference schedule: the raw tensor and the GroupNorm-apply pass never reach HBM. */
