@@ -157,6 +157,13 @@ def _sharded_engine_worker(rank, world, port, q):
         if gather == 'probs':
             ok = ok and float((acc - single_acc).abs().max()) <= 1e-6
         out[name] = (ok, sum(plan.forwards))
+    # 'labels' exchange reduced to rank 0 only (mask_root): the root holds the single-process mask, the other rank its partial one
+    cfg = {'partition_type': 'SIZE', 'partition_size': [32, 32, 32], 'partition_stride': [32, 32, 32]}
+    model, _ = tsw._model(sd, 2, nd, lib, batch=1)
+    _, single_mask = segmentation_volume_device(model, cfg, torch.from_numpy(vol))
+    model, _ = tsw._model(sd, 2, nd, lib, batch=1)
+    _, mask = segmentation_volume_device(model, cfg, torch.from_numpy(vol), shard=(rank, world), gather='labels', mask_root=0)
+    out['labels_to_root'] = (bool(torch.equal(mask, single_mask)) if rank == 0 else bool((mask <= single_mask).all()), 1)
     q.put((rank, out))
     dist.destroy_process_group()
 
@@ -178,6 +185,7 @@ def test_patch_sharded_engine_under_gloo_equals_single_process():
     for r in range(2):
         assert res[r]['tiled_labels'] == (True, 1) and res[r]['tiled_probs'] == (True, 1)         # 2 patches, one per rank
         assert res[r]['overlap_probs'][0] is True
+        assert res[r]['labels_to_root'][0] is True
     assert res[0]['overlap_probs'][1] + res[1]['overlap_probs'][1] == 3                            # 3 overlapping patches in all
 
 
