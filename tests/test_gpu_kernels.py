@@ -227,6 +227,24 @@ def test_forward_default_mode_meets_reduced_precision_bars(lib, arch, cout, monk
     assert rep['max_abs'] <= 1e-2 and rep['agree'] >= 0.999 and min(rep['dice']) >= 0.999, rep
 
 
+@pytest.mark.parametrize('arch', ['vnet', 'vbnet'])
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-3), ('fp32x', 1e-3), ('fp16', 1e-2)])
+def test_forward_sixteen_classes_like_the_reference_test(lib, arch, mode, tol):
+    """The reference's own network test builds a 16-class net (network/vbnet_test.py:9, vnet_test.py): the out-block tail kernels
+    are instantiated up to 16 classes and out_block.conv1 runs zero-padded on the generic tensor-core kernel (the folded
+    narrow-output kernel takes up to 7).  Probabilities against the oracle in the strict and the reduced modes."""
+    sd = oinit.randomize_affine(oinit.init_state_dict(arch, 1, 16, 3), 11)
+    x = seeded_input(17, (2, 1, 32, 32, 32), 'smooth')
+    ref = onet.forward(sd, x)
+    y, resolved = _net_forward(arch, 16, sd, x, mode)
+    assert resolved == mode and tuple(y.shape) == (2, 16, 32, 32, 32)
+    assert float((y.sum(1) - 1).abs().max()) <= 1e-5
+    err = float((y - ref).abs().max())
+    print(arch, '16 classes', mode, 'max|dp| %.3g' % err)
+    assert err <= tol, (arch, mode, err)
+    assert _net_forward(arch, 16, sd, x)[1] == 'fp32x'           # the default mode of a multi-class net
+
+
 def test_forward_vbnet5_plain_fp16_probability_and_agreement_bars(lib):
     """The explicit fast mode on the 5-class VBNet: max|dp| and label agreement meet the bars.  The per-class Dice of the two
     rare classes (780 and 2107 of 262144 voxels, ~2 % of them within 1e-3 of a tie on random-init weights) is recorded, not

@@ -23,7 +23,7 @@ def _net(arch, cout, sd, mode):
     return net.cuda().train()
 
 
-@pytest.mark.parametrize('arch,cout,lossname', [('vnet', 2, 'dice'), ('vbnet', 5, 'focal')])
+@pytest.mark.parametrize('arch,cout,lossname', [('vnet', 2, 'dice'), ('vbnet', 5, 'focal'), ('vnet', 16, 'focal')])
 def test_gradients_match_oracle_autograd_fp32(arch, cout, lossname):
     from segmentation3d.loss.focal_loss import FocalLoss
     from segmentation3d.loss.multi_dice_loss import MultiDiceLoss
